@@ -1,0 +1,131 @@
+/* xfg_stark.h — C ABI of libxfgstark.so, the B200 (sm_100a) proving backend for the XFG burn-mint STARK.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: the path it replaces is the
+ * pure-Rust call `air.prove(trace)` at src/burn_mint_prover.rs:124 (winter_prover::Prover::prove on the types bound at
+ * src/burn_mint_air.rs:479-531).  A Rust `-sys` crate binds exactly these entry points (rust/xfg-stark-gpu-sys,
+ * INTEGRATION.md) and `GpuBurnMintProver: winterfell::Prover` overrides `prove()` with xfg_prove_burn_mint.
+ *
+ * Conventions: plain pointers and sizes; caller owns every host buffer; field elements cross the boundary as canonical
+ * u64 (< p = 2^64 - 2^32 + 1), i.e. `BaseElement::as_int()`; all functions return 0 (XFG_OK) or an XFG_ERR_* code and
+ * never throw or abort.  A context is bound to one device and is NOT thread-safe; distinct contexts are independent.
+ * There is no CPU fallback: without a usable CUDA device xfg_create fails with XFG_ERR_CUDA.
+ */
+#ifndef XFG_STARK_H
+#define XFG_STARK_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "xfg/spec.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xfg_ctx xfg_ctx;
+
+/* replaces winter_air::ProofOptions as built at src/burn_mint_prover.rs:28-35 (argument meaning per SURVEY.md A.2) */
+typedef struct xfg_options {
+  uint32_t num_queries;              /* 1..255 */
+  uint32_t blowup_factor;            /* this backend: 8 */
+  uint32_t grinding_factor;          /* 0..32 */
+  uint32_t field_extension;          /* XFG_EXT_NONE = 1, XFG_EXT_QUADRATIC = 2 */
+  uint32_t fri_folding_factor;       /* this backend: 8 */
+  uint32_t fri_remainder_max_degree; /* 2^k - 1, 7..255 */
+} xfg_options;
+
+/* replaces BurnMintPublicInputs (src/burn_mint_air.rs:23-71) plus the constants XfgBurnMintAir derives from them and the
+ * secret (src/burn_mint_air.rs:124-133, 174-202, 362-365) */
+typedef struct xfg_air_consts {
+  uint64_t pub_inputs[XFG_NUM_PUB_INPUTS]; /* ToElements order */
+  uint64_t txn_hash;                       /* pub.txn_hash as u32 */
+  uint64_t recipient_hash;                 /* pub.recipient_hash as u32 */
+  uint64_t nullifier;                      /* compute_nullifier(secret) */
+  uint64_t commitment;                     /* compute_commitment(secret) */
+} xfg_air_consts;
+
+/* device time per winter-prover tracing span, CUDA-event measured */
+enum {
+  XFG_ST_EXTEND_TRACE = 0, XFG_ST_COMMIT_TRACE, XFG_ST_EVAL_CONSTRAINTS, XFG_ST_COMMIT_CONSTRAINTS, XFG_ST_BUILD_DEEP,
+  XFG_ST_EVAL_DEEP, XFG_ST_FRI_LAYERS, XFG_ST_QUERY_POSITIONS, XFG_ST_BUILD_PROOF, XFG_NUM_STAGES
+};
+typedef struct xfg_stage_times {
+  float stage_ms[XFG_NUM_STAGES];
+  float h2d_ms;      /* trace upload (0 for the *_device entry point) */
+  float device_ms;   /* first kernel .. last kernel, inputs resident */
+  float total_ms;    /* upload .. proof material back on the host */
+  uint32_t kernel_launches;
+} xfg_stage_times;
+
+enum {
+  XFG_OK = 0,
+  XFG_ERR_BAD_ARGS = 1,            /* null pointer, size out of range, non-canonical element */
+  XFG_ERR_BAD_OPTIONS = 2,         /* ProofOptions::new range checks (A.2) */
+  XFG_ERR_UNSUPPORTED_OPTIONS = 3, /* valid for Winterfell, not implemented by this backend (blowup != 8, folding != 8) */
+  XFG_ERR_UNSUPPORTED_EXTENSION = 4, /* mirrors ProverError::UnsupportedFieldExtension (cubic) */
+  XFG_ERR_UNSATISFIED_CONSTRAINT = 5, /* mirrors ProverError::UnsatisfiedTransitionConstraintError / MismatchedConstraintPolynomialDegree */
+  XFG_ERR_BUFFER_TOO_SMALL = 6,    /* *out_len holds the required size */
+  XFG_ERR_CUDA = 7,                /* CUDA runtime error; see xfg_last_error */
+  XFG_ERR_INVALID_INPUT = 8,       /* prove_burn_mint input validation (src/burn_mint_prover.rs:132-208); see xfg_last_error */
+  XFG_ERR_TOO_LARGE = 9,           /* n_log2 exceeds the context's max_n_log2 */
+  XFG_ERR_INTERNAL = 10
+};
+
+/* ---- context ---- */
+/* One context = one device + `num_slots` independent proof workspaces (each with its own stream) sized for traces of up to
+ * 2^max_n_log2 rows.  Replaces nothing in the reference (its prover is a stateless CPU call). */
+int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** out);
+void xfg_destroy(xfg_ctx* ctx);
+const char* xfg_strerror(int code);
+const char* xfg_last_error(const xfg_ctx* ctx);
+
+/* ---- whole proof: replaces `air.prove(trace)` (src/burn_mint_prover.rs:124, winter_prover::Prover::prove) ---- */
+/* trace: column-major, 7 columns x 2^n_log2 rows (TraceTable::init layout, src/burn_mint_air.rs:475), host memory.
+ * out receives StarkProof::to_bytes() (the bytes consumed at src/bin/xfg-stark-cli.rs:533). */
+int xfg_prove_burn_mint(xfg_ctx* ctx, const uint64_t* trace_colmajor, uint32_t n_log2, const xfg_air_consts* air,
+                        const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
+/* same, trace already resident in device memory of ctx's device (d_trace is a device pointer) */
+int xfg_prove_burn_mint_device(xfg_ctx* ctx, const uint64_t* d_trace_colmajor, uint32_t n_log2, const xfg_air_consts* air,
+                               const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
+/* `count` independent proofs of equal size, pipelined over the context's slots (BASELINE config 4; replaces the sequential
+ * loops of examples/winterfell_burn_mint_production.rs:187-195).  traces[i], airs[i] as above; proof i is written at
+ * out + i*out_stride (out_stride >= the largest proof) and its length to out_lens[i]. */
+int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* const* traces, uint32_t n_log2,
+                              const xfg_air_consts* airs, const xfg_options* options, uint8_t* out, size_t out_stride,
+                              size_t* out_lens, float* total_ms);
+
+/* ---- host-side mirror of XfgBurnMintProver (src/burn_mint_prover.rs) ---- */
+/* validate_inputs + secret_to_field_element + compute_recipient_hash + public-input packing (:62-107, :132-221) and the
+ * AIR's Keccak scalars (src/burn_mint_air.rs:124-133, 157-202).  Host-only (3 Keccak-256 calls). */
+int xfg_burn_mint_pack_inputs(xfg_ctx* ctx, uint64_t burn_amount, uint64_t mint_amount, const uint8_t tx_prefix_hash[32],
+                              const uint8_t* recipient_address, size_t recipient_len, const uint8_t* secret, size_t secret_len,
+                              uint32_t network_id, uint32_t target_chain_id, uint32_t commitment_version, xfg_air_consts* out);
+/* XfgBurnMintAir::build_trace (src/burn_mint_air.rs:442-476) generalised to 2^n_log2 rows (state = floor(4i/n)) */
+int xfg_burn_mint_build_trace(const xfg_air_consts* air, uint32_t n_log2, uint64_t* trace_colmajor_out);
+/* XfgBurnMintProver::prove_burn_mint (src/burn_mint_prover.rs:62-129), the reference's 8 arguments + the trace length */
+int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn_amount, uint64_t mint_amount, const uint8_t tx_prefix_hash[32],
+                                    const uint8_t* recipient_address, size_t recipient_len, const uint8_t* secret, size_t secret_len,
+                                    uint32_t network_id, uint32_t target_chain_id, uint32_t commitment_version, uint32_t n_log2,
+                                    const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
+
+/* ---- stage entry points (kernel-level parity tests; host buffers in and out) ---- */
+/* `batch` transforms of 2^n_log2 points, contiguous; inverse != 0 = fft::interpolate_poly, else forward evaluation */
+int xfg_ntt(xfg_ctx* ctx, uint64_t* data, uint32_t n_log2, uint32_t batch, int inverse);
+/* DefaultTraceLde::new (src/burn_mint_air.rs:513): interpolate `cols` (1, 2 or 7) columns, extend by 8 over the coset 7*<w_N>,
+ * commit to rows.  lde_out (optional) = cols x 8n evaluations in natural order; root_out = 32 bytes */
+int xfg_lde_commit(xfg_ctx* ctx, const uint64_t* cols_colmajor, uint32_t n_log2, uint32_t cols, uint64_t* lde_out, uint8_t root_out[32]);
+/* MerkleTree::new over `count` (power of two >= 2) 32-byte leaves; nodes_out (optional) = count node slots as Winterfell */
+int xfg_merkle_root(xfg_ctx* ctx, const uint8_t* leaves, size_t count, uint8_t root_out[32], uint8_t* nodes_out);
+/* DefaultConstraintEvaluator::evaluate over the 2n-point constraint domain.  lde: 7 x 8n natural order; coeffs: 7 transition
+ * then 8 boundary coefficients, `ext` limbs each; out: 2n x ext limbs (element-major), natural order of the CE domain */
+int xfg_eval_constraints(xfg_ctx* ctx, const uint64_t* lde, uint32_t n_log2, const xfg_air_consts* air, uint32_t ext,
+                         const uint64_t* coeffs, uint64_t* out);
+/* folding::apply_drp with folding factor 8 and domain offset 7: evals = 2^nl_log2 x ext limbs (element-major, natural order),
+ * alpha = ext limbs; out = 2^(nl_log2-3) x ext limbs */
+int xfg_fri_fold_layer(xfg_ctx* ctx, const uint64_t* evals, uint32_t nl_log2, uint32_t ext, const uint64_t* alpha, uint64_t* out);
+/* hash_elements of `rows` rows of `limbs` (1, 2, 7, 8 or 16) canonical u64 each, row-major; out = rows x 32 bytes */
+int xfg_hash_rows(xfg_ctx* ctx, const uint64_t* rows_rowmajor, size_t rows, uint32_t limbs, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XFG_STARK_H */

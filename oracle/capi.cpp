@@ -156,6 +156,17 @@ long orc_debug_get(const char* name, u64* out, size_t cap) {
   std::memcpy(out, v.data(), v.size() * 8); return (long)v.size();
 }
 
+// winter-fri folding::apply_drp, folding factor F, offset 7: evals = Nl elements of `deg` limbs (element-major) -> Nl/F
+void orc_fri_fold(const u64* evals, size_t Nl, int deg, size_t F, const u64* alpha, u64* out) {
+  size_t rows = Nl / F; u64 gl_inv = finv(root_of_unity(ilog2(Nl))), oinv = finv(XFG_GENERATOR);
+  std::vector<u64> xinv = power_series(gl_inv, rows, oinv);
+  for (size_t i = 0; i < rows; i++) {
+    if (deg == 1) { std::vector<F1> row(F); for (size_t j = 0; j < F; j++) row[j] = F1(evals[i + j * rows]); out[i] = fold_row<F1>(row.data(), F, xinv[i], F1(alpha[0])).v; }
+    else { std::vector<F2> row(F); for (size_t j = 0; j < F; j++) row[j] = F2(evals[2 * (i + j * rows)], evals[2 * (i + j * rows) + 1]);
+           F2 r = fold_row<F2>(row.data(), F, xinv[i], F2(alpha[0], alpha[1])); out[2 * i] = r.a0; out[2 * i + 1] = r.a1; }
+  }
+}
+
 // returns 0 = accepted, 1 = rejected (reason in err)
 int orc_verify(const u8* proof, size_t len, const u64 pi[12], const u64 consts[4], const uint32_t o[6], char* err, size_t errcap) {
   try {

@@ -10,6 +10,8 @@
 
 namespace orc {
 
+extern int g_threads;
+
 struct BatchMerkleProof {
   std::vector<Digest> leaves;               // in the order of the queried indexes
   std::vector<std::vector<Digest>> nodes;   // one vector per normalised (even) index
@@ -63,8 +65,12 @@ struct MerkleTree {
     size_t n = leaves.size();
     if (n < 2 || (n & (n - 1))) throw std::runtime_error("number of leaves must be a power of two >= 2");
     nodes.assign(n, Digest{});
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && n >= 4096)
     for (size_t i = 0; i < n / 2; i++) nodes[n / 2 + i] = merge(leaves[2 * i], leaves[2 * i + 1]);
-    for (size_t i = n / 2 - 1; i >= 1; i--) nodes[i] = merge(nodes[2 * i], nodes[2 * i + 1]);
+    for (size_t lo = n / 4; lo >= 1; lo >>= 1) {   // level [lo, 2*lo): same values as the serial i = n/2-1 .. 1 loop
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && lo >= 2048)
+      for (size_t i = lo; i < 2 * lo; i++) nodes[i] = merge(nodes[2 * i], nodes[2 * i + 1]);
+    }
   }
   const Digest& root() const { return nodes[1]; }
   unsigned depth() const { return ilog2_(leaves.size()); }

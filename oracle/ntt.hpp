@@ -9,38 +9,45 @@
 
 namespace orc {
 
+extern int g_threads;
+
 inline std::vector<u64> power_series(u64 base, size_t n, u64 first = 1) {
   std::vector<u64> r(n); u64 x = first; for (size_t i = 0; i < n; i++) { r[i] = x; x = fmul(x, base); } return r;
 }
 inline unsigned ilog2(size_t n) { unsigned k = 0; while ((size_t(1) << k) < n) k++; return k; }
 
-// w^i for i < n/2, w = root_of_unity(log2 n) or its inverse
+// per-stage twiddles, contiguous: stage with butterfly span `len` uses w_len^j for j < len/2 (stored at offset len/2)
 inline const std::vector<u64>& twiddles(size_t n, bool inverse) {
   static std::map<std::pair<size_t, bool>, std::vector<u64>> cache;
   auto key = std::make_pair(n, inverse);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
-  u64 w = root_of_unity(ilog2(n)); if (inverse) w = finv(w);
-  return cache[key] = power_series(w, n / 2 ? n / 2 : 1);
+  std::vector<u64> t(n ? n : 1, 1);
+  for (size_t len = 2; len <= n; len <<= 1) {
+    u64 w = root_of_unity(ilog2(len)); if (inverse) w = finv(w);
+    u64 x = 1; for (size_t j = 0; j < len / 2; j++) { t[len / 2 + j] = x; x = fmul(x, w); }
+  }
+  return cache[key] = std::move(t);
 }
 
 template <class E> inline void bit_reverse(E* a, size_t n) {
   unsigned k = ilog2(n);
-  for (size_t i = 0; i < n; i++) {
-    size_t j = 0; for (unsigned b = 0; b < k; b++) if (i >> b & 1) j |= size_t(1) << (k - 1 - b);
+  for (size_t i = 0, j = 0; i < n; i++) {
     if (i < j) std::swap(a[i], a[j]);
+    size_t bit = n >> 1; while (bit && (j & bit)) { j ^= bit; bit >>= 1; } j |= bit;   // reversed-increment
   }
+  (void)k;
 }
 // in-place NTT, natural order in and out; a[k] <- sum_j a[j] w^(jk)
 template <class E> inline void ntt_core(E* a, size_t n, bool inverse) {
   if (n <= 1) return;
-  const std::vector<u64>& tw = twiddles(n, inverse);
+  const u64* tw = twiddles(n, inverse).data();
   bit_reverse(a, n);
   for (size_t len = 2; len <= n; len <<= 1) {
-    size_t half = len / 2, step = n / len;
+    size_t half = len / 2; const u64* t = tw + half;
     for (size_t i = 0; i < n; i += len)
       for (size_t j = 0; j < half; j++) {
-        E u = a[i + j], v = a[i + j + half].mul_base(tw[j * step]);
+        E u = a[i + j], v = a[i + j + half].mul_base(t[j]);
         a[i + j] = u + v; a[i + j + half] = u - v;
       }
   }
@@ -61,9 +68,12 @@ template <class E> inline void interpolate_poly_with_offset(std::vector<E>& a, u
 // winter-math fft::evaluate_poly_with_offset: result[i] = p(offset * w_N^i), N = blowup * len(p)
 template <class E> inline std::vector<E> evaluate_poly_with_offset(const std::vector<E>& p, u64 offset, size_t blowup) {
   size_t n = p.size(), N = n * blowup;
-  std::vector<E> out(N), tmp(n);
+  std::vector<E> out(N);
   u64 g = root_of_unity(ilog2(N));
+  twiddles(n, false);
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic) if (g_threads > 1 && n >= 4096)
   for (size_t k = 0; k < blowup; k++) {
+    std::vector<E> tmp(n);
     u64 s = fmul(offset, fpow(g, k)), x = 1;
     for (size_t j = 0; j < n; j++) { tmp[j] = p[j].mul_base(x); x = fmul(x, s); }
     ntt_core(tmp.data(), n, false);

@@ -57,6 +57,7 @@ def lib():
         L.orc_verify.argtypes = [vp, sz, vp, vp, vp, cp, sz]
         L.orc_debug_get.restype = C.c_long; L.orc_debug_get.argtypes = [cp, vp, sz]
         L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_fri_fold.argtypes = [vp, sz, C.c_int, sz, vp, vp]
         _lib = L
     return _lib
 
@@ -128,6 +129,15 @@ def merkle_prove_batch(leaves: np.ndarray, indexes) -> bytes:
     if k < 0:
         raise ValueError("prove_batch failed")
     return out.raw[:k]
+
+
+def fri_fold(evals: np.ndarray, alpha) -> np.ndarray:
+    """evals: (Nl, deg) u64 element-major; folding factor 8, offset 7 -> (Nl/8, deg)."""
+    e = np.ascontiguousarray(evals, dtype=np.uint64); nl, deg = e.shape
+    a = np.ascontiguousarray(alpha, dtype=np.uint64)
+    out = np.empty((nl // 8, deg), dtype=np.uint64)
+    lib().orc_fri_fold(_p(e), nl, deg, 8, _p(a), _p(out))
+    return out
 
 
 DEFAULT_OPTIONS = (42, 8, 4, 1, 8, 31)   # num_queries, blowup, grinding, ext(1=None,2=Quadratic), folding, rem_max_deg

@@ -1,0 +1,105 @@
+"""GPU parity tests, whole proof: proof bytes from the CUDA backend (through the C ABI) must equal the CPU oracle's bytes
+on the same trace, public inputs and options, and the oracle verifier (independent recomputation) must accept them."""
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_case(xs, index, n_log2):
+    s = orc.synthetic_inputs(index)
+    air = xs.pack_inputs(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"], s["version"])
+    return air, xs.build_trace(air, n_log2)
+
+
+@pytest.mark.parametrize("ext", [1, 2])
+@pytest.mark.parametrize("n_log2", [3, 4, 5, 6, 7, 9, 10, 12, 13, 16])
+def test_proof_bytes_equal_oracle(ctx, n_log2, ext):
+    import xfg_stark_b200 as xs
+    opts = xs.ProofOptions(field_extension=ext)
+    air, trace = gpu_case(xs, n_log2, n_log2)
+    proof = ctx.prove(trace, air, opts)
+    tr, pi, ac = orc.synthetic_case(1 << n_log2, n_log2)
+    assert (tr == trace).all()
+    expect = orc.prove(tr, pi, ac, opts.as_tuple())
+    assert len(proof) == len(expect)
+    assert proof == expect
+    assert orc.verify(proof, pi, ac, opts.as_tuple()) == ""
+
+
+@pytest.mark.parametrize("opts_t", [(42, 8, 0, 1, 8, 31), (1, 8, 4, 2, 8, 7), (255, 8, 10, 1, 8, 255), (27, 8, 16, 2, 8, 63), (100, 8, 20, 1, 8, 15)])
+def test_option_sweep(ctx, opts_t):
+    import xfg_stark_b200 as xs
+    opts = xs.ProofOptions(*opts_t)
+    air, trace = gpu_case(xs, 11, 11)
+    proof = ctx.prove(trace, air, opts)
+    tr, pi, ac = orc.synthetic_case(1 << 11, 11)
+    assert proof == orc.prove(tr, pi, ac, opts_t)
+    assert orc.verify(proof, pi, ac, opts_t) == ""
+
+
+def test_reference_entry_point_64_rows(ctx):
+    """XfgBurnMintProver::prove_burn_mint (src/burn_mint_prover.rs:62-129) with the reference's 64-row trace (BASELINE config 1)."""
+    import xfg_stark_b200 as xs
+    s = orc.synthetic_inputs(0)
+    prover = xs.XfgBurnMintProver.new(128, context=ctx)
+    proof = prover.prove_burn_mint(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"], s["version"])
+    tr, pi, ac = orc.synthetic_case(64, 0)
+    assert proof == orc.prove(tr, pi, ac)
+    assert proof[:21].hex() == "07000006000008010000" "00ffffffff2a080401081f"      # Context bytes, SURVEY.md A.12
+    assert prover.get_proof_size(proof) == len(proof)
+    with pytest.raises(xs.XfgError) as e:
+        prover.prove_burn_mint(1000, 1000, s["tx_prefix_hash"], s["recipient"], s["secret"], 4, 42161, 1)
+    assert e.value.code == 8 and "Burn amount must be exactly" in e.value.message
+
+
+def test_device_resident_trace_and_times(ctx):
+    import torch
+    import xfg_stark_b200 as xs
+    air, trace = gpu_case(xs, 1, 14)
+    d = torch.from_numpy(trace.view(np.int64)).cuda()
+    proof, times = ctx.prove_device(d.data_ptr(), 14, air, want_times=True)
+    assert proof == ctx.prove(trace, air)
+    assert times["kernel_launches"] > 20 and times["device_ms"] > 0
+
+
+def test_batch_equals_single(ctx):
+    import xfg_stark_b200 as xs
+    cases = [gpu_case(xs, i, 10) for i in range(7)]
+    proofs, ms = ctx.prove_batch([t for _, t in cases], [a for a, _ in cases])
+    for i, (air, trace) in enumerate(cases):
+        assert proofs[i] == ctx.prove(trace, air)
+        tr, pi, ac = orc.synthetic_case(1 << 10, i)
+        assert orc.verify(proofs[i], pi, ac) == ""
+    assert ms > 0
+
+
+def test_invalid_trace_is_rejected(ctx):
+    """mirrors ProverError::UnsatisfiedTransitionConstraintError: a state jump of 2 breaks d(d-1) = 0 (src/burn_mint_air.rs:240-246)."""
+    import xfg_stark_b200 as xs
+    air, trace = gpu_case(xs, 2, 8)
+    bad = trace.copy(); bad[4, 100] = 3
+    with pytest.raises(xs.XfgError) as e:
+        ctx.prove(bad, air)
+    assert e.value.code == 5
+    bad = trace.copy(); bad[0, 5] = orc.P          # non-canonical element
+    with pytest.raises(xs.XfgError) as e:
+        ctx.prove(bad, air)
+    assert e.value.code == 1
+    assert ctx.prove(trace, air) == orc.prove(*orc.synthetic_case(256, 2))   # the context stays usable
+
+
+def test_option_errors(ctx):
+    import xfg_stark_b200 as xs
+    air, trace = gpu_case(xs, 0, 6)
+    for o, code in [((42, 8, 4, 3, 8, 31), 4), ((0, 8, 4, 1, 8, 31), 2), ((256, 8, 4, 1, 8, 31), 2), ((42, 6, 4, 1, 8, 31), 2),
+                    ((42, 8, 33, 1, 8, 31), 2), ((42, 8, 4, 1, 8, 30), 2), ((42, 4, 4, 1, 8, 31), 3), ((42, 8, 4, 1, 4, 31), 3)]:
+        with pytest.raises(xs.XfgError) as e:
+            ctx.prove(trace, air, xs.ProofOptions(*o))
+        assert e.value.code == code, o
+    big = np.zeros((7, 1 << 17), dtype=np.uint64)
+    with pytest.raises(xs.XfgError) as e:
+        ctx.prove(big, air)
+    assert e.value.code == 9

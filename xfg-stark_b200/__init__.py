@@ -1,0 +1,18 @@
+"""xfg-stark_b200 — B200 (sm_100a) proving backend for the XFG burn-mint STARK.
+
+The product is ``libxfgstark.so`` (CUDA kernels + C ABI, ``include/xfg_stark.h``).  This package is the thin Python
+host-side mirror of the reference's operator surface for that path, used by the tests and ``bench.py``:
+
+* ``ProofOptions``           — winter_air::ProofOptions as built at src/burn_mint_prover.rs:28-35
+* ``XfgBurnMintProver``      — src/burn_mint_prover.rs:18-237 (``new``/``with_options``/``prove_burn_mint``/...)
+* ``Context``                — one device + workspaces; stage-level entry points for kernel parity tests
+
+There is no CPU fallback: importing works anywhere (so the CPU test-suite can check the exported symbols), but creating
+a ``Context`` without a CUDA device raises ``XfgError``.  The directory name carries a hyphen, so import it through the
+``xfg_stark_b200`` shim at the repo root.
+"""
+from ._binding import (Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgError, AirConsts, STAGE_NAMES, load_library,
+                       library_path, EXPORTED_SYMBOLS, FieldExtension, pack_inputs, build_trace)
+
+__all__ = ["Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgError", "AirConsts", "STAGE_NAMES",
+           "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace"]

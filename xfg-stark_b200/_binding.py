@@ -1,0 +1,304 @@
+"""ctypes binding of libxfgstark.so (include/xfg_stark.h) and the Python mirror of the reference's prover interface."""
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libxfgstark.so")
+
+NUM_STAGES = 9
+STAGE_NAMES = ["extend_execution_trace", "compute_execution_trace_commitment", "evaluate_constraints",
+               "commit_to_constraint_evaluations", "build_deep_composition_poly", "evaluate_deep_composition_poly",
+               "compute_fri_layers", "determine_query_positions", "build_proof_object"]   # winter-prover span names
+EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error", "xfg_prove_burn_mint",
+                    "xfg_prove_burn_mint_device", "xfg_prove_burn_mint_batch", "xfg_burn_mint_pack_inputs",
+                    "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
+                    "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows"]
+
+
+class FieldExtension:           # winterfell::FieldExtension discriminants
+    NONE = 1
+    QUADRATIC = 2
+    CUBIC = 3
+
+
+class XfgError(RuntimeError):
+    """Mirrors XfgStarkError::CryptoError("Prover error: ...") (src/burn_mint_prover.rs:124-126)."""
+
+    def __init__(self, code, message):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class _Options(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("num_queries", "blowup_factor", "grinding_factor", "field_extension",
+                                          "fri_folding_factor", "fri_remainder_max_degree")]
+
+
+class AirConsts(C.Structure):
+    _fields_ = [("pub_inputs", C.c_uint64 * 12), ("txn_hash", C.c_uint64), ("recipient_hash", C.c_uint64),
+                ("nullifier", C.c_uint64), ("commitment", C.c_uint64)]
+
+
+class StageTimes(C.Structure):
+    _fields_ = [("stage_ms", C.c_float * NUM_STAGES), ("h2d_ms", C.c_float), ("device_ms", C.c_float),
+                ("total_ms", C.c_float), ("kernel_launches", C.c_uint32)]
+
+    def as_dict(self):
+        d = {n: float(self.stage_ms[i]) for i, n in enumerate(STAGE_NAMES)}
+        d.update(h2d_ms=float(self.h2d_ms), device_ms=float(self.device_ms), total_ms=float(self.total_ms),
+                 kernel_launches=int(self.kernel_launches))
+        return d
+
+
+@dataclass(frozen=True)
+class ProofOptions:
+    """winter_air::ProofOptions::new(num_queries, blowup_factor, grinding_factor, field_extension, fri_folding_factor,
+    fri_remainder_max_degree); defaults are the reference's (src/burn_mint_prover.rs:28-35)."""
+    num_queries: int = 42
+    blowup_factor: int = 8
+    grinding_factor: int = 4
+    field_extension: int = FieldExtension.NONE
+    fri_folding_factor: int = 8
+    fri_remainder_max_degree: int = 31
+
+    def _c(self):
+        return _Options(self.num_queries, self.blowup_factor, self.grinding_factor, self.field_extension,
+                        self.fri_folding_factor, self.fri_remainder_max_degree)
+
+    def as_tuple(self):
+        return (self.num_queries, self.blowup_factor, self.grinding_factor, self.field_extension,
+                self.fri_folding_factor, self.fri_remainder_max_degree)
+
+
+def library_path():
+    return _SO
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libxfgstark.so (no GPU needed to load it).  Fails loudly if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise XfgError(-1, f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C xfg-stark_b200/csrc); there is no CPU fallback")
+    L = C.CDLL(_SO)
+    vp, u32, u64, sz, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
+    L.xfg_create.argtypes = [i, u32, u32, C.POINTER(vp)]
+    L.xfg_destroy.argtypes = [vp]; L.xfg_destroy.restype = None
+    L.xfg_strerror.argtypes = [i]; L.xfg_strerror.restype = C.c_char_p
+    L.xfg_last_error.argtypes = [vp]; L.xfg_last_error.restype = C.c_char_p
+    prove_tail = [vp, sz, C.POINTER(sz), C.POINTER(StageTimes)]
+    L.xfg_prove_burn_mint.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
+    L.xfg_prove_burn_mint_device.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
+    L.xfg_prove_burn_mint_batch.argtypes = [vp, u32, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options), vp, sz, vp, C.POINTER(C.c_float)]
+    inputs = [u64, u64, vp, vp, sz, vp, sz, u32, u32, u32]
+    L.xfg_burn_mint_pack_inputs.argtypes = [vp] + inputs + [C.POINTER(AirConsts)]
+    L.xfg_burn_mint_build_trace.argtypes = [C.POINTER(AirConsts), u32, vp]
+    L.xfg_prove_burn_mint_from_inputs.argtypes = [vp] + inputs + [u32, C.POINTER(_Options)] + prove_tail
+    L.xfg_ntt.argtypes = [vp, vp, u32, u32, i]
+    L.xfg_lde_commit.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.xfg_merkle_root.argtypes = [vp, vp, sz, vp, vp]
+    L.xfg_eval_constraints.argtypes = [vp, vp, u32, C.POINTER(AirConsts), u32, vp, vp]
+    L.xfg_fri_fold_layer.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.xfg_hash_rows.argtypes = [vp, vp, sz, u32, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+MAX_PROOF_BYTES = 1 << 20
+
+
+def pack_inputs(burn_amount, mint_amount, tx_prefix_hash, recipient_address, secret, network_id, target_chain_id, commitment_version, _ctx=None):
+    """validate_inputs + public-input packing + Keccak scalars (src/burn_mint_prover.rs:62-107, src/burn_mint_air.rs:124-202).  Host only."""
+    L = load_library(); air = AirConsts()
+    h = _ctx._h if _ctx is not None else None
+    rc = L.xfg_burn_mint_pack_inputs(h, burn_amount, mint_amount, bytes(tx_prefix_hash), bytes(recipient_address), len(recipient_address),
+                                     bytes(secret), len(secret), network_id, target_chain_id, commitment_version, C.byref(air))
+    if rc:
+        msg = (L.xfg_last_error(h) or b"").decode() if h else ""
+        raise XfgError(rc, msg or L.xfg_strerror(rc).decode())
+    return air
+
+
+def build_trace(air, n_log2):
+    """XfgBurnMintAir::build_trace (src/burn_mint_air.rs:442-476) for 2**n_log2 rows -> (7, n) uint64.  Host only."""
+    t = np.empty((7, 1 << n_log2), dtype=np.uint64)
+    rc = load_library().xfg_burn_mint_build_trace(C.byref(air), n_log2, _ptr(t))
+    if rc:
+        raise XfgError(rc, "bad arguments")
+    return t
+
+
+class Context:
+    """xfg_ctx: one CUDA device, `num_slots` proof workspaces sized for traces of up to 2**max_n_log2 rows."""
+
+    def __init__(self, device=0, max_n_log2=16, num_slots=1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.xfg_create(device, max_n_log2, num_slots, C.byref(self._h))
+        if rc:
+            raise XfgError(rc, "xfg_create failed: " + self._lib.xfg_strerror(rc).decode() + " (a CUDA device is required; no CPU fallback)")
+        self.device, self.max_n_log2, self.num_slots = device, max_n_log2, num_slots
+
+    def close(self):
+        if self._h:
+            self._lib.xfg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise XfgError(rc, (self._lib.xfg_last_error(self._h) or b"").decode() or self._lib.xfg_strerror(rc).decode())
+
+    # ---- host-side mirror of XfgBurnMintProver's input half ----
+    def pack_inputs(self, burn_amount, mint_amount, tx_prefix_hash, recipient_address, secret, network_id, target_chain_id, commitment_version):
+        return pack_inputs(burn_amount, mint_amount, tx_prefix_hash, recipient_address, secret, network_id, target_chain_id, commitment_version, _ctx=self)
+
+    def build_trace(self, air, n_log2):
+        return build_trace(air, n_log2)
+
+    # ---- whole proof ----
+    def prove(self, trace, air, options=ProofOptions(), want_times=False):
+        """trace: (7, n) uint64 column-major host array (numpy; a pinned torch tensor's numpy view is uploaded without staging)."""
+        t = np.ascontiguousarray(trace, dtype=np.uint64)
+        return self._prove_ptr(self._lib.xfg_prove_burn_mint, _ptr(t), t.shape[1].bit_length() - 1, air, options, want_times)
+
+    def prove_device(self, device_ptr, n_log2, air, options=ProofOptions(), want_times=False):
+        """device_ptr: integer device address of a (7, n) uint64 column-major buffer on this context's device."""
+        return self._prove_ptr(self._lib.xfg_prove_burn_mint_device, C.c_void_p(device_ptr), n_log2, air, options, want_times)
+
+    def _prove_ptr(self, fn, ptr, n_log2, air, options, want_times):
+        out = C.create_string_buffer(MAX_PROOF_BYTES); ln = C.c_size_t(0); st = StageTimes(); o = options._c()
+        self._check(fn(self._h, ptr, n_log2, C.byref(air), C.byref(o), out, len(out), C.byref(ln), C.byref(st) if want_times else None))
+        proof = out.raw[:ln.value]
+        return (proof, st.as_dict()) if want_times else proof
+
+    def prove_batch(self, traces, airs, options=ProofOptions(), out_stride=1 << 17):
+        """traces: list of (7, n) uint64 arrays; airs: list of AirConsts.  Returns (list of proof bytes, device wall ms)."""
+        cnt = len(traces)
+        ts = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+        n_log2 = ts[0].shape[1].bit_length() - 1
+        ptrs = (C.c_void_p * cnt)(*[t.ctypes.data for t in ts])
+        air_arr = (AirConsts * cnt)(*airs)
+        out = np.empty(cnt * out_stride, dtype=np.uint8); lens = np.zeros(cnt, dtype=np.uint64); ms = C.c_float(0); o = options._c()
+        self._check(self._lib.xfg_prove_burn_mint_batch(self._h, cnt, ptrs, n_log2, air_arr, C.byref(o), _ptr(out), out_stride, _ptr(lens), C.byref(ms)))
+        return [out[i * out_stride:i * out_stride + int(lens[i])].tobytes() for i in range(cnt)], float(ms.value)
+
+    def prove_from_inputs(self, burn_amount, mint_amount, tx_prefix_hash, recipient_address, secret, network_id, target_chain_id,
+                          commitment_version, n_log2=6, options=ProofOptions(), want_times=False):
+        out = C.create_string_buffer(MAX_PROOF_BYTES); ln = C.c_size_t(0); st = StageTimes(); o = options._c()
+        self._check(self._lib.xfg_prove_burn_mint_from_inputs(self._h, burn_amount, mint_amount, bytes(tx_prefix_hash), bytes(recipient_address),
+                                                              len(recipient_address), bytes(secret), len(secret), network_id, target_chain_id,
+                                                              commitment_version, n_log2, C.byref(o), out, len(out), C.byref(ln),
+                                                              C.byref(st) if want_times else None))
+        proof = out.raw[:ln.value]
+        return (proof, st.as_dict()) if want_times else proof
+
+    # ---- stage entry points ----
+    def ntt(self, data, inverse=False):
+        """data: (batch, n) uint64; forward evaluation or fft::interpolate_poly per row."""
+        a = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        a2 = a.reshape(-1, a.shape[-1])
+        self._check(self._lib.xfg_ntt(self._h, _ptr(a2), a2.shape[1].bit_length() - 1, a2.shape[0], int(inverse)))
+        return a
+
+    def lde_commit(self, cols, want_lde=True):
+        c = np.ascontiguousarray(cols, dtype=np.uint64); ncols, n = c.shape
+        lde = np.empty((ncols, 8 * n), dtype=np.uint64) if want_lde else None
+        root = C.create_string_buffer(32)
+        self._check(self._lib.xfg_lde_commit(self._h, _ptr(c), n.bit_length() - 1, ncols, _ptr(lde) if want_lde else None, root))
+        return lde, root.raw
+
+    def merkle_root(self, leaves, want_nodes=False):
+        lv = np.ascontiguousarray(leaves, dtype=np.uint8); cnt = lv.shape[0]
+        nodes = np.empty((cnt, 32), dtype=np.uint8) if want_nodes else None
+        root = C.create_string_buffer(32)
+        self._check(self._lib.xfg_merkle_root(self._h, _ptr(lv), cnt, root, _ptr(nodes) if want_nodes else None))
+        return (root.raw, nodes) if want_nodes else root.raw
+
+    def eval_constraints(self, lde, air, ext, coeffs):
+        l = np.ascontiguousarray(lde, dtype=np.uint64); n = l.shape[1] // 8
+        cf = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        out = np.empty((2 * n, ext), dtype=np.uint64)
+        self._check(self._lib.xfg_eval_constraints(self._h, _ptr(l), n.bit_length() - 1, C.byref(air), ext, _ptr(cf), _ptr(out)))
+        return out
+
+    def fri_fold_layer(self, evals, alpha):
+        e = np.ascontiguousarray(evals, dtype=np.uint64); nl, ext = e.shape
+        a = np.ascontiguousarray(alpha, dtype=np.uint64)
+        out = np.empty((nl // 8, ext), dtype=np.uint64)
+        self._check(self._lib.xfg_fri_fold_layer(self._h, _ptr(e), nl.bit_length() - 1, ext, _ptr(a), _ptr(out)))
+        return out
+
+    def hash_rows(self, rows):
+        r = np.ascontiguousarray(rows, dtype=np.uint64); cnt, limbs = r.shape
+        out = np.empty((cnt, 32), dtype=np.uint8)
+        self._check(self._lib.xfg_hash_rows(self._h, _ptr(r), cnt, limbs, _ptr(out)))
+        return out
+
+
+class XfgBurnMintProver:
+    """Python mirror of XfgBurnMintProver (src/burn_mint_prover.rs:18-237) over the CUDA backend.
+
+    `new(security_parameter)` / `with_options(security_parameter, options)` / `prove_burn_mint(8 args)` keep the reference's
+    names and argument meaning; `trace_log2` selects the (normalised) trace length, 6 = the reference's 64 rows.
+    """
+
+    def __init__(self, security_parameter=128, proof_options=None, trace_log2=6, context=None, device=0):
+        self.security_parameter_ = security_parameter
+        self.proof_options_ = proof_options or ProofOptions()
+        self.trace_log2 = trace_log2
+        self.ctx = context or Context(device=device, max_n_log2=max(trace_log2, 6))
+
+    @classmethod
+    def new(cls, security_parameter=128, **kw):
+        return cls(security_parameter, None, **kw)
+
+    @classmethod
+    def with_options(cls, security_parameter, proof_options, **kw):
+        return cls(security_parameter, proof_options, **kw)
+
+    def prove_burn_mint(self, burn_amount, mint_amount, tx_prefix_hash, recipient_address, secret, network_id, target_chain_id, commitment_version):
+        return self.ctx.prove_from_inputs(burn_amount, mint_amount, tx_prefix_hash, recipient_address, secret, network_id, target_chain_id,
+                                          commitment_version, self.trace_log2, self.proof_options_)
+
+    @staticmethod
+    def get_proof_size(proof):
+        return len(proof)
+
+    def security_parameter(self):
+        return self.security_parameter_
+
+    def proof_options(self):
+        return self.proof_options_
+
+    @staticmethod
+    def xfg_to_atomic_units(xfg_amount):   # src/burn_mint_prover.rs:184-186
+        return int(xfg_amount * 10_000_000.0)
+
+    @staticmethod
+    def atomic_units_to_xfg(atomic_units):  # :190-192
+        return atomic_units / 10_000_000.0

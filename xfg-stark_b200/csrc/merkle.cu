@@ -1,0 +1,112 @@
+// merkle.cu — BLAKE3 row hashing fused with the first tree levels, and the upper Merkle levels, for sm_100a.
+//
+// Replaces winter-prover 0.8.3 `RowMatrix::commit_to_rows` + winter-crypto `MerkleTree::new`
+// (reached from DefaultTraceLde::new at src/burn_mint_air.rs:513 and from
+// `Prover::build_constraint_commitment`).  These kernels are integer-pipe bound (one BLAKE3 compression is ~700 32-bit
+// ALU ops against 56-64 input bytes), so every lane keeps a full compression busy: a thread hashes the 8 LDE rows of one
+// trace step (8 leaves = one complete 3-level subtree in the coset-major layout) and reduces them itself; the levels above
+// are reduced 8 -> 1 per thread as well, never by a shrinking tree inside a warp.
+#include "merkle.cuh"
+#include "launch.cuh"
+
+namespace xfg {
+
+template <int NL>
+__global__ void __launch_bounds__(128) commit_rows_kernel(const u64* __restrict__ data, size_t limb_stride, u32 ln, Digest* __restrict__ tree) {
+  const size_t n = size_t(1) << ln, N = n * 8;
+  const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  Digest l1[4];
+#pragma unroll
+  for (int kp = 0; kp < 4; kp++) {
+    Digest d[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k = 2 * kp + h;
+      u64 limbs[NL];
+#pragma unroll
+      for (int j = 0; j < NL; j++) limbs[j] = data[j * limb_stride + (size_t)k * n + m];
+      d[h] = b3_hash_limbs<NL>(limbs);
+      store_digest(tree + N + 8 * m + k, d[h]);
+    }
+    l1[kp] = b3_merge(d[0], d[1]);
+    store_digest(tree + N / 2 + 4 * m + kp, l1[kp]);
+  }
+  Digest a = b3_merge(l1[0], l1[1]), b = b3_merge(l1[2], l1[3]);
+  store_digest(tree + N / 4 + 2 * m, a); store_digest(tree + N / 4 + 2 * m + 1, b);
+  store_digest(tree + N / 8 + m, b3_merge(a, b));
+}
+
+// level of M nodes at [M, 2M) -> levels M/2, M/4, M/8; one thread per 8 children
+__global__ void __launch_bounds__(128) tree_reduce8_kernel(Digest* __restrict__ tree, size_t M) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M / 8) return;
+  Digest l1[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    Digest x = load_digest(tree + M + 8 * t + 2 * j), y = load_digest(tree + M + 8 * t + 2 * j + 1);
+    l1[j] = b3_merge(x, y);
+    store_digest(tree + M / 2 + 4 * t + j, l1[j]);
+  }
+  Digest a = b3_merge(l1[0], l1[1]), b = b3_merge(l1[2], l1[3]);
+  store_digest(tree + M / 4 + 2 * t, a); store_digest(tree + M / 4 + 2 * t + 1, b);
+  store_digest(tree + M / 8 + t, b3_merge(a, b));
+}
+
+// one CTA finishes the tree from a level of M <= 2048 nodes up to the root
+__global__ void __launch_bounds__(1024) tree_top_kernel(Digest* __restrict__ tree, u32 M) {
+  for (u32 lvl = M / 2; lvl >= 1; lvl >>= 1) {
+    for (u32 i = threadIdx.x; i < lvl; i += blockDim.x) {
+      Digest x = load_digest(tree + 2 * (lvl + i)), y = load_digest(tree + 2 * (lvl + i) + 1);
+      store_digest(tree + lvl + i, b3_merge(x, y));
+    }
+    __syncthreads();
+  }
+}
+
+// hash_elements of row-major rows (stage entry point xfg_hash_rows; the pipeline hashes rows inside its fused kernels)
+template <int NL>
+__global__ void __launch_bounds__(128) hash_rows_kernel(const u64* __restrict__ rows, size_t count, Digest* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 limbs[NL];
+#pragma unroll
+  for (int j = 0; j < NL; j++) limbs[j] = rows[i * NL + j];
+  store_digest(out + i, b3_hash_limbs<NL>(limbs));
+}
+void launch_hash_rows(cudaStream_t st, const u64* rows, size_t count, int limbs, Digest* out) {
+  const unsigned blocks = (unsigned)((count + 127) / 128);
+  switch (limbs) {
+    case 1: hash_rows_kernel<1><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 2: hash_rows_kernel<2><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 7: hash_rows_kernel<7><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 8: hash_rows_kernel<8><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 16: hash_rows_kernel<16><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    default: return;
+  }
+  XFG_LAUNCHED(1);
+}
+
+void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree) {
+  const size_t n = size_t(1) << ln; const unsigned blocks = (unsigned)((n + 127) / 128);
+  switch (num_limbs) {
+    case 1: commit_rows_kernel<1><<<blocks, 128, 0, st>>>(data, limb_stride, ln, tree); break;
+    case 2: commit_rows_kernel<2><<<blocks, 128, 0, st>>>(data, limb_stride, ln, tree); break;
+    case 7: commit_rows_kernel<7><<<blocks, 128, 0, st>>>(data, limb_stride, ln, tree); break;
+    default: return;   // callers only pass 1, 2 or XFG_TRACE_WIDTH
+  }
+  XFG_LAUNCHED(1);
+  merkle_build_upper(st, tree, n);
+}
+
+void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M) {
+  while (M > 2048) {
+    const size_t t = M / 8;
+    tree_reduce8_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>(tree, M);
+    XFG_LAUNCHED(1);
+    M /= 8;
+  }
+  if (M >= 2) { tree_top_kernel<<<1, 1024, 0, st>>>(tree, (u32)M); XFG_LAUNCHED(1); }
+}
+
+}  // namespace xfg

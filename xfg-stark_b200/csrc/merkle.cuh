@@ -1,0 +1,19 @@
+// merkle.cuh — interface of the row-hashing / Merkle-tree kernels (see merkle.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "blake3.cuh"
+
+namespace xfg {
+
+// Heap layout of a tree over M leaves: tree[M + i] = leaf i, tree[i] = BLAKE3(tree[2i] || tree[2i+1]) for 1 <= i < M,
+// tree[1] = root (winter-crypto MerkleTree::new keeps the same `nodes` numbering, A.7).
+
+// Leaves of a coset-major matrix (NL limb arrays of 8 cosets x n points each; LDE row i = 8m + k lives at [k*n + m]):
+// hashes the 8 rows of each m and the 3 tree levels above them.  tree has 2*8n digests.
+void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree);
+// Completes the tree above a fully written level of M nodes (heap range [M, 2M)).
+void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M);
+// hash_elements of `count` row-major rows of `limbs` (1, 2, 7, 8, 16) elements
+void launch_hash_rows(cudaStream_t st, const u64* rows, size_t count, int limbs, Digest* out);
+
+}  // namespace xfg

@@ -1,0 +1,538 @@
+// prover.cu — context, per-size plans, the proof pipeline and proof-byte assembly behind the C ABI (include/xfg_stark.h).
+//
+// Replaces winter-prover 0.8.3 `Prover::prove` / `generate_proof` as reached from `air.prove(trace)`
+// (src/burn_mint_prover.rs:124; types bound at src/burn_mint_air.rs:479-531).  Stage order, transcript order and the wire
+// format follow SURVEY.md §3.1 and Appendix A.4-A.12.  Everything between the trace upload and the final copy of the
+// opened rows / authentication nodes runs on the device as one dependent chain of launches on the slot's stream; the host
+// only serialises (`StarkProof::to_bytes`, `BatchMerkleProof::serialize_nodes`).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+#include "../../include/xfg_stark.h"
+#include "burn_mint_host.hpp"
+#include "merkle.cuh"
+#include "ntt.cuh"
+#include "stark_kernels.cuh"
+#include "transcript.cuh"
+#include "launch.cuh"
+
+using namespace xfg;
+
+namespace {
+
+constexpr size_t MATERIAL_WORDS = size_t(1) << 20;   // 8 MiB: opened rows + per-position authentication paths
+constexpr u32 MIN_LOG = 3, MAX_LOG = 24;
+
+struct DevTable { u64* lo = nullptr; u64* hi = nullptr; u32 nhi = 0; };
+
+struct Plan {
+  u32 ln = 0, lN = 0; size_t n = 0, N = 0;
+  u32 rem_max_deg = 0, num_layers = 0, layer_log[MAX_LAYERS + 1] = {0};   // layer_log[l] = log2 |domain of FRI layer l|
+  u32 rem_log = 0, rem_len = 0;
+  u64* slab = nullptr;              // all tables of this plan
+  NttTables ntt{};                  // tw_* are context-wide
+  PowTable wN_inv{};
+  u64 *pre_lo = nullptr, *pre_hi = nullptr; u32 pre_hi_stride = 0;   // s_k = 7 w_N^k, k < 8
+  u64 *un_lo = nullptr, *un_hi = nullptr; u32 un_hi_stride = 0;      // 7^-1, (7 w_2n)^-1
+  u64* d_sk = nullptr;
+  u64 s_k[8] = {0}, zinv0 = 0, zinv1 = 0, g_n = 0, g_last = 0, n_inv = 0, inv2 = 0, rem_ninv = 0;
+  FriConsts fc{};
+};
+
+struct Carve {   // device pointers of one proof, carved from the slot slab for the actual n and extension degree
+  u64 *trace_in, *trace_coef, *lde, *ce_evals, *ce_tmp, *h_coef, *h_lde, *deep, *rem_in, *rem_coef;
+  Digest *trace_tree, *comp_tree;
+  u64* fri_evals[MAX_LAYERS + 1]; Digest* fri_tree[MAX_LAYERS];
+  size_t words;
+};
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  u64* slab = nullptr; size_t slab_words = 0;
+  ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
+  ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;
+  cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
+  // in-flight proof (batch mode)
+  bool busy = false; const Plan* plan = nullptr; int D = 1; xfg_options opt{}; u32 proof_index = 0; bool timed = false;
+  GatherTasks tasks{};
+};
+
+}  // namespace
+
+thread_local unsigned g_xfg_launches = 0;
+
+struct xfg_ctx {
+  int device = 0; u32 max_log = 0;
+  std::vector<Slot> slots;
+  u64 *tw_fwd = nullptr, *tw_inv = nullptr;
+  std::map<u64, Plan> plans;
+  std::string last_error;
+};
+
+namespace {
+
+#define CU(call)                                                                                         \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                                  \
+      ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(e_); return XFG_ERR_CUDA; } } while (0)
+
+int fail(xfg_ctx* ctx, int code, const std::string& msg) { if (ctx) ctx->last_error = msg; return code; }
+
+std::vector<u64> pow_series(u64 base, size_t count) { std::vector<u64> v(count); u64 x = 1; for (size_t i = 0; i < count; i++) { v[i] = x; x = gl_mul(x, base); } return v; }
+
+// ProofOptions::new range checks (A.2) + what this backend implements
+int check_options(xfg_ctx* ctx, const xfg_options* o, u32 n_log2) {
+  auto pow2 = [](u32 x) { return x && !(x & (x - 1)); };
+  if (o->field_extension == XFG_EXT_CUBIC) return fail(ctx, XFG_ERR_UNSUPPORTED_EXTENSION, "UnsupportedFieldExtension: cubic");
+  if (o->field_extension != XFG_EXT_NONE && o->field_extension != XFG_EXT_QUADRATIC) return fail(ctx, XFG_ERR_BAD_OPTIONS, "invalid field extension");
+  if (o->num_queries < 1) return fail(ctx, XFG_ERR_BAD_OPTIONS, "number of queries must be greater than 0");
+  if (o->num_queries > 255) return fail(ctx, XFG_ERR_BAD_OPTIONS, "number of queries cannot be greater than 255");
+  if (!pow2(o->blowup_factor)) return fail(ctx, XFG_ERR_BAD_OPTIONS, "blowup factor must be a power of 2");
+  if (o->blowup_factor < 2 || o->blowup_factor > 128) return fail(ctx, XFG_ERR_BAD_OPTIONS, "blowup factor out of range");
+  if (o->grinding_factor > 32) return fail(ctx, XFG_ERR_BAD_OPTIONS, "grinding factor cannot be greater than 32");
+  if (!pow2(o->fri_folding_factor) || o->fri_folding_factor < 2 || o->fri_folding_factor > 16) return fail(ctx, XFG_ERR_BAD_OPTIONS, "FRI folding factor must be a power of 2 in 2..16");
+  if (o->fri_remainder_max_degree > 255 || !pow2(o->fri_remainder_max_degree + 1)) return fail(ctx, XFG_ERR_BAD_OPTIONS, "FRI polynomial remainder degree must be one less than a power of two");
+  if (o->blowup_factor != 8) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "this backend implements blowup factor 8 (the reference's setting)");
+  if (o->fri_folding_factor != 8) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "this backend implements FRI folding factor 8 (the reference's setting)");
+  if (o->fri_remainder_max_degree < 7) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "this backend needs fri_remainder_max_degree >= 7");
+  if (o->num_queries >= (8u << n_log2)) return fail(ctx, XFG_ERR_BAD_OPTIONS, "number of queries must be smaller than the LDE domain size");
+  return XFG_OK;
+}
+
+int upload_table(xfg_ctx* ctx, u64* d_lo, u64* d_hi, u32 nhi, u64 base) {
+  std::vector<u64> lo = pow_series(base, POW_LO), hi = pow_series(gl_pow(base, POW_LO), nhi);
+  CU(cudaMemcpy(d_lo, lo.data(), POW_LO * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_hi, hi.data(), (size_t)nhi * 8, cudaMemcpyHostToDevice));
+  return XFG_OK;
+}
+
+int get_plan(xfg_ctx* ctx, u32 ln, u32 rem_max_deg, const Plan** out) {
+  const u64 key = ((u64)ln << 32) | rem_max_deg;
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end()) { *out = &it->second; return XFG_OK; }
+  Plan p; p.ln = ln; p.lN = ln + 3; p.n = size_t(1) << ln; p.N = p.n * 8; p.rem_max_deg = rem_max_deg;
+  // FriOptions::num_fri_layers (A.10)
+  { size_t dom = p.N, mx = (size_t)(rem_max_deg + 1) * 8; u32 lg = p.lN; p.layer_log[0] = lg;
+    while (dom > mx) { dom /= 8; lg -= 3; p.num_layers++; if (p.num_layers > MAX_LAYERS) return fail(ctx, XFG_ERR_INTERNAL, "too many FRI layers"); p.layer_log[p.num_layers] = lg; }
+    p.rem_log = lg; p.rem_len = (u32)(dom / 8);
+    if (dom < 8 || p.rem_log > NTT_SINGLE_MAX_LOG || p.rem_len > MAX_REMAINDER) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "FRI remainder domain out of range"); }
+  const u32 nhi_n = (u32)std::max<size_t>(1, p.n >> POW_LO_BITS), nhi_N = (u32)std::max<size_t>(1, p.N >> POW_LO_BITS);
+  // slab: wn_fwd, wn_inv (lo+hi each), wN_inv, pre[8], un[2], s_k[8]
+  const size_t words = 2 * (POW_LO + nhi_n) + (POW_LO + nhi_N) + 8 * (POW_LO + nhi_n) + 2 * (POW_LO + nhi_n) + 8;
+  CU(cudaMalloc(&p.slab, words * 8));
+  u64* w = p.slab;
+  auto take = [&](size_t k) { u64* r = w; w += k; return r; };
+  const u64 wN = gl_root_of_unity(p.lN), wn = gl_root_of_unity(ln);
+  u64 *a, *b; int rc;
+  a = take(POW_LO); b = take(nhi_n); if ((rc = upload_table(ctx, a, b, nhi_n, wn))) return rc; p.ntt.wn_fwd = PowTable{a, b};
+  a = take(POW_LO); b = take(nhi_n); if ((rc = upload_table(ctx, a, b, nhi_n, gl_inv(wn)))) return rc; p.ntt.wn_inv = PowTable{a, b};
+  a = take(POW_LO); b = take(nhi_N); if ((rc = upload_table(ctx, a, b, nhi_N, gl_inv(wN)))) return rc; p.wN_inv = PowTable{a, b};
+  p.pre_lo = take(8 * POW_LO); p.pre_hi = take(8 * (size_t)nhi_n); p.pre_hi_stride = nhi_n;
+  for (u32 k = 0; k < 8; k++) {
+    p.s_k[k] = gl_mul(XFG_GENERATOR, gl_pow(wN, k));
+    if ((rc = upload_table(ctx, p.pre_lo + (size_t)k * POW_LO, p.pre_hi + (size_t)k * nhi_n, nhi_n, p.s_k[k]))) return rc;
+  }
+  p.un_lo = take(2 * POW_LO); p.un_hi = take(2 * (size_t)nhi_n); p.un_hi_stride = nhi_n;
+  if ((rc = upload_table(ctx, p.un_lo, p.un_hi, nhi_n, gl_inv(p.s_k[0])))) return rc;
+  if ((rc = upload_table(ctx, p.un_lo + POW_LO, p.un_hi + nhi_n, nhi_n, gl_inv(p.s_k[4])))) return rc;
+  p.d_sk = take(8);
+  CU(cudaMemcpy(p.d_sk, p.s_k, 64, cudaMemcpyHostToDevice));
+  p.ntt.tw_fwd = ctx->tw_fwd; p.ntt.tw_inv = ctx->tw_inv;
+  p.g_n = wn; p.g_last = gl_pow(wn, p.n - 1);
+  p.zinv0 = gl_inv(gl_sub(gl_pow(p.s_k[0], p.n), 1)); p.zinv1 = gl_inv(gl_sub(gl_pow(p.s_k[4], p.n), 1));
+  p.n_inv = gl_inv((u64)p.n); p.inv2 = gl_inv(2); p.rem_ninv = gl_inv((u64)1 << p.rem_log);
+  const u64 w8i = gl_inv(gl_root_of_unity(3));
+  p.fc.w8i[0] = 1; for (int i = 1; i < 4; i++) p.fc.w8i[i] = gl_mul(p.fc.w8i[i - 1], w8i);
+  p.fc.inv8 = gl_inv(8); p.fc.inv7 = gl_inv(XFG_GENERATOR);
+  auto ins = ctx->plans.emplace(key, p);
+  *out = &ins.first->second; return XFG_OK;
+}
+
+size_t slab_words_for(u32 ln, int D) {
+  const size_t n = size_t(1) << ln, N = 8 * n;
+  size_t w = 7 * n + 7 * n + 7 * N + 8 * N + 2 * D * n + 2 * D * n + D * n + D * N + 8 * N + D * N;
+  w += (size_t)D * N / 7 + 64 * MAX_LAYERS;   // FRI layer evaluations l >= 1
+  w += 8 * N / 7 + 64 * MAX_LAYERS;           // FRI trees
+  w += 2 * (size_t)D * 2048 + 64;             // remainder in / coefficients
+  return w;
+}
+
+void carve(const Slot& s, const Plan& p, int D, Carve& c) {
+  u64* w = s.slab; const size_t n = p.n, N = p.N;
+  auto take = [&](size_t k) { u64* r = w; w += (k + 7) & ~size_t(7); return r; };
+  c.trace_in = take(7 * n); c.trace_coef = take(7 * n); c.lde = take(7 * N);
+  c.trace_tree = reinterpret_cast<Digest*>(take(8 * N));
+  c.ce_evals = take(2 * D * n); c.ce_tmp = take(2 * D * n); c.h_coef = take(D * n); c.h_lde = take(D * N);
+  c.comp_tree = reinterpret_cast<Digest*>(take(8 * N));
+  c.deep = take(D * N);
+  c.fri_evals[0] = c.deep;
+  for (u32 l = 1; l <= p.num_layers; l++) c.fri_evals[l] = take((size_t)D << p.layer_log[l]);
+  for (u32 l = 0; l < p.num_layers; l++) c.fri_tree[l] = reinterpret_cast<Digest*>(take(size_t(1) << p.layer_log[l]));   // 2 * Nl/8 digests
+  c.rem_in = take((size_t)D << p.rem_log); c.rem_coef = take((size_t)D << p.rem_log);
+  c.words = (size_t)(w - s.slab);
+}
+
+// coin seed elements: Context::to_elements() then the public inputs (A.4)
+void seed_elements(u32 ln, const xfg_options& o, const xfg_air_consts& air, u64 out[8 + XFG_NUM_PUB_INPUTS]) {
+  int k = 0;
+  out[k++] = (u64)XFG_TRACE_WIDTH << 8;
+  out[k++] = XFG_P & 0xFFFFFFFFull; out[k++] = XFG_P >> 32;
+  out[k++] = (u64)o.field_extension << 16 | (u64)o.fri_folding_factor << 8 | o.fri_remainder_max_degree;
+  out[k++] = o.grinding_factor; out[k++] = o.blowup_factor; out[k++] = o.num_queries;
+  out[k++] = (u64)(u32)(size_t(1) << ln);
+  for (int i = 0; i < XFG_NUM_PUB_INPUTS; i++) out[k++] = air.pub_inputs[i];
+}
+
+// layout of the material buffer for this proof; fills the gather tasks
+size_t build_gather(const Plan& p, int D, const xfg_options& o, const Carve& c, GatherTasks& g) {
+  const u32 q = o.num_queries; size_t off = 0; u32 t = 0;
+  auto add = [&](const u64* src, const Digest* tree, u64 limb_stride, u64 coset_n, u64 R, u64 M, u32 J, u32 limbs, u32 depth, int layer) {
+    GatherTask& k = g.t[t++]; k.src = src; k.tree = tree; k.limb_stride = limb_stride; k.coset_n = coset_n; k.R = R; k.M = M; k.J = J; k.limbs = limbs;
+    k.depth = depth; k.fri_layer = layer; k.rows_off = off; off += ((size_t)q * J * limbs + 3) & ~size_t(3); k.paths_off = off; off += (size_t)q * depth * 4;
+  };
+  add(c.lde, c.trace_tree, p.N, p.n, 0, p.N, 1, XFG_TRACE_WIDTH, p.lN, -1);
+  add(c.h_lde, c.comp_tree, p.N, p.n, 0, p.N, 1, (u32)D, p.lN, -1);
+  for (u32 l = 0; l < p.num_layers; l++) {
+    const u64 Nl = u64(1) << p.layer_log[l], R = Nl / 8;
+    add(c.fri_evals[l], c.fri_tree[l], l == 0 ? p.N : Nl, l == 0 ? p.n : 0, R, R, 8, (u32)D, p.layer_log[l] - 3, (int)l);
+  }
+  g.count = t; return off;
+}
+
+// ---- enqueue the whole proof on the slot's stream (no host synchronisation) ----
+int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const xfg_air_consts& air, const u64* d_trace, bool timed) {
+  Carve c; carve(s, p, D, c);
+  if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length");
+  cudaStream_t st = s.st; const u32 ln = p.ln; const size_t n = p.n, N = p.N;
+  int ev = 0;
+  auto mark = [&]() { if (timed) cudaEventRecord(s.ev[ev], st); ev++; };
+  const u64* trace_src = d_trace ? d_trace : c.trace_in;
+
+  seed_elements(ln, o, air, s.h_seed);
+  CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (8 + XFG_NUM_PUB_INPUTS) * 8, cudaMemcpyHostToDevice, st));
+  mark();   // ev0: start of device work
+  launch_seed(st, s.d_state, s.d_seed, 8 + XFG_NUM_PUB_INPUTS);
+  launch_check_canonical(st, trace_src, 7 * n, s.d_state);
+
+  // 1 ---- extend_execution_trace: interpolate the 7 columns, evaluate on the 8 cosets s_k * <w_n>
+  { NttJob j{}; j.src = trace_src; j.dst = c.trace_coef; j.ln = ln; j.batch = XFG_TRACE_WIDTH; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
+    j.inverse = true; j.scale = p.n_inv; ntt_batch(st, p.ntt, j); }
+  { NttJob j{}; j.src = c.trace_coef; j.dst = c.lde; j.ln = ln; j.batch = XFG_TRACE_WIDTH * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
+    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; ntt_batch(st, p.ntt, j); }
+  mark();
+  //   ---- compute_execution_trace_commitment
+  merkle_commit_rows(st, c.lde, N, XFG_TRACE_WIDTH, ln, c.trace_tree);
+  launch_trace_root(st, D, s.d_state, c.trace_tree);
+  mark();
+  // 2 ---- evaluate_constraints
+  { AirParams ap; ap.txn = air.txn_hash; ap.rcpt = air.recipient_hash; ap.nullifier = air.nullifier; ap.commitment = air.commitment;
+    ap.assert0[0] = air.pub_inputs[XFG_PI_BURN]; ap.assert0[1] = air.pub_inputs[XFG_PI_MINT]; ap.assert0[2] = air.pub_inputs[XFG_PI_TXN_HASH];
+    ap.assert0[3] = air.pub_inputs[XFG_PI_RECIPIENT_HASH]; ap.assert0[4] = 0; ap.assert0[5] = air.nullifier; ap.assert0[6] = air.commitment;
+    ap.g_last = p.g_last;
+    launch_constraints(st, D, c.lde, ln, ap, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals); }
+  mark();
+  // 3 ---- commit_to_constraint_evaluations: coset interpolation (2 cosets of size n), composition column, LDE, commitment
+  { NttJob j{}; j.src = c.ce_evals; j.dst = c.ce_tmp; j.ln = ln; j.batch = 2 * D; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
+    j.inverse = true; j.scale = p.n_inv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 2; ntt_batch(st, p.ntt, j); }
+  launch_combine(st, c.ce_tmp, ln, D, p.inv2, c.h_coef, s.d_state);
+  { NttJob j{}; j.src = c.h_coef; j.dst = c.h_lde; j.ln = ln; j.batch = D * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
+    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; ntt_batch(st, p.ntt, j); }
+  merkle_commit_rows(st, c.h_lde, N, D, ln, c.comp_tree);
+  launch_constraint_root(st, D, s.d_state, c.comp_tree, p.g_n);
+  mark();
+  // 4 ---- build_deep_composition_poly: OOD frame + coefficients
+  launch_ood(st, D, c.trace_coef, c.h_coef, ln, s.d_state, s.d_partial);
+  launch_ood_finish(st, D, s.d_state, s.d_partial, ood_num_blocks(ln));
+  mark();
+  // 5 ---- evaluate_deep_composition_poly (pointwise) + leaves of the first FRI layer
+  launch_deep(st, D, c.lde, c.h_lde, ln, s.d_state, p.ntt.wn_fwd, p.d_sk, c.deep, p.num_layers ? c.fri_tree[0] : nullptr);
+  mark();
+  // 6 ---- compute_fri_layers
+  for (u32 l = 0; l < p.num_layers; l++) {
+    merkle_build_upper(st, c.fri_tree[l], size_t(1) << (p.layer_log[l] - 3));
+    launch_fri_commit(st, D, s.d_state, c.fri_tree[l], l);
+    launch_fri_fold(st, D, c.fri_evals[l], l == 0 ? N : (size_t(1) << p.layer_log[l]), l == 0, p.layer_log[l], l, s.d_state, p.wN_inv, p.lN, p.fc,
+                    c.fri_evals[l + 1], size_t(1) << p.layer_log[l + 1], l + 1 < p.num_layers ? c.fri_tree[l + 1] : nullptr);
+  }
+  { const u64* rin = c.fri_evals[p.num_layers]; const size_t Rm = size_t(1) << p.rem_log;
+    if (p.num_layers == 0) { launch_coset_to_natural(st, c.deep, c.rem_in, ln, D, N, Rm); rin = c.rem_in; }
+    NttJob j{}; j.src = rin; j.dst = c.rem_coef; j.ln = p.rem_log; j.batch = D; j.src_tstride = Rm; j.dst_tstride = Rm; j.src_div = 1;
+    j.inverse = true; j.scale = p.rem_ninv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 1; ntt_batch(st, p.ntt, j);
+    launch_remainder(st, D, s.d_state, c.rem_coef, Rm, p.rem_len); }
+  mark();
+  // 7 ---- determine_query_positions
+  launch_grind(st, s.d_state, o.grinding_factor);
+  launch_positions(st, s.d_state, o.num_queries, p.lN, p.num_layers);
+  mark();
+  // 8 ---- build_proof_object: gather opened rows + authentication nodes, copy out
+  const size_t mat_words = build_gather(p, D, o, c, s.tasks);
+  if (mat_words > MATERIAL_WORDS) return fail(ctx, XFG_ERR_INTERNAL, "material buffer too small");
+  launch_gather(st, s.tasks, s.d_state, s.d_material);
+  mark();   // end of device work
+  CU(cudaMemcpyAsync(s.h_state, s.d_state, sizeof(ProofState), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s.h_material, s.d_material, mat_words * 8, cudaMemcpyDeviceToHost, st));
+  mark();
+  CU(cudaGetLastError());
+  s.busy = true; s.plan = &p; s.D = D; s.opt = o; s.timed = timed;
+  return XFG_OK;
+}
+
+// ---- host serialisation ----
+struct Out { std::vector<u8> b;
+  void u8_(u32 v) { b.push_back((u8)v); } void u16_(size_t v) { b.push_back((u8)v); b.push_back((u8)(v >> 8)); }
+  void u32_(size_t v) { for (int i = 0; i < 4; i++) b.push_back((u8)(v >> (8 * i))); } void u64_(u64 v) { for (int i = 0; i < 8; i++) b.push_back((u8)(v >> (8 * i))); }
+  void raw(const void* p, size_t n) { const u8* q = (const u8*)p; b.insert(b.end(), q, q + n); } };
+
+// BatchMerkleProof::serialize_nodes of MerkleTree::prove_batch(positions) (A.11), built from the per-position sibling paths:
+// path(q, lvl) = tree[((M + pos[q]) >> lvl) ^ 1]
+void batch_paths(const u32* pos, u32 cnt, const u64* paths, u32 depth, u64 M, Out& out) {
+  auto path = [&](u32 q, u32 lvl) { return reinterpret_cast<const u8*>(paths + ((size_t)q * depth + lvl) * 4); };
+  auto owner = [&](u64 heap_index, u32 lvl) -> int { for (u32 q = 0; q < cnt; q++) if (((M + pos[q]) >> lvl) == heap_index) return (int)q; return -1; };
+  std::set<u64> norm; for (u32 q = 0; q < cnt; q++) norm.insert(pos[q] & ~u64(1));
+  std::vector<std::vector<const u8*>> nodes; std::vector<u64> next;
+  for (u64 index : norm) {
+    std::vector<const u8*> v;
+    for (u64 i = index; i < index + 2; i++) if (owner(M + i, 0) < 0) v.push_back(path((u32)owner(M + (i ^ 1), 0), 0));   // unqueried leaf = sibling of its queried partner
+    nodes.push_back(v); next.push_back((index + M) >> 1);
+  }
+  for (u32 d = 1; d < depth; d++) {
+    std::vector<u64> cur = next; next.clear();
+    size_t i = 0;
+    while (i < cur.size()) {
+      const u64 sib = cur[i] ^ 1;
+      if (i + 1 < cur.size() && cur[i + 1] == sib) i += 1;
+      else nodes[i].push_back(path((u32)owner(cur[i], d), d));   // indexed by position in `cur`, as the reference crate does
+      next.push_back(sib >> 1); i += 1;
+    }
+  }
+  out.u8_((u32)nodes.size());
+  for (auto& v : nodes) { out.u8_((u32)v.size()); for (const u8* d : v) out.raw(d, 32); }
+}
+
+// StarkProof::to_bytes (A.12)
+void assemble(const Plan& p, int D, const xfg_options& o, const ProofState& s, const u64* mat, const GatherTasks& g, std::vector<u8>& bytes) {
+  Out out;
+  // Context
+  out.u8_(XFG_TRACE_WIDTH); out.u8_(0); out.u8_(0); out.u8_(p.ln); out.u16_(0); out.u8_(8); out.u64_(XFG_P);
+  out.u8_(o.num_queries); out.u8_(o.blowup_factor); out.u8_(o.grinding_factor); out.u8_(o.field_extension); out.u8_(o.fri_folding_factor); out.u8_(o.fri_remainder_max_degree);
+  out.u8_(s.num_positions);
+  // Commitments
+  out.u16_(32 * (3 + p.num_layers));
+  out.raw(&s.trace_root, 32); out.raw(&s.constraint_root, 32);
+  for (u32 l = 0; l < p.num_layers; l++) out.raw(&s.fri_roots[l], 32);
+  out.raw(&s.remainder_commitment, 32);
+  // trace + constraint Queries: u32 len + values, u32 len + paths
+  auto queries = [&](const GatherTask& t, const u32* pos, u32 cnt) {
+    const size_t vbytes = (size_t)cnt * t.J * t.limbs * 8;
+    out.u32_(vbytes); out.raw(mat + t.rows_off, vbytes);
+    Out pth; batch_paths(pos, cnt, mat + t.paths_off, t.depth, t.M, pth);
+    out.u32_(pth.b.size()); out.raw(pth.b.data(), pth.b.size());
+  };
+  queries(g.t[0], s.positions, s.num_positions);
+  queries(g.t[1], s.positions, s.num_positions);
+  // OodFrame
+  out.u16_(1 + 2 * XFG_TRACE_WIDTH * D * 8); out.u8_(2);
+  for (int i = 0; i < 2 * XFG_TRACE_WIDTH; i++) for (int l = 0; l < D; l++) out.u64_(s.ood_frame[i][l]);
+  out.u16_(D * 8); for (int l = 0; l < D; l++) out.u64_(s.hz[l]);
+  // FriProof
+  out.u8_(p.num_layers);
+  for (u32 l = 0; l < p.num_layers; l++) queries(g.t[2 + l], s.fri_positions[l], s.fri_num_positions[l]);
+  out.u16_((size_t)s.remainder_len * D * 8);
+  for (u32 i = 0; i < s.remainder_len; i++) for (int l = 0; l < D; l++) out.u64_(s.remainder[i][l]);
+  out.u8_(1);
+  out.u64_(s.nonce);
+  bytes.swap(out.b);
+}
+
+int finish_proof(xfg_ctx* ctx, Slot& s, u8* out, size_t cap, size_t* out_len, xfg_stage_times* times) {
+  CU(cudaStreamSynchronize(s.st));
+  s.busy = false;
+  const ProofState& hs = *s.h_state;
+  if (hs.error_flags & ERR_FLAG_NONCANONICAL) return fail(ctx, XFG_ERR_BAD_ARGS, "non-canonical trace element");
+  if (hs.error_flags & ERR_FLAG_DEGREE) return fail(ctx, XFG_ERR_UNSATISFIED_CONSTRAINT, "UnsatisfiedTransitionConstraintError: the trace does not satisfy the burn-mint AIR (composition polynomial degree too high)");
+  if (hs.error_flags & ERR_FLAG_COIN) return fail(ctx, XFG_ERR_INTERNAL, "FailedToDrawFieldElement");
+  std::vector<u8> bytes; assemble(*s.plan, s.D, s.opt, hs, s.h_material, s.tasks, bytes);
+  if (times && s.timed) {
+    for (int i = 0; i < XFG_NUM_STAGES; i++) cudaEventElapsedTime(&times->stage_ms[i], s.ev[i], s.ev[i + 1]);
+    cudaEventElapsedTime(&times->device_ms, s.ev[0], s.ev[XFG_NUM_STAGES]);
+  }
+  *out_len = bytes.size();
+  if (bytes.size() > cap) return fail(ctx, XFG_ERR_BUFFER_TOO_SMALL, "output buffer too small");
+  std::memcpy(out, bytes.data(), bytes.size());
+  return XFG_OK;
+}
+
+int check_air(xfg_ctx* ctx, const xfg_air_consts* air) {
+  for (int i = 0; i < XFG_NUM_PUB_INPUTS; i++) if (air->pub_inputs[i] >= XFG_P) return fail(ctx, XFG_ERR_BAD_ARGS, "non-canonical public input");
+  if (air->txn_hash >= XFG_P || air->recipient_hash >= XFG_P || air->nullifier >= XFG_P || air->commitment >= XFG_P) return fail(ctx, XFG_ERR_BAD_ARGS, "non-canonical AIR constant");
+  return XFG_OK;
+}
+
+// trace upload: straight from the caller's buffer when it is page-locked (cudaHostAlloc / cudaHostRegister), otherwise staged
+// through the slot's pinned buffer.  Canonicity (< p) is checked on the device.
+int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace) {
+  Carve c; carve(s, p, D, c);
+  if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length");
+  const size_t bytes = 7 * p.n * 8;
+  cudaPointerAttributes at{}; const bool pinned = cudaPointerGetAttributes(&at, h_trace) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();   // unregistered host memory may leave a sticky-free error code behind on older drivers
+  const u64* src = h_trace;
+  if (!pinned) { std::memcpy(s.h_trace, h_trace, bytes); src = s.h_trace; }
+  CU(cudaMemcpyAsync(c.trace_in, src, bytes, cudaMemcpyHostToDevice, s.st));
+  return XFG_OK;
+}
+
+int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log2, const xfg_air_consts* air, const xfg_options* o,
+                 u8* out, size_t cap, size_t* out_len, xfg_stage_times* times) {
+  if (!ctx || !air || !o || !out_len || (!h_trace && !d_trace) || (!out && cap)) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+  if (n_log2 < MIN_LOG || n_log2 > MAX_LOG) return fail(ctx, XFG_ERR_BAD_ARGS, "trace length must be 2^3 .. 2^24");
+  if (n_log2 > ctx->max_log) return fail(ctx, XFG_ERR_TOO_LARGE, "trace longer than the context was created for");
+  int rc;
+  if ((rc = check_options(ctx, o, n_log2)) || (rc = check_air(ctx, air))) return rc;
+  CU(cudaSetDevice(ctx->device));
+  const Plan* p; if ((rc = get_plan(ctx, n_log2, o->fri_remainder_max_degree, &p))) return rc;
+  Slot& s = ctx->slots[0];
+  const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1;
+  g_xfg_launches = 0;
+  if (times) { std::memset(times, 0, sizeof *times); cudaEventRecord(s.ev[XFG_NUM_STAGES + 2], s.st); }
+  if (h_trace && (rc = upload_trace(ctx, s, *p, D, h_trace))) return rc;
+  if ((rc = enqueue_proof(ctx, s, *p, D, *o, *air, d_trace, times != nullptr))) return rc;
+  rc = finish_proof(ctx, s, out, cap, out_len, times);
+  if (times) {
+    cudaEventElapsedTime(&times->h2d_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[0]);
+    cudaEventElapsedTime(&times->total_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[XFG_NUM_STAGES + 1]);
+    times->kernel_launches = g_xfg_launches;
+  }
+  return rc;
+}
+
+}  // namespace
+
+// =============================================================== C ABI ===============================================================
+extern "C" {
+
+const char* xfg_strerror(int code) {
+  switch (code) {
+    case XFG_OK: return "ok";
+    case XFG_ERR_BAD_ARGS: return "bad arguments";
+    case XFG_ERR_BAD_OPTIONS: return "invalid proof options";
+    case XFG_ERR_UNSUPPORTED_OPTIONS: return "proof options not supported by this backend";
+    case XFG_ERR_UNSUPPORTED_EXTENSION: return "UnsupportedFieldExtension";
+    case XFG_ERR_UNSATISFIED_CONSTRAINT: return "UnsatisfiedTransitionConstraintError";
+    case XFG_ERR_BUFFER_TOO_SMALL: return "output buffer too small";
+    case XFG_ERR_CUDA: return "CUDA error";
+    case XFG_ERR_INVALID_INPUT: return "invalid burn-mint input";
+    case XFG_ERR_TOO_LARGE: return "trace too large for this context";
+    default: return "internal error";
+  }
+}
+const char* xfg_last_error(const xfg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** out) {
+  if (!out || max_n_log2 < MIN_LOG || max_n_log2 > MAX_LOG || num_slots < 1 || num_slots > 64) return XFG_ERR_BAD_ARGS;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return XFG_ERR_CUDA;   // no CPU fallback
+  xfg_ctx* ctx = new xfg_ctx; ctx->device = device; ctx->max_log = max_n_log2;
+  auto bail = [&](int rc) { xfg_destroy(ctx); return rc; };
+#define CUB(call) do { if ((call) != cudaSuccess) return bail(XFG_ERR_CUDA); } while (0)
+  CUB(cudaSetDevice(device));
+  ntt_init();
+  { const u64 w = gl_root_of_unity(NTT_TW_LOG); std::vector<u64> f = pow_series(w, 1u << (NTT_TW_LOG - 1)), b = pow_series(gl_inv(w), 1u << (NTT_TW_LOG - 1));
+    CUB(cudaMalloc(&ctx->tw_fwd, f.size() * 8)); CUB(cudaMalloc(&ctx->tw_inv, b.size() * 8));
+    CUB(cudaMemcpy(ctx->tw_fwd, f.data(), f.size() * 8, cudaMemcpyHostToDevice)); CUB(cudaMemcpy(ctx->tw_inv, b.data(), b.size() * 8, cudaMemcpyHostToDevice)); }
+  ctx->slots.resize(num_slots);
+  const size_t words = slab_words_for(max_n_log2, 2), trace_words = size_t(7) << max_n_log2;
+  for (Slot& s : ctx->slots) {
+    CUB(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    CUB(cudaMalloc(&s.slab, words * 8)); s.slab_words = words;
+    CUB(cudaMalloc(&s.d_state, sizeof(ProofState))); CUB(cudaMalloc(&s.d_seed, 64 * 8));
+    CUB(cudaMalloc(&s.d_partial, (size_t)NUM_OOD_POLYS * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
+    CUB(cudaMallocHost(&s.h_state, sizeof(ProofState))); CUB(cudaMallocHost(&s.h_material, MATERIAL_WORDS * 8));
+    CUB(cudaMallocHost(&s.h_seed, 64 * 8)); CUB(cudaMallocHost(&s.h_trace, trace_words * 8));
+    for (auto& e : s.ev) CUB(cudaEventCreate(&e));
+  }
+#undef CUB
+  *out = ctx; return XFG_OK;
+}
+
+void xfg_destroy(xfg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (Slot& s : ctx->slots) {
+    if (s.st) cudaStreamSynchronize(s.st);
+    cudaFree(s.slab); cudaFree(s.d_state); cudaFree(s.d_seed); cudaFree(s.d_partial); cudaFree(s.d_material);
+    cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
+    for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+    if (s.st) cudaStreamDestroy(s.st);
+  }
+  for (auto& kv : ctx->plans) cudaFree(kv.second.slab);
+  cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv);
+  delete ctx;
+}
+
+int xfg_prove_burn_mint(xfg_ctx* ctx, const uint64_t* trace, uint32_t n_log2, const xfg_air_consts* air, const xfg_options* o, uint8_t* out,
+                        size_t cap, size_t* out_len, xfg_stage_times* times) {
+  return prove_common(ctx, trace, nullptr, n_log2, air, o, out, cap, out_len, times);
+}
+int xfg_prove_burn_mint_device(xfg_ctx* ctx, const uint64_t* d_trace, uint32_t n_log2, const xfg_air_consts* air, const xfg_options* o, uint8_t* out,
+                               size_t cap, size_t* out_len, xfg_stage_times* times) {
+  return prove_common(ctx, nullptr, d_trace, n_log2, air, o, out, cap, out_len, times);
+}
+
+int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* const* traces, uint32_t n_log2, const xfg_air_consts* airs,
+                              const xfg_options* o, uint8_t* out, size_t out_stride, size_t* out_lens, float* total_ms) {
+  if (!ctx || !traces || !airs || !o || !out || !out_lens) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+  if (n_log2 < MIN_LOG || n_log2 > MAX_LOG) return fail(ctx, XFG_ERR_BAD_ARGS, "trace length must be 2^3 .. 2^24");
+  if (n_log2 > ctx->max_log) return fail(ctx, XFG_ERR_TOO_LARGE, "trace longer than the context was created for");
+  int rc; if ((rc = check_options(ctx, o, n_log2))) return rc;
+  CU(cudaSetDevice(ctx->device));
+  const Plan* p; if ((rc = get_plan(ctx, n_log2, o->fri_remainder_max_degree, &p))) return rc;
+  const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1; const size_t S = ctx->slots.size();
+  g_xfg_launches = 0;
+  cudaEvent_t e0 = ctx->slots[0].ev[XFG_NUM_STAGES + 2], e1 = ctx->slots[0].ev[XFG_NUM_STAGES + 1];
+  if (total_ms) { CU(cudaDeviceSynchronize()); CU(cudaEventRecord(e0, ctx->slots[0].st)); }
+  int first_err = XFG_OK;
+  for (uint32_t i = 0; i < count; i++) {
+    Slot& s = ctx->slots[i % S];
+    if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
+    if ((rc = check_air(ctx, &airs[i]))) return rc;
+    if (!traces[i]) return fail(ctx, XFG_ERR_BAD_ARGS, "null trace");
+    if ((rc = upload_trace(ctx, s, *p, D, traces[i]))) return rc;
+    s.proof_index = i;
+    if ((rc = enqueue_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) return rc;
+  }
+  for (Slot& s : ctx->slots) if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
+  if (total_ms) { CU(cudaDeviceSynchronize()); CU(cudaEventRecord(e1, ctx->slots[0].st)); CU(cudaEventSynchronize(e1)); cudaEventElapsedTime(total_ms, e0, e1); }
+  return first_err;
+}
+
+int xfg_burn_mint_pack_inputs(xfg_ctx* ctx, uint64_t burn, uint64_t mint, const uint8_t txp[32], const uint8_t* rcpt, size_t rcpt_len, const uint8_t* secret,
+                              size_t secret_len, uint32_t network_id, uint32_t target_chain_id, uint32_t version, xfg_air_consts* out) {
+  if (!txp || !rcpt || !secret || !out) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+  std::string err; int rc = burn_mint_pack_inputs(burn, mint, txp, rcpt, rcpt_len, secret, secret_len, network_id, target_chain_id, version, out, err);
+  if (rc && ctx) ctx->last_error = err;
+  return rc;
+}
+int xfg_burn_mint_build_trace(const xfg_air_consts* air, uint32_t n_log2, uint64_t* t) {
+  if (!air || !t || n_log2 < MIN_LOG || n_log2 > MAX_LOG) return XFG_ERR_BAD_ARGS;
+  burn_mint_build_trace(air, n_log2, t); return XFG_OK;
+}
+int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn, uint64_t mint, const uint8_t txp[32], const uint8_t* rcpt, size_t rcpt_len,
+                                    const uint8_t* secret, size_t secret_len, uint32_t network_id, uint32_t target_chain_id, uint32_t version,
+                                    uint32_t n_log2, const xfg_options* o, uint8_t* out, size_t cap, size_t* out_len, xfg_stage_times* times) {
+  if (!ctx) return XFG_ERR_BAD_ARGS;
+  if (n_log2 < MIN_LOG || n_log2 > ctx->max_log) return fail(ctx, XFG_ERR_TOO_LARGE, "trace longer than the context was created for");
+  xfg_air_consts air; int rc = xfg_burn_mint_pack_inputs(ctx, burn, mint, txp, rcpt, rcpt_len, secret, secret_len, network_id, target_chain_id, version, &air);
+  if (rc) return rc;
+  std::vector<u64> trace((size_t)7 << n_log2);
+  burn_mint_build_trace(&air, n_log2, trace.data());
+  return xfg_prove_burn_mint(ctx, trace.data(), n_log2, &air, o, out, cap, out_len, times);
+}
+
+}  // extern "C"
+
+#include "stage_api.inc"

@@ -1,0 +1,291 @@
+// stark_kernels.cu — the elementwise stages of the burn-mint proof for sm_100a: AIR constraint evaluation, composition
+// coefficients, out-of-domain evaluation, DEEP composition and FRI folding.  All streaming kernels over the coset-major LDE
+// (LDE row i = 8m + k at [k*n + m]), one field element per lane, every global access coalesced along m.
+//
+// Replaces winter-prover 0.8.3 `DefaultConstraintEvaluator::evaluate` + `ConstraintEvaluationTable::combine`,
+// `CompositionPoly::new`, `TracePolyTable::get_ood_frame`, `DeepCompositionPoly::{add_trace_polys, add_composition_poly,
+// evaluate}` and winter-fri `FriProver::build_layers` / `folding::apply_drp`, together
+// with the reference's `Air::evaluate_transition` / `get_assertions` (src/burn_mint_air.rs:335-395).
+#include "stark_kernels.cuh"
+#include "launch.cuh"
+
+namespace xfg {
+
+template <int D> __device__ __forceinline__ Ext<D> ld_ext(const u64 (*p)[2], int i) { return Ext<D>(p[i][0], p[i][1]); }
+template <int D> __device__ __forceinline__ Ext<D> ld_ext1(const u64* p) { return Ext<D>(p[0], p[1]); }
+
+// in-register Montgomery batch inversion of K non-zero base-field values
+template <int K> __device__ __forceinline__ void batch_inv(u64 (&v)[K]) {
+  u64 pre[K]; u64 acc = 1;
+#pragma unroll
+  for (int i = 0; i < K; i++) { pre[i] = acc; acc = gl_mul(acc, v[i]); }
+  acc = gl_inv(acc);
+#pragma unroll
+  for (int i = K - 1; i >= 0; i--) { u64 t = gl_mul(pre[i], acc); acc = gl_mul(acc, v[i]); v[i] = t; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// evaluate_constraints: one thread evaluates CE_PTS points of the constraint-evaluation coset k' (LDE coset 4k').
+//   H(x) = T(x) (x - g^(n-1)) / (x^n - 1) + B0(x) / (x - 1) + B1(x) / (x - g^(n-1))      (A.8)
+// out: [limb][k'][m], k' < 2
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int CE_PTS = 4;
+template <int D>
+__global__ void __launch_bounds__(256) constraint_kernel(const u64* __restrict__ lde, u32 ln, AirParams air, const ProofState* __restrict__ ps,
+                                                          PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out) {
+  const size_t n = size_t(1) << ln, N = 8 * n;
+  const u32 kp = blockIdx.y, k = kp * 4;
+  const size_t per = n / CE_PTS, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per) return;
+  const u64 sk = kp ? s_k1 : s_k0, zinv = kp ? zinv1 : zinv0;
+  Ext<D> tc[XFG_NUM_TRANSITION], bc[XFG_NUM_ASSERTIONS];
+#pragma unroll
+  for (int j = 0; j < XFG_NUM_TRANSITION; j++) tc[j] = ld_ext<D>(ps->tcoef, j);
+#pragma unroll
+  for (int j = 0; j < XFG_NUM_ASSERTIONS; j++) bc[j] = ld_ext<D>(ps->bcoef, j);
+  const u64 large_burn = gl_mul(XFG_STD_BURN, 1000);
+
+  Ext<D> tsum[CE_PTS], b0[CE_PTS], b1[CE_PTS]; u64 xs[CE_PTS], den[2 * CE_PTS];
+#pragma unroll
+  for (int q = 0; q < CE_PTS; q++) {
+    const size_t m = t + q * per, mn = (m + 1) & (n - 1);
+    u64 c[XFG_TRACE_WIDTH];
+#pragma unroll
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) c[j] = lde[(size_t)j * N + (size_t)k * n + m];
+    const u64 nxt4 = lde[(size_t)4 * N + (size_t)k * n + mn];
+    // src/burn_mint_air.rs:356-377
+    u64 r[XFG_NUM_TRANSITION];
+    r[0] = gl_mul(gl_sub(c[0], XFG_STD_BURN), gl_sub(c[0], large_burn));
+    r[1] = gl_sub(c[1], c[0]);
+    r[2] = gl_sub(c[2], air.txn);
+    r[3] = gl_sub(c[3], air.rcpt);
+    const u64 d = gl_sub(nxt4, c[4]); r[4] = gl_mul(d, gl_sub(d, 1));
+    r[5] = gl_sub(c[5], air.nullifier);
+    r[6] = gl_sub(c[6], air.commitment);
+    Ext<D> ts, bs;
+#pragma unroll
+    for (int j = 0; j < XFG_NUM_TRANSITION; j++) ts = ts + mul_base(tc[j], r[j]);
+    // src/burn_mint_air.rs:383-394 in Winterfell's sorted order: step-0 columns 0..6, then (column 4, step n-1)
+#pragma unroll
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) bs = bs + mul_base(bc[j], gl_sub(c[j], air.assert0[j]));
+    tsum[q] = ts; b0[q] = bs; b1[q] = mul_base(bc[XFG_TRACE_WIDTH], gl_sub(c[4], XFG_FINAL_STATE));
+    const u64 x = gl_mul(sk, pow_lookup(wn, m));
+    xs[q] = x; den[2 * q] = gl_sub(x, 1); den[2 * q + 1] = gl_sub(x, air.g_last);
+  }
+  batch_inv<2 * CE_PTS>(den);
+#pragma unroll
+  for (int q = 0; q < CE_PTS; q++) {
+    const size_t m = t + q * per;
+    Ext<D> h = mul_base(tsum[q], gl_mul(gl_sub(xs[q], air.g_last), zinv)) + mul_base(b0[q], den[2 * q]) + mul_base(b1[q], den[2 * q + 1]);
+#pragma unroll
+    for (int l = 0; l < D; l++) out[(size_t)l * 2 * n + (size_t)kp * n + m] = h.limb(l);
+  }
+}
+
+void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams& air, const ProofState* ps, PowTable wn,
+                        u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out) {
+  const size_t per = (size_t(1) << ln) / CE_PTS; dim3 grid((unsigned)((per + 255) / 256), 2);
+  if (D == 1) constraint_kernel<1><<<grid, 256, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
+  else constraint_kernel<2><<<grid, 256, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
+  XFG_LAUNCHED(1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// composition coefficients: after the two size-n inverse NTTs (un-scaled by the coset offsets), the size-2n interpolant is
+//   h[j] = (A0[j] + A1[j]) / 2  for j < n   and   h[n + j] = (A0[j] - A1[j]) / (2 * 7^n), which must vanish (degree check).
+// a: [limb][2][n] -> h: [limb][n]
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) combine_kernel(const u64* __restrict__ a, u32 ln, int D, u64 inv2, u64* __restrict__ h, ProofState* ps) {
+  const size_t n = size_t(1) << ln, j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  bool bad = false;
+  for (int l = 0; l < D; l++) {
+    u64 a0 = a[(size_t)l * 2 * n + j], a1 = a[(size_t)l * 2 * n + n + j];
+    h[(size_t)l * n + j] = gl_mul(gl_add(a0, a1), inv2);
+    bad |= (a0 != a1);
+  }
+  if (bad) atomicOr(&ps->error_flags, ERR_FLAG_DEGREE);
+}
+void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64* h, ProofState* ps) {
+  const size_t n = size_t(1) << ln;
+  combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, ln, D, inv2, h, ps); XFG_LAUNCHED(1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// out-of-domain evaluation: poly p (base-field coefficients) at z and z*g.  Thread t sums c[t + i*TOT] z^(t + i*TOT) by a
+// Horner pass in z^TOT; block partials are added by the transcript kernel.  partial: [poly][block][point][limb]
+// ------------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln,
+                                                   const ProofState* __restrict__ ps, u64* __restrict__ partial) {
+  const size_t n = size_t(1) << ln;
+  const u32 poly = blockIdx.y, nb = gridDim.x;
+  const size_t TOT = (size_t)nb * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64* c = poly < XFG_TRACE_WIDTH ? trace_coef + (size_t)poly * n : h_coef + (size_t)(poly - XFG_TRACE_WIDTH) * n;
+  Ext<D> pt[2] = {ld_ext1<D>(ps->z), ld_ext1<D>(ps->zg)}, acc[2];
+  if (t < n) {
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      Ext<D> step = ext_pow<D>(pt[w], TOT), a;
+      for (size_t i = (n - 1 - t) / TOT + 1; i-- > 0;) a = add_base(a * step, c[t + i * TOT]);
+      acc[w] = a * ext_pow<D>(pt[w], t);
+    }
+  }
+  __shared__ u64 red[256][2][2];
+  for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) red[threadIdx.x][w][l] = l < D ? acc[w].limb(l) : 0;
+  __syncthreads();
+  for (u32 s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) red[threadIdx.x][w][l] = gl_add(red[threadIdx.x][w][l], red[threadIdx.x + s][w][l]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) partial[(((size_t)poly * nb + blockIdx.x) * 2 + w) * 2 + l] = red[0][w][l];
+}
+u32 ood_num_blocks(u32 ln) { size_t n = size_t(1) << ln; size_t b = n / 256; if (b < 1) b = 1; if (b > OOD_MAX_BLOCKS) b = OOD_MAX_BLOCKS; return (u32)b; }
+void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, const ProofState* ps, u64* partial) {
+  dim3 grid(ood_num_blocks(ln), XFG_TRACE_WIDTH + D);
+  if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, ps, partial);
+  else ood_kernel<2><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, ps, partial);
+  XFG_LAUNCHED(1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// DEEP composition, pointwise on the LDE coset (A.9; identical field elements to the coefficient-domain computation):
+//   D(x) = [ (S(x) - C1)(x - zg) + (S_T(x) - C2)(x - z) ] / [ (x - z)(x - zg) ]
+//   S_T = sum_j gamma_j T_j(x),  S = S_T + delta H(x),  C1 = sum_j gamma_j T_j(z) + delta H(z),  C2 = sum_j gamma_j T_j(zg)
+// Thread (k, a) computes the 8 points m = a + j*n/8 - exactly the 8 elements of row 8a + k of the first FRI layer - with one
+// batched inversion, writes them coset-major and hashes the row into the layer-0 FRI tree.
+// ------------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
+                                                    PowTable wn, const u64* __restrict__ s_k, u64* __restrict__ deep, Digest* __restrict__ fri_tree0) {
+  const size_t n = size_t(1) << ln, N = 8 * n, n8 = n / 8;
+  const u32 k = blockIdx.y; const size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n8) return;
+  Ext<D> gam[XFG_TRACE_WIDTH];
+#pragma unroll
+  for (int j = 0; j < XFG_TRACE_WIDTH; j++) gam[j] = ld_ext<D>(ps->dcoef, j);
+  const Ext<D> delta = ld_ext<D>(ps->dcoef, XFG_TRACE_WIDTH), c1 = ld_ext1<D>(ps->deep_c1), c2 = ld_ext1<D>(ps->deep_c2);
+  const Ext<D> z = ld_ext1<D>(ps->z), zg = ld_ext1<D>(ps->zg);
+  const u64 sk = s_k[k];
+  Ext<D> num[8], den[8]; u64 nrm[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const size_t m = a + (size_t)j * n8, idx = (size_t)k * n + m;
+    Ext<D> st;
+#pragma unroll
+    for (int c = 0; c < XFG_TRACE_WIDTH; c++) st = st + mul_base(gam[c], lde[(size_t)c * N + idx]);
+    Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + idx]);
+    const u64 x = gl_mul(sk, pow_lookup(wn, m));
+    // x - z, x - zg as extension elements (x is a base element)
+    Ext<D> xz = Ext<D>(x) - z, xzg = Ext<D>(x) - zg;
+    num[j] = (st + delta * h - c1) * xzg + (st - c2) * xz;
+    den[j] = xz * xzg; nrm[j] = ext_norm(den[j]);
+  }
+  batch_inv<8>(nrm);
+  u64 row[8 * D];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const size_t m = a + (size_t)j * n8, idx = (size_t)k * n + m;
+    Ext<D> v = num[j] * ext_inv_with_norm_inv(den[j], nrm[j]);
+#pragma unroll
+    for (int l = 0; l < D; l++) { deep[(size_t)l * N + idx] = v.limb(l); row[j * D + l] = v.limb(l); }
+  }
+  if (fri_tree0) store_digest(fri_tree0 + n + 8 * a + k, b3_hash_limbs<8 * D>(row));
+}
+void launch_deep(cudaStream_t st, int D, const u64* lde, const u64* hlde, u32 ln, const ProofState* ps, PowTable wn, const u64* s_k,
+                 u64* deep, Digest* fri_tree0) {
+  const size_t n8 = (size_t(1) << ln) / 8; dim3 grid((unsigned)((n8 + 127) / 128), 8);
+  if (D == 1) deep_kernel<1><<<grid, 128, 0, st>>>(lde, hlde, ln, ps, wn, s_k, deep, fri_tree0);
+  else deep_kernel<2><<<grid, 128, 0, st>>>(lde, hlde, ln, ps, wn, s_k, deep, fri_tree0);
+  XFG_LAUNCHED(1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// FRI: fold layer l (Nl values) by 8 with alpha_l into layer l+1 and hash the rows of layer l+1 (A.10).
+// Row r of layer l = values at r + j*Nl/8; x_r = 7 * w_Nl^r (constant offset 7 at every layer);
+// next[r] = P_r(alpha), P_r interpolating the row over x_r * w_8^j:
+//   P_r(alpha) = 1/8 sum_k V_k (alpha / x_r)^k,  V_k = sum_j v_j w_8^(-jk).
+// Thread i' computes the 8 folds r = i' + q*Nl/64 = the 8 elements of row i' of layer l+1.
+// src layout: coset-major when `src_coset` (layer 0 = DEEP evaluations), else natural [limb][i]; dst natural.
+// ------------------------------------------------------------------------------------------------------------------
+
+template <int D>
+__device__ __forceinline__ Ext<D> fold8(const Ext<D> (&v)[8], const FriConsts& fc, Ext<D> beta) {
+  // radix-2 DIT inverse DFT of size 8 (input bit-reversed), twiddles w_8^-j
+  Ext<D> a[8] = {v[0], v[4], v[2], v[6], v[1], v[5], v[3], v[7]};
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) { Ext<D> u = a[i], w = a[i + 1]; a[i] = u + w; a[i + 1] = u - w; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 4) {
+    Ext<D> u = a[i], w = a[i + 2]; a[i] = u + w; a[i + 2] = u - w;
+    u = a[i + 1]; w = mul_base(a[i + 3], fc.w8i[2]); a[i + 1] = u + w; a[i + 3] = u - w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) { Ext<D> u = a[j], w = j ? mul_base(a[j + 4], fc.w8i[j]) : a[j + 4]; a[j] = u + w; a[j + 4] = u - w; }
+  Ext<D> r = a[7];
+#pragma unroll
+  for (int kk = 6; kk >= 0; kk--) r = r * beta + a[kk];
+  return mul_base(r, fc.inv8);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) fri_fold_kernel(const u64* __restrict__ src, size_t src_limb_stride, int src_coset, u32 lNl, u32 layer,
+                                                        const ProofState* __restrict__ ps, PowTable wN_inv, u32 lN, FriConsts fc,
+                                                        u64* __restrict__ dst, size_t dst_limb_stride, Digest* __restrict__ next_tree) {
+  const size_t Nl = size_t(1) << lNl, R = Nl / 8, Rn = R / 8;   // rows of this layer, rows of the next
+  size_t tix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tix >= Rn) return;
+  size_t ip = tix;
+  if (src_coset && Rn >= 8) ip = ((tix % (Rn / 8)) << 3) | (tix / (Rn / 8));   // i' = 8a' + k with a' fastest: coalesced coset-major reads
+  const Ext<D> alpha = ld_ext<D>(ps->alphas, layer);
+  const size_t nrows0 = Nl / 8;   // coset stride n when src is the layer-0 coset-major array (Nl = 8n)
+  u64 row[8 * D];
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const size_t r = ip + (size_t)q * Rn;
+    Ext<D> v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const size_t p = r + (size_t)j * R;
+      const size_t addr = src_coset ? (p & 7) * nrows0 + (p >> 3) : p;
+      for (int l = 0; l < D; l++) v[j].set_limb(l, src[(size_t)l * src_limb_stride + addr]);
+    }
+    // 1 / x_r = 7^-1 * w_N^-(r * N/Nl)
+    const u64 xinv = gl_mul(fc.inv7, pow_lookup(wN_inv, (u64)r << (lN - lNl)));
+    Ext<D> w = fold8<D>(v, fc, mul_base(alpha, xinv));
+#pragma unroll
+    for (int l = 0; l < D; l++) { dst[(size_t)l * dst_limb_stride + r] = w.limb(l); row[q * D + l] = w.limb(l); }
+  }
+  if (next_tree) store_digest(next_tree + Rn + ip, b3_hash_limbs<8 * D>(row));
+}
+void launch_fri_fold(cudaStream_t st, int D, const u64* src, size_t src_limb_stride, int src_coset, u32 lNl, u32 layer, const ProofState* ps,
+                     PowTable wN_inv, u32 lN, const FriConsts& fc, u64* dst, size_t dst_limb_stride, Digest* next_tree) {
+  const size_t Rn = (size_t(1) << lNl) / 64; const unsigned blocks = (unsigned)((Rn + 127) / 128);
+  if (D == 1) fri_fold_kernel<1><<<blocks, 128, 0, st>>>(src, src_limb_stride, src_coset, lNl, layer, ps, wN_inv, lN, fc, dst, dst_limb_stride, next_tree);
+  else fri_fold_kernel<2><<<blocks, 128, 0, st>>>(src, src_limb_stride, src_coset, lNl, layer, ps, wN_inv, lN, fc, dst, dst_limb_stride, next_tree);
+  XFG_LAUNCHED(1);
+}
+
+// coset-major [k*n + m] -> natural [8m + k] (only used when a proof has no FRI layer and the remainder is taken from DEEP directly)
+__global__ void coset_to_natural_kernel(const u64* __restrict__ src, u64* __restrict__ dst, u32 ln, int D, size_t src_limb_stride, size_t dst_limb_stride) {
+  const size_t n = size_t(1) << ln, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 8 * n) return;
+  for (int l = 0; l < D; l++) dst[(size_t)l * dst_limb_stride + i] = src[(size_t)l * src_limb_stride + (i & 7) * n + (i >> 3)];
+}
+void launch_coset_to_natural(cudaStream_t st, const u64* src, u64* dst, u32 ln, int D, size_t src_limb_stride, size_t dst_limb_stride) {
+  const size_t N = size_t(8) << ln;
+  coset_to_natural_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(src, dst, ln, D, src_limb_stride, dst_limb_stride); XFG_LAUNCHED(1);
+}
+
+// every trace element must be a canonical field element (< p); the boundary takes `BaseElement::as_int()` values
+__global__ void __launch_bounds__(256) check_canonical_kernel(const u64* __restrict__ v, size_t count, ProofState* ps) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) bad |= v[i] >= GL_P;
+  if (bad) atomicOr(&ps->error_flags, ERR_FLAG_NONCANONICAL);
+}
+void launch_check_canonical(cudaStream_t st, const u64* v, size_t count, ProofState* ps) {
+  size_t blocks = (count + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+  check_canonical_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, count, ps); XFG_LAUNCHED(1);
+}
+
+}  // namespace xfg

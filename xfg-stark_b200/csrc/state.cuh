@@ -1,0 +1,47 @@
+// state.cuh — device-resident proof state: the Fiat-Shamir transcript and every value derived from it.
+//
+// Plays the role of winter-prover 0.8.3 `ProverChannel` + `DefaultRandomCoin`: the coin and
+// all drawn challenges stay in HBM so that the whole proof is one dependent chain of kernel launches with no host
+// round trip until the final copy-out.
+#pragma once
+#include "blake3.cuh"
+
+namespace xfg {
+
+static constexpr int MAX_Q = XFG_MAX_QUERIES;          // 255
+static constexpr int MAX_LAYERS = XFG_MAX_FRI_LAYERS;  // 16
+static constexpr int MAX_REMAINDER = 256;              // (fri_remainder_max_degree + 1) <= 256 coefficients
+static constexpr int OOD_MAX_BLOCKS = 64;
+static constexpr int NUM_OOD_POLYS = XFG_TRACE_WIDTH + 2;   // 7 trace polys + up to 2 limb polys of H
+
+enum : u32 { ERR_FLAG_DEGREE = 1u, ERR_FLAG_COIN = 2u, ERR_FLAG_NONCANONICAL = 4u };
+
+struct ProofState {
+  // coin
+  Digest seed; u64 counter;
+  // commitments
+  Digest trace_root, constraint_root, fri_roots[MAX_LAYERS], remainder_commitment;
+  // challenges (limbs [2] even when the extension degree is 1)
+  u64 tcoef[XFG_NUM_TRANSITION][2], bcoef[XFG_NUM_ASSERTIONS][2];
+  u64 z[2], zg[2];
+  u64 ood_frame[2 * XFG_TRACE_WIDTH][2];   // T_0(z), T_0(zg), T_1(z), ... (A.9 interleaving)
+  u64 hz[2];
+  u64 dcoef[XFG_TRACE_WIDTH + 1][2];
+  u64 deep_c1[2], deep_c2[2];              // sum_j gamma_j T_j(z) + delta H(z)   and   sum_j gamma_j T_j(zg)
+  u64 alphas[MAX_LAYERS][2];
+  u64 remainder[MAX_REMAINDER][2]; u32 remainder_len;
+  // queries
+  unsigned long long nonce;
+  u32 num_positions; u32 positions[MAX_Q];
+  u32 fri_num_positions[MAX_LAYERS]; u32 fri_positions[MAX_LAYERS][MAX_Q];
+  u32 error_flags;
+};
+
+// AIR constants and boundary values (src/burn_mint_air.rs:335-395), passed by value to the constraint kernel
+struct AirParams {
+  u64 txn, rcpt, nullifier, commitment;     // transition-constraint constants
+  u64 assert0[XFG_TRACE_WIDTH];             // step-0 assertion values, columns 0..6
+  u64 g_last;                               // g^(n-1): transition exemption point and last-step assertion point
+};
+
+}  // namespace xfg
