@@ -1,8 +1,8 @@
 // blake3.cuh — BLAKE3-256 compression for sm_100a, one compression per thread, state and message in registers.
 //
 // Replaces winter-crypto 0.8.3 `hashers::Blake3_256::{hash_elements, merge, merge_with_int}` over blake3 1.8.2
-// (bound as HashFn at src/burn_mint_air.rs:483).  All messages on the proving path are at
-// most one 1024-byte chunk, so only the single-chunk mode is implemented (checked by the callers).
+// (bound as HashFn at src/burn_mint_air.rs:483).  Bulk messages (rows, node pairs) are one or two 64-byte blocks of a single chunk; only the FRI remainder commitment can exceed
+// one 1024-byte chunk (up to 4), handled by the runtime-length tree-mode variant used by the transcript kernels.
 #pragma once
 #include "field.cuh"
 
@@ -32,9 +32,9 @@ XFG_HD u32 b3_rotr(u32 x, int n) {
   XFG_B3_G(s2, s7, s8, s13, m12, m13) XFG_B3_G(s3, s4, s9, s14, m14, m15)
 
 // cv: chaining value (8 words), m: 16 message words; returns the first 8 output words (truncated compression)
-XFG_HD void b3_compress(const u32 cv[8], const u32 m[16], u32 block_len, u32 flags, u32 out[8]) {
+XFG_HD void b3_compress(const u32 cv[8], const u32 m[16], u32 block_len, u32 flags, u32 out[8], u32 chunk_counter = 0) {
   u32 s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = cv[3], s4 = cv[4], s5 = cv[5], s6 = cv[6], s7 = cv[7];
-  u32 s8 = B3_IV0, s9 = B3_IV1, s10 = B3_IV2, s11 = B3_IV3, s12 = 0, s13 = 0, s14 = block_len, s15 = flags;   // counter = 0
+  u32 s8 = B3_IV0, s9 = B3_IV1, s10 = B3_IV2, s11 = B3_IV3, s12 = chunk_counter, s13 = 0, s14 = block_len, s15 = flags;
   // message schedule: round r uses m[perm^r(i)], perm = {2,6,3,10,7,0,4,13,1,11,12,5,9,14,15,8}; written out so that
   // every index is a compile-time constant and the words stay in registers
   XFG_B3_ROUND(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13], m[14], m[15])
@@ -87,18 +87,35 @@ XFG_HD Digest b3_merge_int(const Digest& s, u64 v) {
   m[8] = (u32)v; m[9] = (u32)(v >> 32);
   Digest d; b3_compress(cv, m, 40, B3_SINGLE, d.w); return d;
 }
-// runtime-length variant for the transcript (nl limbs, nl*8 <= 1024); not on the bulk path
-XFG_HD Digest b3_hash_limbs_dyn(const u64* limbs, int nl) {
-  u32 cv[8]; b3_iv(cv); Digest d;
+// runtime-length variant for the transcript (not on the bulk path): one chunk of up to 128 limbs
+XFG_HD void b3_chunk_dyn(const u64* limbs, int nl, u32 chunk_counter, bool root, u32 out[8]) {
+  u32 cv[8]; b3_iv(cv);
   int nb = nl == 0 ? 1 : (nl + 7) / 8;
   for (int b = 0; b < nb; b++) {
     u32 m[16];
     for (int i = 0; i < 8; i++) { int li = b * 8 + i; u64 v = li < nl ? limbs[li] : 0; m[2 * i] = (u32)v; m[2 * i + 1] = (u32)(v >> 32); }
     int rem = nl - b * 8; u32 len = rem >= 8 ? 64 : (rem > 0 ? rem * 8 : 0);
-    u32 flags = (b == 0 ? XFG_B3_CHUNK_START : 0) | (b == nb - 1 ? (XFG_B3_CHUNK_END | XFG_B3_ROOT) : 0);
-    b3_compress(cv, m, len, flags, b == nb - 1 ? d.w : cv);
+    u32 flags = (b == 0 ? XFG_B3_CHUNK_START : 0) | (b == nb - 1 ? (XFG_B3_CHUNK_END | (root ? XFG_B3_ROOT : 0)) : 0);
+    b3_compress(cv, m, len, flags, b == nb - 1 ? out : cv, chunk_counter);
   }
-  return d;
+}
+XFG_HD void b3_parent(const u32 l[8], const u32 r[8], bool root, u32 out[8]) {
+  u32 cv[8]; b3_iv(cv); u32 m[16];
+  for (int i = 0; i < 8; i++) { m[i] = l[i]; m[8 + i] = r[i]; }
+  b3_compress(cv, m, 64, XFG_B3_PARENT | (root ? XFG_B3_ROOT : 0), out);
+}
+// hash of nl limbs, nl <= 512 (4 chunks of 1024 bytes): BLAKE3 tree mode, left subtree = largest power of two of chunks
+XFG_HD Digest b3_hash_limbs_dyn(const u64* limbs, int nl) {
+  Digest d;
+  const int chunks = nl <= 128 ? 1 : (nl + 127) / 128;
+  if (chunks == 1) { b3_chunk_dyn(limbs, nl, 0, true, d.w); return d; }
+  u32 cv[4][8];
+  for (int c = 0; c < chunks; c++) { int cl = nl - c * 128; if (cl > 128) cl = 128; b3_chunk_dyn(limbs + c * 128, cl, (u32)c, false, cv[c]); }
+  if (chunks == 2) { b3_parent(cv[0], cv[1], true, d.w); return d; }
+  u32 l[8]; b3_parent(cv[0], cv[1], false, l);
+  if (chunks == 3) { b3_parent(l, cv[2], true, d.w); return d; }
+  u32 r[8]; b3_parent(cv[2], cv[3], false, r);
+  b3_parent(l, r, true, d.w); return d;
 }
 
 #if defined(__CUDACC__)
