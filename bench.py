@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py — the burn-mint proving benchmark (BASELINE.json: "burn-mint proof latency (ms) @2^20 trace").
+
+One "step" = one complete BurnMintAir proof (trace -> StarkProof bytes) of the named workload on one GPU:
+normalised BurnMintAir, 2^20 rows x 7 columns, blowup 8, quadratic extension, 42 queries, grinding 4, FRI folding 8,
+remainder max degree 31 (BASELINE config 3; synthetic inputs of SURVEY.md §8d).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           # this repo's CUDA backend through the C ABI
+  python bench.py --impl reference [...]                        # the CPU oracle (restatement of the reference's Winterfell
+                                                                # path; the Rust crate cannot be built here) on the host cores
+
+Under torchrun (N > 1) every rank drives its own GPU with its own independent proofs (replicas, no collective on the data
+path: SURVEY.md §8e); the timed region is bracketed by a barrier + synchronize and the max over ranks is reported.
+`value` = milliseconds per proof over the whole job (time of the K-step region / proofs completed by all ranks) with the
+trace already resident in HBM; `e2e` = the same through xfg_prove_burn_mint with the trace in pinned HOST memory (upload
+and proof download inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "burn-mint proof latency (ms) @2^20 trace"
+W_COLS, BLOWUP, CE = 7, 8, 2
+
+
+def algorithmic_bytes(n_log2, e):
+    """each input read once, each output written once; per kernel family of this backend."""
+    n = 1 << n_log2; N = BLOWUP * n; w = W_COLS; c = CE
+    fri = 0; nl = N
+    layers = 0
+    while nl > 256:                       # (rem_max_deg + 1) * blowup = 256
+        fri += 8 * e * nl + (32 + 96 + 8 * e) * nl // 8; nl //= 8; layers += 1
+    return {
+        "ntt.interpolate_trace": 16 * w * n,
+        "ntt.lde_trace": 8 * w * n + 8 * w * N,
+        "commit_rows.trace": 8 * w * N + 32 * N + 96 * (N - N // 8),       # leaves + the 3 fused tree levels
+        "tree_upper.trace": 96 * (N // 8),
+        "constraints": 8 * w * c * n + 8 * e * c * n,
+        "ntt.interpolate_comp": 16 * e * c * n,
+        "combine": 8 * e * c * n + 8 * e * n,
+        "ntt.lde_comp": 8 * e * (n + N),
+        "commit_rows.comp": 8 * e * N + 32 * N + 96 * (N - N // 8),
+        "tree_upper.comp": 96 * (N // 8),
+        "ood": 8 * w * n + 8 * e * n,
+        "deep": 8 * w * N + 8 * e * N + 8 * e * N + 32 * (N // 8),
+        "fri.fold": sum(8 * e * (N >> (3 * l)) + 8 * e * (N >> (3 * l + 3)) for l in range(layers)),
+        "fri.tree": sum(96 * (N >> (3 * l + 3)) for l in range(layers)),
+        "_total_survey": 16 * w * n + 8 * w * n + 8 * w * N + 8 * w * N + 32 * N + 96 * N + 8 * w * c * n + 8 * e * c * n + 16 * e * c * n
+                         + 8 * e * (n + N) + 8 * e * N + 32 * N + 96 * N + 8 * w * n + 8 * e * n + 8 * w * N + 8 * e * N + 8 * e * N + fri,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25); self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_ms(n_log2, ext, budget_s, steps=1):
+    """Times the CPU oracle (all host threads) on a bounded sample of the workload.  Returns (ms per 2^n_log2 proof, cores, sample text)."""
+    import orc
+    cores = orc.max_threads(); orc.set_threads(cores)
+    opts = (42, 8, 4, ext, 8, 31)
+    tr, pi, ac = orc.synthetic_case(1 << 16, 0)
+    t0 = time.perf_counter(); orc.prove(tr, pi, ac, opts); t16 = time.perf_counter() - t0
+    est_full = t16 * (1 << (n_log2 - 16)) * n_log2 / 16.0
+    sample_log = n_log2
+    while sample_log > 16 and est_full * steps > budget_s:
+        est_full /= 2.0 * sample_log / (sample_log - 1); sample_log -= 1
+    tr, pi, ac = orc.synthetic_case(1 << sample_log, 0)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); orc.prove(tr, pi, ac, opts); ts.append(time.perf_counter() - t0)
+    scale = (1 << (n_log2 - sample_log)) * n_log2 / float(sample_log)
+    txt = (f"one full 2^{n_log2}-row proof per step" if sample_log == n_log2 else
+           f"2^{sample_log}-row proof per step, scaled x{scale:.2f} (n log n) to 2^{n_log2}") + f", ext degree {ext}, {cores} OpenMP threads, oracle restatement (not Winterfell)"
+    return [t * 1e3 * scale for t in ts], cores, txt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        pass   # warm-up has no meaning for the CPU arm beyond page-faulting the oracle: the first timed call builds its twiddle caches
+    ms, cores, sample = cpu_reference_ms(args.n_log2, args.ext, budget_s=200.0, steps=max(1, args.steps))
+    v = statistics.mean(ms)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": v, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks) + u32 ARX (BLAKE3)",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    return {"workload": f"BurnMintAir synthetic trace 2^{args.n_log2} rows x 7 cols, blowup 8, {'quadratic' if args.ext == 2 else 'no'} extension, "
+                        f"42 queries, grinding 4, FRI folding 8, remainder max degree 31 (BASELINE config {'3' if args.n_log2 == 20 else '2-like'})",
+            "parallelism": "one independent proof stream per GPU (replicas, no collective)",
+            "l2": "working set ~2 KB per trace row (2.1 GB at 2^20) >> 126 MB L2; no explicit flush between steps",
+            "aggregate": "value = ms per proof over the whole job = time of the K-step region / (K * n_gpus)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-log2", type=int, default=20)
+    ap.add_argument("--ext", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import xfg_stark_b200 as xs
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    opts = xs.ProofOptions(field_extension=args.ext)
+    ctx = xs.Context(device=local, max_n_log2=args.n_log2, num_slots=1)
+    n = 1 << args.n_log2
+    s = xs.synthetic_inputs(rank)
+    air = ctx.pack_inputs(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"], s["version"])
+    h_trace = torch.empty((7, n), dtype=torch.int64).pin_memory()           # pinned host trace (e2e input)
+    h_np = h_trace.numpy().view(np.uint64)
+    h_np[:] = ctx.build_trace(air, args.n_log2)
+    d_trace = h_trace.cuda()                                                 # HBM-resident trace (`value` input)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        """K steps bracketed by barrier + synchronize; CUDA events on torch's stream (each step is host-synchronous);
+        returns the max over ranks of the region time in ms, and the last proof."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record(); e1.synchronize(); barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), last
+
+    dev_fn = lambda: ctx.prove_device(d_trace.data_ptr(), args.n_log2, air, opts, want_times=True)
+    e2e_fn = lambda: ctx.prove(h_np, air, opts, want_times=True)
+    for _ in range(args.warmup):
+        dev_fn()
+    e2e_fn()
+    sampler = ClockSampler(local); sampler.start()
+    dev_ms, (proof, times) = timed_region(dev_fn, args.steps)
+    e2e_ms, (proof2, times2) = timed_region(e2e_fn, args.steps)
+    clocks = sampler.stop()
+    assert proof == proof2, "device-resident and host-buffer proofs differ"
+
+    # per-kernel-family device times (CUDA events on the library's stream around each launcher), 3 profiled proofs
+    ctx.set_profiling(True)
+    acc = {}
+    for _ in range(3):
+        _, t = dev_fn()
+        for name, ms, launches in ctx.get_profile():
+            a = acc.setdefault(name, [0.0, 0]); a[0] += ms / 3.0; a[1] = launches
+    ctx.set_profiling(False)
+    ab = algorithmic_bytes(args.n_log2, args.ext)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kernels = []
+    for name, (ms, launches) in sorted(acc.items(), key=lambda kv: -kv[1][0]):
+        b = ab.get(name)
+        kernels.append({"name": name, "ms": round(ms, 4), "launches": launches, "alg_bytes": b,
+                        "gbps": round(b / ms / 1e6, 1) if b and ms > 0 else None, "frac": round(b / ms / 1e6 / peak, 4) if b and ms > 0 else None})
+    top = kernels[0]
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top["name"])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,
+                "peak_source": peak_src, "launch_ms": top["ms"], "alg_bytes": top["alg_bytes"],
+                "note": "BLAKE3 kernels (commit_rows.*, tree_upper.*, fri.tree) are 32-bit integer-pipe bound, not HBM bound (DESIGN.md)",
+                "whole_proof": {"alg_bytes": ab["_total_survey"], "gbps": round(ab["_total_survey"] / times["device_ms"] / 1e6, 1),
+                                "frac": round(ab["_total_survey"] / times["device_ms"] / 1e6 / peak, 4)}}
+
+    out = {
+        "metric": METRIC, "value": dev_ms / (args.steps * world), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (Goldilocks) + u32 ARX (BLAKE3)", "data": "synthetic", "config": workload_config(args),
+        "proofs_per_s": args.steps * world / (dev_ms / 1e3), "proof_bytes": len(proof),
+        "clocks": clocks,
+        "e2e": {"value": e2e_ms / (args.steps * world), "unit": "ms", "h2d_bytes_per_step": times2["h2d_bytes"], "d2h_bytes_per_step": times2["d2h_bytes"],
+                "proofs_per_s": args.steps * world / (e2e_ms / 1e3)},
+        "gpu_launches": times["kernel_launches"] * args.steps,
+        "device_ms_per_proof": times["device_ms"],
+        "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},
+        "roofline": roofline, "kernels": kernels,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ms, cores, sample = cpu_reference_ms(args.n_log2, args.ext, budget_s=30.0, steps=1)
+        out["cpu_baseline"] = {"value": ms[0], "unit": "ms", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,8 @@ typedef struct xfg_stage_times {
   float device_ms;   /* first kernel .. last kernel, inputs resident */
   float total_ms;    /* upload .. proof material back on the host */
   uint32_t kernel_launches;
+  uint64_t h2d_bytes; /* bytes copied host->device inside the call (trace + coin seed) */
+  uint64_t d2h_bytes; /* bytes copied device->host inside the call (transcript state + opened rows and paths) */
 } xfg_stage_times;
 
 enum {
@@ -77,6 +79,12 @@ int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** ou
 void xfg_destroy(xfg_ctx* ctx);
 const char* xfg_strerror(int code);
 const char* xfg_last_error(const xfg_ctx* ctx);
+
+/* Per-kernel-family device timing (CUDA events on the launching stream around each launcher call) of proofs run with a
+ * non-NULL `times` argument while profiling is on; used by bench.py for the roofline of the dominant kernel.  Replaces
+ * nothing in the reference (winter-prover's tracing spans are inert there). */
+int xfg_set_profiling(xfg_ctx* ctx, int on);
+int xfg_get_profile(xfg_ctx* ctx, uint32_t cap, uint32_t* count, const char** names, float* ms, uint32_t* launches);
 
 /* ---- whole proof: replaces `air.prove(trace)` (src/burn_mint_prover.rs:124, winter_prover::Prover::prove) ---- */
 /* trace: column-major, 7 columns x 2^n_log2 rows (TraceTable::init layout, src/burn_mint_air.rs:475), host memory.

@@ -15,7 +15,7 @@ STAGE_NAMES = ["extend_execution_trace", "compute_execution_trace_commitment", "
 EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error", "xfg_prove_burn_mint",
                     "xfg_prove_burn_mint_device", "xfg_prove_burn_mint_batch", "xfg_burn_mint_pack_inputs",
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
-                    "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows"]
+                    "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_get_profile"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -45,12 +45,12 @@ class AirConsts(C.Structure):
 
 class StageTimes(C.Structure):
     _fields_ = [("stage_ms", C.c_float * NUM_STAGES), ("h2d_ms", C.c_float), ("device_ms", C.c_float),
-                ("total_ms", C.c_float), ("kernel_launches", C.c_uint32)]
+                ("total_ms", C.c_float), ("kernel_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
     def as_dict(self):
         d = {n: float(self.stage_ms[i]) for i, n in enumerate(STAGE_NAMES)}
         d.update(h2d_ms=float(self.h2d_ms), device_ms=float(self.device_ms), total_ms=float(self.total_ms),
-                 kernel_launches=int(self.kernel_launches))
+                 kernel_launches=int(self.kernel_launches), h2d_bytes=int(self.h2d_bytes), d2h_bytes=int(self.d2h_bytes))
         return d
 
 
@@ -109,6 +109,8 @@ def load_library():
     L.xfg_eval_constraints.argtypes = [vp, vp, u32, C.POINTER(AirConsts), u32, vp, vp]
     L.xfg_fri_fold_layer.argtypes = [vp, vp, u32, u32, vp, vp]
     L.xfg_hash_rows.argtypes = [vp, vp, sz, u32, vp]
+    L.xfg_set_profiling.argtypes = [vp, i]
+    L.xfg_get_profile.argtypes = [vp, u32, C.POINTER(u32), vp, vp, vp]
     _lib = L
     return L
 
@@ -216,6 +218,15 @@ class Context:
                                                               C.byref(st) if want_times else None))
         proof = out.raw[:ln.value]
         return (proof, st.as_dict()) if want_times else proof
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.xfg_set_profiling(self._h, int(on)))
+
+    def get_profile(self):
+        """-> list of (kernel family, device ms, launches) of the last proof run with want_times=True while profiling."""
+        cap = 64; cnt = C.c_uint32(0); names = (C.c_char_p * cap)(); ms = (C.c_float * cap)(); ln = (C.c_uint32 * cap)()
+        self._check(self._lib.xfg_get_profile(self._h, cap, C.byref(cnt), names, ms, ln))
+        return [(names[i].decode(), float(ms[i]), int(ln[i])) for i in range(min(cnt.value, cap))]
 
     # ---- stage entry points ----
     def ntt(self, data, inverse=False):

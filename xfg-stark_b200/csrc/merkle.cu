@@ -87,7 +87,7 @@ void launch_hash_rows(cudaStream_t st, const u64* rows, size_t count, int limbs,
   XFG_LAUNCHED(1);
 }
 
-void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree) {
+void launch_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree) {
   const size_t n = size_t(1) << ln; const unsigned blocks = (unsigned)((n + 127) / 128);
   switch (num_limbs) {
     case 1: commit_rows_kernel<1><<<blocks, 128, 0, st>>>(data, limb_stride, ln, tree); break;
@@ -96,7 +96,10 @@ void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, in
     default: return;   // callers only pass 1, 2 or XFG_TRACE_WIDTH
   }
   XFG_LAUNCHED(1);
-  merkle_build_upper(st, tree, n);
+}
+void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree) {
+  launch_commit_rows(st, data, limb_stride, num_limbs, ln, tree);
+  merkle_build_upper(st, tree, size_t(1) << ln);
 }
 
 void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M) {

@@ -50,6 +50,8 @@ struct Carve {   // device pointers of one proof, carved from the slot slab for 
   size_t words;
 };
 
+struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
+
 struct Slot {
   cudaStream_t st = nullptr;
   u64* slab = nullptr; size_t slab_words = 0;
@@ -58,7 +60,9 @@ struct Slot {
   cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
   // in-flight proof (batch mode)
   bool busy = false; const Plan* plan = nullptr; int D = 1; xfg_options opt{}; u32 proof_index = 0; bool timed = false;
-  GatherTasks tasks{};
+  GatherTasks tasks{}; size_t mat_words = 0;
+  // optional per-kernel-family timing (xfg_set_profiling): events around each launcher call on this slot's stream
+  std::vector<cudaEvent_t> pev; std::vector<ProfRec> prof; size_t pev_used = 0;
 };
 
 }  // namespace
@@ -71,6 +75,8 @@ struct xfg_ctx {
   u64 *tw_fwd = nullptr, *tw_inv = nullptr;
   std::map<u64, Plan> plans;
   std::string last_error;
+  bool profiling = false;
+  std::vector<std::string> prof_names; std::vector<float> prof_ms; std::vector<unsigned> prof_launches;   // last profiled proof
 };
 
 namespace {
@@ -210,72 +216,84 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   int ev = 0;
   auto mark = [&]() { if (timed) cudaEventRecord(s.ev[ev], st); ev++; };
   const u64* trace_src = d_trace ? d_trace : c.trace_in;
+  const bool profiling = ctx->profiling && timed;
+  s.prof.clear(); s.pev_used = 0;
+  // PROF(name, launches...) brackets a launcher call with events when profiling is on
+  auto prof_begin = [&](const char* name) { if (!profiling) return; if (s.pev.size() < s.pev_used + 2) { s.pev.resize(s.pev_used + 2, nullptr); }
+    for (size_t i = s.pev_used; i < s.pev_used + 2; i++) if (!s.pev[i]) cudaEventCreate(&s.pev[i]);
+    cudaEventRecord(s.pev[s.pev_used], st); s.prof.push_back(ProfRec{name, s.pev_used, s.pev_used + 1, g_xfg_launches}); s.pev_used += 2; };
+  auto prof_end = [&]() { if (!profiling) return; ProfRec& r = s.prof.back(); cudaEventRecord(s.pev[r.e1], st); r.launches = g_xfg_launches - r.launches; };
+#define PROF(name, ...) do { prof_begin(name); __VA_ARGS__; prof_end(); } while (0)
 
   seed_elements(ln, o, air, s.h_seed);
   CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (8 + XFG_NUM_PUB_INPUTS) * 8, cudaMemcpyHostToDevice, st));
   mark();   // ev0: start of device work
-  launch_seed(st, s.d_state, s.d_seed, 8 + XFG_NUM_PUB_INPUTS);
-  launch_check_canonical(st, trace_src, 7 * n, s.d_state);
+  PROF("transcript", launch_seed(st, s.d_state, s.d_seed, 8 + XFG_NUM_PUB_INPUTS));
+  PROF("check_canonical", launch_check_canonical(st, trace_src, 7 * n, s.d_state));
 
   // 1 ---- extend_execution_trace: interpolate the 7 columns, evaluate on the 8 cosets s_k * <w_n>
   { NttJob j{}; j.src = trace_src; j.dst = c.trace_coef; j.ln = ln; j.batch = XFG_TRACE_WIDTH; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
-    j.inverse = true; j.scale = p.n_inv; ntt_batch(st, p.ntt, j); }
+    j.inverse = true; j.scale = p.n_inv; PROF("ntt.interpolate_trace", ntt_batch(st, p.ntt, j)); }
   { NttJob j{}; j.src = c.trace_coef; j.dst = c.lde; j.ln = ln; j.batch = XFG_TRACE_WIDTH * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
-    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; ntt_batch(st, p.ntt, j); }
+    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_trace", ntt_batch(st, p.ntt, j)); }
   mark();
   //   ---- compute_execution_trace_commitment
-  merkle_commit_rows(st, c.lde, N, XFG_TRACE_WIDTH, ln, c.trace_tree);
-  launch_trace_root(st, D, s.d_state, c.trace_tree);
+  PROF("commit_rows.trace", launch_commit_rows(st, c.lde, N, XFG_TRACE_WIDTH, ln, c.trace_tree));
+  PROF("tree_upper.trace", merkle_build_upper(st, c.trace_tree, n));
+  PROF("transcript", launch_trace_root(st, D, s.d_state, c.trace_tree));
   mark();
   // 2 ---- evaluate_constraints
   { AirParams ap; ap.txn = air.txn_hash; ap.rcpt = air.recipient_hash; ap.nullifier = air.nullifier; ap.commitment = air.commitment;
     ap.assert0[0] = air.pub_inputs[XFG_PI_BURN]; ap.assert0[1] = air.pub_inputs[XFG_PI_MINT]; ap.assert0[2] = air.pub_inputs[XFG_PI_TXN_HASH];
     ap.assert0[3] = air.pub_inputs[XFG_PI_RECIPIENT_HASH]; ap.assert0[4] = 0; ap.assert0[5] = air.nullifier; ap.assert0[6] = air.commitment;
     ap.g_last = p.g_last;
-    launch_constraints(st, D, c.lde, ln, ap, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals); }
+    PROF("constraints", launch_constraints(st, D, c.lde, ln, ap, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals)); }
   mark();
   // 3 ---- commit_to_constraint_evaluations: coset interpolation (2 cosets of size n), composition column, LDE, commitment
   { NttJob j{}; j.src = c.ce_evals; j.dst = c.ce_tmp; j.ln = ln; j.batch = 2 * D; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
-    j.inverse = true; j.scale = p.n_inv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 2; ntt_batch(st, p.ntt, j); }
-  launch_combine(st, c.ce_tmp, ln, D, p.inv2, c.h_coef, s.d_state);
+    j.inverse = true; j.scale = p.n_inv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 2; PROF("ntt.interpolate_comp", ntt_batch(st, p.ntt, j)); }
+  PROF("combine", launch_combine(st, c.ce_tmp, ln, D, p.inv2, c.h_coef, s.d_state));
   { NttJob j{}; j.src = c.h_coef; j.dst = c.h_lde; j.ln = ln; j.batch = D * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
-    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; ntt_batch(st, p.ntt, j); }
-  merkle_commit_rows(st, c.h_lde, N, D, ln, c.comp_tree);
-  launch_constraint_root(st, D, s.d_state, c.comp_tree, p.g_n);
+    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_comp", ntt_batch(st, p.ntt, j)); }
+  PROF("commit_rows.comp", launch_commit_rows(st, c.h_lde, N, D, ln, c.comp_tree));
+  PROF("tree_upper.comp", merkle_build_upper(st, c.comp_tree, n));
+  PROF("transcript", launch_constraint_root(st, D, s.d_state, c.comp_tree, p.g_n));
   mark();
   // 4 ---- build_deep_composition_poly: OOD frame + coefficients
-  launch_ood(st, D, c.trace_coef, c.h_coef, ln, s.d_state, s.d_partial);
-  launch_ood_finish(st, D, s.d_state, s.d_partial, ood_num_blocks(ln));
+  PROF("ood", launch_ood(st, D, c.trace_coef, c.h_coef, ln, s.d_state, s.d_partial));
+  PROF("transcript", launch_ood_finish(st, D, s.d_state, s.d_partial, ood_num_blocks(ln)));
   mark();
   // 5 ---- evaluate_deep_composition_poly (pointwise) + leaves of the first FRI layer
-  launch_deep(st, D, c.lde, c.h_lde, ln, s.d_state, p.ntt.wn_fwd, p.d_sk, c.deep, p.num_layers ? c.fri_tree[0] : nullptr);
+  PROF("deep", launch_deep(st, D, c.lde, c.h_lde, ln, s.d_state, p.ntt.wn_fwd, p.d_sk, c.deep, p.num_layers ? c.fri_tree[0] : nullptr));
   mark();
   // 6 ---- compute_fri_layers
   for (u32 l = 0; l < p.num_layers; l++) {
-    merkle_build_upper(st, c.fri_tree[l], size_t(1) << (p.layer_log[l] - 3));
-    launch_fri_commit(st, D, s.d_state, c.fri_tree[l], l);
-    launch_fri_fold(st, D, c.fri_evals[l], l == 0 ? N : (size_t(1) << p.layer_log[l]), l == 0, p.layer_log[l], l, s.d_state, p.wN_inv, p.lN, p.fc,
-                    c.fri_evals[l + 1], size_t(1) << p.layer_log[l + 1], l + 1 < p.num_layers ? c.fri_tree[l + 1] : nullptr);
+    PROF("fri.tree", merkle_build_upper(st, c.fri_tree[l], size_t(1) << (p.layer_log[l] - 3)));
+    PROF("transcript", launch_fri_commit(st, D, s.d_state, c.fri_tree[l], l));
+    PROF("fri.fold", launch_fri_fold(st, D, c.fri_evals[l], l == 0 ? N : (size_t(1) << p.layer_log[l]), l == 0, p.layer_log[l], l, s.d_state, p.wN_inv, p.lN, p.fc,
+                    c.fri_evals[l + 1], size_t(1) << p.layer_log[l + 1], l + 1 < p.num_layers ? c.fri_tree[l + 1] : nullptr));
   }
   { const u64* rin = c.fri_evals[p.num_layers]; const size_t Rm = size_t(1) << p.rem_log;
     if (p.num_layers == 0) { launch_coset_to_natural(st, c.deep, c.rem_in, ln, D, N, Rm); rin = c.rem_in; }
     NttJob j{}; j.src = rin; j.dst = c.rem_coef; j.ln = p.rem_log; j.batch = D; j.src_tstride = Rm; j.dst_tstride = Rm; j.src_div = 1;
-    j.inverse = true; j.scale = p.rem_ninv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 1; ntt_batch(st, p.ntt, j);
-    launch_remainder(st, D, s.d_state, c.rem_coef, Rm, p.rem_len); }
+    j.inverse = true; j.scale = p.rem_ninv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 1; PROF("fri.remainder", ntt_batch(st, p.ntt, j));
+    PROF("transcript", launch_remainder(st, D, s.d_state, c.rem_coef, Rm, p.rem_len)); }
   mark();
   // 7 ---- determine_query_positions
-  launch_grind(st, s.d_state, o.grinding_factor);
-  launch_positions(st, s.d_state, o.num_queries, p.lN, p.num_layers);
+  PROF("grind", launch_grind(st, s.d_state, o.grinding_factor));
+  PROF("transcript", launch_positions(st, s.d_state, o.num_queries, p.lN, p.num_layers));
   mark();
   // 8 ---- build_proof_object: gather opened rows + authentication nodes, copy out
   const size_t mat_words = build_gather(p, D, o, c, s.tasks);
   if (mat_words > MATERIAL_WORDS) return fail(ctx, XFG_ERR_INTERNAL, "material buffer too small");
-  launch_gather(st, s.tasks, s.d_state, s.d_material);
+  s.mat_words = mat_words;
+  PROF("gather", launch_gather(st, s.tasks, s.d_state, s.d_material));
   mark();   // end of device work
   CU(cudaMemcpyAsync(s.h_state, s.d_state, sizeof(ProofState), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(s.h_material, s.d_material, mat_words * 8, cudaMemcpyDeviceToHost, st));
   mark();
   CU(cudaGetLastError());
+#undef PROF
   s.busy = true; s.plan = &p; s.D = D; s.opt = o; s.timed = timed;
   return XFG_OK;
 }
@@ -351,6 +369,15 @@ int finish_proof(xfg_ctx* ctx, Slot& s, u8* out, size_t cap, size_t* out_len, xf
   CU(cudaStreamSynchronize(s.st));
   s.busy = false;
   const ProofState& hs = *s.h_state;
+  if (!s.prof.empty()) {   // aggregate the per-launcher event pairs by name, in first-seen order
+    ctx->prof_names.clear(); ctx->prof_ms.clear(); ctx->prof_launches.clear();
+    for (const ProfRec& r : s.prof) {
+      float ms = 0; cudaEventElapsedTime(&ms, s.pev[r.e0], s.pev[r.e1]);
+      size_t k = 0; while (k < ctx->prof_names.size() && ctx->prof_names[k] != r.name) k++;
+      if (k == ctx->prof_names.size()) { ctx->prof_names.push_back(r.name); ctx->prof_ms.push_back(0); ctx->prof_launches.push_back(0); }
+      ctx->prof_ms[k] += ms; ctx->prof_launches[k] += r.launches;
+    }
+  }
   if (hs.error_flags & ERR_FLAG_NONCANONICAL) return fail(ctx, XFG_ERR_BAD_ARGS, "non-canonical trace element");
   if (hs.error_flags & ERR_FLAG_DEGREE) return fail(ctx, XFG_ERR_UNSATISFIED_CONSTRAINT, "UnsatisfiedTransitionConstraintError: the trace does not satisfy the burn-mint AIR (composition polynomial degree too high)");
   if (hs.error_flags & ERR_FLAG_COIN) return fail(ctx, XFG_ERR_INTERNAL, "FailedToDrawFieldElement");
@@ -405,6 +432,8 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
     cudaEventElapsedTime(&times->h2d_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[0]);
     cudaEventElapsedTime(&times->total_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[XFG_NUM_STAGES + 1]);
     times->kernel_launches = g_xfg_launches;
+    times->h2d_bytes = (h_trace ? 7 * p->n * 8 : 0) + (8 + XFG_NUM_PUB_INPUTS) * 8;
+    times->d2h_bytes = sizeof(ProofState) + s.mat_words * 8;
   }
   return rc;
 }
@@ -467,11 +496,20 @@ void xfg_destroy(xfg_ctx* ctx) {
     cudaFree(s.slab); cudaFree(s.d_state); cudaFree(s.d_seed); cudaFree(s.d_partial); cudaFree(s.d_material);
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+    for (auto& e : s.pev) if (e) cudaEventDestroy(e);
     if (s.st) cudaStreamDestroy(s.st);
   }
   for (auto& kv : ctx->plans) cudaFree(kv.second.slab);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv);
   delete ctx;
+}
+
+int xfg_set_profiling(xfg_ctx* ctx, int on) { if (!ctx) return XFG_ERR_BAD_ARGS; ctx->profiling = on != 0; return XFG_OK; }
+int xfg_get_profile(xfg_ctx* ctx, uint32_t cap, uint32_t* count, const char** names, float* ms, uint32_t* launches) {
+  if (!ctx || !count) return XFG_ERR_BAD_ARGS;
+  *count = (uint32_t)ctx->prof_names.size();
+  for (uint32_t i = 0; i < *count && i < cap; i++) { if (names) names[i] = ctx->prof_names[i].c_str(); if (ms) ms[i] = ctx->prof_ms[i]; if (launches) launches[i] = ctx->prof_launches[i]; }
+  return XFG_OK;
 }
 
 int xfg_prove_burn_mint(xfg_ctx* ctx, const uint64_t* trace, uint32_t n_log2, const xfg_air_consts* air, const xfg_options* o, uint8_t* out,
