@@ -29,6 +29,23 @@ def test_proof_bytes_equal_oracle(ctx, n_log2, ext):
     assert orc.verify(proof, pi, ac, opts.as_tuple()) == ""
 
 
+@pytest.mark.parametrize("n_log2,ext", [(17, 1), (18, 2), (19, 1), (20, 2)])
+def test_large_proofs_equal_oracle(n_log2, ext):
+    """BASELINE configs 2/3 sizes (up to the 2^20-row, quadratic-extension headline): bytes equal the oracle's, verifier accepts."""
+    import xfg_stark_b200 as xs
+    from test_gpu_stages import big_ctx
+    c = big_ctx()
+    opts = xs.ProofOptions(field_extension=ext)
+    air, trace = gpu_case(xs, n_log2, n_log2)
+    proof = c.prove(trace, air, opts)
+    tr, pi, ac = orc.synthetic_case(1 << n_log2, n_log2)
+    orc.set_threads(orc.max_threads())
+    expect = orc.prove(tr, pi, ac, opts.as_tuple())
+    orc.set_threads(1)
+    assert proof == expect
+    assert orc.verify(proof, pi, ac, opts.as_tuple()) == ""
+
+
 @pytest.mark.parametrize("opts_t", [(42, 8, 0, 1, 8, 31), (1, 8, 4, 2, 8, 7), (255, 8, 10, 1, 8, 255), (27, 8, 16, 2, 8, 63), (100, 8, 20, 1, 8, 15)])
 def test_option_sweep(ctx, opts_t):
     import xfg_stark_b200 as xs

@@ -9,8 +9,53 @@ pytestmark = pytest.mark.gpu
 P = orc.P
 
 
+_BIG = []
+
+
+def big_ctx():
+    """2^20-row context for the sizes that use the 512..1024-point register-radix NTT tiles (created on first use)."""
+    import xfg_stark_b200 as xs
+    if not _BIG:
+        _BIG.append(xs.Context(device=0, max_n_log2=20, num_slots=1))
+    return _BIG[0]
+
+
 def rand_elems(rng, shape):
     return (rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)) % np.uint64(P)
+
+
+EDGE = [0, 1, 2, 0xFFFFFFFF, 1 << 32, (1 << 32) + 1, 1 << 63, P - 1, P - 2, P - (1 << 32), 0xFFFFFFFF00000000, 0xFFFFFFFEFFFFFFFF,
+        P, P + 1, (1 << 64) - 1, (1 << 64) - 2, (1 << 64) - (1 << 32), 0x8000000000000001, 0x00000001FFFFFFFF, 0xFFFFFFFF]
+
+
+def _operands(rng, canonical_b):
+    """all pairs of edge values (incl. weak aliases >= p for `a`) + random values"""
+    ea = np.array(EDGE, dtype=np.uint64)
+    eb = np.array([v for v in EDGE if v < P] if canonical_b else EDGE, dtype=np.uint64)
+    a = np.concatenate([np.repeat(ea, eb.size), rng.integers(0, 1 << 64, size=4096, dtype=np.uint64, endpoint=False)])
+    b = np.concatenate([np.tile(eb, ea.size), rand_elems(rng, (4096,)) if canonical_b else rng.integers(0, 1 << 64, size=4096, dtype=np.uint64, endpoint=False)])
+    return a, b
+
+
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5, 6, 7, 8] + [100 + s for s in (0, 1, 12, 24, 31, 32, 33, 36, 48, 60, 63, 64, 65, 72, 84, 95)])
+def test_field_arithmetic_exact(ctx, op):
+    """device field arithmetic (incl. the weak forms used inside NTT butterflies) against Python big integers, on every pair
+    of edge values: 0, 1, p-1, the non-canonical aliases p..2^64-1, values around 2^32 and 2^63."""
+    rng = np.random.default_rng(op)
+    canonical_b = op in (2, 3, 4, 5)
+    a, b = _operands(rng, canonical_b)
+    if op in (4, 5, 6):
+        a = a % np.uint64(P)
+    got = ctx.field_selftest(op, a, b)
+    ai = [int(x) for x in a]; bi = [int(x) for x in b]
+    if op in (0, 1): exp = [(x * y) % P for x, y in zip(ai, bi)]
+    elif op in (2, 4): exp = [(x + y) % P for x, y in zip(ai, bi)]
+    elif op in (3, 5): exp = [(x - y) % P for x, y in zip(ai, bi)]
+    elif op == 6: exp = [pow(x, P - 2, P) for x in ai]
+    elif op == 7: exp = [(x + ((y & 0xFFFFFFFF) << 32)) % P for x, y in zip(ai, bi)]
+    elif op == 8: exp = [(x - ((y & 0xFFFFFFFF) << 32)) % P for x, y in zip(ai, bi)]
+    else: exp = [(x << (op - 100)) % P for x in ai]
+    assert [int(g) for g in got] == exp
 
 
 @pytest.mark.parametrize("limbs", [1, 2, 7, 8, 16])
@@ -34,13 +79,15 @@ def test_merkle_tree_matches_oracle(ctx, count):
     assert (nodes[1:] == enodes[1:]).all()
 
 
-@pytest.mark.parametrize("n_log2", [3, 4, 6, 9, 11, 12, 13, 15, 16])
+@pytest.mark.parametrize("n_log2", [3, 4, 6, 9, 11, 12, 13, 15, 16, 17, 18, 19, 20])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_ntt_matches_oracle(ctx, n_log2, inverse):
     rng = np.random.default_rng(100 * n_log2 + inverse)
+    c = ctx if n_log2 <= 16 else big_ctx()
     data = rand_elems(rng, (3, 1 << n_log2))
     data[0, :2] = [P - 1, 0]
-    got = ctx.ntt(data, inverse=inverse)
+    data[2, :] = P - 1          # all-(p-1) column: drives sums towards the weak range
+    got = c.ntt(data, inverse=inverse)
     for b in range(3):
         assert (got[b] == orc.ntt(data[b], 1, 1 if inverse else 0)).all()
 

@@ -15,7 +15,7 @@ STAGE_NAMES = ["extend_execution_trace", "compute_execution_trace_commitment", "
 EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error", "xfg_prove_burn_mint",
                     "xfg_prove_burn_mint_device", "xfg_prove_burn_mint_batch", "xfg_burn_mint_pack_inputs",
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
-                    "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_get_profile"]
+                    "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_get_profile", "xfg_field_selftest"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -110,6 +110,7 @@ def load_library():
     L.xfg_fri_fold_layer.argtypes = [vp, vp, u32, u32, vp, vp]
     L.xfg_hash_rows.argtypes = [vp, vp, sz, u32, vp]
     L.xfg_set_profiling.argtypes = [vp, i]
+    L.xfg_field_selftest.argtypes = [vp, u32, vp, vp, sz, vp]
     L.xfg_get_profile.argtypes = [vp, u32, C.POINTER(u32), vp, vp, vp]
     _lib = L
     return L
@@ -262,6 +263,12 @@ class Context:
         a = np.ascontiguousarray(alpha, dtype=np.uint64)
         out = np.empty((nl // 8, ext), dtype=np.uint64)
         self._check(self._lib.xfg_fri_fold_layer(self._h, _ptr(e), nl.bit_length() - 1, ext, _ptr(a), _ptr(out)))
+        return out
+
+    def field_selftest(self, op, a, b):
+        x = np.ascontiguousarray(a, dtype=np.uint64); y = np.ascontiguousarray(b, dtype=np.uint64)
+        out = np.empty_like(x)
+        self._check(self._lib.xfg_field_selftest(self._h, op, _ptr(x), _ptr(y), x.size, _ptr(out)))
         return out
 
     def hash_rows(self, rows):

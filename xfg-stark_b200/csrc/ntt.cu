@@ -13,6 +13,7 @@
 // The coset pre-scale p[j] * s^j of the LDE is fused into the pass-A / single-pass load; 1/n and the coset un-scale
 // c[j] * s^-j of interpolate_poly_with_offset into the last store.
 #include "ntt.cuh"
+#include "field_weak.cuh"
 #include "launch.cuh"
 
 namespace xfg {
@@ -81,6 +82,131 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(NttPass p) {
   }
 }
 
+
+// =====================================================================================================================
+// ntt_pass_r16 — the fast path for tiles of 2^8 .. 2^12 points: Stockham auto-sort passes of radix 16 / 8 / 4 held in
+// registers.  Each thread owns 16 elements per pass (one radix-16 item, two radix-8 items or four radix-4 items), so a pass
+// is: load 16 values from shared memory, multiply by the inter-pass twiddles w_{Ns*R}^(k*r), run the in-register DFTs,
+// barrier, store, barrier.  Inside a radix-R DFT (R <= 16) every twiddle is a power of two (w_16 = 2^12, w_8 = 2^24,
+// w_4 = 2^48, w_2 = 2^96 = -1), i.e. shifts and carry fix-ups on weak values instead of 64x64-bit multiplications; a
+// 1024-point tile needs 1.7 full multiplications per element instead of 5.  Same load/store stages as ntt_pass.
+// =====================================================================================================================
+__host__ __device__ constexpr int brev_c(int x, int bits) { int r = 0; for (int i = 0; i < bits; i++) if (x >> i & 1) r |= 1 << (bits - 1 - i); return r; }
+
+// (a, b) <- (a + w b, a - w b) with w = 2^S (forward) or w = 2^-S = -2^(96-S) (inverse); a, b weak in and out
+template <int S, bool INV> __device__ __forceinline__ void bfly_pow2(u64& a, u64& b) {
+  if (S == 0) { const u64 t = w_canon(b); const u64 x = w_add_c(a, t), y = w_sub_c(a, t); a = x; b = y; }
+  else if (!INV) { const u64 t = w_canon(w_mul_pow2<S>(b)); const u64 x = w_add_c(a, t), y = w_sub_c(a, t); a = x; b = y; }
+  else { const u64 t = w_canon(w_mul_pow2<(96 - S) % 96>(b)); const u64 x = w_sub_c(a, t), y = w_add_c(a, t); a = x; b = y; }
+}
+// radix-2 DIT over registers; element i of the (bit-reversed) working order lives in v[brev(i)], so the natural-order
+// output k ends up in v[brev(k)] and no register is ever moved
+template <int LOGR, bool INV, int STAGE, int IDX> struct DftStep {
+  static __device__ __forceinline__ void run(u64 (&v)[1 << LOGR]) {
+    constexpr int half = 1 << STAGE, j = IDX & (half - 1), g = IDX >> STAGE, i0 = g * 2 * half + j, i1 = i0 + half;
+    bfly_pow2<j * (96 / half), INV>(v[brev_c(i0, LOGR)], v[brev_c(i1, LOGR)]);
+    DftStep<LOGR, INV, STAGE, IDX + 1>::run(v);
+  }
+};
+template <int LOGR, bool INV, int STAGE> struct DftStep<LOGR, INV, STAGE, (1 << LOGR) / 2> {
+  static __device__ __forceinline__ void run(u64 (&v)[1 << LOGR]) { DftStep<LOGR, INV, STAGE + 1, 0>::run(v); }
+};
+template <int LOGR, bool INV> struct DftStep<LOGR, INV, LOGR, 0> { static __device__ __forceinline__ void run(u64 (&)[1 << LOGR]) {} };
+
+template <int LOGR, bool INV>
+__device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __restrict__ TW, u32 Llog, u32 Tlog, u32 TP, u32 ns_log, u32 tid, u32 nthreads) {
+  constexpr int R = 1 << LOGR, ITEMS = 16 / R;
+  const u32 Tm = (1u << Tlog) - 1, stride = 1u << (Llog - LOGR), nsm = (1u << ns_log) - 1, tsh = Llog - ns_log - LOGR;
+  u64 v[ITEMS][R];
+#pragma unroll
+  for (int q = 0; q < ITEMS; q++) {
+    const u32 w = tid + q * nthreads, col = w & Tm, j = w >> Tlog, k = j & nsm;
+#pragma unroll
+    for (int r = 0; r < R; r++) v[q][r] = S[(j + r * stride) * TP + col];
+    if (ns_log) {
+#pragma unroll
+      for (int r = 1; r < R; r++) v[q][r] = w_mul(v[q][r], TW[(k * r) << tsh]);
+    }
+    DftStep<LOGR, INV, 0, 0>::run(v[q]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < ITEMS; q++) {
+    const u32 w = tid + q * nthreads, col = w & Tm, j = w >> Tlog, k = j & nsm;
+    const u32 j0 = ((j >> ns_log) << (ns_log + LOGR)) | k;
+#pragma unroll
+    for (int r = 0; r < R; r++) S[(j0 + ((u32)r << ns_log)) * TP + col] = v[q][brev_c(r, LOGR)];
+  }
+  __syncthreads();
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(1024) ntt_pass_r16(NttPass p) {
+  extern __shared__ u64 smem[];
+  const u32 L = 1u << p.Llog, T = 1u << p.Tlog, TP = T + 1, nthreads = blockDim.x;
+  u64* S = smem; u64* TW = smem + (size_t)L * TP;   // TW[i] = w_L^(+-i), full circle
+  const u32 tid = threadIdx.x, tile = blockIdx.x, tr = blockIdx.y;
+  const u64* src = p.src + (size_t)(tr / p.src_div) * p.src_tstride;
+  u64* dst = p.dst + (size_t)tr * p.dst_tstride;
+  const u32 coset = tr % p.src_div;
+  for (u32 i = tid; i < L; i += nthreads) {
+    const u32 h = i & (L / 2 - 1); const u64 t = p.tw[(size_t)h << (NTT_TW_LOG - p.Llog)];
+    TW[i] = i < L / 2 ? t : gl_neg(t);
+  }
+  const u64 col0 = (u64)tile << p.Tlog;
+  PowTable pre; pre.lo = p.pre_lo ? p.pre_lo + (size_t)coset * POW_LO : nullptr; pre.hi = p.pre_hi ? p.pre_hi + (size_t)coset * p.pre_hi_stride : nullptr;
+  for (u32 e = tid; e < L * T; e += nthreads) {
+    const u32 c = e & (T - 1), r = e >> p.Tlog;
+    const u64 gi = (u64)r * p.in_row_stride + col0 + c;
+    u64 v = src[gi];
+    if (pre.lo) v = gl_mul(v, pow_lookup(pre, gi));
+    S[r * TP + c] = v;
+  }
+  __syncthreads();
+  u32 ns_log = 0;
+  for (u32 ps = 0; ps < p.num_radix; ps++) {
+    const u32 lr = (p.radix_logs >> (4 * ps)) & 15;
+    if (lr == 4) stockham_pass<4, INV>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+    else if (lr == 3) stockham_pass<3, INV>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+    else stockham_pass<2, INV>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+    ns_log += lr;
+  }
+  if (p.store_transposed) {
+    PowTable it; it.lo = p.it_lo; it.hi = p.it_hi;
+    for (u32 e = tid; e < L * T; e += nthreads) {
+      const u32 k = e & (L - 1), c = e >> p.Llog;
+      u64 v = S[k * TP + c];
+      const u64 ex = (col0 + c) * (u64)k;
+      v = ex ? gl_mul(v, pow_lookup(it, ex)) : w_canon(v);
+      dst[(col0 + c) * (u64)L + k] = v;
+    }
+  } else {
+    PowTable post; post.lo = p.post_lo ? p.post_lo + (size_t)(tr % p.post_div) * POW_LO : nullptr;
+    post.hi = p.post_hi ? p.post_hi + (size_t)(tr % p.post_div) * p.post_hi_stride : nullptr;
+    for (u32 e = tid; e < L * T; e += nthreads) {
+      const u32 c = e & (T - 1), k = e >> p.Tlog;
+      u64 v = S[k * TP + c];
+      const u64 go = (u64)k * p.out_row_stride + col0 + c;
+      if (p.scale != 1) v = gl_mul(v, p.scale); else v = w_canon(v);
+      if (post.lo) v = gl_mul(v, pow_lookup(post, go));
+      dst[go] = v;
+    }
+  }
+}
+
+static size_t r16_smem(u32 Llog, u32 Tlog) { const size_t L = size_t(1) << Llog, TP = (size_t(1) << Tlog) + 1; return (L * TP + L) * sizeof(u64); }
+static u32 r16_tlog(u32 Llog) { return Llog >= 12 ? 2 : 13 - Llog; }                       // 8192 elements per CTA (16384 at 2^12)
+static void r16_radices(u32 Llog, u32& count, u32& packed) {                               // 8:(4,4) 9:(4,3,2) 10:(4,4,2) 11:(4,4,3) 12:(4,4,4)
+  static const u32 tbl[5][3] = {{4, 4, 0}, {4, 3, 2}, {4, 4, 2}, {4, 4, 3}, {4, 4, 4}};
+  const u32* r = tbl[Llog - 8]; count = r[2] ? 3 : 2; packed = r[0] | (r[1] << 4) | (r[2] << 8);
+}
+static void launch_r16(cudaStream_t st, NttPass p, bool inverse, u32 tiles, u32 batch) {
+  r16_radices(p.Llog, p.num_radix, p.radix_logs);
+  const u32 threads = (1u << (p.Llog + p.Tlog)) / 16; const size_t sm = r16_smem(p.Llog, p.Tlog);
+  if (inverse) ntt_pass_r16<true><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false><<<dim3(tiles, batch), threads, sm, st>>>(p);
+  XFG_LAUNCHED(1);
+}
+
 size_t ntt_pass_smem(u32 Llog, u32 Tlog) {
   size_t L = size_t(1) << Llog, T = size_t(1) << Tlog, TP = T > 1 ? T + 1 : 1;
   return (L * TP + L / 2) * sizeof(u64);
@@ -90,6 +216,8 @@ void ntt_init() {
   static bool done = false;
   if (done) return;
   cudaFuncSetAttribute(ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_pass_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
   done = true;
 }
 
@@ -112,18 +240,21 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   }
   // four-step: n = n1 * n2 with n2 = 2^l2 (pass A length), n1 = 2^l1 (pass B length)
   const u32 l2 = ln / 2, l1 = ln - l2;
+  const bool fast = l2 >= 8;            // register-radix Stockham tiles (2^8 .. 2^12 points)
   const u32 Tlog = l1 > 11 ? 2 : 3;     // 2^12-point tiles only fit 4 columns
   // pass A
   p.src = job.src; p.dst = job.dst; p.Llog = l2; p.Tlog = Tlog; p.in_row_stride = u64(1) << l1; p.out_row_stride = 0;
   p.store_transposed = 1; p.scale = 1;
   p.it_lo = job.inverse ? tb.wn_inv.lo : tb.wn_fwd.lo; p.it_hi = job.inverse ? tb.wn_inv.hi : tb.wn_fwd.hi;
-  ntt_pass<<<dim3((1u << l1) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l2, Tlog), st>>>(p); XFG_LAUNCHED(1);
+  if (fast) { p.Tlog = r16_tlog(l2); launch_r16(st, p, job.inverse, (1u << l1) >> p.Tlog, job.batch); }
+  else { ntt_pass<<<dim3((1u << l1) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l2, Tlog), st>>>(p); XFG_LAUNCHED(1); }
   // pass B (in place on dst)
   p.src = job.dst; p.dst = job.dst; p.src_div = 1; p.src_tstride = job.dst_tstride;
   p.pre_lo = nullptr; p.pre_hi = nullptr;
   p.Llog = l1; p.in_row_stride = u64(1) << l2; p.out_row_stride = u64(1) << l2; p.store_transposed = 0; p.scale = job.scale;
   p.post_lo = job.post_lo; p.post_hi = job.post_hi; p.post_hi_stride = job.post_hi_stride;
-  ntt_pass<<<dim3((1u << l2) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l1, Tlog), st>>>(p); XFG_LAUNCHED(1);
+  if (fast) { p.Tlog = r16_tlog(l1); launch_r16(st, p, job.inverse, (1u << l2) >> p.Tlog, job.batch); }
+  else { ntt_pass<<<dim3((1u << l2) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l1, Tlog), st>>>(p); XFG_LAUNCHED(1); }
 }
 
 }  // namespace xfg

@@ -20,6 +20,7 @@ struct NttPass {
   const u64* it_lo; const u64* it_hi;
   const u64* post_lo; const u64* post_hi; u32 post_hi_stride; u32 post_div;
   u64 scale;
+  u32 num_radix, radix_logs;   // ntt_pass_r16: Stockham pass radices, 4 bits each (log2), first pass in the low nibble
 };
 
 // device tables owned by a plan (one per trace length)

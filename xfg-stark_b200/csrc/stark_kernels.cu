@@ -8,6 +8,7 @@
 // with the reference's `Air::evaluate_transition` / `get_assertions` (src/burn_mint_air.rs:335-395).
 #include "stark_kernels.cuh"
 #include "launch.cuh"
+#include "field_weak.cuh"
 
 namespace xfg {
 
@@ -286,6 +287,34 @@ __global__ void __launch_bounds__(256) check_canonical_kernel(const u64* __restr
 void launch_check_canonical(cudaStream_t st, const u64* v, size_t count, ProofState* ps) {
   size_t blocks = (count + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
   check_canonical_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, count, ps); XFG_LAUNCHED(1);
+}
+
+// ---- field self-test (xfg_field_selftest): exercises the canonical and the weak arithmetic on caller-chosen operands ----
+template <int S> __device__ __forceinline__ bool pow2_case(u32 op, u64 a, u64& r) { if (op == 100 + S) { r = w_canon(w_mul_pow2<S>(a)); return true; } return false; }
+__global__ void field_selftest_kernel(u32 op, const u64* __restrict__ a, const u64* __restrict__ b, size_t n, u64* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 x = a[i], y = b[i]; u64 r = 0;
+  switch (op) {
+    case 0: r = gl_mul(x, y); break;                       // any u64 operands -> canonical
+    case 1: r = w_canon(w_mul(x, y)); break;               // any u64 operands
+    case 2: r = w_canon(w_add_c(x, y)); break;             // x weak, y canonical
+    case 3: r = w_canon(w_sub_c(x, y)); break;             // x weak, y canonical
+    case 4: r = gl_add(x, y); break;                       // canonical operands
+    case 5: r = gl_sub(x, y); break;
+    case 6: r = gl_inv(x); break;
+    case 7: r = w_canon(w_add_hi32(x, (u32)y)); break;
+    case 8: r = w_canon(w_sub_hi32(x, (u32)y)); break;
+    default:
+      pow2_case<0>(op, x, r) || pow2_case<1>(op, x, r) || pow2_case<12>(op, x, r) || pow2_case<24>(op, x, r) || pow2_case<31>(op, x, r) ||
+      pow2_case<32>(op, x, r) || pow2_case<33>(op, x, r) || pow2_case<36>(op, x, r) || pow2_case<48>(op, x, r) || pow2_case<60>(op, x, r) ||
+      pow2_case<63>(op, x, r) || pow2_case<64>(op, x, r) || pow2_case<65>(op, x, r) || pow2_case<72>(op, x, r) || pow2_case<84>(op, x, r) ||
+      pow2_case<95>(op, x, r);
+  }
+  out[i] = r;
+}
+void launch_field_selftest(cudaStream_t st, u32 op, const u64* a, const u64* b, size_t n, u64* out) {
+  field_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, a, b, n, out); XFG_LAUNCHED(1);
 }
 
 }  // namespace xfg
