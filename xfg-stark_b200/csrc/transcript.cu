@@ -5,98 +5,110 @@
 // send_ood_*, commit_fri_layer, draw_fri_alpha, grind_query_seed, get_query_positions}`, winter-crypto
 // `DefaultRandomCoin`, winter-fri `fold_positions` and the row/path collection of `DefaultTraceLde::query`,
 // `ConstraintCommitment::query`, `FriProver::build_proof` (A.4, A.5, A.9-A.11).
-// The serial steps are single-thread kernels (a handful of BLAKE3 compressions each) so the proof needs no host round trip.
+// The serial steps are single-warp kernels (lanes hash candidate counters in parallel) so the proof needs no host round trip.
 #include "transcript.cuh"
 #include "launch.cuh"
 
 namespace xfg {
 
-struct Coin {
-  Digest seed; u64 counter;
-  __device__ void reseed(const Digest& d) { seed = b3_merge(seed, d); counter = 0; }
-  __device__ Digest next() { counter += 1; return b3_merge_int(seed, counter); }
-  // draw::<E>(): first 8*D bytes of next(); every limb must be canonical, else retry (A.5)
-  template <int D> __device__ bool draw(u64 out[2]) {
-    for (int t = 0; t < XFG_COIN_MAX_DRAWS; t++) {
-      Digest d = next();
-      u64 v0 = (u64)d.w[0] | ((u64)d.w[1] << 32), v1 = (u64)d.w[2] | ((u64)d.w[3] << 32);
-      if (v0 < GL_P && (D == 1 || v1 < GL_P)) { out[0] = v0; out[1] = D == 2 ? v1 : 0; return true; }
-    }
-    out[0] = out[1] = 0; return false;
-  }
-};
+// ---- coin (one warp per transcript kernel; lanes hash candidate counters in parallel, results are identical to the serial
+// winter-crypto loop because the k-th accepted value is the k-th valid candidate in counter order) ----
+struct Coin { Digest seed; u64 counter; };
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ Digest bcast_digest(const Digest& d, int src) { Digest r; for (int i = 0; i < 8; i++) r.w[i] = __shfl_sync(0xFFFFFFFFu, d.w[i], src); return r; }
 __device__ __forceinline__ Coin coin_load(const ProofState* ps) { Coin c; c.seed = ps->seed; c.counter = ps->counter; return c; }
-__device__ __forceinline__ void coin_store(ProofState* ps, const Coin& c) { ps->seed = c.seed; ps->counter = c.counter; }
+__device__ __forceinline__ void coin_store(ProofState* ps, const Coin& c) { if (lane_id() == 0) { ps->seed = c.seed; ps->counter = c.counter; } }
+// reseed(d): seed = BLAKE3(seed || d), counter = 0 (every lane computes the same value; the state stays warp-uniform)
+__device__ __forceinline__ void coin_reseed(Coin& c, const Digest& d) { c.seed = b3_merge(c.seed, d); c.counter = 0; }
+// `count` consecutive draw::<E>() calls: first 8*D bytes of next(); every limb must be canonical, else the candidate is skipped (A.5)
+template <int D> __device__ bool coin_draw_many(Coin& c, u32 count, u64 (*out)[2]) {
+  u32 got = 0;
+  for (int round = 0; round < 40 && got < count; round++) {
+    const Digest d = b3_merge_int(c.seed, c.counter + 1 + lane_id());
+    const u64 v0 = (u64)d.w[0] | ((u64)d.w[1] << 32), v1 = (u64)d.w[2] | ((u64)d.w[3] << 32);
+    const bool valid = v0 < GL_P && (D == 1 || v1 < GL_P);
+    const u32 mask = __ballot_sync(0xFFFFFFFFu, valid), rank = __popc(mask & ((1u << lane_id()) - 1)), need = count - got;
+    if (valid && rank < need) { out[got + rank][0] = v0; out[got + rank][1] = D == 2 ? v1 : 0; }
+    const u32 nvalid = __popc(mask);
+    if (nvalid >= need) { c.counter += __fns(mask, 0, need) + 1; got = count; }     // counter stops at the last consumed candidate
+    else { c.counter += 32; got += nvalid; }
+  }
+  __syncwarp();
+  return got == count;
+}
 template <int D> __device__ __forceinline__ Ext<D> ldx(const u64* p) { return Ext<D>(p[0], p[1]); }
 template <int D> __device__ __forceinline__ void stx(u64* p, Ext<D> v) { p[0] = v.limb(0); p[1] = D == 2 ? v.limb(1) : 0; }
 
 // coin = hash_elements(context elements || public inputs)  (A.4)
-__global__ void seed_kernel(ProofState* ps, const u64* __restrict__ seed_limbs, int count) {
-  ps->seed = b3_hash_limbs_dyn(seed_limbs, count); ps->counter = 0; ps->error_flags = 0; ps->nonce = ~0ull;
+__global__ void __launch_bounds__(32) seed_kernel(ProofState* ps, const u64* __restrict__ seed_limbs, int count) {
+  if (lane_id() == 0) { ps->seed = b3_hash_limbs_dyn(seed_limbs, count); ps->counter = 0; ps->error_flags = 0; ps->nonce = ~0ull; }
 }
-template <int D> __global__ void trace_root_kernel(ProofState* ps, const Digest* __restrict__ tree) {
-  Coin c = coin_load(ps); Digest root = tree[1]; ps->trace_root = root; c.reseed(root);
-  bool ok = true;
-  for (int j = 0; j < XFG_NUM_TRANSITION; j++) ok &= c.draw<D>(ps->tcoef[j]);   // transition coefficients first, then boundary (A.8)
-  for (int j = 0; j < XFG_NUM_ASSERTIONS; j++) ok &= c.draw<D>(ps->bcoef[j]);
-  if (!ok) ps->error_flags |= ERR_FLAG_COIN;
+template <int D> __global__ void __launch_bounds__(32) trace_root_kernel(ProofState* ps, const Digest* __restrict__ tree) {
+  Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
+  // transition coefficients first, then boundary (A.8): tcoef[7] and bcoef[8] are contiguous in ProofState
+  const bool ok = coin_draw_many<D>(c, XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS, ps->tcoef);
+  if (lane_id() == 0) { ps->trace_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
   coin_store(ps, c);
 }
-template <int D> __global__ void constraint_root_kernel(ProofState* ps, const Digest* __restrict__ tree, u64 g_n) {
-  Coin c = coin_load(ps); Digest root = tree[1]; ps->constraint_root = root; c.reseed(root);
-  if (!c.draw<D>(ps->z)) ps->error_flags |= ERR_FLAG_COIN;
-  stx<D>(ps->zg, mul_base(ldx<D>(ps->z), g_n));
+template <int D> __global__ void __launch_bounds__(32) constraint_root_kernel(ProofState* ps, const Digest* __restrict__ tree, u64 g_n) {
+  Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
+  const bool ok = coin_draw_many<D>(c, 1, &ps->z);
+  if (lane_id() == 0) { ps->constraint_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; stx<D>(ps->zg, mul_base(ldx<D>(ps->z), g_n)); }
   coin_store(ps, c);
 }
 // sums the OOD partials, sends the frame and H(z) to the coin, draws the DEEP coefficients (A.9)
-template <int D> __global__ void ood_finish_kernel(ProofState* ps, const u64* __restrict__ partial, u32 nb) {
+template <int D> __global__ void __launch_bounds__(32) ood_finish_kernel(ProofState* ps, const u64* __restrict__ partial, u32 nb) {
+  __shared__ u64 sums[NUM_OOD_POLYS][2][2];
   Coin c = coin_load(ps);
-  u64 sums[NUM_OOD_POLYS][2][2];
-  for (int p = 0; p < XFG_TRACE_WIDTH + D; p++)
-    for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) {
-      u64 s = 0; for (u32 b = 0; b < nb; b++) s = gl_add(s, partial[(((size_t)p * nb + b) * 2 + w) * 2 + l]);
-      sums[p][w][l] = s;
-    }
-  u64 limbs[2 * XFG_TRACE_WIDTH * 2]; int k = 0;
-  for (int j = 0; j < XFG_TRACE_WIDTH; j++) for (int w = 0; w < 2; w++) {      // interleaved per column (A.9, D)
-    ps->ood_frame[2 * j + w][0] = sums[j][w][0]; ps->ood_frame[2 * j + w][1] = D == 2 ? sums[j][w][1] : 0;
-    for (int l = 0; l < D; l++) limbs[k++] = sums[j][w][l];
+  for (u32 t = lane_id(); t < (XFG_TRACE_WIDTH + D) * 4; t += 32) {
+    const u32 p = t >> 2, w = (t >> 1) & 1, l = t & 1;
+    u64 s = 0; for (u32 b = 0; b < nb; b++) s = gl_add(s, partial[(((size_t)p * nb + b) * 2 + w) * 2 + l]);
+    sums[p][w][l] = s;
   }
-  c.reseed(b3_hash_limbs_dyn(limbs, k));
+  __syncwarp();
+  u64 limbs[2 * XFG_TRACE_WIDTH * 2]; int k = 0;
+  for (int j = 0; j < XFG_TRACE_WIDTH; j++) for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) limbs[k++] = sums[j][w][l];   // interleaved per column (A.9)
+  coin_reseed(c, b3_hash_limbs_dyn(limbs, k));
   // H(z) = P_limb0(z) + phi * P_limb1(z), phi = (0,1): (a0,a1) * phi = (-2 a1, a0 + a1)
   Ext<D> hz = ldx<D>(sums[XFG_TRACE_WIDTH][0]);
-  if (D == 2) { u64 a0 = sums[XFG_TRACE_WIDTH + 1][0][0], a1 = sums[XFG_TRACE_WIDTH + 1][0][1]; hz = hz + Ext<D>(gl_neg(gl_dbl(a1)), gl_add(a0, a1)); }
-  stx<D>(ps->hz, hz);
+  if (D == 2) { const u64 a0 = sums[XFG_TRACE_WIDTH + 1][0][0], a1 = sums[XFG_TRACE_WIDTH + 1][0][1]; hz = hz + Ext<D>(gl_neg(gl_dbl(a1)), gl_add(a0, a1)); }
   u64 hl[2] = {hz.limb(0), hz.limb(1)};
-  c.reseed(b3_hash_limbs_dyn(hl, D));
-  bool ok = true;
-  for (int j = 0; j <= XFG_TRACE_WIDTH; j++) ok &= c.draw<D>(ps->dcoef[j]);   // 7 trace coefficients, then 1 composition column
-  if (!ok) ps->error_flags |= ERR_FLAG_COIN;
-  Ext<D> c1, c2;
-  for (int j = 0; j < XFG_TRACE_WIDTH; j++) {
-    Ext<D> g = ldx<D>(ps->dcoef[j]);
-    c1 = c1 + g * ldx<D>(ps->ood_frame[2 * j]); c2 = c2 + g * ldx<D>(ps->ood_frame[2 * j + 1]);
+  coin_reseed(c, b3_hash_limbs_dyn(hl, D));
+  const bool ok = coin_draw_many<D>(c, XFG_TRACE_WIDTH + 1, ps->dcoef);      // 7 trace coefficients, then 1 composition column
+  if (lane_id() == 0) {
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) for (int w = 0; w < 2; w++) { ps->ood_frame[2 * j + w][0] = sums[j][w][0]; ps->ood_frame[2 * j + w][1] = D == 2 ? sums[j][w][1] : 0; }
+    stx<D>(ps->hz, hz);
+    if (!ok) ps->error_flags |= ERR_FLAG_COIN;
+    Ext<D> c1, c2;
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) {
+      const Ext<D> g = ldx<D>(ps->dcoef[j]);
+      c1 = c1 + g * ldx<D>(sums[j][0]); c2 = c2 + g * ldx<D>(sums[j][1]);
+    }
+    c1 = c1 + ldx<D>(ps->dcoef[XFG_TRACE_WIDTH]) * hz;
+    stx<D>(ps->deep_c1, c1); stx<D>(ps->deep_c2, c2);
   }
-  c1 = c1 + ldx<D>(ps->dcoef[XFG_TRACE_WIDTH]) * hz;
-  stx<D>(ps->deep_c1, c1); stx<D>(ps->deep_c2, c2);
   coin_store(ps, c);
 }
-template <int D> __global__ void fri_commit_kernel(ProofState* ps, const Digest* __restrict__ tree, u32 layer) {
-  Coin c = coin_load(ps); Digest root = tree[1]; ps->fri_roots[layer] = root; c.reseed(root);
-  if (!c.draw<D>(ps->alphas[layer])) ps->error_flags |= ERR_FLAG_COIN;
+template <int D> __global__ void __launch_bounds__(32) fri_commit_kernel(ProofState* ps, const Digest* __restrict__ tree, u32 layer) {
+  Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
+  const bool ok = coin_draw_many<D>(c, 1, &ps->alphas[layer]);
+  if (lane_id() == 0) { ps->fri_roots[layer] = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
   coin_store(ps, c);
 }
 // remainder = first `len` coefficients; commitment = hash_elements(remainder); reseed (A.10)
-template <int D> __global__ void remainder_kernel(ProofState* ps, const u64* __restrict__ coef, size_t limb_stride, u32 len) {
+template <int D> __global__ void __launch_bounds__(32) remainder_kernel(ProofState* ps, const u64* __restrict__ coef, size_t limb_stride, u32 len) {
+  __shared__ u64 limbs[MAX_REMAINDER * 2];
   Coin c = coin_load(ps);
-  u64 limbs[MAX_REMAINDER * 2];
-  for (u32 i = 0; i < len; i++) for (int l = 0; l < 2; l++) {
-    u64 v = l < D ? coef[(size_t)l * limb_stride + i] : 0;
-    ps->remainder[i][l] = v; if (l < D) limbs[i * D + l] = v;
+  for (u32 t = lane_id(); t < len * 2; t += 32) {
+    const u32 i = t >> 1, l = t & 1; const u64 v = l < (u32)D ? coef[(size_t)l * limb_stride + i] : 0;
+    ps->remainder[i][l] = v; if (l < (u32)D) limbs[i * D + l] = v;
   }
-  ps->remainder_len = len;
-  Digest d = b3_hash_limbs_dyn(limbs, len * D);
-  ps->remainder_commitment = d; c.reseed(d);
+  __syncwarp();
+  Digest d;
+  if (lane_id() == 0) d = b3_hash_limbs_dyn(limbs, len * D);
+  d = bcast_digest(d, 0);
+  coin_reseed(c, d);
+  if (lane_id() == 0) { ps->remainder_len = len; ps->remainder_commitment = d; }
   coin_store(ps, c);
 }
 // grinding: smallest nonce >= 1 with trailing_zeros(LE head of BLAKE3(seed || nonce)) >= grinding_factor (A.5).
@@ -113,30 +125,52 @@ __global__ void __launch_bounds__(256) grind_kernel(ProofState* ps, u32 grinding
     if ((head & mask) == 0) { atomicMin(&ps->nonce, (unsigned long long)nonce); break; }
   }
 }
-// draw_integers(q, N, nonce) -> sort -> dedup; then fold_positions per FRI layer (A.5, A.10)
-__global__ void positions_kernel(ProofState* ps, u32 num_queries, u32 lN, u32 num_layers) {
+// draw_integers(q, N, nonce) -> sort -> dedup; then fold_positions per FRI layer (A.5, A.10).  One warp: lanes hash the q
+// counters in parallel, rank-sort in shared memory, and compact with ballots (order-preserving, as the reference).
+__global__ void __launch_bounds__(32) positions_kernel(ProofState* ps, u32 num_queries, u32 lN, u32 num_layers) {
+  __shared__ u32 raw[256], srt[256], cur[256], nxt[256];
+  __shared__ u32 s_cnt;
   Coin c = coin_load(ps);
   c.seed = b3_merge_int(c.seed, ps->nonce); c.counter = 0;
-  const u64 mask = (1ull << lN) - 1;
-  u32 pos[MAX_Q];
-  for (u32 i = 0; i < num_queries; i++) { Digest d = c.next(); pos[i] = (u32)(((u64)d.w[0] | ((u64)d.w[1] << 32)) & mask); }
-  for (u32 i = 1; i < num_queries; i++) { u32 v = pos[i]; int j = (int)i - 1; while (j >= 0 && pos[j] > v) { pos[j + 1] = pos[j]; j--; } pos[j + 1] = v; }
-  u32 cnt = 0;
-  for (u32 i = 0; i < num_queries; i++) if (i == 0 || pos[i] != pos[i - 1]) pos[cnt++] = pos[i];
-  ps->num_positions = cnt;
-  for (u32 i = 0; i < cnt; i++) ps->positions[i] = pos[i];
-  u32 lNl = lN;
-  for (u32 l = 0; l < num_layers; l++) {
-    const u32 tmask = (1u << (lNl - 3)) - 1; u32 fc = 0;
-    for (u32 i = 0; i < cnt; i++) {                    // order-preserving dedup, not re-sorted
-      u32 q = pos[i] & tmask; bool dup = false;
-      for (u32 j = 0; j < fc; j++) if (ps->fri_positions[l][j] == q) { dup = true; break; }
-      if (!dup) ps->fri_positions[l][fc++] = q;
-    }
-    ps->fri_num_positions[l] = fc;
-    cnt = fc; for (u32 i = 0; i < cnt; i++) pos[i] = ps->fri_positions[l][i];
-    lNl -= 3;
+  const u64 mask = (1ull << lN) - 1; const u32 lane = lane_id();
+  for (u32 i = lane; i < num_queries; i += 32) { const Digest d = b3_merge_int(c.seed, (u64)i + 1); raw[i] = (u32)(((u64)d.w[0] | ((u64)d.w[1] << 32)) & mask); }
+  c.counter = num_queries;
+  __syncwarp();
+  for (u32 i = lane; i < num_queries; i += 32) {       // stable rank sort
+    const u32 v = raw[i]; u32 r = 0;
+    for (u32 j = 0; j < num_queries; j++) r += (raw[j] < v) || (raw[j] == v && j < i);
+    srt[r] = v;
   }
+  __syncwarp();
+  // order-preserving compaction of `keep` flags: out[] gets the kept values, returns the count (warp-uniform)
+  auto compact = [&](const u32* in, u32 n, u32 vmask, bool sorted_input, u32* out) -> u32 {
+    u32 base = 0;
+    for (u32 i0 = 0; i0 < n; i0 += 32) {
+      const u32 i = i0 + lane; bool keep = false; u32 v = 0;
+      if (i < n) {
+        v = in[i] & vmask;
+        if (sorted_input) keep = (i == 0) || ((in[i - 1] & vmask) != v);
+        else { keep = true; for (u32 j = 0; j < i; j++) if ((in[j] & vmask) == v) { keep = false; break; } }
+      }
+      const u32 m = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) out[base + __popc(m & ((1u << lane) - 1))] = v;
+      base += __popc(m);
+    }
+    __syncwarp();
+    return base;
+  };
+  u32 cnt = compact(srt, num_queries, 0xFFFFFFFFu, true, cur);
+  for (u32 i = lane; i < cnt; i += 32) ps->positions[i] = cur[i];
+  if (lane == 0) ps->num_positions = cnt;
+  u32 lNl = lN; u32* a = cur; u32* b = nxt;
+  for (u32 l = 0; l < num_layers; l++) {
+    const u32 fc = compact(a, cnt, (1u << (lNl - 3)) - 1, false, b);       // fold_positions: p mod (Nl/8), first occurrence kept
+    for (u32 i = lane; i < fc; i += 32) ps->fri_positions[l][i] = b[i];
+    if (lane == 0) ps->fri_num_positions[l] = fc;
+    cnt = fc; u32* t = a; a = b; b = t; lNl -= 3;
+    __syncwarp();
+  }
+  (void)s_cnt;
   coin_store(ps, c);
 }
 
@@ -160,25 +194,25 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherTasks tasks, const Pr
   }
 }
 
-void launch_seed(cudaStream_t st, ProofState* ps, const u64* seed_limbs, int count) { seed_kernel<<<1, 1, 0, st>>>(ps, seed_limbs, count); XFG_LAUNCHED(1); }
+void launch_seed(cudaStream_t st, ProofState* ps, const u64* seed_limbs, int count) { seed_kernel<<<1, 32, 0, st>>>(ps, seed_limbs, count); XFG_LAUNCHED(1); }
 void launch_trace_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree) {
-  if (D == 1) trace_root_kernel<1><<<1, 1, 0, st>>>(ps, tree); else trace_root_kernel<2><<<1, 1, 0, st>>>(ps, tree);
+  if (D == 1) trace_root_kernel<1><<<1, 32, 0, st>>>(ps, tree); else trace_root_kernel<2><<<1, 32, 0, st>>>(ps, tree);
   XFG_LAUNCHED(1);
 }
 void launch_constraint_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u64 g_n) {
-  if (D == 1) constraint_root_kernel<1><<<1, 1, 0, st>>>(ps, tree, g_n); else constraint_root_kernel<2><<<1, 1, 0, st>>>(ps, tree, g_n);
+  if (D == 1) constraint_root_kernel<1><<<1, 32, 0, st>>>(ps, tree, g_n); else constraint_root_kernel<2><<<1, 32, 0, st>>>(ps, tree, g_n);
   XFG_LAUNCHED(1);
 }
 void launch_ood_finish(cudaStream_t st, int D, ProofState* ps, const u64* partial, u32 nb) {
-  if (D == 1) ood_finish_kernel<1><<<1, 1, 0, st>>>(ps, partial, nb); else ood_finish_kernel<2><<<1, 1, 0, st>>>(ps, partial, nb);
+  if (D == 1) ood_finish_kernel<1><<<1, 32, 0, st>>>(ps, partial, nb); else ood_finish_kernel<2><<<1, 32, 0, st>>>(ps, partial, nb);
   XFG_LAUNCHED(1);
 }
 void launch_fri_commit(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u32 layer) {
-  if (D == 1) fri_commit_kernel<1><<<1, 1, 0, st>>>(ps, tree, layer); else fri_commit_kernel<2><<<1, 1, 0, st>>>(ps, tree, layer);
+  if (D == 1) fri_commit_kernel<1><<<1, 32, 0, st>>>(ps, tree, layer); else fri_commit_kernel<2><<<1, 32, 0, st>>>(ps, tree, layer);
   XFG_LAUNCHED(1);
 }
 void launch_remainder(cudaStream_t st, int D, ProofState* ps, const u64* coef, size_t limb_stride, u32 len) {
-  if (D == 1) remainder_kernel<1><<<1, 1, 0, st>>>(ps, coef, limb_stride, len); else remainder_kernel<2><<<1, 1, 0, st>>>(ps, coef, limb_stride, len);
+  if (D == 1) remainder_kernel<1><<<1, 32, 0, st>>>(ps, coef, limb_stride, len); else remainder_kernel<2><<<1, 32, 0, st>>>(ps, coef, limb_stride, len);
   XFG_LAUNCHED(1);
 }
 void launch_grind(cudaStream_t st, ProofState* ps, u32 grinding) {
@@ -187,7 +221,7 @@ void launch_grind(cudaStream_t st, ProofState* ps, u32 grinding) {
   grind_kernel<<<blocks, 256, 0, st>>>(ps, grinding);
   XFG_LAUNCHED(1);
 }
-void launch_positions(cudaStream_t st, ProofState* ps, u32 num_queries, u32 lN, u32 num_layers) { positions_kernel<<<1, 1, 0, st>>>(ps, num_queries, lN, num_layers); XFG_LAUNCHED(1); }
+void launch_positions(cudaStream_t st, ProofState* ps, u32 num_queries, u32 lN, u32 num_layers) { positions_kernel<<<1, 32, 0, st>>>(ps, num_queries, lN, num_layers); XFG_LAUNCHED(1); }
 void launch_gather(cudaStream_t st, const GatherTasks& tasks, const ProofState* ps, u64* out) {
   gather_kernel<<<dim3(4, tasks.count), 256, 0, st>>>(tasks, ps, out);
   XFG_LAUNCHED(1);
