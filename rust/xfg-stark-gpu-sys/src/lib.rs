@@ -1,0 +1,86 @@
+//! Raw bindings, one item per declaration of `include/xfg_stark.h` (kept in the same order).
+//! The product crate `xfg-stark` has `#![deny(unsafe_code)]` (src/lib.rs:17), hence this separate `-sys` crate.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+pub const XFG_NUM_PUB_INPUTS: usize = 12;
+pub const XFG_NUM_STAGES: usize = 9;
+pub const XFG_EXT_NONE: u32 = 1;
+pub const XFG_EXT_QUADRATIC: u32 = 2;
+
+pub const XFG_OK: c_int = 0;
+pub const XFG_ERR_BAD_ARGS: c_int = 1;
+pub const XFG_ERR_BAD_OPTIONS: c_int = 2;
+pub const XFG_ERR_UNSUPPORTED_OPTIONS: c_int = 3;
+pub const XFG_ERR_UNSUPPORTED_EXTENSION: c_int = 4;
+pub const XFG_ERR_UNSATISFIED_CONSTRAINT: c_int = 5;
+pub const XFG_ERR_BUFFER_TOO_SMALL: c_int = 6;
+pub const XFG_ERR_CUDA: c_int = 7;
+pub const XFG_ERR_INVALID_INPUT: c_int = 8;
+pub const XFG_ERR_TOO_LARGE: c_int = 9;
+
+#[repr(C)]
+pub struct xfg_ctx { _private: [u8; 0] }
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct xfg_options {
+    pub num_queries: u32,
+    pub blowup_factor: u32,
+    pub grinding_factor: u32,
+    pub field_extension: u32,
+    pub fri_folding_factor: u32,
+    pub fri_remainder_max_degree: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct xfg_air_consts {
+    pub pub_inputs: [u64; XFG_NUM_PUB_INPUTS],
+    pub txn_hash: u64,
+    pub recipient_hash: u64,
+    pub nullifier: u64,
+    pub commitment: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct xfg_stage_times {
+    pub stage_ms: [f32; XFG_NUM_STAGES],
+    pub h2d_ms: f32,
+    pub device_ms: f32,
+    pub total_ms: f32,
+    pub kernel_launches: u32,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+}
+
+extern "C" {
+    pub fn xfg_create(device: c_int, max_n_log2: u32, num_slots: u32, out: *mut *mut xfg_ctx) -> c_int;
+    pub fn xfg_destroy(ctx: *mut xfg_ctx);
+    pub fn xfg_strerror(code: c_int) -> *const c_char;
+    pub fn xfg_last_error(ctx: *const xfg_ctx) -> *const c_char;
+    pub fn xfg_set_profiling(ctx: *mut xfg_ctx, on: c_int) -> c_int;
+    pub fn xfg_get_profile(ctx: *mut xfg_ctx, cap: u32, count: *mut u32, names: *mut *const c_char, ms: *mut f32, launches: *mut u32) -> c_int;
+    pub fn xfg_prove_burn_mint(ctx: *mut xfg_ctx, trace_colmajor: *const u64, n_log2: u32, air: *const xfg_air_consts, options: *const xfg_options,
+                               out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_prove_burn_mint_device(ctx: *mut xfg_ctx, d_trace_colmajor: *const u64, n_log2: u32, air: *const xfg_air_consts,
+                                      options: *const xfg_options, out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_prove_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, traces: *const *const u64, n_log2: u32, airs: *const xfg_air_consts,
+                                     options: *const xfg_options, out: *mut u8, out_stride: usize, out_lens: *mut usize, total_ms: *mut f32) -> c_int;
+    pub fn xfg_burn_mint_pack_inputs(ctx: *mut xfg_ctx, burn_amount: u64, mint_amount: u64, tx_prefix_hash: *const u8, recipient_address: *const u8,
+                                     recipient_len: usize, secret: *const u8, secret_len: usize, network_id: u32, target_chain_id: u32,
+                                     commitment_version: u32, out: *mut xfg_air_consts) -> c_int;
+    pub fn xfg_burn_mint_build_trace(air: *const xfg_air_consts, n_log2: u32, trace_colmajor_out: *mut u64) -> c_int;
+    pub fn xfg_prove_burn_mint_from_inputs(ctx: *mut xfg_ctx, burn_amount: u64, mint_amount: u64, tx_prefix_hash: *const u8, recipient_address: *const u8,
+                                           recipient_len: usize, secret: *const u8, secret_len: usize, network_id: u32, target_chain_id: u32,
+                                           commitment_version: u32, n_log2: u32, options: *const xfg_options, out: *mut u8, out_cap: usize,
+                                           out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_ntt(ctx: *mut xfg_ctx, data: *mut u64, n_log2: u32, batch: u32, inverse: c_int) -> c_int;
+    pub fn xfg_lde_commit(ctx: *mut xfg_ctx, cols_colmajor: *const u64, n_log2: u32, cols: u32, lde_out: *mut u64, root_out: *mut u8) -> c_int;
+    pub fn xfg_merkle_root(ctx: *mut xfg_ctx, leaves: *const u8, count: usize, root_out: *mut u8, nodes_out: *mut u8) -> c_int;
+    pub fn xfg_eval_constraints(ctx: *mut xfg_ctx, lde: *const u64, n_log2: u32, air: *const xfg_air_consts, ext: u32, coeffs: *const u64, out: *mut u64) -> c_int;
+    pub fn xfg_fri_fold_layer(ctx: *mut xfg_ctx, evals: *const u64, nl_log2: u32, ext: u32, alpha: *const u64, out: *mut u64) -> c_int;
+    pub fn xfg_field_selftest(ctx: *mut xfg_ctx, op: u32, a: *const u64, b: *const u64, n: usize, out: *mut u64) -> c_int;
+    pub fn xfg_hash_rows(ctx: *mut xfg_ctx, rows_rowmajor: *const u64, rows: usize, limbs: u32, out: *mut u8) -> c_int;
+}

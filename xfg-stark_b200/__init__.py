@@ -14,6 +14,7 @@ a ``Context`` without a CUDA device raises ``XfgError``.  The directory name car
 from ._binding import (Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgError, AirConsts, STAGE_NAMES, load_library,
                        library_path, EXPORTED_SYMBOLS, FieldExtension, pack_inputs, build_trace)
 from .synthetic import synthetic_inputs
+from . import multi
 
 __all__ = ["Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgError", "AirConsts", "STAGE_NAMES",
-           "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "synthetic_inputs"]
+           "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "synthetic_inputs", "multi"]
