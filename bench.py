@@ -207,6 +207,7 @@ def main():
     import xfg_stark_b200 as xs
     from xfg_stark_b200 import multi
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line
     torch.cuda.set_device(local)
     multi.init("nccl", torch.device("cuda", local))
     if args.workload == "batch":

@@ -53,7 +53,9 @@ struct Carve {   // device pointers of one proof, carved from the slot slab for 
 struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 
 struct Slot {
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, copy_st = nullptr;         // copy_st: column-wise trace upload overlapped with the first NTTs
+  cudaEvent_t col_ev[XFG_TRACE_WIDTH] = {nullptr};
+  bool split_upload = false;
   u64* slab = nullptr; size_t slab_words = 0;
   ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
   ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;
@@ -229,13 +231,17 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (8 + XFG_NUM_PUB_INPUTS) * 8, cudaMemcpyHostToDevice, st));
   mark();   // ev0: start of device work
   PROF("transcript", launch_seed(st, s.d_state, s.d_seed, 8 + XFG_NUM_PUB_INPUTS));
-  PROF("check_canonical", launch_check_canonical(st, trace_src, 7 * n, s.d_state));
-
   // 1 ---- extend_execution_trace: interpolate the 7 columns, evaluate on the 8 cosets s_k * <w_n>
-  { NttJob j{}; j.src = trace_src; j.dst = c.trace_coef; j.ln = ln; j.batch = XFG_TRACE_WIDTH; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
-    j.inverse = true; j.scale = p.n_inv; PROF("ntt.interpolate_trace", ntt_batch(st, p.ntt, j)); }
-  { NttJob j{}; j.src = c.trace_coef; j.dst = c.lde; j.ln = ln; j.batch = XFG_TRACE_WIDTH * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
-    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_trace", ntt_batch(st, p.ntt, j)); }
+  const int groups = (s.split_upload && !d_trace) ? XFG_TRACE_WIDTH : 1, per = XFG_TRACE_WIDTH / groups;   // per column while the upload is in flight
+  for (int g = 0; g < groups; g++) {
+    const size_t off = (size_t)g * per * n;
+    if (groups > 1) CU(cudaStreamWaitEvent(st, s.col_ev[g], 0));
+    PROF("check_canonical", launch_check_canonical(st, trace_src + off, (size_t)per * n, s.d_state));
+    { NttJob j{}; j.src = trace_src + off; j.dst = c.trace_coef + off; j.ln = ln; j.batch = per; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
+      j.inverse = true; j.scale = p.n_inv; PROF("ntt.interpolate_trace", ntt_batch(st, p.ntt, j)); }
+    { NttJob j{}; j.src = c.trace_coef + off; j.dst = c.lde + off * 8; j.ln = ln; j.batch = per * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
+      j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_trace", ntt_batch(st, p.ntt, j)); }
+  }
   mark();
   //   ---- compute_execution_trace_commitment
   PROF("commit_rows.trace", launch_commit_rows(st, c.lde, N, XFG_TRACE_WIDTH, ln, c.trace_tree));
@@ -400,7 +406,7 @@ int check_air(xfg_ctx* ctx, const xfg_air_consts* air) {
 
 // trace upload: straight from the caller's buffer when it is page-locked (cudaHostAlloc / cudaHostRegister), otherwise staged
 // through the slot's pinned buffer.  Canonicity (< p) is checked on the device.
-int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace) {
+int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace, bool allow_split) {
   Carve c; carve(s, p, D, c);
   if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length");
   const size_t bytes = 7 * p.n * 8;
@@ -408,7 +414,15 @@ int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace
   cudaGetLastError();   // unregistered host memory may leave a sticky-free error code behind on older drivers
   const u64* src = h_trace;
   if (!pinned) { std::memcpy(s.h_trace, h_trace, bytes); src = s.h_trace; }
-  CU(cudaMemcpyAsync(c.trace_in, src, bytes, cudaMemcpyHostToDevice, s.st));
+  s.split_upload = allow_split && p.ln >= 17;
+  if (s.split_upload) {      // one copy + event per column on the copy stream; column c's NTTs start as soon as column c has landed
+    for (int col = 0; col < XFG_TRACE_WIDTH; col++) {
+      CU(cudaMemcpyAsync(c.trace_in + (size_t)col * p.n, src + (size_t)col * p.n, p.n * 8, cudaMemcpyHostToDevice, s.copy_st));
+      CU(cudaEventRecord(s.col_ev[col], s.copy_st));
+    }
+  } else {
+    CU(cudaMemcpyAsync(c.trace_in, src, bytes, cudaMemcpyHostToDevice, s.st));
+  }
   return XFG_OK;
 }
 
@@ -425,7 +439,8 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1;
   g_xfg_launches = 0;
   if (times) { std::memset(times, 0, sizeof *times); cudaEventRecord(s.ev[XFG_NUM_STAGES + 2], s.st); }
-  if (h_trace && (rc = upload_trace(ctx, s, *p, D, h_trace))) return rc;
+  s.split_upload = false;
+  if (h_trace && (rc = upload_trace(ctx, s, *p, D, h_trace, true))) return rc;
   if ((rc = enqueue_proof(ctx, s, *p, D, *o, *air, d_trace, times != nullptr))) return rc;
   rc = finish_proof(ctx, s, out, cap, out_len, times);
   if (times) {
@@ -476,7 +491,8 @@ int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** ou
   ctx->slots.resize(num_slots);
   const size_t words = slab_words_for(max_n_log2, 2), trace_words = size_t(7) << max_n_log2;
   for (Slot& s : ctx->slots) {
-    CUB(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)); CUB(cudaStreamCreateWithFlags(&s.copy_st, cudaStreamNonBlocking));
+    for (auto& e : s.col_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaMalloc(&s.slab, words * 8)); s.slab_words = words;
     CUB(cudaMalloc(&s.d_state, sizeof(ProofState))); CUB(cudaMalloc(&s.d_seed, 64 * 8));
     CUB(cudaMalloc(&s.d_partial, (size_t)NUM_OOD_POLYS * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
@@ -497,6 +513,8 @@ void xfg_destroy(xfg_ctx* ctx) {
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
+    for (auto& e : s.col_ev) if (e) cudaEventDestroy(e);
+    if (s.copy_st) cudaStreamDestroy(s.copy_st);
     if (s.st) cudaStreamDestroy(s.st);
   }
   for (auto& kv : ctx->plans) cudaFree(kv.second.slab);
@@ -539,7 +557,7 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
     if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
     if ((rc = check_air(ctx, &airs[i]))) return rc;
     if (!traces[i]) return fail(ctx, XFG_ERR_BAD_ARGS, "null trace");
-    if ((rc = upload_trace(ctx, s, *p, D, traces[i]))) return rc;
+    if ((rc = upload_trace(ctx, s, *p, D, traces[i], false))) return rc;
     s.proof_index = i;
     if ((rc = enqueue_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) return rc;
   }
