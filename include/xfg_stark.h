@@ -115,6 +115,23 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn_amount, uint64_t
                                     uint32_t network_id, uint32_t target_chain_id, uint32_t commitment_version, uint32_t n_log2,
                                     const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
 
+/* ---- one wide trace sharded over the GPUs of a box (BASELINE config 5) ----
+ * Replaces DefaultTraceLde::new (src/burn_mint_air.rs:513: interpolate_columns + evaluate_polys_over + commit_to_rows +
+ * MerkleTree::new) for a W-column x 2^n_log2-row trace: rank r interpolates and extends columns [r*W/G, (r+1)*W/G); the last
+ * NTT pass stores each LDE element directly into the receive buffer of the rank that owns its row (peer stores over NVLink,
+ * the all-to-all is fused into the kernel); after a cross-rank barrier every rank hashes its rows [r*N/G, (r+1)*N/G) and
+ * returns its subtree root; the caller all-gathers the G roots and finishes the top levels with xfg_merkle_root. */
+typedef struct xfg_wide xfg_wide;
+int xfg_wide_create(xfg_ctx* ctx, uint32_t n_log2, uint32_t total_cols, uint32_t num_ranks, uint32_t rank, xfg_wide** out);
+void xfg_wide_destroy(xfg_wide* w);
+void* xfg_wide_recv_ptr(xfg_wide* w);                                   /* device pointer of this rank's receive buffer */
+int xfg_wide_ipc_handle(xfg_wide* w, uint8_t out[64]);                  /* cudaIpcMemHandle_t of the receive buffer */
+int xfg_wide_open_peers(xfg_wide* w, const uint8_t* handles);           /* num_ranks x 64 bytes (one process per GPU) */
+int xfg_wide_set_peer_ptrs(xfg_wide* w, void* const* ptrs);             /* all ranks in one process */
+int xfg_wide_extend(xfg_wide* w, const uint64_t* d_cols_local, float* device_ms);   /* device pointer, W/G x n column-major */
+int xfg_wide_commit(xfg_wide* w, uint8_t subtree_root[32], float* device_ms);       /* call after a barrier across ranks */
+int xfg_wide_read_recv(xfg_wide* w, uint64_t* out);                     /* test hook: W x 8 x n/G elements */
+
 /* ---- stage entry points (kernel-level parity tests; host buffers in and out) ---- */
 /* `batch` transforms of 2^n_log2 points, contiguous; inverse != 0 = fft::interpolate_poly, else forward evaluation */
 int xfg_ntt(xfg_ctx* ctx, uint64_t* data, uint32_t n_log2, uint32_t batch, int inverse);

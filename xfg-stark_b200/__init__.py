@@ -11,10 +11,10 @@ There is no CPU fallback: importing works anywhere (so the CPU test-suite can ch
 a ``Context`` without a CUDA device raises ``XfgError``.  The directory name carries a hyphen, so import it through the
 ``xfg_stark_b200`` shim at the repo root.
 """
-from ._binding import (Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgError, AirConsts, STAGE_NAMES, load_library,
+from ._binding import (WideTrace, Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgError, AirConsts, STAGE_NAMES, load_library,
                        library_path, EXPORTED_SYMBOLS, FieldExtension, pack_inputs, build_trace)
 from .synthetic import synthetic_inputs
 from . import multi
 
-__all__ = ["Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgError", "AirConsts", "STAGE_NAMES",
+__all__ = ["WideTrace", "Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgError", "AirConsts", "STAGE_NAMES",
            "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "synthetic_inputs", "multi"]

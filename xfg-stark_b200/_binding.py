@@ -15,7 +15,9 @@ STAGE_NAMES = ["extend_execution_trace", "compute_execution_trace_commitment", "
 EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error", "xfg_prove_burn_mint",
                     "xfg_prove_burn_mint_device", "xfg_prove_burn_mint_batch", "xfg_burn_mint_pack_inputs",
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
-                    "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_get_profile", "xfg_field_selftest"]
+                    "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
+                    "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
+                    "xfg_wide_commit", "xfg_wide_read_recv"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -110,6 +112,15 @@ def load_library():
     L.xfg_fri_fold_layer.argtypes = [vp, vp, u32, u32, vp, vp]
     L.xfg_hash_rows.argtypes = [vp, vp, sz, u32, vp]
     L.xfg_set_profiling.argtypes = [vp, i]
+    L.xfg_wide_create.argtypes = [vp, u32, u32, u32, u32, C.POINTER(vp)]
+    L.xfg_wide_destroy.argtypes = [vp]; L.xfg_wide_destroy.restype = None
+    L.xfg_wide_recv_ptr.argtypes = [vp]; L.xfg_wide_recv_ptr.restype = vp
+    L.xfg_wide_ipc_handle.argtypes = [vp, vp]
+    L.xfg_wide_open_peers.argtypes = [vp, vp]
+    L.xfg_wide_set_peer_ptrs.argtypes = [vp, vp]
+    L.xfg_wide_extend.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.xfg_wide_commit.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.xfg_wide_read_recv.argtypes = [vp, vp]
     L.xfg_field_selftest.argtypes = [vp, u32, vp, vp, sz, vp]
     L.xfg_get_profile.argtypes = [vp, u32, C.POINTER(u32), vp, vp, vp]
     _lib = L
@@ -276,6 +287,45 @@ class Context:
         out = np.empty((cnt, 32), dtype=np.uint8)
         self._check(self._lib.xfg_hash_rows(self._h, _ptr(r), cnt, limbs, _ptr(out)))
         return out
+
+
+class WideTrace:
+    """xfg_wide: this rank's share of one wide trace (BASELINE config 5): W/G columns in, rows [r*N/G, (r+1)*N/G) of all W
+    columns out (the all-to-all is fused into the last NTT pass as peer stores), then the local Merkle subtree."""
+
+    def __init__(self, ctx, n_log2, total_cols, num_ranks, rank):
+        self.ctx, self.n_log2, self.total_cols, self.num_ranks, self.rank = ctx, n_log2, total_cols, num_ranks, rank
+        self._h = C.c_void_p()
+        ctx._check(ctx._lib.xfg_wide_create(ctx._h, n_log2, total_cols, num_ranks, rank, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.xfg_wide_destroy(self._h); self._h = C.c_void_p()
+
+    def recv_ptr(self):
+        return self.ctx._lib.xfg_wide_recv_ptr(self._h)
+
+    def ipc_handle(self):
+        buf = C.create_string_buffer(64); self.ctx._check(self.ctx._lib.xfg_wide_ipc_handle(self._h, buf)); return buf.raw
+
+    def open_peers(self, handles):
+        """handles: list of num_ranks 64-byte IPC handles (entry r from rank r), one process per GPU."""
+        self.ctx._check(self.ctx._lib.xfg_wide_open_peers(self._h, b"".join(handles)))
+
+    def set_peer_ptrs(self, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*ptrs); self.ctx._check(self.ctx._lib.xfg_wide_set_peer_ptrs(self._h, arr))
+
+    def extend(self, device_ptr):
+        ms = C.c_float(0); self.ctx._check(self.ctx._lib.xfg_wide_extend(self._h, C.c_void_p(device_ptr), C.byref(ms))); return float(ms.value)
+
+    def commit(self):
+        root = C.create_string_buffer(32); ms = C.c_float(0)
+        self.ctx._check(self.ctx._lib.xfg_wide_commit(self._h, root, C.byref(ms))); return root.raw, float(ms.value)
+
+    def read_recv(self):
+        n_local = (1 << self.n_log2) // self.num_ranks
+        out = np.empty((self.total_cols, 8, n_local), dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.xfg_wide_read_recv(self._h, _ptr(out))); return out
 
 
 class XfgBurnMintProver:

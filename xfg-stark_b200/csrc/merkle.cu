@@ -37,6 +37,45 @@ __global__ void __launch_bounds__(128) commit_rows_kernel(const u64* __restrict_
   store_digest(tree + N / 8 + m, b3_merge(a, b));
 }
 
+// Wide rows (config 5: W = 64 columns): same thread shape, but the row is streamed through the BLAKE3 chunk 8 limbs (one
+// 64-byte block) at a time instead of being held in registers.  data[j*limb_stride + k*n + m], num_limbs <= 128.
+__global__ void __launch_bounds__(128) commit_rows_wide_kernel(const u64* __restrict__ data, size_t limb_stride, u32 num_limbs, u32 ln, Digest* __restrict__ tree) {
+  const size_t n = size_t(1) << ln, N = n * 8;
+  const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const u32 nb = (num_limbs + 7) / 8;
+  Digest l1[4];
+#pragma unroll 1
+  for (int kp = 0; kp < 4; kp++) {
+    Digest d[2];
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      const int k = 2 * kp + h;
+      const u64* row = data + (size_t)k * n + m;
+      u32 cv[8]; b3_iv(cv);
+      for (u32 b = 0; b < nb; b++) {
+        u32 msg[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const u32 li = b * 8 + i; const u64 v = li < num_limbs ? row[(size_t)li * limb_stride] : 0; msg[2 * i] = (u32)v; msg[2 * i + 1] = (u32)(v >> 32); }
+        const u32 rem = num_limbs - b * 8, len = rem >= 8 ? 64 : rem * 8;
+        const u32 flags = (b == 0 ? XFG_B3_CHUNK_START : 0) | (b == nb - 1 ? (XFG_B3_CHUNK_END | XFG_B3_ROOT) : 0);
+        b3_compress(cv, msg, len, flags, b == nb - 1 ? d[h].w : cv);
+      }
+      store_digest(tree + N + 8 * m + k, d[h]);
+    }
+    l1[kp] = b3_merge(d[0], d[1]);
+    store_digest(tree + N / 2 + 4 * m + kp, l1[kp]);
+  }
+  Digest a = b3_merge(l1[0], l1[1]), b = b3_merge(l1[2], l1[3]);
+  store_digest(tree + N / 4 + 2 * m, a); store_digest(tree + N / 4 + 2 * m + 1, b);
+  store_digest(tree + N / 8 + m, b3_merge(a, b));
+}
+void launch_commit_rows_wide(cudaStream_t st, const u64* data, size_t limb_stride, u32 num_limbs, u32 ln, Digest* tree) {
+  const size_t n = size_t(1) << ln;
+  commit_rows_wide_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(data, limb_stride, num_limbs, ln, tree);
+  XFG_LAUNCHED(1);
+}
+
 // level of M nodes at [M, 2M) -> levels M/2, M/4, M/8; one thread per 8 children
 __global__ void __launch_bounds__(128) tree_reduce8_kernel(Digest* __restrict__ tree, size_t M) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -12,6 +12,8 @@ namespace xfg {
 // hashes the 8 rows of each m and the 3 tree levels above them.  tree has 2*8n digests.
 // leaf hashing + 3 levels only (levels N .. N/8); merkle_commit_rows = this + merkle_build_upper(tree, n)
 void launch_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree);
+// rows of up to 128 limbs (one BLAKE3 chunk), streamed block by block; same outputs as launch_commit_rows
+void launch_commit_rows_wide(cudaStream_t st, const u64* data, size_t limb_stride, u32 num_limbs, u32 ln, Digest* tree);
 void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree);
 // Completes the tree above a fully written level of M nodes (heap range [M, 2M)).
 void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M);

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(NttPass p) {
       u64 go = (u64)k * p.out_row_stride + col0 + c;
       if (p.scale != 1) v = gl_mul(v, p.scale);
       if (post.lo) v = gl_mul(v, pow_lookup(post, go));
-      dst[go] = v;
+      if (p.peer_log) p.peer[go >> p.peer_log][(size_t)tr * (u64(1) << p.peer_log) + (go & ((u64(1) << p.peer_log) - 1))] = v;   // row owner = m / n_local
+      else dst[go] = v;
     }
   }
 }
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(1024) ntt_pass_r16(NttPass p) {
       const u64 go = (u64)k * p.out_row_stride + col0 + c;
       if (p.scale != 1) v = gl_mul(v, p.scale); else v = w_canon(v);
       if (post.lo) v = gl_mul(v, pow_lookup(post, go));
-      dst[go] = v;
+      if (p.peer_log) p.peer[go >> p.peer_log][(size_t)tr * (u64(1) << p.peer_log) + (go & ((u64(1) << p.peer_log) - 1))] = v;   // fused all-to-all: store to the row owner
+      else dst[go] = v;
     }
   }
 }
@@ -235,6 +237,7 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
     p.src = job.src; p.dst = job.dst; p.Llog = ln; p.Tlog = 0; p.in_row_stride = 1; p.out_row_stride = 1;
     p.store_transposed = 0; p.scale = job.scale;
     p.post_lo = job.post_lo; p.post_hi = job.post_hi; p.post_hi_stride = job.post_hi_stride;
+    p.peer_log = job.peer_log; for (int i = 0; i < NTT_MAX_PEERS; i++) p.peer[i] = job.peer[i];
     ntt_pass<<<dim3(1, job.batch), NTT_THREADS, ntt_pass_smem(ln, 0), st>>>(p); XFG_LAUNCHED(1);
     return;
   }
@@ -253,6 +256,7 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   p.pre_lo = nullptr; p.pre_hi = nullptr;
   p.Llog = l1; p.in_row_stride = u64(1) << l2; p.out_row_stride = u64(1) << l2; p.store_transposed = 0; p.scale = job.scale;
   p.post_lo = job.post_lo; p.post_hi = job.post_hi; p.post_hi_stride = job.post_hi_stride;
+  p.peer_log = job.peer_log; for (int i = 0; i < NTT_MAX_PEERS; i++) p.peer[i] = job.peer[i];
   if (fast) { p.Tlog = r16_tlog(l1); launch_r16(st, p, job.inverse, (1u << l2) >> p.Tlog, job.batch); }
   else { ntt_pass<<<dim3((1u << l2) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l1, Tlog), st>>>(p); XFG_LAUNCHED(1); }
 }

@@ -7,7 +7,8 @@ namespace xfg {
 
 static constexpr int NTT_THREADS = 256;
 static constexpr u32 NTT_TW_LOG = 12;          // twiddle table holds w_4096^i, i < 2048
-static constexpr u32 NTT_SINGLE_MAX_LOG = 11;  // transforms up to 2^11 points run as one shared-memory pass
+static constexpr u32 NTT_SINGLE_MAX_LOG = 11;
+static constexpr int NTT_MAX_PEERS = 8;       // one 8-GPU box  // transforms up to 2^11 points run as one shared-memory pass
 
 struct NttPass {
   const u64* src; u64* dst;
@@ -21,6 +22,9 @@ struct NttPass {
   const u64* post_lo; const u64* post_hi; u32 post_hi_stride; u32 post_div;
   u64 scale;
   u32 num_radix, radix_logs;   // ntt_pass_r16: Stockham pass radices, 4 bits each (log2), first pass in the low nibble
+  // fused all-to-all (config 5): when peer_log != 0 the last store of output element m of transform t goes to
+  // peer[m >> peer_log][t * 2^peer_log + (m mod 2^peer_log)] (peer pointers may be NVLink-mapped memory of other GPUs)
+  u64* peer[NTT_MAX_PEERS]; u32 peer_log;
 };
 
 // device tables owned by a plan (one per trace length)
@@ -39,6 +43,7 @@ struct NttJob {
   const u64* pre_lo; const u64* pre_hi; u32 pre_hi_stride;
   // if post_lo != null, output element j is multiplied by base_c^j, c = t % post_div
   const u64* post_lo; const u64* post_hi; u32 post_hi_stride; u32 post_div;
+  u64* peer[NTT_MAX_PEERS]; u32 peer_log;   // see NttPass
 };
 
 void ntt_init();

@@ -592,3 +592,4 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn, uint64_t mint, 
 }  // extern "C"
 
 #include "stage_api.inc"
+#include "wide.inc"
