@@ -190,8 +190,10 @@ def main():
     ap.add_argument("--n-log2", type=int, default=20)
     ap.add_argument("--ext", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="latency", choices=["latency", "batch"],
-                    help="latency: the headline (one 2^n proof per step); batch: BASELINE config 4, 1024 independent 2^16 proofs sharded over the GPUs")
+    ap.add_argument("--workload", default="latency", choices=["latency", "batch", "wide"],
+                    help="latency: the headline (one 2^n proof per step); batch: BASELINE config 4, 1024 independent 2^16 proofs sharded over "
+                         "the GPUs; wide: BASELINE config 5, one 64-column x 2^24-row trace, column-sharded LDE with the all-to-all fused into the "
+                         "last NTT pass, then row hashing (needs --gpus >= 2 for a real exchange)")
     ap.add_argument("--batch-total", type=int, default=1024)
     ap.add_argument("--slots", type=int, default=4)
     args = ap.parse_args()
@@ -201,13 +203,17 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.workload == "wide":
+        import wide_worker
+        wide_worker.run(args.n_log2 if args.n_log2 != 20 else 24, 64, steps=max(1, args.steps))
+        return
 
     import numpy as np
     import torch
     import xfg_stark_b200 as xs
     from xfg_stark_b200 import multi
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line
+    os.environ["NCCL_DEBUG"] = os.environ.get("XFG_NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line
     torch.cuda.set_device(local)
     multi.init("nccl", torch.device("cuda", local))
     if args.workload == "batch":

@@ -32,6 +32,55 @@ multi.finalize()
 '''
 
 
+WIDE_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import orc
+from xfg_stark_b200 import multi
+rank, world, _ = multi.rank_world()
+multi.init("gloo")
+W, n_log2 = 8, 8
+n = 1 << n_log2; N = 8 * n; wl = W // world; n_local = n // world
+rng = np.random.default_rng(99)                       # every rank builds the same wide trace and keeps only its columns
+trace = rng.integers(0, 1 << 63, size=(W, n), dtype=np.uint64) %% np.uint64(orc.P)
+mine = trace[rank * wl:(rank + 1) * wl]
+# column-sharded interpolation + LDE (oracle stands in for the CUDA kernels), coset-major [col][k][m]
+lde = np.stack([orc.lde(orc.ntt(c, 1, 1)).reshape(n, 8).T for c in mine])           # (wl, 8, n)
+# all-to-all: destination r gets m in [r*n_local, (r+1)*n_local) of my columns
+send = np.ascontiguousarray(np.stack([lde[:, :, r * n_local:(r + 1) * n_local] for r in range(world)]))   # (world, wl, 8, n_local)
+recv = np.empty_like(send)
+dist.all_to_all_single(torch.from_numpy(recv.view(np.int64)), torch.from_numpy(send.view(np.int64)))
+rows = recv.reshape(world * wl, 8, n_local)          # [global column][k][m_local]: source rank s contributed columns s*wl..
+# rows i = 8 m + k of my range, all W columns -> leaves -> subtree root
+mat = rows.transpose(0, 2, 1).reshape(W, 8 * n_local)                                  # natural row order within my range
+leaves = orc.hash_rows(mat)
+root, _ = orc.merkle(leaves)
+r = torch.frombuffer(bytearray(root), dtype=torch.uint8)
+roots = [torch.empty_like(r) for _ in range(world)]
+dist.all_gather(roots, r)
+final, _ = orc.merkle(torch.stack(roots).numpy())
+# single-process answer
+full = np.stack([orc.lde(orc.ntt(c, 1, 1)) for c in trace])
+exp, _ = orc.merkle(orc.hash_rows(full))
+print(json.dumps({"rank": rank, "ok": final == exp}))
+multi.finalize()
+'''
+
+
+def test_wide_trace_sharding_logic_world_size_2(tmp_path):
+    """config 5 dataflow (column-sharded LDE -> all-to-all by row ranges -> row hashing -> all-gather of subtree roots) on gloo,
+    with the oracle standing in for the kernels: the sharded commitment equals the single-process one."""
+    script = tmp_path / "wide.py"
+    script.write_text(WIDE_WORKER % (ROOT, ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    recs = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(recs) == 2 and all(r["ok"] for r in recs)
+
+
 def free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 

@@ -18,7 +18,7 @@ def run(n_log2, W, steps=1, check=False, seed=1234):
     import torch.distributed as dist
     import xfg_stark_b200 as xs
     from xfg_stark_b200 import multi
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ["NCCL_DEBUG"] = os.environ.get("XFG_NCCL_DEBUG", "WARN")
     rank, world, local = multi.rank_world()
     torch.cuda.set_device(local)
     multi.init("nccl", torch.device("cuda", local))
