@@ -45,7 +45,13 @@ XFG_HD u64 gl_mul(u64 a, u64 b) {
 }
 XFG_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
 XFG_HD u64 gl_pow(u64 b, u64 e) { u64 r = 1; while (e) { if (e & 1) r = gl_mul(r, b); b = gl_mul(b, b); e >>= 1; } return r; }
-XFG_HD u64 gl_sqr_n(u64 a, int n) { for (int i = 0; i < n; i++) a = gl_sqr(a); return a; }
+XFG_HD u64 gl_sqr_n(u64 a, int n) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1   // keep the 64 squarings of an inversion out of the instruction stream (the callers are I-cache bound otherwise)
+#endif
+  for (int i = 0; i < n; i++) a = gl_sqr(a);
+  return a;
+}
 // a^(p-2), p - 2 = (2^31 - 1) * 2^33 + (2^32 - 1); 0 -> 0
 XFG_HD u64 gl_inv(u64 x) {
   u64 t2 = gl_mul(gl_sqr(x), x), t3 = gl_mul(gl_sqr(t2), x);

@@ -30,24 +30,24 @@ template <int K> __device__ __forceinline__ void batch_inv(u64 (&v)[K]) {
 //   H(x) = T(x) (x - g^(n-1)) / (x^n - 1) + B0(x) / (x - 1) + B1(x) / (x - g^(n-1))      (A.8)
 // out: [limb][k'][m], k' < 2
 // ------------------------------------------------------------------------------------------------------------------
-static constexpr int CE_PTS = 4;
+static constexpr int CE_PTS = 4, CE_THREADS = 128;
+// The loops over the CE_PTS points are NOT unrolled and the per-point intermediates live in shared memory ([point][word][thread],
+// conflict-free): the fully unrolled version was 160 KB of SASS and stalled on instruction fetch (ncu: no_instruction).
 template <int D>
-__global__ void __launch_bounds__(256) constraint_kernel(const u64* __restrict__ lde, u32 ln, AirParams air, const ProofState* __restrict__ ps,
-                                                          PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out) {
+__global__ void __launch_bounds__(CE_THREADS) constraint_kernel(const u64* __restrict__ lde, u32 ln, AirParams air, const ProofState* __restrict__ ps,
+                                                                 PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out) {
+  __shared__ u64 sh[CE_PTS][2 * D + 2][CE_THREADS];      // per point: u (D), w (D), d, prefix
+  __shared__ u64 sc[(XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS) * 2];
   const size_t n = size_t(1) << ln, N = 8 * n;
-  const u32 kp = blockIdx.y, k = kp * 4;
-  const size_t per = n / CE_PTS, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 kp = blockIdx.y, k = kp * 4, tid = threadIdx.x;
+  const size_t per = n / CE_PTS, t = (size_t)blockIdx.x * blockDim.x + tid;
+  if (tid < (XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS) * 2) sc[tid] = (&ps->tcoef[0][0])[tid];   // tcoef[7][2] then bcoef[8][2], contiguous
+  __syncthreads();
   if (t >= per) return;
   const u64 sk = kp ? s_k1 : s_k0, zinv = kp ? zinv1 : zinv0;
-  Ext<D> tc[XFG_NUM_TRANSITION], bc[XFG_NUM_ASSERTIONS];
-#pragma unroll
-  for (int j = 0; j < XFG_NUM_TRANSITION; j++) tc[j] = ld_ext<D>(ps->tcoef, j);
-#pragma unroll
-  for (int j = 0; j < XFG_NUM_ASSERTIONS; j++) bc[j] = ld_ext<D>(ps->bcoef, j);
   const u64 large_burn = gl_mul(XFG_STD_BURN, 1000);
-
-  Ext<D> tsum[CE_PTS], b0[CE_PTS], b1[CE_PTS]; u64 xs[CE_PTS], den[2 * CE_PTS];
-#pragma unroll
+  u64 acc = 1;
+#pragma unroll 1
   for (int q = 0; q < CE_PTS; q++) {
     const size_t m = t + q * per, mn = (m + 1) & (n - 1);
     u64 c[XFG_TRACE_WIDTH];
@@ -65,29 +65,36 @@ __global__ void __launch_bounds__(256) constraint_kernel(const u64* __restrict__
     r[6] = gl_sub(c[6], air.commitment);
     Ext<D> ts, bs;
 #pragma unroll
-    for (int j = 0; j < XFG_NUM_TRANSITION; j++) ts = ts + mul_base(tc[j], r[j]);
+    for (int j = 0; j < XFG_NUM_TRANSITION; j++) ts = ts + mul_base(Ext<D>(sc[2 * j], sc[2 * j + 1]), r[j]);
     // src/burn_mint_air.rs:383-394 in Winterfell's sorted order: step-0 columns 0..6, then (column 4, step n-1)
 #pragma unroll
-    for (int j = 0; j < XFG_TRACE_WIDTH; j++) bs = bs + mul_base(bc[j], gl_sub(c[j], air.assert0[j]));
-    tsum[q] = ts; b0[q] = bs; b1[q] = mul_base(bc[XFG_TRACE_WIDTH], gl_sub(c[4], XFG_FINAL_STATE));
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) bs = bs + mul_base(Ext<D>(sc[2 * (XFG_NUM_TRANSITION + j)], sc[2 * (XFG_NUM_TRANSITION + j) + 1]), gl_sub(c[j], air.assert0[j]));
+    const Ext<D> b1 = mul_base(Ext<D>(sc[2 * (XFG_NUM_TRANSITION + XFG_TRACE_WIDTH)], sc[2 * (XFG_NUM_TRANSITION + XFG_TRACE_WIDTH) + 1]), gl_sub(c[4], XFG_FINAL_STATE));
     const u64 x = gl_mul(sk, pow_lookup(wn, m));
-    xs[q] = x; den[2 * q] = gl_sub(x, 1); den[2 * q + 1] = gl_sub(x, air.g_last);
+    const u64 xm1 = gl_sub(x, 1), xml = gl_sub(x, air.g_last);
+    //   H = T (x - g_last) / (x^n - 1)  +  [ B0 (x - g_last) + B1 (x - 1) ] / [ (x - 1)(x - g_last) ]
+    const Ext<D> u = mul_base(ts, gl_mul(xml, zinv)), w = mul_base(bs, xml) + mul_base(b1, xm1);
+    const u64 dd = gl_mul(xm1, xml);
+#pragma unroll
+    for (int l = 0; l < D; l++) { sh[q][l][tid] = u.limb(l); sh[q][D + l][tid] = w.limb(l); }
+    sh[q][2 * D][tid] = dd; sh[q][2 * D + 1][tid] = acc;
+    acc = gl_mul(acc, dd);
   }
-  batch_inv<2 * CE_PTS>(den);
-#pragma unroll
-  for (int q = 0; q < CE_PTS; q++) {
+  acc = gl_inv(acc);
+#pragma unroll 1
+  for (int q = CE_PTS - 1; q >= 0; q--) {
     const size_t m = t + q * per;
-    Ext<D> h = mul_base(tsum[q], gl_mul(gl_sub(xs[q], air.g_last), zinv)) + mul_base(b0[q], den[2 * q]) + mul_base(b1[q], den[2 * q + 1]);
+    const u64 dinv = gl_mul(sh[q][2 * D + 1][tid], acc); acc = gl_mul(acc, sh[q][2 * D][tid]);
 #pragma unroll
-    for (int l = 0; l < D; l++) out[(size_t)l * 2 * n + (size_t)kp * n + m] = h.limb(l);
+    for (int l = 0; l < D; l++) out[(size_t)l * 2 * n + (size_t)kp * n + m] = gl_add(sh[q][l][tid], gl_mul(sh[q][D + l][tid], dinv));
   }
 }
 
 void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams& air, const ProofState* ps, PowTable wn,
                         u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out) {
-  const size_t per = (size_t(1) << ln) / CE_PTS; dim3 grid((unsigned)((per + 255) / 256), 2);
-  if (D == 1) constraint_kernel<1><<<grid, 256, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
-  else constraint_kernel<2><<<grid, 256, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
+  const size_t per = (size_t(1) << ln) / CE_PTS; dim3 grid((unsigned)((per + CE_THREADS - 1) / CE_THREADS), 2);
+  if (D == 1) constraint_kernel<1><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
+  else constraint_kernel<2><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
   XFG_LAUNCHED(1);
 }
 
@@ -156,48 +163,63 @@ void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef
 // Thread (k, a) computes the 8 points m = a + j*n/8 - exactly the 8 elements of row 8a + k of the first FRI layer - with one
 // batched inversion, writes them coset-major and hashes the row into the layer-0 FRI tree.
 // ------------------------------------------------------------------------------------------------------------------
+static constexpr int DEEP_THREADS = 128;
+// Loops over the 8 points are rolled and the per-point intermediates (numerator, x, norm, prefix product) are staged in shared
+// memory [point][word][thread]; the unrolled version was 277 KB of SASS, 136 registers, and stalled on instruction fetch.
 template <int D>
-__global__ void __launch_bounds__(128) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
-                                                    PowTable wn, const u64* __restrict__ s_k, u64* __restrict__ deep, Digest* __restrict__ fri_tree0) {
+__global__ void __launch_bounds__(DEEP_THREADS) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
+                                                             PowTable wn, const u64* __restrict__ s_k, u64 w8, u64* __restrict__ deep, Digest* __restrict__ fri_tree0) {
+  __shared__ u64 sh[8][D + 3][DEEP_THREADS];          // per point: numerator -> result (D), x, norm, prefix
+  __shared__ u64 sc[2 * (XFG_TRACE_WIDTH + 1) + 8];   // dcoef[8][2], then c1, c2, z, zg
   const size_t n = size_t(1) << ln, N = 8 * n, n8 = n / 8;
-  const u32 k = blockIdx.y; const size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 k = blockIdx.y, tid = threadIdx.x; const size_t a = (size_t)blockIdx.x * blockDim.x + tid;
+  if (tid < 2 * (XFG_TRACE_WIDTH + 1)) sc[tid] = (&ps->dcoef[0][0])[tid];
+  else if (tid < 2 * (XFG_TRACE_WIDTH + 1) + 8) { const u32 i = tid - 2 * (XFG_TRACE_WIDTH + 1); const u64* src = i < 2 ? ps->deep_c1 : i < 4 ? ps->deep_c2 : i < 6 ? ps->z : ps->zg; sc[tid] = src[i & 1]; }
+  __syncthreads();
   if (a >= n8) return;
-  Ext<D> gam[XFG_TRACE_WIDTH];
-#pragma unroll
-  for (int j = 0; j < XFG_TRACE_WIDTH; j++) gam[j] = ld_ext<D>(ps->dcoef, j);
-  const Ext<D> delta = ld_ext<D>(ps->dcoef, XFG_TRACE_WIDTH), c1 = ld_ext1<D>(ps->deep_c1), c2 = ld_ext1<D>(ps->deep_c2);
-  const Ext<D> z = ld_ext1<D>(ps->z), zg = ld_ext1<D>(ps->zg);
-  const u64 sk = s_k[k];
-  Ext<D> num[8], den[8]; u64 nrm[8];
-#pragma unroll
+  const u64* cc = sc + 2 * (XFG_TRACE_WIDTH + 1);
+  const Ext<D> delta(sc[2 * XFG_TRACE_WIDTH], sc[2 * XFG_TRACE_WIDTH + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]), z(cc[4], cc[5]), zg(cc[6], cc[7]);
+  u64 x = gl_mul(s_k[k], pow_lookup(wn, a)), acc = 1;      // x_j = x_0 * w_8^j  (m = a + j n/8)
+#pragma unroll 1
   for (int j = 0; j < 8; j++) {
-    const size_t m = a + (size_t)j * n8, idx = (size_t)k * n + m;
+    const size_t idx = (size_t)k * n + a + (size_t)j * n8;
     Ext<D> st;
 #pragma unroll
-    for (int c = 0; c < XFG_TRACE_WIDTH; c++) st = st + mul_base(gam[c], lde[(size_t)c * N + idx]);
+    for (int c = 0; c < XFG_TRACE_WIDTH; c++) st = st + mul_base(Ext<D>(sc[2 * c], sc[2 * c + 1]), lde[(size_t)c * N + idx]);
     Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + idx]);
-    const u64 x = gl_mul(sk, pow_lookup(wn, m));
-    // x - z, x - zg as extension elements (x is a base element)
-    Ext<D> xz = Ext<D>(x) - z, xzg = Ext<D>(x) - zg;
-    num[j] = (st + delta * h - c1) * xzg + (st - c2) * xz;
-    den[j] = xz * xzg; nrm[j] = ext_norm(den[j]);
-  }
-  batch_inv<8>(nrm);
-  u64 row[8 * D];
+    const Ext<D> xz = Ext<D>(x) - z, xzg = Ext<D>(x) - zg;
+    const Ext<D> num = (st + delta * h - c1) * xzg + (st - c2) * xz;
+    const u64 nrm = ext_norm(xz * xzg);
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const size_t m = a + (size_t)j * n8, idx = (size_t)k * n + m;
-    Ext<D> v = num[j] * ext_inv_with_norm_inv(den[j], nrm[j]);
-#pragma unroll
-    for (int l = 0; l < D; l++) { deep[(size_t)l * N + idx] = v.limb(l); row[j * D + l] = v.limb(l); }
+    for (int l = 0; l < D; l++) sh[j][l][tid] = num.limb(l);
+    sh[j][D][tid] = x; sh[j][D + 1][tid] = nrm; sh[j][D + 2][tid] = acc;
+    acc = gl_mul(acc, nrm); x = gl_mul(x, w8);
   }
-  if (fri_tree0) store_digest(fri_tree0 + n + 8 * a + k, b3_hash_limbs<8 * D>(row));
+  acc = gl_inv(acc);
+#pragma unroll 1
+  for (int j = 7; j >= 0; j--) {
+    const size_t idx = (size_t)k * n + a + (size_t)j * n8;
+    const u64 ninv = gl_mul(sh[j][D + 2][tid], acc); acc = gl_mul(acc, sh[j][D + 1][tid]);
+    const u64 xj = sh[j][D][tid];
+    const Ext<D> den = (Ext<D>(xj) - z) * (Ext<D>(xj) - zg);
+    Ext<D> num; for (int l = 0; l < D; l++) num.set_limb(l, sh[j][l][tid]);
+    const Ext<D> v = num * ext_inv_with_norm_inv(den, ninv);
+#pragma unroll
+    for (int l = 0; l < D; l++) { deep[(size_t)l * N + idx] = v.limb(l); sh[j][l][tid] = v.limb(l); }
+  }
+  if (fri_tree0) {
+    u64 row[8 * D];
+#pragma unroll
+    for (int j = 0; j < 8; j++) for (int l = 0; l < D; l++) row[j * D + l] = sh[j][l][tid];
+    store_digest(fri_tree0 + n + 8 * a + k, b3_hash_limbs<8 * D>(row));
+  }
 }
 void launch_deep(cudaStream_t st, int D, const u64* lde, const u64* hlde, u32 ln, const ProofState* ps, PowTable wn, const u64* s_k,
                  u64* deep, Digest* fri_tree0) {
-  const size_t n8 = (size_t(1) << ln) / 8; dim3 grid((unsigned)((n8 + 127) / 128), 8);
-  if (D == 1) deep_kernel<1><<<grid, 128, 0, st>>>(lde, hlde, ln, ps, wn, s_k, deep, fri_tree0);
-  else deep_kernel<2><<<grid, 128, 0, st>>>(lde, hlde, ln, ps, wn, s_k, deep, fri_tree0);
+  const size_t n8 = (size_t(1) << ln) / 8; dim3 grid((unsigned)((n8 + DEEP_THREADS - 1) / DEEP_THREADS), 8);
+  const u64 w8 = gl_root_of_unity(3);
+  if (D == 1) deep_kernel<1><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, wn, s_k, w8, deep, fri_tree0);
+  else deep_kernel<2><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, wn, s_k, w8, deep, fri_tree0);
   XFG_LAUNCHED(1);
 }
 
@@ -240,8 +262,8 @@ __global__ void __launch_bounds__(128) fri_fold_kernel(const u64* __restrict__ s
   if (src_coset && Rn >= 8) ip = ((tix % (Rn / 8)) << 3) | (tix / (Rn / 8));   // i' = 8a' + k with a' fastest: coalesced coset-major reads
   const Ext<D> alpha = ld_ext<D>(ps->alphas, layer);
   const size_t nrows0 = Nl / 8;   // coset stride n when src is the layer-0 coset-major array (Nl = 8n)
-  u64 row[8 * D];
-#pragma unroll
+  __shared__ u64 sh[8 * D][128];  // the 8 folded values of this thread = one row of the next layer (rolled loop: the unrolled kernel was 300 KB of SASS)
+#pragma unroll 1
   for (int q = 0; q < 8; q++) {
     const size_t r = ip + (size_t)q * Rn;
     Ext<D> v[8];
@@ -255,9 +277,14 @@ __global__ void __launch_bounds__(128) fri_fold_kernel(const u64* __restrict__ s
     const u64 xinv = gl_mul(fc.inv7, pow_lookup(wN_inv, (u64)r << (lN - lNl)));
     Ext<D> w = fold8<D>(v, fc, mul_base(alpha, xinv));
 #pragma unroll
-    for (int l = 0; l < D; l++) { dst[(size_t)l * dst_limb_stride + r] = w.limb(l); row[q * D + l] = w.limb(l); }
+    for (int l = 0; l < D; l++) { dst[(size_t)l * dst_limb_stride + r] = w.limb(l); sh[q * D + l][threadIdx.x] = w.limb(l); }
   }
-  if (next_tree) store_digest(next_tree + Rn + ip, b3_hash_limbs<8 * D>(row));
+  if (next_tree) {
+    u64 row[8 * D];
+#pragma unroll
+    for (int i = 0; i < 8 * D; i++) row[i] = sh[i][threadIdx.x];
+    store_digest(next_tree + Rn + ip, b3_hash_limbs<8 * D>(row));
+  }
 }
 void launch_fri_fold(cudaStream_t st, int D, const u64* src, size_t src_limb_stride, int src_coset, u32 lNl, u32 layer, const ProofState* ps,
                      PowTable wN_inv, u32 lN, const FriConsts& fc, u64* dst, size_t dst_limb_stride, Digest* next_tree) {
