@@ -76,6 +76,24 @@ __device__ __forceinline__ u64 w_mul(u64 a, u64 b) {
   return w_reduce128(lo, hi);
 }
 
+// Dot-product accumulator: sum of up to 2^32 full 128-bit products kept un-reduced in 160 bits (lo, hi, top) and reduced once:
+//   lo + hi*2^64 + top*2^128 = reduce128(lo, hi) - top*2^32   (2^128 = -2^32 mod p)
+// One term costs the 4 IMAD.WIDE of the product + 5 carry-chain additions instead of a full multiply-reduce-add (~46 instr).
+struct DotAcc {
+  u64 lo, hi; u32 top;
+  __device__ __forceinline__ DotAcc() : lo(0), hi(0), top(0) {}
+  __device__ __forceinline__ void fma(u64 a, u64 b) {      // operands may be weak
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    const u64 ll = (u64)a0 * b0;
+    const u64 t1 = (u64)a0 * b1 + (ll >> 32);
+    const u64 t2 = (u64)a1 * b0 + (u32)t1;
+    const u64 ph = (u64)a1 * b1 + (t1 >> 32) + (t2 >> 32);
+    const u64 pl = (t2 << 32) | (u32)ll;
+    asm("{\n\t add.cc.u64 %0, %0, %3;\n\t addc.cc.u64 %1, %1, %4;\n\t addc.u32 %2, %2, 0;\n\t}" : "+l"(lo), "+l"(hi), "+r"(top) : "l"(pl), "l"(ph));
+  }
+  __device__ __forceinline__ u64 result() const { return w_canon(w_sub_hi32(w_reduce128(lo, hi), top)); }   // canonical
+};
+
 // x * 2^S for a compile-time S in [0, 96), x weak -> weak.  With S = 32q + t and y = x << t = y2*2^64 + y1*2^32 + y0 (y2 < 2^t):
 //   q = 0:  (y1:y0) + y2*2^32 - y2
 //   q = 1:  (y0:0)  + y1*2^32 - y1 - y2                 (2^96 = -1)

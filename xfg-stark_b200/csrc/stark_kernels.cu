@@ -63,12 +63,16 @@ __global__ void __launch_bounds__(CE_THREADS) constraint_kernel(const u64* __res
     const u64 d = gl_sub(nxt4, c[4]); r[4] = gl_mul(d, gl_sub(d, 1));
     r[5] = gl_sub(c[5], air.nullifier);
     r[6] = gl_sub(c[6], air.commitment);
-    Ext<D> ts, bs;
+    // random linear combinations as un-reduced dot products (DotAcc), one reduction per limb
+    DotAcc ta[D], ba[D];
 #pragma unroll
-    for (int j = 0; j < XFG_NUM_TRANSITION; j++) ts = ts + mul_base(Ext<D>(sc[2 * j], sc[2 * j + 1]), r[j]);
+    for (int j = 0; j < XFG_NUM_TRANSITION; j++) for (int l = 0; l < D; l++) ta[l].fma(sc[2 * j + l], r[j]);
     // src/burn_mint_air.rs:383-394 in Winterfell's sorted order: step-0 columns 0..6, then (column 4, step n-1)
 #pragma unroll
-    for (int j = 0; j < XFG_TRACE_WIDTH; j++) bs = bs + mul_base(Ext<D>(sc[2 * (XFG_NUM_TRANSITION + j)], sc[2 * (XFG_NUM_TRANSITION + j) + 1]), gl_sub(c[j], air.assert0[j]));
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) { const u64 dj = gl_sub(c[j], air.assert0[j]); for (int l = 0; l < D; l++) ba[l].fma(sc[2 * (XFG_NUM_TRANSITION + j) + l], dj); }
+    Ext<D> ts, bs;
+#pragma unroll
+    for (int l = 0; l < D; l++) { ts.set_limb(l, ta[l].result()); bs.set_limb(l, ba[l].result()); }
     const Ext<D> b1 = mul_base(Ext<D>(sc[2 * (XFG_NUM_TRANSITION + XFG_TRACE_WIDTH)], sc[2 * (XFG_NUM_TRANSITION + XFG_TRACE_WIDTH) + 1]), gl_sub(c[4], XFG_FINAL_STATE));
     const u64 x = gl_mul(sk, pow_lookup(wn, m));
     const u64 xm1 = gl_sub(x, 1), xml = gl_sub(x, air.g_last);
@@ -127,28 +131,45 @@ template <int D>
 __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln,
                                                    const ProofState* __restrict__ ps, u64* __restrict__ partial) {
   const size_t n = size_t(1) << ln;
-  const u32 poly = blockIdx.y, nb = gridDim.x;
-  const size_t TOT = (size_t)nb * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 poly = blockIdx.y, nb = gridDim.x, tid = threadIdx.x;
+  const size_t TOT = (size_t)nb * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + tid;
   const u64* c = poly < XFG_TRACE_WIDTH ? trace_coef + (size_t)poly * n : h_coef + (size_t)(poly - XFG_TRACE_WIDTH) * n;
-  Ext<D> pt[2] = {ld_ext1<D>(ps->z), ld_ext1<D>(ps->zg)}, acc[2];
+  // powers of the two evaluation points shared by the block: sq[w][b] = pt_w^(2^b), b < 32 (one lane per (w, b) chain would be
+  // serial anyway: thread w squares 31 times), then every thread assembles pt^t and pt^TOT from the set bits of t / TOT
+  __shared__ u64 sq[2][32][2];
+  if (tid < 2) {
+    Ext<D> x = ld_ext1<D>(tid == 0 ? ps->z : ps->zg);
+    for (int b = 0; b < 32; b++) { sq[tid][b][0] = x.limb(0); sq[tid][b][1] = D == 2 ? x.limb(1) : 0; x = x * x; }
+  }
+  __syncthreads();
+  auto pw = [&](int w, size_t e) { Ext<D> r(1); for (int b = 0; b < 32; b++) if ((e >> b) & 1) r = r * Ext<D>(sq[w][b][0], sq[w][b][1]); return r; };
+  // table of (pt^TOT)^i, i < n/TOT, so that a thread's share  sum_i c[t + i TOT] pt^(i TOT)  is a plain dot product of base-field
+  // coefficients with table limbs: accumulated un-reduced (DotAcc), 4 cheap fma per coefficient instead of 2 extension Horner steps
+  __shared__ u64 tab[OOD_MAX_STEPS][2][2];
+  const size_t steps = n > TOT ? n / TOT : 1;
+  for (size_t i = tid; i < steps; i += blockDim.x) for (int w = 0; w < 2; w++) { const Ext<D> v = pw(w, i * TOT); tab[i][w][0] = v.limb(0); tab[i][w][1] = D == 2 ? v.limb(1) : 0; }
+  __syncthreads();
+  Ext<D> acc[2];
   if (t < n) {
+    DotAcc d[2][D];
+    for (size_t i = 0; i < steps; i++) {
+      const u64 cv = c[t + i * TOT];
 #pragma unroll
-    for (int w = 0; w < 2; w++) {
-      Ext<D> step = ext_pow<D>(pt[w], TOT), a;
-      for (size_t i = (n - 1 - t) / TOT + 1; i-- > 0;) a = add_base(a * step, c[t + i * TOT]);
-      acc[w] = a * ext_pow<D>(pt[w], t);
+      for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) d[w][l].fma(cv, tab[i][w][l]);
     }
+#pragma unroll 1
+    for (int w = 0; w < 2; w++) { Ext<D> a; for (int l = 0; l < D; l++) a.set_limb(l, d[w][l].result()); acc[w] = a * pw(w, t); }
   }
   __shared__ u64 red[256][2][2];
-  for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) red[threadIdx.x][w][l] = l < D ? acc[w].limb(l) : 0;
+  for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) red[tid][w][l] = l < D ? acc[w].limb(l) : 0;
   __syncthreads();
   for (u32 s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) red[threadIdx.x][w][l] = gl_add(red[threadIdx.x][w][l], red[threadIdx.x + s][w][l]);
+    if (tid < s) for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) red[tid][w][l] = gl_add(red[tid][w][l], red[tid + s][w][l]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) partial[(((size_t)poly * nb + blockIdx.x) * 2 + w) * 2 + l] = red[0][w][l];
+  if (tid == 0) for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) partial[(((size_t)poly * nb + blockIdx.x) * 2 + w) * 2 + l] = red[0][w][l];
 }
-u32 ood_num_blocks(u32 ln) { size_t n = size_t(1) << ln; size_t b = n / 256; if (b < 1) b = 1; if (b > OOD_MAX_BLOCKS) b = OOD_MAX_BLOCKS; return (u32)b; }
+u32 ood_num_blocks(u32 ln) { size_t n = size_t(1) << ln; size_t b = n / 256; if (b < 1) b = 1; if (b > OOD_MAX_BLOCKS) b = OOD_MAX_BLOCKS; return (u32)b; }   // 64 x 256 threads per polynomial: Horner chains of n / 16384 steps
 void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, const ProofState* ps, u64* partial) {
   dim3 grid(ood_num_blocks(ln), XFG_TRACE_WIDTH + D);
   if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, ps, partial);
@@ -183,9 +204,10 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_kernel(const u64* __restric
 #pragma unroll 1
   for (int j = 0; j < 8; j++) {
     const size_t idx = (size_t)k * n + a + (size_t)j * n8;
-    Ext<D> st;
+    DotAcc sa[D];     // S_T = sum_c gamma_c T_c(x): un-reduced dot product, one reduction per limb
 #pragma unroll
-    for (int c = 0; c < XFG_TRACE_WIDTH; c++) st = st + mul_base(Ext<D>(sc[2 * c], sc[2 * c + 1]), lde[(size_t)c * N + idx]);
+    for (int c = 0; c < XFG_TRACE_WIDTH; c++) { const u64 tv = lde[(size_t)c * N + idx]; for (int l = 0; l < D; l++) sa[l].fma(sc[2 * c + l], tv); }
+    Ext<D> st; for (int l = 0; l < D; l++) st.set_limb(l, sa[l].result());
     Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + idx]);
     const Ext<D> xz = Ext<D>(x) - z, xzg = Ext<D>(x) - zg;
     const Ext<D> num = (st + delta * h - c1) * xzg + (st - c2) * xz;
@@ -332,6 +354,7 @@ __global__ void field_selftest_kernel(u32 op, const u64* __restrict__ a, const u
     case 6: r = gl_inv(x); break;
     case 7: r = w_canon(w_add_hi32(x, (u32)y)); break;
     case 8: r = w_canon(w_sub_hi32(x, (u32)y)); break;
+    case 9: { DotAcc d; for (int i = 0; i < 37; i++) d.fma(x, y); d.fma(y, y); r = d.result(); } break;      // 37 x*y + y*y, any u64 operands
     default:
       pow2_case<0>(op, x, r) || pow2_case<1>(op, x, r) || pow2_case<12>(op, x, r) || pow2_case<24>(op, x, r) || pow2_case<31>(op, x, r) ||
       pow2_case<32>(op, x, r) || pow2_case<33>(op, x, r) || pow2_case<36>(op, x, r) || pow2_case<48>(op, x, r) || pow2_case<60>(op, x, r) ||

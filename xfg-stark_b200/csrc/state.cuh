@@ -12,6 +12,7 @@ static constexpr int MAX_Q = XFG_MAX_QUERIES;          // 255
 static constexpr int MAX_LAYERS = XFG_MAX_FRI_LAYERS;  // 16
 static constexpr int MAX_REMAINDER = 256;              // (fri_remainder_max_degree + 1) <= 256 coefficients
 static constexpr int OOD_MAX_BLOCKS = 64;
+static constexpr int OOD_MAX_STEPS = 1024;             // n / (OOD_MAX_BLOCKS * 256) at n = 2^24
 static constexpr int NUM_OOD_POLYS = XFG_TRACE_WIDTH + 2;   // 7 trace polys + up to 2 limb polys of H
 
 enum : u32 { ERR_FLAG_DEGREE = 1u, ERR_FLAG_COIN = 2u, ERR_FLAG_NONCANONICAL = 4u };
