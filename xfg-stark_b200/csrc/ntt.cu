@@ -26,9 +26,12 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(NttPass p) {
   u64* S = smem;                   // S[row * TP + col]
   u64* TW = smem + (size_t)L * TP; // w_L^i, i < L/2
   const u32 tid = threadIdx.x, tile = blockIdx.x, tr = blockIdx.y;
-  const u64* src = p.src + (size_t)(tr / p.src_div) * p.src_tstride;
-  u64* dst = p.dst + (size_t)tr * p.dst_tstride;
-  const u32 coset = tr % p.src_div;
+  // transform tr = (group, sub): group selects the source polynomial, sub the coset.  coset_map (4 bits per entry, 0 = identity)
+  // lets a job compute a subset of the cosets: table / output slot of sub is map[sub], the output has dst_cosets slots per group
+  const u32 grp = tr / p.src_div, sub = tr % p.src_div;
+  const u32 coset = p.coset_map ? (u32)((p.coset_map >> (4 * sub)) & 15) : sub;
+  u64* dst = p.dst + (p.coset_map ? (size_t)grp * p.dst_cosets + coset : (size_t)tr) * p.dst_tstride;
+  const u64* src = p.src_is_dst ? dst : p.src + (size_t)grp * p.src_tstride;
 
   for (u32 i = tid; i < L / 2; i += NTT_THREADS) TW[i] = p.tw[(size_t)i << (NTT_TW_LOG - p.Llog)];
 
@@ -147,9 +150,12 @@ __global__ void __launch_bounds__(1024) ntt_pass_r16(NttPass p) {
   const u32 L = 1u << p.Llog, T = 1u << p.Tlog, TP = T + 1, nthreads = blockDim.x;
   u64* S = smem; u64* TW = smem + (size_t)L * TP;   // TW[i] = w_L^(+-i), full circle
   const u32 tid = threadIdx.x, tile = blockIdx.x, tr = blockIdx.y;
-  const u64* src = p.src + (size_t)(tr / p.src_div) * p.src_tstride;
-  u64* dst = p.dst + (size_t)tr * p.dst_tstride;
-  const u32 coset = tr % p.src_div;
+  // transform tr = (group, sub): group selects the source polynomial, sub the coset.  coset_map (4 bits per entry, 0 = identity)
+  // lets a job compute a subset of the cosets: table / output slot of sub is map[sub], the output has dst_cosets slots per group
+  const u32 grp = tr / p.src_div, sub = tr % p.src_div;
+  const u32 coset = p.coset_map ? (u32)((p.coset_map >> (4 * sub)) & 15) : sub;
+  u64* dst = p.dst + (p.coset_map ? (size_t)grp * p.dst_cosets + coset : (size_t)tr) * p.dst_tstride;
+  const u64* src = p.src_is_dst ? dst : p.src + (size_t)grp * p.src_tstride;
   for (u32 i = tid; i < L; i += nthreads) {
     const u32 h = i & (L / 2 - 1); const u64 t = p.tw[(size_t)h << (NTT_TW_LOG - p.Llog)];
     TW[i] = i < L / 2 ? t : gl_neg(t);
@@ -233,6 +239,7 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   p.src_tstride = job.src_tstride; p.dst_tstride = job.dst_tstride;
   p.pre_lo = job.pre_lo; p.pre_hi = job.pre_hi; p.pre_hi_stride = job.pre_hi_stride;
   p.post_div = job.post_div ? job.post_div : 1;
+  p.coset_map = job.coset_map; p.dst_cosets = job.dst_cosets;
   if (ln <= NTT_SINGLE_MAX_LOG) {
     p.src = job.src; p.dst = job.dst; p.Llog = ln; p.Tlog = 0; p.in_row_stride = 1; p.out_row_stride = 1;
     p.store_transposed = 0; p.scale = job.scale;
@@ -252,7 +259,7 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   if (fast) { p.Tlog = r16_tlog(l2); launch_r16(st, p, job.inverse, (1u << l1) >> p.Tlog, job.batch); }
   else { ntt_pass<<<dim3((1u << l1) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l2, Tlog), st>>>(p); XFG_LAUNCHED(1); }
   // pass B (in place on dst)
-  p.src = job.dst; p.dst = job.dst; p.src_div = 1; p.src_tstride = job.dst_tstride;
+  p.src = job.dst; p.dst = job.dst; p.src_is_dst = 1;                      // pass B: in place on the slot pass A wrote
   p.pre_lo = nullptr; p.pre_hi = nullptr;
   p.Llog = l1; p.in_row_stride = u64(1) << l2; p.out_row_stride = u64(1) << l2; p.store_transposed = 0; p.scale = job.scale;
   p.post_lo = job.post_lo; p.post_hi = job.post_hi; p.post_hi_stride = job.post_hi_stride;

@@ -25,6 +25,7 @@ struct NttPass {
   // fused all-to-all (config 5): when peer_log != 0 the last store of output element m of transform t goes to
   // peer[m >> peer_log][t * 2^peer_log + (m mod 2^peer_log)] (peer pointers may be NVLink-mapped memory of other GPUs)
   u64* peer[NTT_MAX_PEERS]; u32 peer_log;
+  u32 coset_map, dst_cosets, src_is_dst;
 };
 
 // device tables owned by a plan (one per trace length)
@@ -44,6 +45,7 @@ struct NttJob {
   // if post_lo != null, output element j is multiplied by base_c^j, c = t % post_div
   const u64* post_lo; const u64* post_hi; u32 post_hi_stride; u32 post_div;
   u64* peer[NTT_MAX_PEERS]; u32 peer_log;   // see NttPass
+  u32 coset_map, dst_cosets;                // optional subset of cosets, see ntt_pass
 };
 
 void ntt_init();
