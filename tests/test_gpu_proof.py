@@ -108,6 +108,35 @@ def test_invalid_trace_is_rejected(ctx):
     assert ctx.prove(trace, air) == orc.prove(*orc.synthetic_case(256, 2))   # the context stays usable
 
 
+def test_output_buffer_too_small_and_empty_batch(ctx):
+    import ctypes as C
+    import xfg_stark_b200 as xs
+    air, trace = gpu_case(xs, 0, 6)
+    lib = xs.load_library()
+    out = C.create_string_buffer(100); ln = C.c_size_t(0); o = xs.ProofOptions()._c()
+    rc = lib.xfg_prove_burn_mint(ctx._h, trace.ctypes.data_as(C.c_void_p), 6, C.byref(air), C.byref(o), out, len(out), C.byref(ln), None)
+    assert rc == 6 and ln.value == len(ctx.prove(trace, air))          # XFG_ERR_BUFFER_TOO_SMALL, *out_len = required size
+    rc = lib.xfg_prove_burn_mint(ctx._h, None, 6, C.byref(air), C.byref(o), out, len(out), C.byref(ln), None)
+    assert rc == 1                                                      # XFG_ERR_BAD_ARGS
+    proofs, _ = ctx.prove_batch([], [])
+    assert proofs == []
+
+
+def test_stage_times_and_profile(ctx):
+    import xfg_stark_b200 as xs
+    air, trace = gpu_case(xs, 3, 12)
+    ctx.set_profiling(True)
+    proof, times = ctx.prove(trace, air, want_times=True)
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    assert set(xs.STAGE_NAMES) <= set(times) and all(times[k] >= 0 for k in xs.STAGE_NAMES)
+    names = [p[0] for p in prof]
+    for fam in ("ntt.lde_trace", "commit_rows.trace", "constraints", "deep", "fri.fold", "transcript", "gather"):
+        assert fam in names
+    assert sum(p[2] for p in prof) == times["kernel_launches"]
+    assert times["h2d_bytes"] >= 7 * 4096 * 8 and times["d2h_bytes"] > 0
+
+
 def test_option_errors(ctx):
     import xfg_stark_b200 as xs
     air, trace = gpu_case(xs, 0, 6)

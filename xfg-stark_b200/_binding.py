@@ -213,6 +213,8 @@ class Context:
     def prove_batch(self, traces, airs, options=ProofOptions(), out_stride=1 << 17):
         """traces: list of (7, n) uint64 arrays; airs: list of AirConsts.  Returns (list of proof bytes, device wall ms)."""
         cnt = len(traces)
+        if cnt == 0:
+            return [], 0.0
         ts = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
         n_log2 = ts[0].shape[1].bit_length() - 1
         ptrs = (C.c_void_p * cnt)(*[t.ctypes.data for t in ts])

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(1024) ntt_pass_r16(NttPass p) {
 }
 
 static size_t r16_smem(u32 Llog, u32 Tlog) { const size_t L = size_t(1) << Llog, TP = (size_t(1) << Tlog) + 1; return (L * TP + L) * sizeof(u64); }
-static u32 r16_tlog(u32 Llog) { return Llog >= 12 ? 2 : 13 - Llog; }                       // 8192 elements per CTA (16384 at 2^12)
+static u32 r16_tlog(u32 Llog) { return Llog >= 10 ? 2 : 12 - Llog; }                       // 4096 elements per CTA (more with 2^11, 2^12-point tiles): 4+ CTAs per SM
 static void r16_radices(u32 Llog, u32& count, u32& packed) {                               // 8:(4,4) 9:(4,3,2) 10:(4,4,2) 11:(4,4,3) 12:(4,4,4)
   static const u32 tbl[5][3] = {{4, 4, 0}, {4, 3, 2}, {4, 4, 2}, {4, 4, 3}, {4, 4, 4}};
   const u32* r = tbl[Llog - 8]; count = r[2] ? 3 : 2; packed = r[0] | (r[1] << 4) | (r[2] << 8);
