@@ -117,9 +117,9 @@ template <int LOGR, bool INV, int STAGE> struct DftStep<LOGR, INV, STAGE, (1 << 
 };
 template <int LOGR, bool INV> struct DftStep<LOGR, INV, LOGR, 0> { static __device__ __forceinline__ void run(u64 (&)[1 << LOGR]) {} };
 
-template <int LOGR, bool INV>
+template <int LOGR, bool INV, int EPT>
 __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __restrict__ TW, u32 Llog, u32 Tlog, u32 TP, u32 ns_log, u32 tid, u32 nthreads) {
-  constexpr int R = 1 << LOGR, ITEMS = 16 / R;
+  constexpr int R = 1 << LOGR, ITEMS = EPT / R;
   const u32 Tm = (1u << Tlog) - 1, stride = 1u << (Llog - LOGR), nsm = (1u << ns_log) - 1, tsh = Llog - ns_log - LOGR;
   u64 v[ITEMS][R];
 #pragma unroll
@@ -144,8 +144,8 @@ __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __
   __syncthreads();
 }
 
-template <bool INV>
-__global__ void __launch_bounds__(1024) ntt_pass_r16(NttPass p) {
+template <bool INV, int EPT>
+__global__ void __launch_bounds__(EPT == 16 ? 1024 : 256) ntt_pass_r16(NttPass p) {
   extern __shared__ u64 smem[];
   const u32 L = 1u << p.Llog, T = 1u << p.Tlog, TP = T + 1, nthreads = blockDim.x;
   u64* S = smem; u64* TW = smem + (size_t)L * TP;   // TW[i] = w_L^(+-i), full circle
@@ -173,9 +173,10 @@ __global__ void __launch_bounds__(1024) ntt_pass_r16(NttPass p) {
   u32 ns_log = 0;
   for (u32 ps = 0; ps < p.num_radix; ps++) {
     const u32 lr = (p.radix_logs >> (4 * ps)) & 15;
-    if (lr == 4) stockham_pass<4, INV>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
-    else if (lr == 3) stockham_pass<3, INV>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
-    else stockham_pass<2, INV>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+    if (EPT >= 32 && lr == 5) stockham_pass<(EPT >= 32 ? 5 : 4), INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+    else if (lr == 4) stockham_pass<4, INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+    else if (lr == 3) stockham_pass<3, INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+    else stockham_pass<2, INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
     ns_log += lr;
   }
   if (p.store_transposed) {
@@ -204,14 +205,20 @@ __global__ void __launch_bounds__(1024) ntt_pass_r16(NttPass p) {
 
 static size_t r16_smem(u32 Llog, u32 Tlog) { const size_t L = size_t(1) << Llog, TP = (size_t(1) << Tlog) + 1; return (L * TP + L) * sizeof(u64); }
 static u32 r16_tlog(u32 Llog) { return Llog >= 10 ? 2 : 12 - Llog; }                       // 4096 elements per CTA (more with 2^11, 2^12-point tiles): 4+ CTAs per SM
-static void r16_radices(u32 Llog, u32& count, u32& packed) {                               // 8:(4,4) 9:(4,3,2) 10:(4,4,2) 11:(4,4,3) 12:(4,4,4)
-  static const u32 tbl[5][3] = {{4, 4, 0}, {4, 3, 2}, {4, 4, 2}, {4, 4, 3}, {4, 4, 4}};
-  const u32* r = tbl[Llog - 8]; count = r[2] ? 3 : 2; packed = r[0] | (r[1] << 4) | (r[2] << 8);
+// Elements per thread: 16.  A 32-element variant (radix-32 passes, 1024 = 32 x 32, one pass fewer) was measured and is slower
+// (136 registers -> 12 warps/SM: LDE of the trace 2.41 ms vs 1.76 ms), so only EPT = 16 is instantiated.
+static int r16_ept() { return 16; }
+static void r16_radices(u32 Llog, u32 ept, u32& count, u32& packed) {
+  // 16 elements per thread: 8:(4,4) 9:(4,3,2) 10:(4,4,2) 11:(4,4,3) 12:(4,4,4);  32 per thread: 8:(5,3) 9:(5,4) 10:(5,5) 11:(4,4,3) 12:(4,4,4)
+  static const u32 t16[5][3] = {{4, 4, 0}, {4, 3, 2}, {4, 4, 2}, {4, 4, 3}, {4, 4, 4}};
+  static const u32 t32[5][3] = {{5, 3, 0}, {5, 4, 0}, {5, 5, 0}, {4, 4, 3}, {4, 4, 4}};
+  const u32* r = (ept == 32 ? t32 : t16)[Llog - 8]; count = r[2] ? 3 : 2; packed = r[0] | (r[1] << 4) | (r[2] << 8);
 }
 static void launch_r16(cudaStream_t st, NttPass p, bool inverse, u32 tiles, u32 batch) {
-  r16_radices(p.Llog, p.num_radix, p.radix_logs);
-  const u32 threads = (1u << (p.Llog + p.Tlog)) / 16; const size_t sm = r16_smem(p.Llog, p.Tlog);
-  if (inverse) ntt_pass_r16<true><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false><<<dim3(tiles, batch), threads, sm, st>>>(p);
+  const u32 ept = r16_ept();
+  r16_radices(p.Llog, ept, p.num_radix, p.radix_logs);
+  const u32 threads = (1u << (p.Llog + p.Tlog)) / ept; const size_t sm = r16_smem(p.Llog, p.Tlog);
+  if (inverse) ntt_pass_r16<true, 16><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false, 16><<<dim3(tiles, batch), threads, sm, st>>>(p);
   XFG_LAUNCHED(1);
 }
 
@@ -224,8 +231,8 @@ void ntt_init() {
   static bool done = false;
   if (done) return;
   cudaFuncSetAttribute(ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_pass_smem(12, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
   done = true;
 }
 
