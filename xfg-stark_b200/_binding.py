@@ -6,7 +6,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libxfgstark.so")
+_SO = os.environ.get("XFG_LIB") or os.path.join(_HERE, "libxfgstark.so")   # XFG_LIB: debug override (A/B builds)
 
 NUM_STAGES = 9
 STAGE_NAMES = ["extend_execution_trace", "compute_execution_trace_commitment", "evaluate_constraints",

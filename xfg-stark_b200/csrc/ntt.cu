@@ -144,8 +144,11 @@ __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __
   __syncthreads();
 }
 
-template <bool INV, int EPT>
-__global__ void __launch_bounds__(EPT == 16 ? 1024 : 256) ntt_pass_r16(NttPass p) {
+#ifndef XFG_R16_MINB
+#define XFG_R16_MINB 2   // 64 registers: measured best (1: 126 regs 2.26 ms, 2: 1.77 ms, 3: 1.84 ms, 4: 1.95 ms for the 2^20 trace LDE)
+#endif
+template <bool INV, int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pass_r16(NttPass p) {
   extern __shared__ u64 smem[];
   const u32 L = 1u << p.Llog, T = 1u << p.Tlog, TP = T + 1, nthreads = blockDim.x;
   u64* S = smem; u64* TW = smem + (size_t)L * TP;   // TW[i] = w_L^(+-i), full circle
@@ -218,7 +221,9 @@ static void launch_r16(cudaStream_t st, NttPass p, bool inverse, u32 tiles, u32 
   const u32 ept = r16_ept();
   r16_radices(p.Llog, ept, p.num_radix, p.radix_logs);
   const u32 threads = (1u << (p.Llog + p.Tlog)) / ept; const size_t sm = r16_smem(p.Llog, p.Tlog);
-  if (inverse) ntt_pass_r16<true, 16><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false, 16><<<dim3(tiles, batch), threads, sm, st>>>(p);
+  // 2^12-point tiles need 1024 threads (64 registers); everything else runs 256-512 threads and may use up to 128 registers
+  if (threads > 512) { if (inverse) ntt_pass_r16<true, 16, 1024><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false, 16, 1024><<<dim3(tiles, batch), threads, sm, st>>>(p); }
+  else { if (inverse) ntt_pass_r16<true, 16, 512><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false, 16, 512><<<dim3(tiles, batch), threads, sm, st>>>(p); }
   XFG_LAUNCHED(1);
 }
 
@@ -231,8 +236,10 @@ void ntt_init() {
   static bool done = false;
   if (done) return;
   cudaFuncSetAttribute(ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_pass_smem(12, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
   done = true;
 }
 
