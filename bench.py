@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--n-log2", type=int, default=20)
     ap.add_argument("--ext", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-preload", action="store_true", help="skip the 0.6 s untimed load loop before the timed region (deterministic launch count for ncu)")
     ap.add_argument("--workload", default="latency", choices=["latency", "batch", "wide"],
                     help="latency: the headline (one 2^n proof per step); batch: BASELINE config 4, 1024 independent 2^16 proofs sharded over "
                          "the GPUs; wide: BASELINE config 5, one 64-column x 2^24-row trace, column-sharded LDE with the all-to-all fused into the "
@@ -250,7 +251,7 @@ def main():
         dev_fn()
     e2e_fn()
     sampler = ClockSampler(local); sampler.start()
-    t_end = time.time() + 0.6
+    t_end = time.time() + (0.0 if args.no_preload else 0.6)
     while time.time() < t_end:            # keep the GPU under the same load until the sampler has a few readings (untimed)
         dev_fn()
     dev_ms, (proof, times) = timed_region(dev_fn, args.steps)

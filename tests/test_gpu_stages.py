@@ -93,6 +93,18 @@ def test_ntt_matches_oracle(ctx, n_log2, inverse):
         assert (got[b] == orc.ntt(data[b], 1, 1 if inverse else 0)).all()
 
 
+@pytest.mark.parametrize("n_log2", [21, 22, 23, 24])
+def test_ntt_largest_tiles_match_oracle(n_log2):
+    """2^21 .. 2^24 points: the 2^11- and 2^12-point register-radix tiles (1024-thread CTAs) used by the wide trace of config 5"""
+    import xfg_stark_b200 as xs
+    rng = np.random.default_rng(n_log2)
+    data = rand_elems(rng, (1, 1 << n_log2))
+    with xs.Context(device=0, max_n_log2=n_log2, num_slots=1) as c:
+        fwd = c.ntt(data)
+        assert (fwd[0] == orc.ntt(data[0], 1, 0)).all()
+        assert (c.ntt(fwd, inverse=True) == data).all()
+
+
 def test_ntt_round_trip_full_size(ctx):
     """size-independent property at the context's largest size: interpolate(evaluate(p)) == p, and linearity."""
     rng = np.random.default_rng(7)
