@@ -84,6 +84,9 @@ const char* xfg_last_error(const xfg_ctx* ctx);
  * non-NULL `times` argument while profiling is on; used by bench.py for the roofline of the dominant kernel.  Replaces
  * nothing in the reference (winter-prover's tracing spans are inert there). */
 int xfg_set_profiling(xfg_ctx* ctx, int on);
+/* Whole-proof CUDA graphs (default on): proofs run without per-stage timing and without split upload replay a graph captured on
+ * first use per (trace length, options, slot), which removes ~50 kernel-launch calls per proof from the host thread. */
+int xfg_set_graphs(xfg_ctx* ctx, int on);
 int xfg_get_profile(xfg_ctx* ctx, uint32_t cap, uint32_t* count, const char** names, float* ms, uint32_t* launches);
 
 /* ---- whole proof: replaces `air.prove(trace)` (src/burn_mint_prover.rs:124, winter_prover::Prover::prove) ---- */

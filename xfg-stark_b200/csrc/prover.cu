@@ -11,6 +11,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <tuple>
 #include <vector>
 #include "../../include/xfg_stark.h"
 #include "burn_mint_host.hpp"
@@ -50,6 +51,10 @@ struct Carve {   // device pointers of one proof, carved from the slot slab for 
   size_t words;
 };
 
+struct GraphKey {
+  const void* plan; const void* trace; int D; u32 q, g;
+  bool operator<(const GraphKey& o) const { return std::tie(plan, trace, D, q, g) < std::tie(o.plan, o.trace, o.D, o.q, o.g); }
+};
 struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 
 struct Slot {
@@ -59,10 +64,12 @@ struct Slot {
   u64* slab = nullptr; size_t slab_words = 0;
   ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
   ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;
+  AirParams* d_air = nullptr; AirParams* h_air = nullptr;
+  std::map<GraphKey, cudaGraphExec_t> graphs;            // whole-proof CUDA graphs, one per (plan, extension, options, trace pointer)
   cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
   // in-flight proof (batch mode)
   bool busy = false; const Plan* plan = nullptr; int D = 1; xfg_options opt{}; u32 proof_index = 0; bool timed = false;
-  GatherTasks tasks{}; size_t mat_words = 0;
+  GatherTasks tasks{}; size_t mat_words = 0; unsigned graph_launches = 0;
   // optional per-kernel-family timing (xfg_set_profiling): events around each launcher call on this slot's stream
   std::vector<cudaEvent_t> pev; std::vector<ProfRec> prof; size_t pev_used = 0;
 };
@@ -77,7 +84,7 @@ struct xfg_ctx {
   u64 *tw_fwd = nullptr, *tw_inv = nullptr;
   std::map<u64, Plan> plans;
   std::string last_error;
-  bool profiling = false;
+  bool profiling = false, graphs = true;
   std::vector<std::string> prof_names; std::vector<float> prof_ms; std::vector<unsigned> prof_launches;   // last profiled proof
 };
 
@@ -211,7 +218,16 @@ size_t build_gather(const Plan& p, int D, const xfg_options& o, const Carve& c, 
 }
 
 // ---- enqueue the whole proof on the slot's stream (no host synchronisation) ----
-int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const xfg_air_consts& air, const u64* d_trace, bool timed) {
+void prepare_inputs(Slot& s, const Plan& p, const xfg_options& o, const xfg_air_consts& air) {
+  seed_elements(p.ln, o, air, s.h_seed);
+  AirParams& ap = *s.h_air;
+  ap.txn = air.txn_hash; ap.rcpt = air.recipient_hash; ap.nullifier = air.nullifier; ap.commitment = air.commitment;
+  ap.assert0[0] = air.pub_inputs[XFG_PI_BURN]; ap.assert0[1] = air.pub_inputs[XFG_PI_MINT]; ap.assert0[2] = air.pub_inputs[XFG_PI_TXN_HASH];
+  ap.assert0[3] = air.pub_inputs[XFG_PI_RECIPIENT_HASH]; ap.assert0[4] = 0; ap.assert0[5] = air.nullifier; ap.assert0[6] = air.commitment;
+  ap.g_last = p.g_last;
+}
+
+int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const u64* d_trace, bool timed) {
   Carve c; carve(s, p, D, c);
   if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length");
   cudaStream_t st = s.st; const u32 ln = p.ln; const size_t n = p.n, N = p.N;
@@ -227,8 +243,10 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   auto prof_end = [&]() { if (!profiling) return; ProfRec& r = s.prof.back(); cudaEventRecord(s.pev[r.e1], st); r.launches = g_xfg_launches - r.launches; };
 #define PROF(name, ...) do { prof_begin(name); __VA_ARGS__; prof_end(); } while (0)
 
-  seed_elements(ln, o, air, s.h_seed);
+  // per-proof inputs (coin seed elements, AIR constants) were written to pinned memory by prepare_inputs(); copying them here keeps
+  // the whole launch sequence replayable as a CUDA graph
   CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (8 + XFG_NUM_PUB_INPUTS) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(s.d_air, s.h_air, sizeof(AirParams), cudaMemcpyHostToDevice, st));
   mark();   // ev0: start of device work
   PROF("transcript", launch_seed(st, s.d_state, s.d_seed, 8 + XFG_NUM_PUB_INPUTS));
   // 1 ---- extend_execution_trace: interpolate the 7 columns, evaluate on the 8 cosets s_k * <w_n>
@@ -249,11 +267,7 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   PROF("transcript", launch_trace_root(st, D, s.d_state, c.trace_tree));
   mark();
   // 2 ---- evaluate_constraints
-  { AirParams ap; ap.txn = air.txn_hash; ap.rcpt = air.recipient_hash; ap.nullifier = air.nullifier; ap.commitment = air.commitment;
-    ap.assert0[0] = air.pub_inputs[XFG_PI_BURN]; ap.assert0[1] = air.pub_inputs[XFG_PI_MINT]; ap.assert0[2] = air.pub_inputs[XFG_PI_TXN_HASH];
-    ap.assert0[3] = air.pub_inputs[XFG_PI_RECIPIENT_HASH]; ap.assert0[4] = 0; ap.assert0[5] = air.nullifier; ap.assert0[6] = air.commitment;
-    ap.g_last = p.g_last;
-    PROF("constraints", launch_constraints(st, D, c.lde, ln, ap, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals)); }
+  PROF("constraints", launch_constraints(st, D, c.lde, ln, s.d_air, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals));
   mark();
   // 3 ---- commit_to_constraint_evaluations: coset interpolation (2 cosets of size n), composition column, LDE, commitment
   { NttJob j{}; j.src = c.ce_evals; j.dst = c.ce_tmp; j.ln = ln; j.batch = 2 * D; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
@@ -307,6 +321,36 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   CU(cudaGetLastError());
 #undef PROF
   s.busy = true; s.plan = &p; s.D = D; s.opt = o; s.timed = timed;
+  return XFG_OK;
+}
+
+// Runs the proof's launch sequence: as a cached CUDA graph (captured on first use per plan / extension / options / trace pointer)
+// when no per-stage timing is requested and the upload is not split, otherwise launch by launch.
+int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const xfg_air_consts& air, const u64* d_trace, bool timed) {
+  prepare_inputs(s, p, o, air);
+  const bool use_graph = ctx->graphs && !timed && !ctx->profiling && !(s.split_upload && !d_trace);
+  if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);
+  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor};
+  auto it = s.graphs.find(key);
+  if (it == s.graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
+    const unsigned before = g_xfg_launches;
+    const int rc = enqueue_proof(ctx, s, p, D, o, d_trace, false);
+    const cudaError_t ce = cudaStreamEndCapture(s.st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { ctx->last_error = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return XFG_ERR_CUDA; }
+    cudaGraphExec_t exec = nullptr;
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = s.graphs.emplace(key, exec).first;
+    s.graph_launches = g_xfg_launches - before;
+  } else {
+    Carve c; carve(s, p, D, c); s.mat_words = build_gather(p, D, o, c, s.tasks);
+    g_xfg_launches += s.graph_launches;
+    s.busy = true; s.plan = &p; s.D = D; s.opt = o; s.timed = false; s.prof.clear();
+  }
+  CU(cudaGraphLaunch(it->second, s.st));
   return XFG_OK;
 }
 
@@ -447,7 +491,7 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
   if (times) { std::memset(times, 0, sizeof *times); cudaEventRecord(s.ev[XFG_NUM_STAGES + 2], s.st); }
   s.split_upload = false;
   if (h_trace && (rc = upload_trace(ctx, s, *p, D, h_trace, true))) return rc;
-  if ((rc = enqueue_proof(ctx, s, *p, D, *o, *air, d_trace, times != nullptr))) return rc;
+  if ((rc = launch_proof(ctx, s, *p, D, *o, *air, d_trace, times != nullptr))) return rc;
   rc = finish_proof(ctx, s, out, cap, out_len, times);
   if (times) {
     cudaEventElapsedTime(&times->h2d_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[0]);
@@ -504,6 +548,7 @@ int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** ou
     CUB(cudaMalloc(&s.d_partial, (size_t)NUM_OOD_POLYS * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
     CUB(cudaMallocHost(&s.h_state, sizeof(ProofState))); CUB(cudaMallocHost(&s.h_material, MATERIAL_WORDS * 8));
     CUB(cudaMallocHost(&s.h_seed, 64 * 8)); CUB(cudaMallocHost(&s.h_trace, trace_words * 8));
+    CUB(cudaMalloc(&s.d_air, sizeof(AirParams))); CUB(cudaMallocHost(&s.h_air, sizeof(AirParams)));
     for (auto& e : s.ev) CUB(cudaEventCreate(&e));
   }
 #undef CUB
@@ -517,6 +562,8 @@ void xfg_destroy(xfg_ctx* ctx) {
     if (s.st) cudaStreamSynchronize(s.st);
     cudaFree(s.slab); cudaFree(s.d_state); cudaFree(s.d_seed); cudaFree(s.d_partial); cudaFree(s.d_material);
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
+    cudaFree(s.d_air); cudaFreeHost(s.h_air);
+    for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
     for (auto& e : s.col_ev) if (e) cudaEventDestroy(e);
@@ -528,6 +575,7 @@ void xfg_destroy(xfg_ctx* ctx) {
   delete ctx;
 }
 
+int xfg_set_graphs(xfg_ctx* ctx, int on) { if (!ctx) return XFG_ERR_BAD_ARGS; ctx->graphs = on != 0; return XFG_OK; }
 int xfg_set_profiling(xfg_ctx* ctx, int on) { if (!ctx) return XFG_ERR_BAD_ARGS; ctx->profiling = on != 0; return XFG_OK; }
 int xfg_get_profile(xfg_ctx* ctx, uint32_t cap, uint32_t* count, const char** names, float* ms, uint32_t* launches) {
   if (!ctx || !count) return XFG_ERR_BAD_ARGS;
@@ -565,7 +613,7 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
     if (!traces[i]) return fail(ctx, XFG_ERR_BAD_ARGS, "null trace");
     if ((rc = upload_trace(ctx, s, *p, D, traces[i], false))) return rc;
     s.proof_index = i;
-    if ((rc = enqueue_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) return rc;
+    if ((rc = launch_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) return rc;
   }
   for (Slot& s : ctx->slots) if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
   if (total_ms) { CU(cudaDeviceSynchronize()); CU(cudaEventRecord(e1, ctx->slots[0].st)); CU(cudaEventSynchronize(e1)); cudaEventElapsedTime(total_ms, e0, e1); }

@@ -34,10 +34,11 @@ static constexpr int CE_PTS = 4, CE_THREADS = 128;
 // The loops over the CE_PTS points are NOT unrolled and the per-point intermediates live in shared memory ([point][word][thread],
 // conflict-free): the fully unrolled version was 160 KB of SASS and stalled on instruction fetch (ncu: no_instruction).
 template <int D>
-__global__ void __launch_bounds__(CE_THREADS) constraint_kernel(const u64* __restrict__ lde, u32 ln, AirParams air, const ProofState* __restrict__ ps,
+__global__ void __launch_bounds__(CE_THREADS) constraint_kernel(const u64* __restrict__ lde, u32 ln, const AirParams* __restrict__ airp, const ProofState* __restrict__ ps,
                                                                  PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out) {
   __shared__ u64 sh[CE_PTS][2 * D + 2][CE_THREADS];      // per point: u (D), w (D), d, prefix
   __shared__ u64 sc[(XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS) * 2];
+  const AirParams air = *airp;                            // AIR constants live in device memory so that the launch is CUDA-graph replayable
   const size_t n = size_t(1) << ln, N = 8 * n;
   const u32 kp = blockIdx.y, k = kp * 4, tid = threadIdx.x;
   const size_t per = n / CE_PTS, t = (size_t)blockIdx.x * blockDim.x + tid;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(CE_THREADS) constraint_kernel(const u64* __res
   }
 }
 
-void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams& air, const ProofState* ps, PowTable wn,
+void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams* air, const ProofState* ps, PowTable wn,
                         u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out) {
   const size_t per = (size_t(1) << ln) / CE_PTS; dim3 grid((unsigned)((per + CE_THREADS - 1) / CE_THREADS), 2);
   if (D == 1) constraint_kernel<1><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);

@@ -6,7 +6,7 @@
 namespace xfg {
 
 struct FriConsts { u64 w8i[4]; u64 inv8; u64 inv7; };   // w_8^-1 powers 0..3, 8^-1, 7^-1
-void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams& air, const ProofState* ps, PowTable wn,
+void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams* d_air, const ProofState* ps, PowTable wn,
                         u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out);
 void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64* h, ProofState* ps);
 u32 ood_num_blocks(u32 ln);
