@@ -333,6 +333,7 @@ int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options&
   const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor};
   auto it = s.graphs.find(key);
   if (it == s.graphs.end()) {
+    if (s.graphs.size() >= 16) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second); s.graphs.clear(); }   // bounded cache (callers that keep changing the device trace pointer)
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
     const unsigned before = g_xfg_launches;
