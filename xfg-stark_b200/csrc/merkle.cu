@@ -92,38 +92,21 @@ __global__ void __launch_bounds__(128) tree_reduce8_kernel(Digest* __restrict__ 
   store_digest(tree + M / 8 + t, b3_merge(a, b));
 }
 
-// one CTA finishes the tree from a level of M <= 2048 nodes up to the root
+// one CTA finishes the tree from a level of M <= 2048 nodes up to the root.  Every level is written to the heap (authentication
+// paths need all nodes) but the next level reads its children from shared memory (ping-pong buffers), so a level costs one
+// compression latency + a barrier instead of a global-memory round trip; the last levels run inside one warp.
 __global__ void __launch_bounds__(1024) tree_top_kernel(Digest* __restrict__ tree, u32 M) {
+  __shared__ Digest bufA[1024], bufB[512];
+  Digest* out = bufA; Digest* in = nullptr;
   for (u32 lvl = M / 2; lvl >= 1; lvl >>= 1) {
     for (u32 i = threadIdx.x; i < lvl; i += blockDim.x) {
-      Digest x = load_digest(tree + 2 * (lvl + i)), y = load_digest(tree + 2 * (lvl + i) + 1);
-      store_digest(tree + lvl + i, b3_merge(x, y));
+      const Digest x = in ? in[2 * i] : load_digest(tree + 2 * (lvl + i)), y = in ? in[2 * i + 1] : load_digest(tree + 2 * (lvl + i) + 1);
+      const Digest d = b3_merge(x, y);
+      out[i] = d; store_digest(tree + lvl + i, d);
     }
-    __syncthreads();
+    if (lvl > 16) __syncthreads(); else __syncwarp();     // levels of <= 16 nodes are produced and consumed by warp 0 only
+    in = out; out = (out == bufA) ? bufB : bufA;
   }
-}
-
-// hash_elements of row-major rows (stage entry point xfg_hash_rows; the pipeline hashes rows inside its fused kernels)
-template <int NL>
-__global__ void __launch_bounds__(128) hash_rows_kernel(const u64* __restrict__ rows, size_t count, Digest* __restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  u64 limbs[NL];
-#pragma unroll
-  for (int j = 0; j < NL; j++) limbs[j] = rows[i * NL + j];
-  store_digest(out + i, b3_hash_limbs<NL>(limbs));
-}
-void launch_hash_rows(cudaStream_t st, const u64* rows, size_t count, int limbs, Digest* out) {
-  const unsigned blocks = (unsigned)((count + 127) / 128);
-  switch (limbs) {
-    case 1: hash_rows_kernel<1><<<blocks, 128, 0, st>>>(rows, count, out); break;
-    case 2: hash_rows_kernel<2><<<blocks, 128, 0, st>>>(rows, count, out); break;
-    case 7: hash_rows_kernel<7><<<blocks, 128, 0, st>>>(rows, count, out); break;
-    case 8: hash_rows_kernel<8><<<blocks, 128, 0, st>>>(rows, count, out); break;
-    case 16: hash_rows_kernel<16><<<blocks, 128, 0, st>>>(rows, count, out); break;
-    default: return;
-  }
-  XFG_LAUNCHED(1);
 }
 
 void launch_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree) {
