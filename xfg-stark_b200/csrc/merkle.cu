@@ -109,6 +109,29 @@ __global__ void __launch_bounds__(1024) tree_top_kernel(Digest* __restrict__ tre
   }
 }
 
+// hash_elements of row-major rows (stage entry point xfg_hash_rows; the pipeline hashes rows inside its fused kernels)
+template <int NL>
+__global__ void __launch_bounds__(128) hash_rows_kernel(const u64* __restrict__ rows, size_t count, Digest* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 limbs[NL];
+#pragma unroll
+  for (int j = 0; j < NL; j++) limbs[j] = rows[i * NL + j];
+  store_digest(out + i, b3_hash_limbs<NL>(limbs));
+}
+void launch_hash_rows(cudaStream_t st, const u64* rows, size_t count, int limbs, Digest* out) {
+  const unsigned blocks = (unsigned)((count + 127) / 128);
+  switch (limbs) {
+    case 1: hash_rows_kernel<1><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 2: hash_rows_kernel<2><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 7: hash_rows_kernel<7><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 8: hash_rows_kernel<8><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    case 16: hash_rows_kernel<16><<<blocks, 128, 0, st>>>(rows, count, out); break;
+    default: return;
+  }
+  XFG_LAUNCHED(1);
+}
+
 void launch_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree) {
   const size_t n = size_t(1) << ln; const unsigned blocks = (unsigned)((n + 127) / 128);
   switch (num_limbs) {
