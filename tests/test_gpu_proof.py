@@ -149,3 +149,27 @@ def test_option_errors(ctx):
     with pytest.raises(xs.XfgError) as e:
         ctx.prove(big, air)
     assert e.value.code == 9
+
+
+def test_random_cases_equal_oracle(ctx):
+    """seeded sweep over trace lengths, extensions, query counts, grinding factors, remainder degrees and input sets"""
+    import random
+    import xfg_stark_b200 as xs
+    rng = random.Random(20261018)
+    for case in range(24):
+        n_log2 = rng.choice([3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+        opts_t = (rng.randrange(1, min(255, (8 << n_log2) - 1) + 1), 8, rng.randrange(0, 13), rng.choice([1, 2]), 8, rng.choice([7, 15, 31, 63, 127]))
+        index = rng.randrange(1 << 20)
+        air, trace = gpu_case(xs, index, n_log2)
+        tr, pi, ac = orc.synthetic_case(1 << n_log2, index)
+        try:
+            expect = orc.prove(tr, pi, ac, opts_t)
+        except RuntimeError:
+            continue
+        try:
+            proof = ctx.prove(trace, air, xs.ProofOptions(*opts_t))
+        except xs.XfgError as e:
+            assert e.code == 3, (case, n_log2, opts_t, e)       # only "unsupported options" may differ from the oracle's coverage
+            continue
+        assert proof == expect, (case, n_log2, opts_t)
+        assert orc.verify(proof, pi, ac, opts_t) == ""

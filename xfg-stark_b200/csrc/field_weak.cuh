@@ -76,6 +76,12 @@ __device__ __forceinline__ u64 w_mul(u64 a, u64 b) {
   return w_reduce128(lo, hi);
 }
 
+// two-level power table lookup with a weak result (see pow_lookup in field.cuh)
+__device__ __forceinline__ u64 w_pow_lookup(const PowTable& t, u64 e) {
+  const u64 l = t.lo[e & (POW_LO - 1)], h = e >> POW_LO_BITS;
+  return h ? w_mul(l, t.hi[h]) : l;
+}
+
 // Dot-product accumulator: sum of up to 2^32 full 128-bit products kept un-reduced in 160 bits (lo, hi, top) and reduced once:
 //   lo + hi*2^64 + top*2^128 = reduce128(lo, hi) - top*2^32   (2^128 = -2^32 mod p)
 // One term costs the 4 IMAD.WIDE of the product + 5 carry-chain additions instead of a full multiply-reduce-add (~46 instr).

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
     const u32 c = e & (T - 1), r = e >> p.Tlog;
     const u64 gi = (u64)r * p.in_row_stride + col0 + c;
     u64 v = src[gi];
-    if (pre.lo) v = gl_mul(v, pow_lookup(pre, gi));
+    if (pre.lo) v = w_mul(v, w_pow_lookup(pre, gi));      // weak product: the butterflies accept any u64 residue
     S[r * TP + c] = v;
   }
   __syncthreads();
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
       const u32 k = e & (L - 1), c = e >> p.Llog;
       u64 v = S[k * TP + c];
       const u64 ex = (col0 + c) * (u64)k;
-      v = ex ? gl_mul(v, pow_lookup(it, ex)) : w_canon(v);
+      v = w_canon(ex ? w_mul(v, w_pow_lookup(it, ex)) : v);
       dst[(col0 + c) * (u64)L + k] = v;
     }
   } else {
