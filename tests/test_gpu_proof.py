@@ -173,3 +173,16 @@ def test_random_cases_equal_oracle(ctx):
             continue
         assert proof == expect, (case, n_log2, opts_t)
         assert orc.verify(proof, pi, ac, opts_t) == ""
+
+
+def test_two_contexts_two_devices_one_process():
+    """distinct contexts are independent (include/xfg_stark.h): one process driving two GPUs gets the same bytes from both"""
+    import torch
+    import xfg_stark_b200 as xs
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    air, trace = gpu_case(xs, 5, 16)
+    with xs.Context(device=0, max_n_log2=16) as c0, xs.Context(device=1, max_n_log2=16) as c1:
+        p0 = c0.prove(trace, air); p1 = c1.prove(trace, air); p0b = c0.prove(trace, air)
+    assert p0 == p1 == p0b
+    assert p0 == orc.prove(*orc.synthetic_case(1 << 16, 5))

@@ -232,9 +232,10 @@ size_t ntt_pass_smem(u32 Llog, u32 Tlog) {
   return (L * TP + L / 2) * sizeof(u64);
 }
 
-void ntt_init() {
-  static bool done = false;
-  if (done) return;
+// Opt-in dynamic shared memory sizes are per device: called by every xfg_create for its own device (and lazily by ntt_batch).
+void ntt_init(bool force) {
+  static thread_local bool done = false;
+  if (done && !force) return;
   cudaFuncSetAttribute(ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_pass_smem(12, 2));
   cudaFuncSetAttribute(ntt_pass_r16<false, 16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
   cudaFuncSetAttribute(ntt_pass_r16<true, 16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
@@ -245,7 +246,7 @@ void ntt_init() {
 
 // Enqueue a batch of `batch` length-2^ln transforms.  src != dst is required when ln > NTT_SINGLE_MAX_LOG.
 void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
-  ntt_init();
+  ntt_init(false);
   const u32 ln = job.ln;
   NttPass p{};
   p.tw = job.inverse ? tb.tw_inv : tb.tw_fwd;

@@ -48,7 +48,7 @@ struct NttJob {
   u32 coset_map, dst_cosets;                // optional subset of cosets, see ntt_pass
 };
 
-void ntt_init();
+void ntt_init(bool force);
 void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job);
 
 }  // namespace xfg
