@@ -147,12 +147,54 @@ void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, in
   merkle_build_upper(st, tree, size_t(1) << ln);
 }
 
+// Fused upper tree for 2048 < M <= 2^20: CTA b reduces the 1024 nodes [M + 1024 b, M + 1024 (b+1)) to the node M/1024 + b through
+// shared memory (10 levels, every level also written to the heap); the last CTA to finish (ticket counter kept in the unused
+// heap slot 0, zeroed by the caller) then reduces the M/1024 subtree roots to the root.  One launch instead of 3-4.
+__device__ __forceinline__ void smem_tree_levels(Digest* __restrict__ tree, size_t first_parent_level, size_t offset, u32 count, Digest* bufA, Digest* bufB) {
+  // reduces `count` (power of two, <= 2048) nodes at heap indices [2*(first_parent_level + offset) ...) ; parents of level size L live at L + offset_L
+  Digest* out = bufA; Digest* in = nullptr;
+  size_t lvl = first_parent_level, off = offset;
+  for (u32 c = count / 2; c >= 1; c >>= 1, lvl >>= 1, off >>= 1) {
+    for (u32 i = threadIdx.x; i < c; i += blockDim.x) {
+      const size_t node = lvl + off + i;
+      const Digest x = in ? in[2 * i] : load_digest(tree + 2 * node), y = in ? in[2 * i + 1] : load_digest(tree + 2 * node + 1);
+      const Digest d = b3_merge(x, y);
+      out[i] = d; store_digest(tree + node, d);
+    }
+    if (c > 16) __syncthreads(); else __syncwarp();
+    in = out; out = (out == bufA) ? bufB : bufA;
+  }
+}
+__global__ void __launch_bounds__(512) tree_upper_fused_kernel(Digest* __restrict__ tree, size_t M) {
+  __shared__ Digest bufA[512], bufB[256];
+  __shared__ bool is_last;
+  smem_tree_levels(tree, M / 2, (size_t)blockIdx.x * 512, 1024, bufA, bufB);     // -> node M/1024 + blockIdx.x
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(tree);
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (is_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const u32 roots = (u32)(M / 1024);                                              // <= 1024
+  smem_tree_levels(tree, roots / 2, 0, roots, bufA, bufB);
+}
+
 void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M) {
-  while (M > 2048) {
+  // big levels: 8 -> 1 per thread (every lane busy for 7 compressions); from 2^17 nodes down: one fused launch
+  while (M > (size_t(1) << 17)) {
     const size_t t = M / 8;
     tree_reduce8_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>(tree, M);
     XFG_LAUNCHED(1);
     M /= 8;
+  }
+  if (M > 2048) {
+    cudaMemsetAsync(tree, 0, sizeof(unsigned), st);
+    tree_upper_fused_kernel<<<(unsigned)(M / 1024), 512, 0, st>>>(tree, M); XFG_LAUNCHED(1);
+    return;
   }
   if (M >= 2) { tree_top_kernel<<<1, 1024, 0, st>>>(tree, (u32)M); XFG_LAUNCHED(1); }
 }
