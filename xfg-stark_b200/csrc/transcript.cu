@@ -41,7 +41,13 @@ template <int D> __device__ __forceinline__ void stx(u64* p, Ext<D> v) { p[0] = 
 
 // coin = hash_elements(context elements || public inputs)  (A.4)
 __global__ void __launch_bounds__(32) seed_kernel(ProofState* ps, const u64* __restrict__ seed_limbs, int count) {
-  if (lane_id() == 0) { ps->seed = b3_hash_limbs_dyn(seed_limbs, count); ps->counter = 0; ps->error_flags = 0; ps->nonce = ~0ull; }
+  if (lane_id() == 0) {
+    u64 l[8 + XFG_NUM_PUB_INPUTS];
+#pragma unroll
+    for (int i = 0; i < 8 + XFG_NUM_PUB_INPUTS; i++) l[i] = seed_limbs[i];
+    ps->seed = count == 8 + XFG_NUM_PUB_INPUTS ? b3_hash_limbs<8 + XFG_NUM_PUB_INPUTS>(l) : b3_hash_limbs_dyn(seed_limbs, count);
+    ps->counter = 0; ps->error_flags = 0; ps->nonce = ~0ull;
+  }
 }
 template <int D> __global__ void __launch_bounds__(32) trace_root_kernel(ProofState* ps, const Digest* __restrict__ tree) {
   Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
@@ -60,20 +66,27 @@ template <int D> __global__ void __launch_bounds__(32) constraint_root_kernel(Pr
 template <int D> __global__ void __launch_bounds__(32) ood_finish_kernel(ProofState* ps, const u64* __restrict__ partial, u32 nb) {
   __shared__ u64 sums[NUM_OOD_POLYS][2][2];
   Coin c = coin_load(ps);
-  for (u32 t = lane_id(); t < (XFG_TRACE_WIDTH + D) * 4; t += 32) {
+  // every sum is spread over the warp: lane b adds partials b, b+32, ... then a shuffle tree (exact arithmetic: any order)
+  for (u32 t = 0; t < (XFG_TRACE_WIDTH + D) * 4; t++) {
     const u32 p = t >> 2, w = (t >> 1) & 1, l = t & 1;
-    u64 s = 0; for (u32 b = 0; b < nb; b++) s = gl_add(s, partial[(((size_t)p * nb + b) * 2 + w) * 2 + l]);
-    sums[p][w][l] = s;
+    u64 s = 0; for (u32 b = lane_id(); b < nb; b += 32) s = gl_add(s, partial[(((size_t)p * nb + b) * 2 + w) * 2 + l]);
+    for (int o = 16; o > 0; o >>= 1) s = gl_add(s, __shfl_xor_sync(0xFFFFFFFFu, s, o));
+    if (lane_id() == 0) sums[p][w][l] = s;
   }
   __syncwarp();
-  u64 limbs[2 * XFG_TRACE_WIDTH * 2]; int k = 0;
-  for (int j = 0; j < XFG_TRACE_WIDTH; j++) for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) limbs[k++] = sums[j][w][l];   // interleaved per column (A.9)
-  coin_reseed(c, b3_hash_limbs_dyn(limbs, k));
+  u64 limbs[2 * XFG_TRACE_WIDTH * D];
+#pragma unroll
+  for (int j = 0; j < XFG_TRACE_WIDTH; j++)
+#pragma unroll
+    for (int w = 0; w < 2; w++)
+#pragma unroll
+      for (int l = 0; l < D; l++) limbs[(2 * j + w) * D + l] = sums[j][w][l];   // interleaved per column (A.9)
+  coin_reseed(c, b3_hash_limbs<2 * XFG_TRACE_WIDTH * D>(limbs));
   // H(z) = P_limb0(z) + phi * P_limb1(z), phi = (0,1): (a0,a1) * phi = (-2 a1, a0 + a1)
   Ext<D> hz = ldx<D>(sums[XFG_TRACE_WIDTH][0]);
   if (D == 2) { const u64 a0 = sums[XFG_TRACE_WIDTH + 1][0][0], a1 = sums[XFG_TRACE_WIDTH + 1][0][1]; hz = hz + Ext<D>(gl_neg(gl_dbl(a1)), gl_add(a0, a1)); }
   u64 hl[2] = {hz.limb(0), hz.limb(1)};
-  coin_reseed(c, b3_hash_limbs_dyn(hl, D));
+  coin_reseed(c, b3_hash_limbs<D>(hl));
   const bool ok = coin_draw_many<D>(c, XFG_TRACE_WIDTH + 1, ps->dcoef);      // 7 trace coefficients, then 1 composition column
   if (lane_id() == 0) {
     for (int j = 0; j < XFG_TRACE_WIDTH; j++) for (int w = 0; w < 2; w++) { ps->ood_frame[2 * j + w][0] = sums[j][w][0]; ps->ood_frame[2 * j + w][1] = D == 2 ? sums[j][w][1] : 0; }
