@@ -186,3 +186,21 @@ def test_two_contexts_two_devices_one_process():
         p0 = c0.prove(trace, air); p1 = c1.prove(trace, air); p0b = c0.prove(trace, air)
     assert p0 == p1 == p0b
     assert p0 == orc.prove(*orc.synthetic_case(1 << 16, 5))
+
+
+def test_batch_error_leaves_context_usable(ctx):
+    """one bad proof in a batch (non-canonical public input) is reported, nothing dangles, and the context keeps working"""
+    import xfg_stark_b200 as xs
+    cases = [gpu_case(xs, i, 9) for i in range(5)]
+    airs = [a for a, _ in cases]; traces = [t for _, t in cases]
+    bad = xs.AirConsts.from_buffer_copy(bytes(airs[3])); bad.pub_inputs[9] = orc.P + 5
+    with pytest.raises(xs.XfgError) as e:
+        ctx.prove_batch(traces, airs[:3] + [bad] + airs[4:])
+    assert e.value.code == 1
+    bad_trace = traces[2].copy(); bad_trace[4, 17] = 2            # breaks the state-transition constraint of proof 2 only
+    with pytest.raises(xs.XfgError) as e:
+        ctx.prove_batch(traces[:2] + [bad_trace] + traces[3:], airs)
+    assert e.value.code == 5
+    proofs, _ = ctx.prove_batch(traces, airs)
+    for i, (air, trace) in enumerate(cases):
+        assert proofs[i] == orc.prove(*orc.synthetic_case(1 << 9, i))

@@ -449,6 +449,12 @@ int finish_proof(xfg_ctx* ctx, Slot& s, u8* out, size_t cap, size_t* out_len, xf
   return XFG_OK;
 }
 
+// waits for and discards every in-flight proof (error paths of the batch entry point; also run before any new call so that a
+// failed batch can never leave a slot pointing at a caller buffer that no longer exists)
+void drain_slots(xfg_ctx* ctx) {
+  for (Slot& s : ctx->slots) if (s.busy) { cudaStreamSynchronize(s.st); s.busy = false; }
+}
+
 int check_air(xfg_ctx* ctx, const xfg_air_consts* air) {
   for (int i = 0; i < XFG_NUM_PUB_INPUTS; i++) if (air->pub_inputs[i] >= XFG_P) return fail(ctx, XFG_ERR_BAD_ARGS, "non-canonical public input");
   if (air->txn_hash >= XFG_P || air->recipient_hash >= XFG_P || air->nullifier >= XFG_P || air->commitment >= XFG_P) return fail(ctx, XFG_ERR_BAD_ARGS, "non-canonical AIR constant");
@@ -485,6 +491,7 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
   int rc;
   if ((rc = check_options(ctx, o, n_log2)) || (rc = check_air(ctx, air))) return rc;
   CU(cudaSetDevice(ctx->device));
+  drain_slots(ctx);
   const Plan* p; if ((rc = get_plan(ctx, n_log2, o->fri_remainder_max_degree, &p))) return rc;
   Slot& s = ctx->slots[0];
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1;
@@ -601,6 +608,7 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
   if (n_log2 > ctx->max_log) return fail(ctx, XFG_ERR_TOO_LARGE, "trace longer than the context was created for");
   int rc; if ((rc = check_options(ctx, o, n_log2))) return rc;
   CU(cudaSetDevice(ctx->device));
+  drain_slots(ctx);
   const Plan* p; if ((rc = get_plan(ctx, n_log2, o->fri_remainder_max_degree, &p))) return rc;
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1; const size_t S = ctx->slots.size();
   g_xfg_launches = 0;
@@ -610,11 +618,11 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
   for (uint32_t i = 0; i < count; i++) {
     Slot& s = ctx->slots[i % S];
     if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
-    if ((rc = check_air(ctx, &airs[i]))) return rc;
-    if (!traces[i]) return fail(ctx, XFG_ERR_BAD_ARGS, "null trace");
-    if ((rc = upload_trace(ctx, s, *p, D, traces[i], false))) return rc;
+    if ((rc = check_air(ctx, &airs[i]))) { drain_slots(ctx); return rc; }
+    if (!traces[i]) { drain_slots(ctx); return fail(ctx, XFG_ERR_BAD_ARGS, "null trace"); }
+    if ((rc = upload_trace(ctx, s, *p, D, traces[i], false))) { drain_slots(ctx); return rc; }
     s.proof_index = i;
-    if ((rc = launch_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) return rc;
+    if ((rc = launch_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) { drain_slots(ctx); return rc; }
   }
   for (Slot& s : ctx->slots) if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
   if (total_ms) { CU(cudaDeviceSynchronize()); CU(cudaEventRecord(e1, ctx->slots[0].st)); CU(cudaEventSynchronize(e1)); cudaEventElapsedTime(total_ms, e0, e1); }
