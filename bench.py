@@ -301,6 +301,22 @@ def main():
                 "whole_proof": {"alg_bytes": ab["_total_survey"], "gbps": round(ab["_total_survey"] / times["device_ms"] / 1e6, 1),
                                 "frac": round(ab["_total_survey"] / times["device_ms"] / 1e6 / peak, 4)}}
 
+    # integer-pipe roofline of the BLAKE3 kernels: measured ALU-pipe peak (LOP3/SHF microbenchmark, no memory
+    # traffic) against compressions/s x 570 ALU-pipe instructions per compression (SASS count of commit_rows_kernel<7>: 8551 / 15)
+    int_peak = ctx.int_pipe_peak()
+    n_rows = 1 << args.n_log2; ALU_PER_COMPRESSION = 570
+    fri_leaves = []; nl = 8 * n_rows
+    while nl > 256:
+        fri_leaves.append(nl // 8); nl //= 8
+    compressions = {"commit_rows.trace": 15 * n_rows, "commit_rows.comp": 15 * n_rows, "tree_upper.trace": n_rows - 1, "tree_upper.comp": n_rows - 1,
+                    "fri.tree": sum(r - 1 for r in fri_leaves)}
+    int_pipe = {"peak_gops": round(int_peak, 1), "unit": "1e9 ALU-pipe instructions/s (measured, LOP3+SHF chains)", "alu_instr_per_compression": ALU_PER_COMPRESSION, "kernels": {}}
+    for name, (ms, _) in acc.items():
+        if name in compressions and ms > 0:
+            g = compressions[name] * ALU_PER_COMPRESSION / ms / 1e6
+            int_pipe["kernels"][name] = {"compressions": compressions[name], "gcompressions_per_s": round(compressions[name] / ms / 1e6, 2),
+                                         "achieved_gops": round(g, 1), "frac": round(g / int_peak, 4)}
+
     out = {
         "metric": METRIC, "value": dev_ms / (args.steps * world), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
@@ -312,7 +328,7 @@ def main():
         "gpu_launches": times["kernel_launches"] * args.steps,
         "device_ms_per_proof": times["device_ms"],
         "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},
-        "roofline": roofline, "kernels": kernels,
+        "roofline": roofline, "int_pipe": int_pipe, "kernels": kernels,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ms, cores, sample = cpu_reference_ms(args.n_log2, args.ext, budget_s=30.0, steps=1)

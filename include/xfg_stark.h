@@ -153,6 +153,9 @@ int xfg_fri_fold_layer(xfg_ctx* ctx, const uint64_t* evals, uint32_t nl_log2, ui
 /* element-wise field self-test of the device arithmetic (winter-math f64::BaseElement): op 0 mul, 1 weak mul,
  * 2 weak add, 3 weak sub, 4 add, 5 sub, 6 inv, 7/8 weak +- b*2^32, 100+S multiply by 2^S; out[i] = canonical result */
 int xfg_field_selftest(xfg_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
+/* measured peak of the 32-bit integer ALU pipe (IADD3 / LOP3 / SHF mix, no memory traffic), 1e9 operations per second: the roofline
+ * denominator of the BLAKE3 kernels; replaces nothing in the reference */
+int xfg_int_pipe_peak(xfg_ctx* ctx, double* gops);
 /* hash_elements of `rows` rows of `limbs` (1, 2, 7, 8 or 16) canonical u64 each, row-major; out = rows x 32 bytes */
 int xfg_hash_rows(xfg_ctx* ctx, const uint64_t* rows_rowmajor, size_t rows, uint32_t limbs, uint8_t* out);
 

@@ -339,6 +339,27 @@ void launch_check_canonical(cudaStream_t st, const u64* v, size_t count, ProofSt
   check_canonical_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, count, ps); XFG_LAUNCHED(1);
 }
 
+// ---- 32-bit integer-pipe peak (xfg_int_pipe_peak): 8 independent chains per thread of the BLAKE3 operation mix
+// (LOP3 xor, IADD3, SHF rotate - all ALU-pipe instructions; 4 per group, checked in SASS), no memory traffic: the roofline denominator of the hashing kernels
+__global__ void __launch_bounds__(256) int_peak_kernel(const u32* __restrict__ in, u32* __restrict__ out, u32 iters) {
+  u32 x[8], y = in[threadIdx.x & 31], z = in[32 + (threadIdx.x & 31)];
+#pragma unroll
+  for (int c = 0; c < 8; c++) x[c] = in[(threadIdx.x + c) & 63];
+  for (u32 i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 8; c++)   // xor, rotate, xor, rotate: 4 instructions that only the ALU pipe executes and ptxas cannot fuse or move (it turns
+                                    // plain adds into IMAD on the FMA pipe and add-after-rotate into one LEA.HI, which would blur the count)
+        asm volatile("xor.b32 %0, %0, %2;\n\t shf.r.wrap.b32 %0, %0, %0, 7;\n\t xor.b32 %0, %0, %1;\n\t shf.r.wrap.b32 %0, %0, %0, 11;" : "+r"(x[c]) : "r"(y), "r"(z));
+  }
+  u32 acc = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) acc ^= x[c];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+void launch_int_peak(cudaStream_t st, const u32* in, u32* out, u32 blocks, u32 iters) { int_peak_kernel<<<blocks, 256, 0, st>>>(in, out, iters); XFG_LAUNCHED(1); }
+
 // ---- field self-test (xfg_field_selftest): exercises the canonical and the weak arithmetic on caller-chosen operands ----
 template <int S> __device__ __forceinline__ bool pow2_case(u32 op, u64 a, u64& r) { if (op == 100 + S) { r = w_canon(w_mul_pow2<S>(a)); return true; } return false; }
 __global__ void field_selftest_kernel(u32 op, const u64* __restrict__ a, const u64* __restrict__ b, size_t n, u64* __restrict__ out) {
