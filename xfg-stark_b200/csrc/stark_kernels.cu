@@ -186,12 +186,32 @@ void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef
 // batched inversion, writes them coset-major and hashes the row into the layer-0 FRI tree.
 // ------------------------------------------------------------------------------------------------------------------
 static constexpr int DEEP_THREADS = 128;
-// Loops over the 8 points are rolled and the per-point intermediates (numerator, x, norm, prefix product) are staged in shared
-// memory [point][word][thread]; the unrolled version was 277 KB of SASS, 136 registers, and stalled on instruction fetch.
+// 1 / (x - w) for a base-field x and an extension point w = (w0, w1):  (x - w)^-1 = conj / norm with
+//   u = x - w0,  conj = (u - w1, w1),  norm = u (u - w1) + 2 w1^2           (degree 2; one multiplication)
+//   conj = 1,    norm = x - w0                                              (degree 1)
+// and for P = (p0, p1):  P * conj = (p0 (u - w1) - 2 p1 w1,  p1 u + p0 w1)  - four products, accumulated un-reduced.
+template <int D> struct DeepPoint { u64 w0, w1, m2w1, k2w1sq; };   // w, -2 w1, 2 w1^2
+template <int D> __device__ __forceinline__ u64 deep_norm(const DeepPoint<D>& w, u64 x, u64& u) {
+  u = gl_sub(x, w.w0);
+  if (D == 1) return u;
+  return gl_add(gl_mul(u, gl_sub(u, w.w1)), w.k2w1sq);
+}
+template <int D> __device__ __forceinline__ Ext<D> deep_mul_conj(const DeepPoint<D>& w, u64 u, Ext<D> p) {
+  if (D == 1) return p;
+  DotAcc c0, c1;
+  c0.fma(p.limb(0), gl_sub(u, w.w1)); c0.fma(p.limb(1), w.m2w1);
+  c1.fma(p.limb(1), u); c1.fma(p.limb(0), w.w1);
+  return Ext<D>(c0.result(), c1.result());
+}
+// Loops over the 8 points are rolled and the per-point intermediates (numerator, norm product, prefix product) are staged in
+// shared memory [point][word][thread]; the unrolled version was 277 KB of SASS, 136 registers, and stalled on instruction fetch.
+//   D(x) = P / (x - z) + Q / (x - zg) = [ (P conj_z) n_zg + (Q conj_zg) n_z ] / (n_z n_zg),   P = S_T + delta H - C1,  Q = S_T - C2
+// so a point costs one base-field inversion (batched over the thread's 8 points) and no extension-field multiplication
+// besides delta * H.
 template <int D>
 __global__ void __launch_bounds__(DEEP_THREADS) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
                                                              PowTable wn, const u64* __restrict__ s_k, u64 w8, u64* __restrict__ deep, Digest* __restrict__ fri_tree0) {
-  __shared__ u64 sh[8][D + 3][DEEP_THREADS];          // per point: numerator -> result (D), x, norm, prefix
+  __shared__ u64 sh[8][D + 2][DEEP_THREADS];          // per point: numerator -> result (D), n_z n_zg, prefix
   __shared__ u64 sc[2 * (XFG_TRACE_WIDTH + 1) + 8];   // dcoef[8][2], then c1, c2, z, zg
   const size_t n = size_t(1) << ln, N = 8 * n, n8 = n / 8;
   const u32 k = blockIdx.y, tid = threadIdx.x; const size_t a = (size_t)blockIdx.x * blockDim.x + tid;
@@ -200,7 +220,8 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_kernel(const u64* __restric
   __syncthreads();
   if (a >= n8) return;
   const u64* cc = sc + 2 * (XFG_TRACE_WIDTH + 1);
-  const Ext<D> delta(sc[2 * XFG_TRACE_WIDTH], sc[2 * XFG_TRACE_WIDTH + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]), z(cc[4], cc[5]), zg(cc[6], cc[7]);
+  const Ext<D> delta(sc[2 * XFG_TRACE_WIDTH], sc[2 * XFG_TRACE_WIDTH + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]);
+  const DeepPoint<D> pz{cc[4], cc[5], gl_neg(gl_dbl(cc[5])), gl_dbl(gl_sqr(cc[5]))}, pzg{cc[6], cc[7], gl_neg(gl_dbl(cc[7])), gl_dbl(gl_sqr(cc[7]))};
   u64 x = gl_mul(s_k[k], pow_lookup(wn, a)), acc = 1;      // x_j = x_0 * w_8^j  (m = a + j n/8)
 #pragma unroll 1
   for (int j = 0; j < 8; j++) {
@@ -210,25 +231,22 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_kernel(const u64* __restric
     for (int c = 0; c < XFG_TRACE_WIDTH; c++) { const u64 tv = lde[(size_t)c * N + idx]; for (int l = 0; l < D; l++) sa[l].fma(sc[2 * c + l], tv); }
     Ext<D> st; for (int l = 0; l < D; l++) st.set_limb(l, sa[l].result());
     Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + idx]);
-    const Ext<D> xz = Ext<D>(x) - z, xzg = Ext<D>(x) - zg;
-    const Ext<D> num = (st + delta * h - c1) * xzg + (st - c2) * xz;
-    const u64 nrm = ext_norm(xz * xzg);
+    u64 uz, uzg;
+    const u64 nz = deep_norm<D>(pz, x, uz), nzg = deep_norm<D>(pzg, x, uzg);
+    const Ext<D> pc = deep_mul_conj<D>(pz, uz, st + delta * h - c1), qc = deep_mul_conj<D>(pzg, uzg, st - c2);
 #pragma unroll
-    for (int l = 0; l < D; l++) sh[j][l][tid] = num.limb(l);
-    sh[j][D][tid] = x; sh[j][D + 1][tid] = nrm; sh[j][D + 2][tid] = acc;
-    acc = gl_mul(acc, nrm); x = gl_mul(x, w8);
+    for (int l = 0; l < D; l++) { DotAcc m; m.fma(pc.limb(l), nzg); m.fma(qc.limb(l), nz); sh[j][l][tid] = m.result(); }
+    const u64 den = gl_mul(nz, nzg);
+    sh[j][D][tid] = den; sh[j][D + 1][tid] = acc;
+    acc = gl_mul(acc, den); x = gl_mul(x, w8);
   }
   acc = gl_inv(acc);
 #pragma unroll 1
   for (int j = 7; j >= 0; j--) {
     const size_t idx = (size_t)k * n + a + (size_t)j * n8;
-    const u64 ninv = gl_mul(sh[j][D + 2][tid], acc); acc = gl_mul(acc, sh[j][D + 1][tid]);
-    const u64 xj = sh[j][D][tid];
-    const Ext<D> den = (Ext<D>(xj) - z) * (Ext<D>(xj) - zg);
-    Ext<D> num; for (int l = 0; l < D; l++) num.set_limb(l, sh[j][l][tid]);
-    const Ext<D> v = num * ext_inv_with_norm_inv(den, ninv);
+    const u64 dinv = gl_mul(sh[j][D + 1][tid], acc); acc = gl_mul(acc, sh[j][D][tid]);
 #pragma unroll
-    for (int l = 0; l < D; l++) { deep[(size_t)l * N + idx] = v.limb(l); sh[j][l][tid] = v.limb(l); }
+    for (int l = 0; l < D; l++) { const u64 v = gl_mul(sh[j][l][tid], dinv); deep[(size_t)l * N + idx] = v; sh[j][l][tid] = v; }
   }
   if (fri_tree0) {
     u64 row[8 * D];
