@@ -204,3 +204,19 @@ def test_batch_error_leaves_context_usable(ctx):
     proofs, _ = ctx.prove_batch(traces, airs)
     for i, (air, trace) in enumerate(cases):
         assert proofs[i] == orc.prove(*orc.synthetic_case(1 << 9, i))
+
+
+def test_maximum_size_proof_2p22_equals_oracle():
+    """a 2^22-row trace (N = 2^25 LDE points, 6 FRI layers, 2^11-point NTT tiles): beyond the headline size, still byte-equal"""
+    import xfg_stark_b200 as xs
+    n_log2 = 22
+    opts = xs.ProofOptions()
+    air, trace = gpu_case(xs, 7, n_log2)
+    with xs.Context(device=0, max_n_log2=n_log2, num_slots=1) as c:
+        proof = c.prove(trace, air, opts)
+    tr, pi, ac = orc.synthetic_case(1 << n_log2, 7)
+    orc.set_threads(orc.max_threads())
+    expect = orc.prove(tr, pi, ac, opts.as_tuple())
+    orc.set_threads(1)
+    assert proof == expect
+    assert orc.verify(proof, pi, ac, opts.as_tuple()) == ""
