@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
     const u32 c = e & (T - 1), r = e >> p.Tlog;
     const u64 gi = (u64)r * p.in_row_stride + col0 + c;
     u64 v = src[gi];
-    if (pre.lo) v = w_mul(v, w_pow_lookup(pre, gi));      // weak product: the butterflies accept any u64 residue
+    if (p.pre_row) v = w_mul(v, p.pre_row[((size_t)coset << p.Llog) + r]);   // base^(r * in_row_stride); base^(col0 + c) is folded into it_tab
+    else if (pre.lo) v = w_mul(v, w_pow_lookup(pre, gi));                    // weak product: the butterflies accept any u64 residue
     S[r * TP + c] = v;
   }
   __syncthreads();
@@ -184,12 +185,14 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
   }
   if (p.store_transposed) {
     PowTable it; it.lo = p.it_lo; it.hi = p.it_hi;
+    const u64* itab = p.it_tab ? p.it_tab + (size_t)coset * p.it_tstride : nullptr;
     for (u32 e = tid; e < L * T; e += nthreads) {
       const u32 k = e & (L - 1), c = e >> p.Llog;
       u64 v = S[k * TP + c];
-      const u64 ex = (col0 + c) * (u64)k;
-      v = w_canon(ex ? w_mul(v, w_pow_lookup(it, ex)) : v);
-      dst[(col0 + c) * (u64)L + k] = v;
+      const u64 di = (col0 + c) * (u64)L + k;
+      if (itab) v = w_canon(w_mul(v, itab[di]));
+      else { const u64 ex = (col0 + c) * (u64)k; v = w_canon(ex ? w_mul(v, w_pow_lookup(it, ex)) : v); }
+      dst[di] = v;
     }
   } else {
     PowTable post; post.lo = p.post_lo ? p.post_lo + (size_t)(tr % p.post_div) * POW_LO : nullptr;
@@ -198,8 +201,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
       const u32 c = e & (T - 1), k = e >> p.Tlog;
       u64 v = S[k * TP + c];
       const u64 go = (u64)k * p.out_row_stride + col0 + c;
-      if (p.scale != 1) v = gl_mul(v, p.scale); else v = w_canon(v);
-      if (post.lo) v = gl_mul(v, pow_lookup(post, go));
+      if (p.post_tab) v = w_canon(w_mul(v, p.post_tab[(size_t)(tr % p.post_div) * p.post_tstride + go]));
+      else {
+        if (p.scale != 1) v = gl_mul(v, p.scale); else v = w_canon(v);
+        if (post.lo) v = gl_mul(v, pow_lookup(post, go));
+      }
       if (p.peer_log) p.peer[go >> p.peer_log][(size_t)tr * (u64(1) << p.peer_log) + (go & ((u64(1) << p.peer_log) - 1))] = v;   // fused all-to-all: store to the row owner
       else dst[go] = v;
     }
@@ -266,21 +272,67 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   // four-step: n = n1 * n2 with n2 = 2^l2 (pass A length), n1 = 2^l1 (pass B length)
   const u32 l2 = ln / 2, l1 = ln - l2;
   const bool fast = l2 >= 8;            // register-radix Stockham tiles (2^8 .. 2^12 points)
+  // direct twiddle tables (NttTables): picked when the job's lookup tables are the ones the direct tables were built from
+  const bool have_direct = fast && tb.d_ln == ln;
+  const bool dir_coset = have_direct && !job.inverse && job.scale == 1 && job.pre_lo && job.pre_lo == tb.d_pre_id && !job.post_lo;
+  const bool dir_inv = have_direct && job.inverse && !job.pre_lo && job.scale == tb.d_scale && (!job.post_lo || job.post_lo == tb.d_post_id);
   const u32 Tlog = l1 > 11 ? 2 : 3;     // 2^12-point tiles only fit 4 columns
   // pass A
   p.src = job.src; p.dst = job.dst; p.Llog = l2; p.Tlog = Tlog; p.in_row_stride = u64(1) << l1; p.out_row_stride = 0;
   p.store_transposed = 1; p.scale = 1;
   p.it_lo = job.inverse ? tb.wn_inv.lo : tb.wn_fwd.lo; p.it_hi = job.inverse ? tb.wn_inv.hi : tb.wn_fwd.hi;
+  if (dir_coset) { p.pre_row = tb.d_pre_row; p.it_tab = tb.d_it_coset; p.it_tstride = u64(1) << ln; }
+  if (dir_inv) { p.it_tab = tb.d_it_inv; p.it_tstride = 0; }
   if (fast) { p.Tlog = r16_tlog(l2); launch_r16(st, p, job.inverse, (1u << l1) >> p.Tlog, job.batch); }
   else { ntt_pass<<<dim3((1u << l1) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l2, Tlog), st>>>(p); XFG_LAUNCHED(1); }
   // pass B (in place on dst)
   p.src = job.dst; p.dst = job.dst; p.src_is_dst = 1;                      // pass B: in place on the slot pass A wrote
-  p.pre_lo = nullptr; p.pre_hi = nullptr;
+  p.pre_lo = nullptr; p.pre_hi = nullptr; p.pre_row = nullptr; p.it_tab = nullptr;
   p.Llog = l1; p.in_row_stride = u64(1) << l2; p.out_row_stride = u64(1) << l2; p.store_transposed = 0; p.scale = job.scale;
   p.post_lo = job.post_lo; p.post_hi = job.post_hi; p.post_hi_stride = job.post_hi_stride;
+  if (dir_inv) {   // 1/n already applied by d_it_inv
+    p.scale = 1;
+    if (job.post_lo) { p.post_tab = tb.d_post; p.post_tstride = u64(1) << ln; p.post_lo = nullptr; p.post_hi = nullptr; }
+  }
   p.peer_log = job.peer_log; for (int i = 0; i < NTT_MAX_PEERS; i++) p.peer[i] = job.peer[i];
   if (fast) { p.Tlog = r16_tlog(l1); launch_r16(st, p, job.inverse, (1u << l2) >> p.Tlog, job.batch); }
   else { ntt_pass<<<dim3((1u << l2) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l1, Tlog), st>>>(p); XFG_LAUNCHED(1); }
+}
+
+// ---- direct twiddle tables (NttTables::d_*) ----
+__global__ void fill_it_kernel(u64* __restrict__ out, u32 ln, u32 l2, PowTable wn, u64 scale, PowTable base) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >> ln) return;
+  const u64 j1 = i >> l2, k2 = i & ((u64(1) << l2) - 1);
+  u64 v = gl_mul(pow_lookup(wn, j1 * k2), scale);
+  if (base.lo) v = gl_mul(v, pow_lookup(base, j1));
+  out[i] = v;
+}
+__global__ void fill_pow_kernel(u64* __restrict__ out, size_t count, u32 shift, PowTable base) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = pow_lookup(base, (u64)i << shift);
+}
+size_t ntt_direct_words(u32 ln, u32 cosets, u32 posts) {
+  if (ln < NTT_DIRECT_MIN_LOG || ln > NTT_DIRECT_MAX_LOG) return 0;
+  const size_t n = size_t(1) << ln, n2 = size_t(1) << (ln / 2);
+  return n + cosets * n + cosets * n2 + posts * n;
+}
+void ntt_build_direct(NttTables& tb, u32 ln, u64* storage, u64 scale, const u64* pre_lo, const u64* pre_hi, u32 pre_hi_stride, u32 cosets,
+                      const u64* post_lo, const u64* post_hi, u32 post_hi_stride, u32 posts) {
+  if (!ntt_direct_words(ln, cosets, posts)) return;
+  const size_t n = size_t(1) << ln; const u32 l2 = ln / 2, l1 = ln - l2; const size_t n2 = size_t(1) << l2;
+  const unsigned blocks = (unsigned)(n / 256);
+  u64* it_inv = storage; u64* it_coset = it_inv + n; u64* pre_row = it_coset + cosets * n; u64* post = pre_row + cosets * n2;
+  fill_it_kernel<<<blocks, 256>>>(it_inv, ln, l2, tb.wn_inv, scale, PowTable{nullptr, nullptr});
+  for (u32 c = 0; c < cosets; c++) {
+    const PowTable base{pre_lo + (size_t)c * POW_LO, pre_hi + (size_t)c * pre_hi_stride};
+    fill_it_kernel<<<blocks, 256>>>(it_coset + (size_t)c * n, ln, l2, tb.wn_fwd, 1, base);
+    fill_pow_kernel<<<(unsigned)((n2 + 255) / 256), 256>>>(pre_row + (size_t)c * n2, n2, l1, base);
+  }
+  for (u32 c = 0; c < posts; c++)
+    fill_pow_kernel<<<blocks, 256>>>(post + (size_t)c * n, n, 0, PowTable{post_lo + (size_t)c * POW_LO, post_hi + (size_t)c * post_hi_stride});
+  tb.d_it_inv = it_inv; tb.d_it_coset = it_coset; tb.d_pre_row = pre_row; tb.d_post = posts ? post : nullptr;
+  tb.d_pre_id = pre_lo; tb.d_post_id = posts ? post_lo : nullptr; tb.d_scale = scale; tb.d_ln = ln;
 }
 
 }  // namespace xfg

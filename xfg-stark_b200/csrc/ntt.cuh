@@ -26,13 +26,29 @@ struct NttPass {
   // peer[m >> peer_log][t * 2^peer_log + (m mod 2^peer_log)] (peer pointers may be NVLink-mapped memory of other GPUs)
   u64* peer[NTT_MAX_PEERS]; u32 peer_log;
   u32 coset_map, dst_cosets, src_is_dst;
+  // direct (one 8-byte load per element) twiddle tables of a four-step transform, see NttTables; they replace pre_*, it_*, post_*
+  const u64* pre_row; const u64* it_tab; u64 it_tstride; const u64* post_tab; u64 post_tstride;
 };
 
 // device tables owned by a plan (one per trace length)
 struct NttTables {
   const u64* tw_fwd; const u64* tw_inv;   // w_4096^(+-i), i < 2048
   PowTable wn_fwd, wn_inv;                // powers of w_n and w_n^-1 (exponents < n)
+  // Optional full-size tables for the four-step transforms of this length (n = n1 * n2, pass A = n1 column transforms of length n2).
+  // The NTT kernels are bound by the integer pipe, not by HBM, so trading a two-level power lookup + 64-bit modular multiplication
+  // per element for one more 8-byte load (mostly L2 hits: the tables are shared by all columns) is a net win.
+  //   d_it_inv   [n]            (j1, k2) at j1*n2 + k2:  w_n^-(j1*k2) * d_scale             inverse transforms with scale == d_scale
+  //   d_it_coset [cosets][n]                              w_n^(j1*k2)  * base_c^j1           forward coset transforms (pre table == d_pre_id)
+  //   d_pre_row  [cosets][n2]   row j2:                   base_c^(j2*n1)                     the rest of the coset pre-scale base_c^(j1 + n1*j2)
+  //   d_post     [posts][n]     output j:                 post_base_c^j                      inverse coset transforms (post table == d_post_id)
+  const u64* d_it_inv = nullptr; const u64* d_it_coset = nullptr; const u64* d_pre_row = nullptr; const u64* d_post = nullptr;
+  const u64* d_pre_id = nullptr; const u64* d_post_id = nullptr; u64 d_scale = 0; u32 d_ln = 0;
 };
+// words of device memory ntt_build_direct needs / fill the tables (synchronous on stream 0); direct tables exist for 16 <= ln <= NTT_DIRECT_MAX_LOG
+static constexpr u32 NTT_DIRECT_MIN_LOG = 16, NTT_DIRECT_MAX_LOG = 22;
+size_t ntt_direct_words(u32 ln, u32 cosets, u32 posts);
+void ntt_build_direct(NttTables& tb, u32 ln, u64* storage, u64 scale, const u64* pre_lo, const u64* pre_hi, u32 pre_hi_stride, u32 cosets,
+                      const u64* post_lo, const u64* post_hi, u32 post_hi_stride, u32 posts);
 
 // transform t (0 <= t < batch) reads src + (t / src_div) * src_tstride and writes dst + t * dst_tstride;
 // if pre_lo != null, input element j is first multiplied by base_c^j, c = t % src_div, table c at pre_lo + c*4096 / pre_hi + c*pre_hi_stride

@@ -35,6 +35,7 @@ struct Plan {
   u32 rem_max_deg = 0, num_layers = 0, layer_log[MAX_LAYERS + 1] = {0};   // layer_log[l] = log2 |domain of FRI layer l|
   u32 rem_log = 0, rem_len = 0;
   u64* slab = nullptr;              // all tables of this plan
+  u64* direct = nullptr;            // NttTables::d_* storage (optional)
   NttTables ntt{};                  // tw_* are context-wide
   PowTable wN_inv{};
   u64 *pre_lo = nullptr, *pre_hi = nullptr; u32 pre_hi_stride = 0;   // s_k = 7 w_N^k, k < 8
@@ -159,6 +160,15 @@ int get_plan(xfg_ctx* ctx, u32 ln, u32 rem_max_deg, const Plan** out) {
   p.g_n = wn; p.g_last = gl_pow(wn, p.n - 1);
   p.zinv0 = gl_inv(gl_sub(gl_pow(p.s_k[0], p.n), 1)); p.zinv1 = gl_inv(gl_sub(gl_pow(p.s_k[4], p.n), 1));
   p.n_inv = gl_inv((u64)p.n); p.inv2 = gl_inv(2); p.rem_ninv = gl_inv((u64)1 << p.rem_log);
+  // full-size twiddle tables for the four-step transforms (88 MB at n = 2^20; XFG_NTT_DIRECT=0 keeps the two-level lookups, for A/B runs)
+  { const char* e = getenv("XFG_NTT_DIRECT"); const size_t dw = (e && e[0] == '0') ? 0 : ntt_direct_words(ln, 8, 2);
+    if (dw) {
+      if (cudaMalloc(&p.direct, dw * 8) != cudaSuccess) { cudaGetLastError(); p.direct = nullptr; }   // optional: fall back to the lookups
+      else {
+        ntt_build_direct(p.ntt, ln, p.direct, p.n_inv, p.pre_lo, p.pre_hi, p.pre_hi_stride, 8, p.un_lo, p.un_hi, p.un_hi_stride, 2);
+        CU(cudaDeviceSynchronize());
+      }
+    } }
   const u64 w8i = gl_inv(gl_root_of_unity(3));
   p.fc.w8i[0] = 1; for (int i = 1; i < 4; i++) p.fc.w8i[i] = gl_mul(p.fc.w8i[i - 1], w8i);
   p.fc.inv8 = gl_inv(8); p.fc.inv7 = gl_inv(XFG_GENERATOR);
@@ -582,7 +592,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     if (s.copy_st) cudaStreamDestroy(s.copy_st);
     if (s.st) cudaStreamDestroy(s.st);
   }
-  for (auto& kv : ctx->plans) cudaFree(kv.second.slab);
+  for (auto& kv : ctx->plans) { cudaFree(kv.second.slab); cudaFree(kv.second.direct); }
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv);
   delete ctx;
 }
