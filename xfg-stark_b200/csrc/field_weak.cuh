@@ -15,56 +15,52 @@ namespace xfg {
 
 __device__ __forceinline__ u64 w_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
 
-// weak -> canonical
+// weak -> canonical.  x >= p  <=>  x + EPS carries out of bit 64, and then x - p = x + EPS (mod 2^64): add, select on the carry (4 instructions)
 __device__ __forceinline__ u64 w_canon(u64 x) {
-  u32 lo = (u32)x, hi = (u32)(x >> 32);
-  if (hi == 0xFFFFFFFFu && lo != 0) { lo -= 1; hi = 0; }   // x >= p  <=>  hi = 2^32-1 and lo >= 1;  x - p = lo - 1
-  return w_pack(lo, hi);
+  u32 r0, r1;
+  asm("{\n\t .reg .pred p; .reg .u32 c, t0, t1;\n\t add.cc.u32 t0, %2, 0xffffffff;\n\t addc.cc.u32 t1, %3, 0;\n\t addc.u32 c, 0, 0;\n\t setp.ne.u32 p, c, 0;\n\t"
+      "selp.b32 %0, t0, %2, p;\n\t selp.b32 %1, t1, %3, p;\n\t}"
+      : "=r"(r0), "=r"(r1) : "r"((u32)x), "r"((u32)(x >> 32)));
+  return w_pack(r0, r1);
 }
 
 // a (weak) + b (canonical) -> weak.  a + b < 2^64 + p, so after a carry the wrapped sum is < p and adding EPS cannot carry again.
+// The carry mask is built as setp/selp so that ptxas keeps it one SEL on the carry predicate (5 instructions in all).
 __device__ __forceinline__ u64 w_add_c(u64 a, u64 b) {
-  u32 s0, s1, m;
-  asm("{\n\t add.cc.u32 %0, %3, %5;\n\t addc.cc.u32 %1, %4, %6;\n\t addc.u32 %2, 0, 0;\n\t neg.s32 %2, %2;\n\t add.cc.u32 %0, %0, %2;\n\t addc.u32 %1, %1, 0;\n\t}"
-      : "=&r"(s0), "=&r"(s1), "=&r"(m) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  u32 s0, s1;
+  asm("{\n\t .reg .pred p; .reg .u32 c, m;\n\t add.cc.u32 %0, %2, %4;\n\t addc.cc.u32 %1, %3, %5;\n\t addc.u32 c, 0, 0;\n\t setp.ne.u32 p, c, 0;\n\t"
+      "selp.b32 m, 0xffffffff, 0, p;\n\t add.cc.u32 %0, %0, m;\n\t addc.u32 %1, %1, 0;\n\t}"
+      : "=&r"(s0), "=&r"(s1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
   return w_pack(s0, s1);
 }
-// a (weak) - b (canonical) -> weak.  After a borrow the wrapped difference is >= 2^64 - (p-1) = EPS + ... >= EPS, so subtracting EPS cannot borrow again.
+// a (weak) - b (canonical) -> weak.  After a borrow the wrapped difference is >= 2^64 - (p-1) >= EPS, so subtracting EPS cannot borrow again.
 __device__ __forceinline__ u64 w_sub_c(u64 a, u64 b) {
   u32 s0, s1, m;
   asm("{\n\t sub.cc.u32 %0, %3, %5;\n\t subc.cc.u32 %1, %4, %6;\n\t subc.u32 %2, 0, 0;\n\t sub.cc.u32 %0, %0, %2;\n\t subc.u32 %1, %1, 0;\n\t}"
       : "=&r"(s0), "=&r"(s1), "=&r"(m) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
   return w_pack(s0, s1);
 }
-// r (weak) + c * 2^32, c < 2^32 -> weak.  Carry out of the high word = +2^64 = +EPS; the wrapped high word is <= 2^32 - 2, so no second carry.
-__device__ __forceinline__ u64 w_add_hi32(u64 r, u32 c) {
-  u32 r0, r1, m;
-  asm("{\n\t add.cc.u32 %1, %4, %5;\n\t addc.u32 %2, 0, 0;\n\t neg.s32 %2, %2;\n\t add.cc.u32 %0, %3, %2;\n\t addc.u32 %1, %1, 0;\n\t}"
-      : "=&r"(r0), "=&r"(r1), "=&r"(m) : "r"((u32)r), "r"((u32)(r >> 32)), "r"(c));
+// a * EPS = a * 2^64 (mod p) for a < 2^32: one IMAD.WIDE on the FMA pipe; the result is canonical (<= 2^64 - 2^33 + 1 < p)
+__device__ __forceinline__ u64 w_mul_eps(u32 a) { u64 r; asm("mul.wide.u32 %0, %1, 0xffffffff;" : "=l"(r) : "r"(a)); return r; }
+// a * EPS + (b1:b0) for a < 2^32 and any u64 (b1:b0) -> weak: IMAD.WIDE with the 64-bit addend, then the carry fix.  The high word of
+// a * EPS is at most 2^32 - 2, so bit 64 was carried out exactly when the sum's high word is below b1 (one 32-bit compare); the
+// wrapped sum is then <= 2^64 - 2^33, so + EPS cannot carry again.
+__device__ __forceinline__ u64 w_eps_madd(u32 a, u32 b0, u32 b1) {
+  u32 r0, r1;
+  asm("{\n\t .reg .u64 r, b; .reg .pred p; .reg .u32 m;\n\t mov.b64 b, {%3, %4};\n\t mad.wide.u32 r, %2, 0xffffffff, b;\n\t mov.b64 {%0, %1}, r;\n\t"
+      "setp.lt.u32 p, %1, %4;\n\t selp.b32 m, 0xffffffff, 0, p;\n\t add.cc.u32 %0, %0, m;\n\t addc.u32 %1, %1, 0;\n\t}"
+      : "=&r"(r0), "=&r"(r1) : "r"(a), "r"(b0), "r"(b1));
   return w_pack(r0, r1);
 }
-// r (weak) - c * 2^32, c < 2^32 -> weak.  Borrow = -2^64 = -EPS; the wrapped high word is >= 1, so subtracting EPS (< 2^32) cannot borrow again.
-__device__ __forceinline__ u64 w_sub_hi32(u64 r, u32 c) {
-  u32 r0, r1, m;
-  asm("{\n\t sub.cc.u32 %1, %4, %5;\n\t subc.u32 %2, 0, 0;\n\t sub.cc.u32 %0, %3, %2;\n\t subc.u32 %1, %1, 0;\n\t}"
-      : "=&r"(r0), "=&r"(r1), "=&r"(m) : "r"((u32)r), "r"((u32)(r >> 32)), "r"(c));
-  return w_pack(r0, r1);
-}
-// r (weak) - c, c < 2^32 -> weak (c is canonical, see w_sub_c)
+// r (weak) + c * 2^32, c < 2^32 -> weak
+__device__ __forceinline__ u64 w_add_hi32(u64 r, u32 c) { return w_add_c(r, w_pack(0u, c)); }   // c * 2^32 <= 2^64 - 2^32 < p: canonical
+// r (weak) - c * 2^32, c < 2^32 -> weak
+__device__ __forceinline__ u64 w_sub_hi32(u64 r, u32 c) { return w_sub_c(r, w_pack(0u, c)); }
+// r (weak) - c, c < 2^32 -> weak
 __device__ __forceinline__ u64 w_sub32(u64 r, u32 c) { return w_sub_c(r, (u64)c); }
 
-// 128-bit (lo, hi) -> weak residue:  lo - hi_hi + hi_lo * EPS
-__device__ __forceinline__ u64 w_reduce128(u64 lo, u64 hi) {
-  u32 t0, t1, m, u1;
-  asm("{\n\t"
-      "sub.cc.u32 %0, %4, %7;\n\t subc.cc.u32 %1, %5, 0;\n\t subc.u32 %2, 0, 0;\n\t"     // t = lo - hi_hi           (borrow mask in %2)
-      "sub.cc.u32 %0, %0, %2;\n\t subc.u32 %1, %1, 0;\n\t"                               // borrow: t -= EPS          (t >= 2^64 - 2^32 + 1 > EPS: no second borrow)
-      "sub.cc.u32 %2, 0, %6;\n\t subc.u32 %3, %6, 0;\n\t"                                // u = hi_lo * 2^32 - hi_lo  (u <= 2^64 - 2^33 + 1)
-      "add.cc.u32 %0, %0, %2;\n\t addc.cc.u32 %1, %1, %3;\n\t addc.u32 %2, 0, 0;\n\t neg.s32 %2, %2;\n\t"   // r = t + u     (carry mask in %2)
-      "add.cc.u32 %0, %0, %2;\n\t addc.u32 %1, %1, 0;\n\t}"                              // carry: r += EPS           (wrapped r < u <= 2^64 - 2^33 + 1: no second carry)
-      : "=&r"(t0), "=&r"(t1), "=&r"(m), "=&r"(u1) : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
-  return w_pack(t0, t1);
-}
+// 128-bit (lo, hi) -> weak residue:  (lo - hi_hi) + hi_lo * EPS.  lo is any u64 (weak), hi_hi < 2^32 is canonical.
+__device__ __forceinline__ u64 w_reduce128(u64 lo, u64 hi) { const u64 t = w_sub_c(lo, hi >> 32); return w_eps_madd((u32)hi, (u32)t, (u32)(t >> 32)); }
 // a * b for any u64 a, b (weak operands allowed) -> weak
 __device__ __forceinline__ u64 w_mul(u64 a, u64 b) {
   const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
@@ -101,18 +97,20 @@ struct DotAcc {
 };
 
 // x * 2^S for a compile-time S in [0, 96), x weak -> weak.  With S = 32q + t and y = x << t = y2*2^64 + y1*2^32 + y0 (y2 < 2^t):
-//   q = 0:  (y1:y0) + y2*2^32 - y2
-//   q = 1:  (y0:0)  + y1*2^32 - y1 - y2                 (2^96 = -1)
-//   q = 2:  (y0:0)  - y0 - y1 - y2*2^32                 (2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32)
+//   q = 0:  (y1:y0) + y2*EPS                            (2^64 = EPS)
+//   q = 1:  (y0:0)  + y1*EPS - y2                       (2^96 = -1)
+//   q = 2:  y0*EPS  - (y2:y1)                           (2^96 = -1, 2^128 = -2^32)
+// The EPS products are single IMAD.WIDE instructions with the other term as the 64-bit addend (w_eps_madd; FMA pipe, which these
+// kernels leave mostly idle): 8 / 13 / 9 instructions for q = 0 / 1 / 2.
 template <int S> __device__ __forceinline__ u64 w_mul_pow2(u64 x) {
   static_assert(S >= 0 && S < 96, "shift out of range");
   if (S == 0) return x;
   constexpr int q = S / 32, t = S % 32;
   const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
   const u32 y0 = t ? (x0 << t) : x0, y1 = t ? __funnelshift_l(x0, x1, t) : x1, y2 = t ? (x1 >> (32 - t)) : 0u;
-  if (q == 0) { u64 r = w_pack(y0, y1); if (t) { r = w_add_hi32(r, y2); r = w_sub32(r, y2); } return r; }
-  if (q == 1) { u64 r = w_pack(0u, y0); r = w_add_hi32(r, y1); r = w_sub32(r, y1); if (t) r = w_sub32(r, y2); return r; }
-  u64 r = w_pack(0u, y0); r = w_sub32(r, y0); r = w_sub32(r, y1); if (t) r = w_sub_hi32(r, y2); return r;
+  if (q == 0) return w_eps_madd(y2, y0, y1);
+  if (q == 1) { const u64 r = w_eps_madd(y1, 0u, y0); return t ? w_sub32(r, y2) : r; }
+  return w_sub_c(w_mul_eps(y0), w_pack(y1, y2));        // (y2:y1) < 2^63: canonical
 }
 
 }  // namespace xfg

@@ -150,28 +150,49 @@ __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __
 template <bool INV, int EPT, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pass_r16(NttPass p) {
   extern __shared__ u64 smem[];
-  const u32 L = 1u << p.Llog, T = 1u << p.Tlog, TP = T + 1, nthreads = blockDim.x;
+  const u32 L = 1u << p.Llog, T = 1u << p.Tlog, TP = T + 1, nthreads = blockDim.x;   // nthreads * EPT == L * T
   u64* S = smem; u64* TW = smem + (size_t)L * TP;   // TW[i] = w_L^(+-i), full circle
-  const u32 tid = threadIdx.x, tile = blockIdx.x, tr = blockIdx.y;
+  const u32 tid = threadIdx.x, tile = blockIdx.x;
   // transform tr = (group, sub): group selects the source polynomial, sub the coset.  coset_map (4 bits per entry, 0 = identity)
-  // lets a job compute a subset of the cosets: table / output slot of sub is map[sub], the output has dst_cosets slots per group
-  const u32 grp = tr / p.src_div, sub = tr % p.src_div;
+  // lets a job compute a subset of the cosets: table / output slot of sub is map[sub], the output has dst_cosets slots per group.
+  // With grp_fast the launch order walks the groups (columns) of one coset first, so that the coset's direct twiddle table is
+  // re-read from the L2 and not from HBM.
+  const u32 ngrp = gridDim.y / p.src_div;
+  const u32 grp = p.grp_fast ? blockIdx.y % ngrp : blockIdx.y / p.src_div, sub = p.grp_fast ? blockIdx.y / ngrp : blockIdx.y % p.src_div;
+  const u32 tr = grp * p.src_div + sub;
   const u32 coset = p.coset_map ? (u32)((p.coset_map >> (4 * sub)) & 15) : sub;
   u64* dst = p.dst + (p.coset_map ? (size_t)grp * p.dst_cosets + coset : (size_t)tr) * p.dst_tstride;
   const u64* src = p.src_is_dst ? dst : p.src + (size_t)grp * p.src_tstride;
-  for (u32 i = tid; i < L; i += nthreads) {
-    const u32 h = i & (L / 2 - 1); const u64 t = p.tw[(size_t)h << (NTT_TW_LOG - p.Llog)];
-    TW[i] = i < L / 2 ? t : gl_neg(t);
-  }
   const u64 col0 = (u64)tile << p.Tlog;
-  PowTable pre; pre.lo = p.pre_lo ? p.pre_lo + (size_t)coset * POW_LO : nullptr; pre.hi = p.pre_hi ? p.pre_hi + (size_t)coset * p.pre_hi_stride : nullptr;
-  for (u32 e = tid; e < L * T; e += nthreads) {
-    const u32 c = e & (T - 1), r = e >> p.Tlog;
-    const u64 gi = (u64)r * p.in_row_stride + col0 + c;
-    u64 v = src[gi];
-    if (p.pre_row) v = w_mul(v, p.pre_row[((size_t)coset << p.Llog) + r]);   // base^(r * in_row_stride); base^(col0 + c) is folded into it_tab
-    else if (pre.lo) v = w_mul(v, w_pow_lookup(pre, gi));                    // weak product: the butterflies accept any u64 residue
-    S[r * TP + c] = v;
+
+  // ---- load: CH global loads of a thread are issued before their first use (the plain loop over shared-memory stores would
+  // serialise them: the compiler cannot prove that `src` does not alias shared memory) ----
+  constexpr int CH = 8;
+  {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const u32 j = tid + i * nthreads, h = j & (L / 2 - 1); if (j < L) { const u64 t = __ldg(p.tw + ((size_t)h << (NTT_TW_LOG - p.Llog))); TW[j] = j < L / 2 ? t : gl_neg(t); } }
+    const u32 c = tid & (T - 1), r0 = tid >> p.Tlog, rstep = nthreads >> p.Tlog;
+    const u64* sp = src + (u64)r0 * p.in_row_stride + col0 + c; const u64 step = (u64)rstep * p.in_row_stride;
+    if (p.pre_lo && !p.pre_row) {     // two-level power lookups (no direct tables for this length): rolled, one element at a time
+      PowTable pre; pre.lo = p.pre_lo + (size_t)coset * POW_LO; pre.hi = p.pre_hi + (size_t)coset * p.pre_hi_stride;
+      const u64 g0 = (u64)r0 * p.in_row_stride + col0 + c;
+#pragma unroll 1
+      for (int i = 0; i < EPT; i++) S[(r0 + i * rstep) * TP + c] = w_mul(sp[i * step], w_pow_lookup(pre, g0 + i * step));
+    } else {
+      const u64* pr = p.pre_row ? p.pre_row + ((size_t)coset << p.Llog) + r0 : nullptr;   // base^(r * in_row_stride); base^(col0 + c) is folded into it_tab
+#pragma unroll
+      for (int h = 0; h < EPT; h += CH) {
+        u64 v[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) v[i] = sp[(h + i) * step];
+        if (pr) {
+#pragma unroll
+          for (int i = 0; i < CH; i++) v[i] = w_mul(v[i], __ldg(pr + (h + i) * rstep));      // weak product: the butterflies accept any u64 residue
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) S[(r0 + (h + i) * rstep) * TP + c] = v[i];
+      }
+    }
   }
   __syncthreads();
   u32 ns_log = 0;
@@ -183,31 +204,66 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
     else stockham_pass<2, INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
     ns_log += lr;
   }
+  // ---- store ----
   if (p.store_transposed) {
-    PowTable it; it.lo = p.it_lo; it.hi = p.it_hi;
-    const u64* itab = p.it_tab ? p.it_tab + (size_t)coset * p.it_tstride : nullptr;
-    for (u32 e = tid; e < L * T; e += nthreads) {
-      const u32 k = e & (L - 1), c = e >> p.Llog;
-      u64 v = S[k * TP + c];
-      const u64 di = (col0 + c) * (u64)L + k;
-      if (itab) v = w_canon(w_mul(v, itab[di]));
-      else { const u64 ex = (col0 + c) * (u64)k; v = w_canon(ex ? w_mul(v, w_pow_lookup(it, ex)) : v); }
-      dst[di] = v;
+    // Y[(col0 + c) * L + k] = S[k][c] * w_n^((col0 + c) * k)
+    if (p.it_tab) {
+      const u64* itab = p.it_tab + (size_t)coset * p.it_tstride;
+#pragma unroll
+      for (int h = 0; h < EPT; h += CH) {
+        u64 w[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) { const u32 e = tid + (h + i) * nthreads, k = e & (L - 1), c = e >> p.Llog; w[i] = __ldg(itab + (col0 + c) * (u64)L + k); }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+          const u32 e = tid + (h + i) * nthreads, k = e & (L - 1), c = e >> p.Llog;
+          dst[(col0 + c) * (u64)L + k] = w_canon(w_mul(S[k * TP + c], w[i]));
+        }
+      }
+    } else {
+      PowTable it; it.lo = p.it_lo; it.hi = p.it_hi;
+#pragma unroll 1
+      for (int i = 0; i < EPT; i++) {
+        const u32 e = tid + i * nthreads, k = e & (L - 1), c = e >> p.Llog;
+        u64 v = S[k * TP + c];
+        const u64 ex = (col0 + c) * (u64)k;
+        v = w_canon(ex ? w_mul(v, w_pow_lookup(it, ex)) : v);
+        dst[(col0 + c) * (u64)L + k] = v;
+      }
     }
   } else {
-    PowTable post; post.lo = p.post_lo ? p.post_lo + (size_t)(tr % p.post_div) * POW_LO : nullptr;
-    post.hi = p.post_hi ? p.post_hi + (size_t)(tr % p.post_div) * p.post_hi_stride : nullptr;
-    for (u32 e = tid; e < L * T; e += nthreads) {
-      const u32 c = e & (T - 1), k = e >> p.Tlog;
-      u64 v = S[k * TP + c];
-      const u64 go = (u64)k * p.out_row_stride + col0 + c;
-      if (p.post_tab) v = w_canon(w_mul(v, p.post_tab[(size_t)(tr % p.post_div) * p.post_tstride + go]));
-      else {
-        if (p.scale != 1) v = gl_mul(v, p.scale); else v = w_canon(v);
-        if (post.lo) v = gl_mul(v, pow_lookup(post, go));
+    const u32 c = tid & (T - 1), k0 = tid >> p.Tlog, kstep = nthreads >> p.Tlog;
+    const u64 g0 = (u64)k0 * p.out_row_stride + col0 + c, gstep = (u64)kstep * p.out_row_stride;
+    if (p.post_lo || p.scale != 1) {   // two-level power lookups / separate scale (no direct tables for this length): rolled
+      PowTable post; post.lo = p.post_lo ? p.post_lo + (size_t)(tr % p.post_div) * POW_LO : nullptr;
+      post.hi = p.post_hi ? p.post_hi + (size_t)(tr % p.post_div) * p.post_hi_stride : nullptr;
+#pragma unroll 1
+      for (int i = 0; i < EPT; i++) {
+        u64 x = S[(k0 + i * kstep) * TP + c];
+        const u64 go = g0 + i * gstep;
+        if (p.scale != 1) x = gl_mul(x, p.scale); else x = w_canon(x);
+        if (post.lo) x = gl_mul(x, pow_lookup(post, go));
+        if (p.peer_log) p.peer[go >> p.peer_log][(size_t)tr * (u64(1) << p.peer_log) + (go & ((u64(1) << p.peer_log) - 1))] = x;
+        else dst[go] = x;
       }
-      if (p.peer_log) p.peer[go >> p.peer_log][(size_t)tr * (u64(1) << p.peer_log) + (go & ((u64(1) << p.peer_log) - 1))] = v;   // fused all-to-all: store to the row owner
-      else dst[go] = v;
+    } else {
+      const u64* pt = p.post_tab ? p.post_tab + (size_t)(tr % p.post_div) * p.post_tstride + g0 : nullptr;
+#pragma unroll
+      for (int h = 0; h < EPT; h += CH) {
+        u64 w[CH];
+        if (pt) {
+#pragma unroll
+          for (int i = 0; i < CH; i++) w[i] = __ldg(pt + (h + i) * gstep);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+          u64 x = S[(k0 + (h + i) * kstep) * TP + c];
+          const u64 go = g0 + (h + i) * gstep;
+          x = w_canon(pt ? w_mul(x, w[i]) : x);
+          if (p.peer_log) p.peer[go >> p.peer_log][(size_t)tr * (u64(1) << p.peer_log) + (go & ((u64(1) << p.peer_log) - 1))] = x;   // fused all-to-all: store to the row owner
+          else dst[go] = x;
+        }
+      }
     }
   }
 }
@@ -281,7 +337,7 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   p.src = job.src; p.dst = job.dst; p.Llog = l2; p.Tlog = Tlog; p.in_row_stride = u64(1) << l1; p.out_row_stride = 0;
   p.store_transposed = 1; p.scale = 1;
   p.it_lo = job.inverse ? tb.wn_inv.lo : tb.wn_fwd.lo; p.it_hi = job.inverse ? tb.wn_inv.hi : tb.wn_fwd.hi;
-  if (dir_coset) { p.pre_row = tb.d_pre_row; p.it_tab = tb.d_it_coset; p.it_tstride = u64(1) << ln; }
+  if (dir_coset) { p.pre_row = tb.d_pre_row; p.it_tab = tb.d_it_coset; p.it_tstride = u64(1) << ln; p.grp_fast = 1; }
   if (dir_inv) { p.it_tab = tb.d_it_inv; p.it_tstride = 0; }
   if (fast) { p.Tlog = r16_tlog(l2); launch_r16(st, p, job.inverse, (1u << l1) >> p.Tlog, job.batch); }
   else { ntt_pass<<<dim3((1u << l1) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l2, Tlog), st>>>(p); XFG_LAUNCHED(1); }

@@ -28,6 +28,7 @@ struct NttPass {
   u32 coset_map, dst_cosets, src_is_dst;
   // direct (one 8-byte load per element) twiddle tables of a four-step transform, see NttTables; they replace pre_*, it_*, post_*
   const u64* pre_row; const u64* it_tab; u64 it_tstride; const u64* post_tab; u64 post_tstride;
+  u32 grp_fast;   // ntt_pass_r16: blockIdx.y = sub * groups + group instead of group * src_div + sub
 };
 
 // device tables owned by a plan (one per trace length)
