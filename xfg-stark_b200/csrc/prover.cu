@@ -25,6 +25,11 @@ using namespace xfg;
 
 namespace {
 
+// Split upload of a large trace: column groups {0} {1} {2,3} {4,5,6}.  Small groups first so that the NTTs start after one column's
+// copy time; larger groups later, because a one-column launch fills the GPU for 3.5 waves only (tail effect) and the copy
+// of the later columns is hidden behind the earlier groups' NTTs anyway.
+constexpr int UPLOAD_GROUPS = 4;
+constexpr int UPLOAD_GROUP_START[UPLOAD_GROUPS + 1] = {0, 1, 2, 4, XFG_TRACE_WIDTH};
 constexpr size_t MATERIAL_WORDS = size_t(1) << 20;   // 8 MiB: opened rows + per-position authentication paths
 constexpr u32 MIN_LOG = 3, MAX_LOG = 24;
 
@@ -264,9 +269,9 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   // the HBM-resident path column by column as well - to keep one column's 64 MB four-step intermediate inside the L2 - was
   // measured: 7x smaller grids cost more (5.88 vs 5.46 ms per proof) than the saved DRAM traffic gains on these ALU-bound kernels.)
   const bool waits = s.split_upload && !d_trace;
-  const int groups = waits ? XFG_TRACE_WIDTH : 1, per = XFG_TRACE_WIDTH / groups;
-  for (int g = 0; g < groups; g++) {
-    const size_t off = (size_t)g * per * n;
+  for (int g = 0; g < (waits ? UPLOAD_GROUPS : 1); g++) {
+    const int c0 = waits ? UPLOAD_GROUP_START[g] : 0, per = waits ? UPLOAD_GROUP_START[g + 1] - c0 : XFG_TRACE_WIDTH;
+    const size_t off = (size_t)c0 * n;
     if (waits) CU(cudaStreamWaitEvent(st, s.col_ev[g], 0));
     PROF("check_canonical", launch_check_canonical(st, trace_src + off, (size_t)per * n, s.d_state));
     { NttJob j{}; j.src = trace_src + off; j.dst = c.trace_coef + off; j.ln = ln; j.batch = per; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
@@ -486,10 +491,11 @@ int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace
   const u64* src = h_trace;
   if (!pinned) { std::memcpy(s.h_trace, h_trace, bytes); src = s.h_trace; }
   s.split_upload = allow_split && p.ln >= 17;
-  if (s.split_upload) {      // one copy + event per column on the copy stream; column c's NTTs start as soon as column c has landed
-    for (int col = 0; col < XFG_TRACE_WIDTH; col++) {
-      CU(cudaMemcpyAsync(c.trace_in + (size_t)col * p.n, src + (size_t)col * p.n, p.n * 8, cudaMemcpyHostToDevice, s.copy_st));
-      CU(cudaEventRecord(s.col_ev[col], s.copy_st));
+  if (s.split_upload) {      // one copy + event per column group on the copy stream; a group's NTTs start as soon as it has landed
+    for (int g = 0; g < UPLOAD_GROUPS; g++) {
+      const size_t c0 = UPLOAD_GROUP_START[g], c1 = UPLOAD_GROUP_START[g + 1];
+      CU(cudaMemcpyAsync(c.trace_in + c0 * p.n, src + c0 * p.n, (c1 - c0) * p.n * 8, cudaMemcpyHostToDevice, s.copy_st));
+      CU(cudaEventRecord(s.col_ev[g], s.copy_st));
     }
   } else {
     CU(cudaMemcpyAsync(c.trace_in, src, bytes, cudaMemcpyHostToDevice, s.st));
