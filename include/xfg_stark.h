@@ -135,6 +135,43 @@ int xfg_wide_extend(xfg_wide* w, const uint64_t* d_cols_local, float* device_ms)
 int xfg_wide_commit(xfg_wide* w, uint8_t subtree_root[32], float* device_ms);       /* call after a barrier across ranks */
 int xfg_wide_read_recv(xfg_wide* w, uint64_t* out);                     /* test hook: W x 8 x n/G elements */
 
+/* ---- batch verification ----
+ * Replaces the sequential loop of BatchBurnMintVerifier (src/burn_mint_verifier.rs:371-408) around
+ * XfgBurnMintVerifier::verify_with_winterfell -> winterfell::verify::<XfgBurnMintAir, Blake3_256, DefaultRandomCoin>
+ * (src/burn_mint_verifier.rs:265-283): one thread block per proof replays the transcript, rebuilds every batch Merkle root,
+ * recomputes the DEEP composition at the queried positions and checks the FRI folds and the remainder.
+ * results[i] = XFG_VERIFY_OK or the first failing check, named after winterfell::VerifierError / winter_fri::VerifierError.
+ * The return value is XFG_OK when the batch ran, whatever the verdicts.  `acceptable` plays the role of AcceptableOptions::OptionSet
+ * with one entry (src/burn_mint_verifier.rs:270-276); air[i] are the public inputs and AIR constants of proof i. */
+enum {
+  XFG_VERIFY_OK = 0,
+  XFG_VERIFY_MALFORMED = 1,                        /* ProofDeserializationError: lengths, layout, non-canonical field element */
+  XFG_VERIFY_UNACCEPTABLE_OPTIONS = 2,             /* UnacceptableProofOptions */
+  XFG_VERIFY_INCONSISTENT_OOD = 3,                 /* InconsistentOodConstraintEvaluations */
+  XFG_VERIFY_POW_FAILED = 4,                       /* QuerySeedProofOfWorkVerificationFailed */
+  XFG_VERIFY_NUM_QUERIES_MISMATCH = 5,             /* proof's num_unique_queries differs from the drawn positions */
+  XFG_VERIFY_TRACE_QUERY_MISMATCH = 6,             /* TraceQueryDoesNotMatchCommitment */
+  XFG_VERIFY_CONSTRAINT_QUERY_MISMATCH = 7,        /* ConstraintQueryDoesNotMatchCommitment */
+  XFG_VERIFY_FRI_LAYER_COMMITMENT_MISMATCH = 8,    /* FriVerifierError::LayerCommitmentMismatch */
+  XFG_VERIFY_FRI_INVALID_LAYER_FOLDING = 9,        /* FriVerifierError::InvalidLayerFolding */
+  XFG_VERIFY_FRI_REMAINDER_COMMITMENT_MISMATCH = 10,
+  XFG_VERIFY_FRI_REMAINDER_DEGREE_MISMATCH = 11,
+  XFG_VERIFY_FRI_INVALID_REMAINDER_FOLDING = 12,
+  XFG_VERIFY_FRI_DEGREE_TRUNCATION = 13,
+  XFG_VERIFY_COIN = 14                             /* RandomCoinError::FailedToDrawFieldElement */
+};
+typedef struct xfg_verify_times {
+  float host_parse_ms; /* walking the length prefixes + staging copy */
+  float h2d_ms;        /* proof bytes to the device */
+  float kernel_ms;     /* verify_kernel */
+  float total_ms;      /* whole call, wall clock */
+  uint64_t h2d_bytes, d2h_bytes;
+} xfg_verify_times;
+int xfg_verify_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint8_t* const* proofs, const size_t* proof_lens,
+                               const xfg_air_consts* air /* count entries */, const xfg_options* acceptable,
+                               int32_t* results /* count entries */, xfg_verify_times* times /* optional */);
+const char* xfg_verify_strerror(int code);
+
 /* ---- stage entry points (kernel-level parity tests; host buffers in and out) ---- */
 /* `batch` transforms of 2^n_log2 points, contiguous; inverse != 0 = fft::interpolate_poly, else forward evaluation */
 int xfg_ntt(xfg_ctx* ctx, uint64_t* data, uint32_t n_log2, uint32_t batch, int inverse);

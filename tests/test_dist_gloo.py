@@ -27,7 +27,7 @@ for i in mine:
 multi.barrier()
 mx = multi.max_over_ranks(10.0 + rank)
 tot = multi.sum_over_ranks(len(mine))
-print(json.dumps({"rank": rank, "mine": mine, "max": mx, "total": tot, "digs": digs}))
+open(os.path.join(os.environ["XFG_TEST_OUT"], "rank%%d.json" %% rank), "w").write(json.dumps({"rank": rank, "mine": mine, "max": mx, "total": tot, "digs": digs}))
 multi.finalize()
 '''
 
@@ -63,7 +63,7 @@ final, _ = orc.merkle(torch.stack(roots).numpy())
 # single-process answer
 full = np.stack([orc.lde(orc.ntt(c, 1, 1)) for c in trace])
 exp, _ = orc.merkle(orc.hash_rows(full))
-print(json.dumps({"rank": rank, "ok": final == exp}))
+open(os.path.join(os.environ["XFG_TEST_OUT"], "rank%%d.json" %% rank), "w").write(json.dumps({"rank": rank, "ok": final == exp}))
 multi.finalize()
 '''
 
@@ -75,10 +75,15 @@ def test_wide_trace_sharding_logic_world_size_2(tmp_path):
     script.write_text(WIDE_WORKER % (ROOT, ROOT))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), str(script)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    recs = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    recs = run_ranks(cmd, tmp_path)
     assert len(recs) == 2 and all(r["ok"] for r in recs)
+
+
+def run_ranks(cmd, tmp_path):
+    """runs the torchrun command; every rank writes its record to its own file (two processes sharing one stdout pipe can interleave)"""
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "XFG_TEST_OUT": str(tmp_path)})
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [json.loads((tmp_path / f).read_text()) for f in sorted(os.listdir(tmp_path)) if f.startswith("rank")]
 
 
 def free_port():
@@ -90,9 +95,7 @@ def test_world_size_2_sharding_and_reductions(tmp_path):
     script.write_text(WORKER % (ROOT, ROOT))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), str(script)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    recs = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    recs = run_ranks(cmd, tmp_path)
     assert len(recs) == 2
     by = {r["rank"]: r for r in recs}
     assert by[0]["mine"] == [0, 2, 4] and by[1]["mine"] == [1, 3]

@@ -5,16 +5,17 @@ host-side mirror of the reference's operator surface for that path, used by the 
 
 * ``ProofOptions``           — winter_air::ProofOptions as built at src/burn_mint_prover.rs:28-35
 * ``XfgBurnMintProver``      — src/burn_mint_prover.rs:18-237 (``new``/``with_options``/``prove_burn_mint``/...)
+* ``XfgBurnMintVerifier`` / ``BatchBurnMintVerifier`` — src/burn_mint_verifier.rs:18-408 over the CUDA batch verifier
 * ``Context``                — one device + workspaces; stage-level entry points for kernel parity tests
 
 There is no CPU fallback: importing works anywhere (so the CPU test-suite can check the exported symbols), but creating
 a ``Context`` without a CUDA device raises ``XfgError``.  The directory name carries a hyphen, so import it through the
 ``xfg_stark_b200`` shim at the repo root.
 """
-from ._binding import (WideTrace, Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgError, AirConsts, STAGE_NAMES, load_library,
+from ._binding import (WideTrace, Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgBurnMintVerifier, BatchBurnMintVerifier, XfgError, AirConsts, STAGE_NAMES, load_library,
                        library_path, EXPORTED_SYMBOLS, FieldExtension, pack_inputs, build_trace)
 from .synthetic import synthetic_inputs
 from . import multi
 
-__all__ = ["WideTrace", "Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgError", "AirConsts", "STAGE_NAMES",
+__all__ = ["WideTrace", "Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgBurnMintVerifier", "BatchBurnMintVerifier", "XfgError", "AirConsts", "STAGE_NAMES",
            "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "synthetic_inputs", "multi"]

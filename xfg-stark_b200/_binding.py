@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
-                    "xfg_wide_commit", "xfg_wide_read_recv"]
+                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -54,6 +54,14 @@ class StageTimes(C.Structure):
         d.update(h2d_ms=float(self.h2d_ms), device_ms=float(self.device_ms), total_ms=float(self.total_ms),
                  kernel_launches=int(self.kernel_launches), h2d_bytes=int(self.h2d_bytes), d2h_bytes=int(self.d2h_bytes))
         return d
+
+
+class VerifyTimes(C.Structure):
+    _fields_ = [("host_parse_ms", C.c_float), ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("total_ms", C.c_float),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 @dataclass(frozen=True)
@@ -105,6 +113,8 @@ def load_library():
     L.xfg_burn_mint_pack_inputs.argtypes = [vp] + inputs + [C.POINTER(AirConsts)]
     L.xfg_burn_mint_build_trace.argtypes = [C.POINTER(AirConsts), u32, vp]
     L.xfg_prove_burn_mint_from_inputs.argtypes = [vp] + inputs + [u32, C.POINTER(_Options)] + prove_tail
+    L.xfg_verify_burn_mint_batch.argtypes = [vp, u32, vp, vp, C.POINTER(AirConsts), C.POINTER(_Options), vp, C.POINTER(VerifyTimes)]
+    L.xfg_verify_strerror.argtypes = [i]; L.xfg_verify_strerror.restype = C.c_char_p
     L.xfg_ntt.argtypes = [vp, vp, u32, u32, i]
     L.xfg_lde_commit.argtypes = [vp, vp, u32, u32, vp, vp]
     L.xfg_merkle_root.argtypes = [vp, vp, sz, vp, vp]
@@ -225,6 +235,21 @@ class Context:
         out = np.empty(cnt * out_stride, dtype=np.uint8); lens = np.zeros(cnt, dtype=np.uint64); ms = C.c_float(0); o = options._c()
         self._check(self._lib.xfg_prove_burn_mint_batch(self._h, cnt, ptrs, n_log2, air_arr, C.byref(o), _ptr(out), out_stride, _ptr(lens), C.byref(ms)))
         return [out[i * out_stride:i * out_stride + int(lens[i])].tobytes() for i in range(cnt)], float(ms.value)
+
+    def verify_batch(self, proofs, airs, options=ProofOptions(), want_times=False):
+        """proofs: list of proof bytes; airs: list of AirConsts (public inputs + AIR constants of each proof).
+        Returns a list of rejection reasons ('' = accepted), named after winterfell's VerifierError variants."""
+        cnt = len(proofs)
+        if cnt == 0:
+            return ([], VerifyTimes().as_dict()) if want_times else []
+        bufs = [np.frombuffer(bytes(p), dtype=np.uint8) if len(p) else np.zeros(1, dtype=np.uint8) for p in proofs]
+        ptrs = (C.c_void_p * cnt)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_size_t * cnt)(*[len(p) for p in proofs])
+        air_arr = (AirConsts * cnt)(*airs)
+        res = np.zeros(cnt, dtype=np.int32); vt = VerifyTimes(); o = options._c()
+        self._check(self._lib.xfg_verify_burn_mint_batch(self._h, cnt, ptrs, lens, air_arr, C.byref(o), _ptr(res), C.byref(vt)))
+        out = [self._lib.xfg_verify_strerror(int(r)).decode() for r in res]
+        return (out, vt.as_dict()) if want_times else out
 
     def prove_from_inputs(self, burn_amount, mint_amount, tx_prefix_hash, recipient_address, secret, network_id, target_chain_id,
                           commitment_version, n_log2=6, options=ProofOptions(), want_times=False):
@@ -382,3 +407,50 @@ class XfgBurnMintProver:
     @staticmethod
     def atomic_units_to_xfg(atomic_units):  # :190-192
         return atomic_units / 10_000_000.0
+
+
+class XfgBurnMintVerifier:
+    """Python mirror of XfgBurnMintVerifier (src/burn_mint_verifier.rs:18-358) over the CUDA batch verifier.
+
+    `verify_with_winterfell(proof, air)` raises XfgError with the rejection reason, as the reference maps any
+    winterfell::VerifierError to XfgStarkError::CryptoError("STARK verification failed: ...") (src/burn_mint_verifier.rs:278-282);
+    `verify_with_public_inputs` returns a bool.  `air` is the AirConsts of the statement (public inputs and derived constants).
+    """
+
+    def __init__(self, security_parameter=128, proof_options=None, context=None, device=0):
+        self.security_parameter_ = security_parameter
+        self.proof_options_ = proof_options or ProofOptions()
+        self.ctx = context or Context(device=device, max_n_log2=6)
+
+    @classmethod
+    def new(cls, security_parameter=128, **kw):
+        return cls(security_parameter, None, **kw)
+
+    def security_parameter(self):
+        return self.security_parameter_
+
+    def verify_with_winterfell(self, proof, air):
+        reason = self.ctx.verify_batch([proof], [air], self.proof_options_)[0]
+        if reason:
+            raise XfgError(0, "STARK verification failed: " + reason)
+
+    def verify_with_public_inputs(self, proof, air):
+        return self.ctx.verify_batch([proof], [air], self.proof_options_)[0] == ""
+
+
+class BatchBurnMintVerifier:
+    """Python mirror of BatchBurnMintVerifier (src/burn_mint_verifier.rs:371-408): one kernel launch verifies the whole batch."""
+
+    def __init__(self, security_parameter=128, proof_options=None, context=None, device=0):
+        self.verifier = XfgBurnMintVerifier(security_parameter, proof_options, context, device)
+
+    @classmethod
+    def new(cls, security_parameter=128, **kw):
+        return cls(security_parameter, None, **kw)
+
+    def verify_batch(self, proofs_and_airs):
+        proofs = [p for p, _ in proofs_and_airs]; airs = [a for _, a in proofs_and_airs]
+        return [r == "" for r in self.verifier.ctx.verify_batch(proofs, airs, self.verifier.proof_options_)]
+
+    def verify_all(self, proofs_and_airs):
+        return all(self.verify_batch(proofs_and_airs))

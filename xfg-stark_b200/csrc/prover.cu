@@ -6,6 +6,7 @@
 // opened rows / authentication nodes runs on the device as one dependent chain of launches on the slot's stream; the host
 // only serialises (`StarkProof::to_bytes`, `BatchMerkleProof::serialize_nodes`).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -19,6 +20,7 @@
 #include "ntt.cuh"
 #include "stark_kernels.cuh"
 #include "transcript.cuh"
+#include "verify.cuh"
 #include "launch.cuh"
 
 using namespace xfg;
@@ -84,8 +86,11 @@ struct Slot {
 
 thread_local unsigned g_xfg_launches = 0;
 
+struct VerifyBufs { u8* h = nullptr; u8* d = nullptr; size_t cap = 0; };   // grow-only pinned staging + device copy of a verification batch
+
 struct xfg_ctx {
   int device = 0; u32 max_log = 0;
+  VerifyBufs vbufs;
   std::vector<Slot> slots;
   u64 *tw_fwd = nullptr, *tw_inv = nullptr;
   std::map<u64, Plan> plans;
@@ -551,6 +556,26 @@ const char* xfg_strerror(int code) {
     default: return "internal error";
   }
 }
+const char* xfg_verify_strerror(int code) {
+  switch (code) {
+    case XFG_VERIFY_OK: return "";
+    case XFG_VERIFY_MALFORMED: return "ProofDeserializationError";
+    case XFG_VERIFY_UNACCEPTABLE_OPTIONS: return "UnacceptableProofOptions";
+    case XFG_VERIFY_INCONSISTENT_OOD: return "InconsistentOodConstraintEvaluations";
+    case XFG_VERIFY_POW_FAILED: return "QuerySeedProofOfWorkVerificationFailed";
+    case XFG_VERIFY_NUM_QUERIES_MISMATCH: return "NumberOfQueriesMismatch";
+    case XFG_VERIFY_TRACE_QUERY_MISMATCH: return "TraceQueryDoesNotMatchCommitment";
+    case XFG_VERIFY_CONSTRAINT_QUERY_MISMATCH: return "ConstraintQueryDoesNotMatchCommitment";
+    case XFG_VERIFY_FRI_LAYER_COMMITMENT_MISMATCH: return "LayerCommitmentMismatch";
+    case XFG_VERIFY_FRI_INVALID_LAYER_FOLDING: return "InvalidLayerFolding";
+    case XFG_VERIFY_FRI_REMAINDER_COMMITMENT_MISMATCH: return "RemainderCommitmentMismatch";
+    case XFG_VERIFY_FRI_REMAINDER_DEGREE_MISMATCH: return "RemainderDegreeMismatch";
+    case XFG_VERIFY_FRI_INVALID_REMAINDER_FOLDING: return "InvalidRemainderFolding";
+    case XFG_VERIFY_FRI_DEGREE_TRUNCATION: return "DegreeTruncation";
+    case XFG_VERIFY_COIN: return "FailedToDrawFieldElement";
+    default: return "unknown verification error";
+  }
+}
 const char* xfg_last_error(const xfg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
 int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** out) {
@@ -599,6 +624,8 @@ void xfg_destroy(xfg_ctx* ctx) {
     if (s.st) cudaStreamDestroy(s.st);
   }
   for (auto& kv : ctx->plans) { cudaFree(kv.second.slab); cudaFree(kv.second.direct); }
+  if (ctx->vbufs.h) cudaFreeHost(ctx->vbufs.h);
+  if (ctx->vbufs.d) cudaFree(ctx->vbufs.d);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv);
   delete ctx;
 }
@@ -676,3 +703,4 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn, uint64_t mint, 
 
 #include "stage_api.inc"
 #include "wide.inc"
+#include "verify_api.inc"

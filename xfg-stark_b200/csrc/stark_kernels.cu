@@ -274,25 +274,6 @@ void launch_deep(cudaStream_t st, int D, const u64* lde, const u64* hlde, u32 ln
 // ------------------------------------------------------------------------------------------------------------------
 
 template <int D>
-__device__ __forceinline__ Ext<D> fold8(const Ext<D> (&v)[8], const FriConsts& fc, Ext<D> beta) {
-  // radix-2 DIT inverse DFT of size 8 (input bit-reversed), twiddles w_8^-j
-  Ext<D> a[8] = {v[0], v[4], v[2], v[6], v[1], v[5], v[3], v[7]};
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) { Ext<D> u = a[i], w = a[i + 1]; a[i] = u + w; a[i + 1] = u - w; }
-#pragma unroll
-  for (int i = 0; i < 8; i += 4) {
-    Ext<D> u = a[i], w = a[i + 2]; a[i] = u + w; a[i + 2] = u - w;
-    u = a[i + 1]; w = mul_base(a[i + 3], fc.w8i[2]); a[i + 1] = u + w; a[i + 3] = u - w;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; j++) { Ext<D> u = a[j], w = j ? mul_base(a[j + 4], fc.w8i[j]) : a[j + 4]; a[j] = u + w; a[j + 4] = u - w; }
-  Ext<D> r = a[7];
-#pragma unroll
-  for (int kk = 6; kk >= 0; kk--) r = r * beta + a[kk];
-  return mul_base(r, fc.inv8);
-}
-
-template <int D>
 __global__ void __launch_bounds__(128) fri_fold_kernel(const u64* __restrict__ src, size_t src_limb_stride, int src_coset, u32 lNl, u32 layer,
                                                         const ProofState* __restrict__ ps, PowTable wN_inv, u32 lN, FriConsts fc,
                                                         u64* __restrict__ dst, size_t dst_limb_stride, Digest* __restrict__ next_tree) {

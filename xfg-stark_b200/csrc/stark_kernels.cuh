@@ -6,6 +6,28 @@
 namespace xfg {
 
 struct FriConsts { u64 w8i[4]; u64 inv8; u64 inv7; };   // w_8^-1 powers 0..3, 8^-1, 7^-1
+#if defined(__CUDACC__)
+// P(beta * x_r) for the polynomial P of degree < 8 interpolating v[j] at x_r * w_8^j, i.e. apply_drp's fold with beta = alpha / x_r
+// (shared by the prover's FRI layers and the verifier's per-query fold check)
+template <int D>
+__device__ __forceinline__ Ext<D> fold8(const Ext<D> (&v)[8], const FriConsts& fc, Ext<D> beta) {
+  // radix-2 DIT inverse DFT of size 8 (input bit-reversed), twiddles w_8^-j
+  Ext<D> a[8] = {v[0], v[4], v[2], v[6], v[1], v[5], v[3], v[7]};
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) { Ext<D> u = a[i], w = a[i + 1]; a[i] = u + w; a[i + 1] = u - w; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 4) {
+    Ext<D> u = a[i], w = a[i + 2]; a[i] = u + w; a[i + 2] = u - w;
+    u = a[i + 1]; w = mul_base(a[i + 3], fc.w8i[2]); a[i + 1] = u + w; a[i + 3] = u - w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) { Ext<D> u = a[j], w = j ? mul_base(a[j + 4], fc.w8i[j]) : a[j + 4]; a[j] = u + w; a[j + 4] = u - w; }
+  Ext<D> r = a[7];
+#pragma unroll
+  for (int kk = 6; kk >= 0; kk--) r = r * beta + a[kk];
+  return mul_base(r, fc.inv8);
+}
+#endif
 void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams* d_air, const ProofState* ps, PowTable wn,
                         u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out);
 void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64* h, ProofState* ps);
