@@ -12,6 +12,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 #include "../../include/xfg_stark.h"
