@@ -55,6 +55,18 @@ pub struct xfg_stage_times {
     pub d2h_bytes: u64,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct xfg_verify_times {
+    pub host_parse_ms: f32,
+    pub h2d_ms: f32,
+    pub kernel_ms: f32,
+    pub total_ms: f32,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+}
+pub const XFG_VERIFY_OK: i32 = 0;
+
 extern "C" {
     pub fn xfg_create(device: c_int, max_n_log2: u32, num_slots: u32, out: *mut *mut xfg_ctx) -> c_int;
     pub fn xfg_destroy(ctx: *mut xfg_ctx);
@@ -76,6 +88,9 @@ extern "C" {
                                            recipient_len: usize, secret: *const u8, secret_len: usize, network_id: u32, target_chain_id: u32,
                                            commitment_version: u32, n_log2: u32, options: *const xfg_options, out: *mut u8, out_cap: usize,
                                            out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_verify_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, proofs: *const *const u8, proof_lens: *const usize, air: *const xfg_air_consts,
+                                      acceptable: *const xfg_options, results: *mut i32, times: *mut xfg_verify_times) -> c_int;
+    pub fn xfg_verify_strerror(code: c_int) -> *const c_char;
     pub fn xfg_ntt(ctx: *mut xfg_ctx, data: *mut u64, n_log2: u32, batch: u32, inverse: c_int) -> c_int;
     pub fn xfg_lde_commit(ctx: *mut xfg_ctx, cols_colmajor: *const u64, n_log2: u32, cols: u32, lde_out: *mut u64, root_out: *mut u8) -> c_int;
     pub fn xfg_merkle_root(ctx: *mut xfg_ctx, leaves: *const u8, count: usize, root_out: *mut u8, nodes_out: *mut u8) -> c_int;
