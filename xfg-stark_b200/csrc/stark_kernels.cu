@@ -308,9 +308,42 @@ __global__ void __launch_bounds__(128) fri_fold_kernel(const u64* __restrict__ s
     store_digest(next_tree + Rn + ip, b3_hash_limbs<8 * D>(row));
   }
 }
+// Small layers (fewer next-layer rows than the GPU has thread slots): one fold per thread, the 8 threads of a next-layer row are
+// adjacent lanes; lane 0 of the group hashes the row from shared memory.  Cuts the serial depth of a layer from 8 folds to 1.
+template <int D>
+__global__ void __launch_bounds__(128) fri_fold_small_kernel(const u64* __restrict__ src, size_t src_limb_stride, u32 lNl, u32 layer,
+                                                              const ProofState* __restrict__ ps, PowTable wN_inv, u32 lN, FriConsts fc,
+                                                              u64* __restrict__ dst, size_t dst_limb_stride, Digest* __restrict__ next_tree) {
+  const size_t Nl = size_t(1) << lNl, R = Nl / 8, Rn = R / 8;
+  const size_t tix = (size_t)blockIdx.x * blockDim.x + threadIdx.x, ip = tix >> 3; const u32 q = (u32)tix & 7, g = threadIdx.x >> 3;
+  __shared__ u64 sh[16][8 * D];
+  if (ip < Rn) {
+    const size_t r = ip + (size_t)q * Rn;
+    Ext<D> v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) for (int l = 0; l < D; l++) v[j].set_limb(l, src[(size_t)l * src_limb_stride + r + (size_t)j * R]);
+    const u64 xinv = gl_mul(fc.inv7, pow_lookup(wN_inv, (u64)r << (lN - lNl)));
+    const Ext<D> w = fold8<D>(v, fc, mul_base(ld_ext<D>(ps->alphas, layer), xinv));
+#pragma unroll
+    for (int l = 0; l < D; l++) { dst[(size_t)l * dst_limb_stride + r] = w.limb(l); sh[g][q * D + l] = w.limb(l); }
+  }
+  __syncthreads();
+  if (next_tree && ip < Rn && q == 0) {
+    u64 row[8 * D];
+#pragma unroll
+    for (int i = 0; i < 8 * D; i++) row[i] = sh[g][i];
+    store_digest(next_tree + Rn + ip, b3_hash_limbs<8 * D>(row));
+  }
+}
 void launch_fri_fold(cudaStream_t st, int D, const u64* src, size_t src_limb_stride, int src_coset, u32 lNl, u32 layer, const ProofState* ps,
                      PowTable wN_inv, u32 lN, const FriConsts& fc, u64* dst, size_t dst_limb_stride, Digest* next_tree) {
   const size_t Rn = (size_t(1) << lNl) / 64; const unsigned blocks = (unsigned)((Rn + 127) / 128);
+  if (!src_coset && Rn <= 148 * 128 * 2) {
+    const unsigned sb = (unsigned)((Rn * 8 + 127) / 128);
+    if (D == 1) fri_fold_small_kernel<1><<<sb, 128, 0, st>>>(src, src_limb_stride, lNl, layer, ps, wN_inv, lN, fc, dst, dst_limb_stride, next_tree);
+    else fri_fold_small_kernel<2><<<sb, 128, 0, st>>>(src, src_limb_stride, lNl, layer, ps, wN_inv, lN, fc, dst, dst_limb_stride, next_tree);
+    XFG_LAUNCHED(1); return;
+  }
   if (D == 1) fri_fold_kernel<1><<<blocks, 128, 0, st>>>(src, src_limb_stride, src_coset, lNl, layer, ps, wN_inv, lN, fc, dst, dst_limb_stride, next_tree);
   else fri_fold_kernel<2><<<blocks, 128, 0, st>>>(src, src_limb_stride, src_coset, lNl, layer, ps, wN_inv, lN, fc, dst, dst_limb_stride, next_tree);
   XFG_LAUNCHED(1);
