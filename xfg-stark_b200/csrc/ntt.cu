@@ -144,13 +144,26 @@ __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __
   __syncthreads();
 }
 
+// tile shape and radix plan of ntt_pass_r16 as functions of the tile length (shared by the host launcher and the specialised kernels):
+// 4096 elements per CTA (more with 2^11, 2^12-point tiles), 16 per thread: 8:(4,4) 9:(4,3,2) 10:(4,4,2) 11:(4,4,3) 12:(4,4,4)
+__host__ __device__ constexpr u32 r16_tlog_c(u32 Llog) { return Llog >= 10 ? 2 : 12 - Llog; }
+__host__ __device__ constexpr u32 r16_radix_count_c(u32 Llog) { return Llog == 8 ? 2 : 3; }
+__host__ __device__ constexpr u32 r16_radix_packed_c(u32 Llog) {
+  return Llog == 8 ? 0x44u : Llog == 9 ? 0x234u : Llog == 10 ? 0x244u : Llog == 11 ? 0x344u : 0x444u;
+}
+
 #ifndef XFG_R16_MINB
 #define XFG_R16_MINB 2   // 64 registers: measured best (1: 126 regs 2.26 ms, 2: 1.77 ms, 3: 1.84 ms, 4: 1.95 ms for the 2^20 trace LDE)
 #endif
-template <bool INV, int EPT, int MAXT>
+// LLOG != 0 specialises the kernel for 2^LLOG-point tiles of the standard shape: tile length, column count, thread count and the
+// radix plan become compile-time constants, which turns the shared-memory index arithmetic of every pass (a fifth of the
+// instructions of the generic kernel) into immediate offsets.  LLOG = 0 is the generic kernel (any shape the launcher passes).
+template <bool INV, int EPT, int MAXT, int LLOG>
 __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pass_r16(NttPass p) {
   extern __shared__ u64 smem[];
-  const u32 L = 1u << p.Llog, T = 1u << p.Tlog, TP = T + 1, nthreads = blockDim.x;   // nthreads * EPT == L * T
+  const u32 Llog = LLOG ? (u32)LLOG : p.Llog, Tlog = LLOG ? r16_tlog_c(LLOG) : p.Tlog;
+  const u32 L = 1u << Llog, T = 1u << Tlog, TP = T + 1, nthreads = LLOG ? (L * T) / EPT : blockDim.x;   // nthreads * EPT == L * T
+  const u32 num_radix = LLOG ? r16_radix_count_c(LLOG) : p.num_radix, radix_logs = LLOG ? r16_radix_packed_c(LLOG) : p.radix_logs;
   u64* S = smem; u64* TW = smem + (size_t)L * TP;   // TW[i] = w_L^(+-i), full circle
   const u32 tid = threadIdx.x, tile = blockIdx.x;
   // transform tr = (group, sub): group selects the source polynomial, sub the coset.  coset_map (4 bits per entry, 0 = identity)
@@ -163,15 +176,15 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
   const u32 coset = p.coset_map ? (u32)((p.coset_map >> (4 * sub)) & 15) : sub;
   u64* dst = p.dst + (p.coset_map ? (size_t)grp * p.dst_cosets + coset : (size_t)tr) * p.dst_tstride;
   const u64* src = p.src_is_dst ? dst : p.src + (size_t)grp * p.src_tstride;
-  const u64 col0 = (u64)tile << p.Tlog;
+  const u64 col0 = (u64)tile << Tlog;
 
   // ---- load: CH global loads of a thread are issued before their first use (the plain loop over shared-memory stores would
   // serialise them: the compiler cannot prove that `src` does not alias shared memory) ----
   constexpr int CH = 8;
   {
 #pragma unroll 4
-    for (u32 j = tid; j < L; j += nthreads) { const u32 h = j & (L / 2 - 1); const u64 t = __ldg(p.tw + ((size_t)h << (NTT_TW_LOG - p.Llog))); TW[j] = j < L / 2 ? t : gl_neg(t); }
-    const u32 c = tid & (T - 1), r0 = tid >> p.Tlog, rstep = nthreads >> p.Tlog;
+    for (u32 j = tid; j < L; j += nthreads) { const u32 h = j & (L / 2 - 1); const u64 t = __ldg(p.tw + ((size_t)h << (NTT_TW_LOG - Llog))); TW[j] = j < L / 2 ? t : gl_neg(t); }
+    const u32 c = tid & (T - 1), r0 = tid >> Tlog, rstep = nthreads >> Tlog;
     const u64* sp = src + (u64)r0 * p.in_row_stride + col0 + c; const u64 step = (u64)rstep * p.in_row_stride;
     if (p.pre_lo && !p.pre_row) {     // two-level power lookups (no direct tables for this length): rolled, one element at a time
       PowTable pre; pre.lo = p.pre_lo + (size_t)coset * POW_LO; pre.hi = p.pre_hi + (size_t)coset * p.pre_hi_stride;
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
 #pragma unroll 1
       for (int i = 0; i < EPT; i++) S[(r0 + i * rstep) * TP + c] = w_mul(sp[i * step], w_pow_lookup(pre, g0 + i * step));
     } else {
-      const u64* pr = p.pre_row ? p.pre_row + ((size_t)coset << p.Llog) + r0 : nullptr;   // base^(r * in_row_stride); base^(col0 + c) is folded into it_tab
+      const u64* pr = p.pre_row ? p.pre_row + ((size_t)coset << Llog) + r0 : nullptr;   // base^(r * in_row_stride); base^(col0 + c) is folded into it_tab
 #pragma unroll
       for (int h = 0; h < EPT; h += CH) {
         u64 v[CH];
@@ -196,12 +209,13 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
   }
   __syncthreads();
   u32 ns_log = 0;
-  for (u32 ps = 0; ps < p.num_radix; ps++) {
-    const u32 lr = (p.radix_logs >> (4 * ps)) & 15;
-    if (EPT >= 32 && lr == 5) stockham_pass<(EPT >= 32 ? 5 : 4), INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
-    else if (lr == 4) stockham_pass<4, INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
-    else if (lr == 3) stockham_pass<3, INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
-    else stockham_pass<2, INV, EPT>(S, TW, p.Llog, p.Tlog, TP, ns_log, tid, nthreads);
+#pragma unroll
+  for (u32 ps = 0; ps < num_radix; ps++) {
+    const u32 lr = (radix_logs >> (4 * ps)) & 15;
+    if (EPT >= 32 && lr == 5) stockham_pass<(EPT >= 32 ? 5 : 4), INV, EPT>(S, TW, Llog, Tlog, TP, ns_log, tid, nthreads);
+    else if (lr == 4) stockham_pass<4, INV, EPT>(S, TW, Llog, Tlog, TP, ns_log, tid, nthreads);
+    else if (lr == 3) stockham_pass<3, INV, EPT>(S, TW, Llog, Tlog, TP, ns_log, tid, nthreads);
+    else stockham_pass<2, INV, EPT>(S, TW, Llog, Tlog, TP, ns_log, tid, nthreads);
     ns_log += lr;
   }
   // ---- store ----
@@ -213,10 +227,10 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
       for (int h = 0; h < EPT; h += CH) {
         u64 w[CH];
 #pragma unroll
-        for (int i = 0; i < CH; i++) { const u32 e = tid + (h + i) * nthreads, k = e & (L - 1), c = e >> p.Llog; w[i] = __ldg(itab + (col0 + c) * (u64)L + k); }
+        for (int i = 0; i < CH; i++) { const u32 e = tid + (h + i) * nthreads, k = e & (L - 1), c = e >> Llog; w[i] = __ldg(itab + (col0 + c) * (u64)L + k); }
 #pragma unroll
         for (int i = 0; i < CH; i++) {
-          const u32 e = tid + (h + i) * nthreads, k = e & (L - 1), c = e >> p.Llog;
+          const u32 e = tid + (h + i) * nthreads, k = e & (L - 1), c = e >> Llog;
           dst[(col0 + c) * (u64)L + k] = w_canon(w_mul(S[k * TP + c], w[i]));
         }
       }
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
       PowTable it; it.lo = p.it_lo; it.hi = p.it_hi;
 #pragma unroll 1
       for (int i = 0; i < EPT; i++) {
-        const u32 e = tid + i * nthreads, k = e & (L - 1), c = e >> p.Llog;
+        const u32 e = tid + i * nthreads, k = e & (L - 1), c = e >> Llog;
         u64 v = S[k * TP + c];
         const u64 ex = (col0 + c) * (u64)k;
         v = w_canon(ex ? w_mul(v, w_pow_lookup(it, ex)) : v);
@@ -232,7 +246,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
       }
     }
   } else {
-    const u32 c = tid & (T - 1), k0 = tid >> p.Tlog, kstep = nthreads >> p.Tlog;
+    const u32 c = tid & (T - 1), k0 = tid >> Tlog, kstep = nthreads >> Tlog;
     const u64 g0 = (u64)k0 * p.out_row_stride + col0 + c, gstep = (u64)kstep * p.out_row_stride;
     if (p.post_lo || p.scale != 1) {   // two-level power lookups / separate scale (no direct tables for this length): rolled
       PowTable post; post.lo = p.post_lo ? p.post_lo + (size_t)(tr % p.post_div) * POW_LO : nullptr;
@@ -280,13 +294,27 @@ static void r16_radices(u32 Llog, u32 ept, u32& count, u32& packed) {
   static const u32 t32[5][3] = {{5, 3, 0}, {5, 4, 0}, {5, 5, 0}, {4, 4, 3}, {4, 4, 4}};
   const u32* r = (ept == 32 ? t32 : t16)[Llog - 8]; count = r[2] ? 3 : 2; packed = r[0] | (r[1] << 4) | (r[2] << 8);
 }
+template <bool INV> static void launch_r16_t(cudaStream_t st, const NttPass& p, dim3 grid, u32 threads, size_t sm, bool standard) {
+  if (standard) {
+    switch (p.Llog) {
+      case 8: ntt_pass_r16<INV, 16, 512, 8><<<grid, threads, sm, st>>>(p); return;
+      case 9: ntt_pass_r16<INV, 16, 512, 9><<<grid, threads, sm, st>>>(p); return;
+      case 10: ntt_pass_r16<INV, 16, 512, 10><<<grid, threads, sm, st>>>(p); return;
+      case 11: ntt_pass_r16<INV, 16, 512, 11><<<grid, threads, sm, st>>>(p); return;
+      case 12: ntt_pass_r16<INV, 16, 1024, 12><<<grid, threads, sm, st>>>(p); return;
+      default: break;
+    }
+  }
+  if (threads > 512) ntt_pass_r16<INV, 16, 1024, 0><<<grid, threads, sm, st>>>(p);
+  else ntt_pass_r16<INV, 16, 512, 0><<<grid, threads, sm, st>>>(p);
+}
 static void launch_r16(cudaStream_t st, NttPass p, bool inverse, u32 tiles, u32 batch) {
   const u32 ept = r16_ept();
   r16_radices(p.Llog, ept, p.num_radix, p.radix_logs);
   const u32 threads = (1u << (p.Llog + p.Tlog)) / ept; const size_t sm = r16_smem(p.Llog, p.Tlog);
-  // 2^12-point tiles need 1024 threads (64 registers); everything else runs 256-512 threads and may use up to 128 registers
-  if (threads > 512) { if (inverse) ntt_pass_r16<true, 16, 1024><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false, 16, 1024><<<dim3(tiles, batch), threads, sm, st>>>(p); }
-  else { if (inverse) ntt_pass_r16<true, 16, 512><<<dim3(tiles, batch), threads, sm, st>>>(p); else ntt_pass_r16<false, 16, 512><<<dim3(tiles, batch), threads, sm, st>>>(p); }
+  // 2^12-point tiles need 1024 threads (64 registers); everything else runs 256-512 threads
+  const bool standard = ept == 16 && p.Tlog == r16_tlog_c(p.Llog) && p.radix_logs == r16_radix_packed_c(p.Llog) && p.num_radix == r16_radix_count_c(p.Llog);
+  if (inverse) launch_r16_t<true>(st, p, dim3(tiles, batch), threads, sm, standard); else launch_r16_t<false>(st, p, dim3(tiles, batch), threads, sm, standard);
   XFG_LAUNCHED(1);
 }
 
@@ -300,10 +328,16 @@ void ntt_init(bool force) {
   static thread_local bool done = false;
   if (done && !force) return;
   cudaFuncSetAttribute(ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_pass_smem(12, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(10, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(10, 2));
   done = true;
 }
 

@@ -208,8 +208,11 @@ template <int D> __device__ __forceinline__ Ext<D> deep_mul_conj(const DeepPoint
 //   D(x) = P / (x - z) + Q / (x - zg) = [ (P conj_z) n_zg + (Q conj_zg) n_z ] / (n_z n_zg),   P = S_T + delta H - C1,  Q = S_T - C2
 // so a point costs one base-field inversion (batched over the thread's 8 points) and no extension-field multiplication
 // besides delta * H.
+#ifndef XFG_DEEP_MINB
+#define XFG_DEEP_MINB 1
+#endif
 template <int D>
-__global__ void __launch_bounds__(DEEP_THREADS) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
+__global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
                                                              PowTable wn, const u64* __restrict__ s_k, u64 w8, u64* __restrict__ deep, Digest* __restrict__ fri_tree0) {
   __shared__ u64 sh[8][D + 2][DEEP_THREADS];          // per point: numerator -> result (D), n_z n_zg, prefix
   __shared__ u64 sc[2 * (XFG_TRACE_WIDTH + 1) + 8];   // dcoef[8][2], then c1, c2, z, zg
