@@ -31,10 +31,13 @@ template <int K> __device__ __forceinline__ void batch_inv(u64 (&v)[K]) {
 // out: [limb][k'][m], k' < 2
 // ------------------------------------------------------------------------------------------------------------------
 static constexpr int CE_PTS = 4, CE_THREADS = 128;
+#ifndef XFG_CE_MINB
+#define XFG_CE_MINB 4
+#endif
 // The loops over the CE_PTS points are NOT unrolled and the per-point intermediates live in shared memory ([point][word][thread],
 // conflict-free): the fully unrolled version was 160 KB of SASS and stalled on instruction fetch (ncu: no_instruction).
 template <int D>
-__global__ void __launch_bounds__(CE_THREADS) constraint_kernel(const u64* __restrict__ lde, u32 ln, const AirParams* __restrict__ airp, const ProofState* __restrict__ ps,
+__global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(const u64* __restrict__ lde, u32 ln, const AirParams* __restrict__ airp, const ProofState* __restrict__ ps,
                                                                  PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out) {
   __shared__ u64 sh[CE_PTS][2 * D + 2][CE_THREADS];      // per point: u (D), w (D), d, prefix
   __shared__ u64 sc[(XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS) * 2];
@@ -209,7 +212,7 @@ template <int D> __device__ __forceinline__ Ext<D> deep_mul_conj(const DeepPoint
 // so a point costs one base-field inversion (batched over the thread's 8 points) and no extension-field multiplication
 // besides delta * H.
 #ifndef XFG_DEEP_MINB
-#define XFG_DEEP_MINB 1
+#define XFG_DEEP_MINB 4   // 122 registers, no spills: measured 0.652 ms; 3 (146 regs) 0.664, unconstrained (152) 0.662, 5 (96 regs, 24 B spilled) 0.740, 6-7: 0.69
 #endif
 template <int D>
 __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
