@@ -46,7 +46,7 @@ struct NttTables {
   const u64* d_pre_id = nullptr; const u64* d_post_id = nullptr; u64 d_scale = 0; u32 d_ln = 0;
 };
 // words of device memory ntt_build_direct needs / fill the tables (synchronous on stream 0); direct tables exist for 16 <= ln <= NTT_DIRECT_MAX_LOG
-static constexpr u32 NTT_DIRECT_MIN_LOG = 16, NTT_DIRECT_MAX_LOG = 22;
+static constexpr u32 NTT_DIRECT_MIN_LOG = 16, NTT_DIRECT_MAX_LOG = 24;   // 1.4 GB of tables at 2^24 (falls back to the lookups when the allocation fails)
 size_t ntt_direct_words(u32 ln, u32 cosets, u32 posts);
 void ntt_build_direct(NttTables& tb, u32 ln, u64* storage, u64 scale, const u64* pre_lo, const u64* pre_hi, u32 pre_hi_stride, u32 cosets,
                       const u64* post_lo, const u64* post_hi, u32 post_hi_stride, u32 posts);

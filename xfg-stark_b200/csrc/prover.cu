@@ -171,7 +171,7 @@ int get_plan(xfg_ctx* ctx, u32 ln, u32 rem_max_deg, const Plan** out) {
   p.g_n = wn; p.g_last = gl_pow(wn, p.n - 1);
   p.zinv0 = gl_inv(gl_sub(gl_pow(p.s_k[0], p.n), 1)); p.zinv1 = gl_inv(gl_sub(gl_pow(p.s_k[4], p.n), 1));
   p.n_inv = gl_inv((u64)p.n); p.inv2 = gl_inv(2); p.rem_ninv = gl_inv((u64)1 << p.rem_log);
-  // full-size twiddle tables for the four-step transforms (88 MB at n = 2^20; XFG_NTT_DIRECT=0 keeps the two-level lookups, for A/B runs)
+  // full-size twiddle tables for the four-step transforms (88 MB at n = 2^20, 1.4 GB at 2^24; XFG_NTT_DIRECT=0 keeps the two-level lookups, for A/B runs)
   { const char* e = getenv("XFG_NTT_DIRECT"); const size_t dw = (e && e[0] == '0') ? 0 : ntt_direct_words(ln, 8, 2);
     if (dw) {
       if (cudaMalloc(&p.direct, dw * 8) != cudaSuccess) { cudaGetLastError(); p.direct = nullptr; }   // optional: fall back to the lookups
