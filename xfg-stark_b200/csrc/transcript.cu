@@ -36,17 +36,30 @@ template <int D> __global__ void __launch_bounds__(32) constraint_root_kernel(Pr
   coin_store(ps, c);
 }
 // sums the OOD partials, sends the frame and H(z) to the coin, draws the DEEP coefficients (A.9)
-template <int D> __global__ void __launch_bounds__(32) ood_finish_kernel(ProofState* ps, const u64* __restrict__ partial, u32 nb) {
+// Block of (7 + D) warps: warp p first sums the partials of polynomial p (all loads of a lane issued together: one memory latency
+// instead of one per sum), then warp 0 alone continues with the transcript.
+template <int D> __global__ void __launch_bounds__(32 * NUM_OOD_POLYS) ood_finish_kernel(ProofState* ps, const u64* __restrict__ partial, u32 nb) {
   __shared__ u64 sums[NUM_OOD_POLYS][2][2];
-  Coin c = coin_load(ps);
-  // every sum is spread over the warp: lane b adds partials b, b+32, ... then a shuffle tree (exact arithmetic: any order)
-  for (u32 t = 0; t < (XFG_TRACE_WIDTH + D) * 4; t++) {
-    const u32 p = t >> 2, w = (t >> 1) & 1, l = t & 1;
-    u64 s = 0; for (u32 b = lane_id(); b < nb; b += 32) s = gl_add(s, partial[(((size_t)p * nb + b) * 2 + w) * 2 + l]);
-    for (int o = 16; o > 0; o >>= 1) s = gl_add(s, __shfl_xor_sync(0xFFFFFFFFu, s, o));
-    if (lane_id() == 0) sums[p][w][l] = s;
+  __shared__ u64 cpart[2][XFG_TRACE_WIDTH + 1][2];
+  {
+    const u32 p = threadIdx.x >> 5;        // exact arithmetic: any summation order gives the same field element
+    u64 v[OOD_MAX_BLOCKS / 32][4];
+#pragma unroll
+    for (u32 i = 0; i < OOD_MAX_BLOCKS / 32; i++) { const u32 b = lane_id() + 32 * i;
+#pragma unroll
+      for (u32 q = 0; q < 4; q++) v[i][q] = b < nb ? partial[((size_t)p * nb + b) * 4 + q] : 0; }
+#pragma unroll
+    for (u32 q = 0; q < 4; q++) {
+      u64 s = 0;
+#pragma unroll
+      for (u32 i = 0; i < OOD_MAX_BLOCKS / 32; i++) s = gl_add(s, v[i][q]);
+      for (int o = 16; o > 0; o >>= 1) s = gl_add(s, __shfl_xor_sync(0xFFFFFFFFu, s, o));
+      if (lane_id() == 0) sums[p][q >> 1][q & 1] = s;
+    }
   }
-  __syncwarp();
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  Coin c = coin_load(ps);
   u64 limbs[2 * XFG_TRACE_WIDTH * D];
 #pragma unroll
   for (int j = 0; j < XFG_TRACE_WIDTH; j++)
@@ -61,16 +74,22 @@ template <int D> __global__ void __launch_bounds__(32) ood_finish_kernel(ProofSt
   u64 hl[2] = {hz.limb(0), hz.limb(1)};
   coin_reseed(c, b3_hash_limbs<D>(hl));
   const bool ok = coin_draw_many<D>(c, XFG_TRACE_WIDTH + 1, ps->dcoef);      // 7 trace coefficients, then 1 composition column
+  __syncwarp();
+  // C1 = sum_j gamma_j T_j(z) + delta H(z), C2 = sum_j gamma_j T_j(zg): lane (w, j) computes one product, lane 0 adds them up
+  if (lane_id() < 2 * (XFG_TRACE_WIDTH + 1)) {
+    const u32 w = lane_id() / (XFG_TRACE_WIDTH + 1), j = lane_id() % (XFG_TRACE_WIDTH + 1);
+    Ext<D> t;
+    if (j < XFG_TRACE_WIDTH) t = ldx<D>(ps->dcoef[j]) * ldx<D>(sums[j][w]);
+    else if (w == 0) t = ldx<D>(ps->dcoef[XFG_TRACE_WIDTH]) * hz;
+    stx<D>(cpart[w][j], t);
+  }
+  __syncwarp();
   if (lane_id() == 0) {
     for (int j = 0; j < XFG_TRACE_WIDTH; j++) for (int w = 0; w < 2; w++) { ps->ood_frame[2 * j + w][0] = sums[j][w][0]; ps->ood_frame[2 * j + w][1] = D == 2 ? sums[j][w][1] : 0; }
     stx<D>(ps->hz, hz);
     if (!ok) ps->error_flags |= ERR_FLAG_COIN;
     Ext<D> c1, c2;
-    for (int j = 0; j < XFG_TRACE_WIDTH; j++) {
-      const Ext<D> g = ldx<D>(ps->dcoef[j]);
-      c1 = c1 + g * ldx<D>(sums[j][0]); c2 = c2 + g * ldx<D>(sums[j][1]);
-    }
-    c1 = c1 + ldx<D>(ps->dcoef[XFG_TRACE_WIDTH]) * hz;
+    for (int j = 0; j <= XFG_TRACE_WIDTH; j++) { c1 = c1 + ldx<D>(cpart[0][j]); c2 = c2 + ldx<D>(cpart[1][j]); }
     stx<D>(ps->deep_c1, c1); stx<D>(ps->deep_c2, c2);
   }
   coin_store(ps, c);
@@ -190,7 +209,7 @@ void launch_constraint_root(cudaStream_t st, int D, ProofState* ps, const Digest
   XFG_LAUNCHED(1);
 }
 void launch_ood_finish(cudaStream_t st, int D, ProofState* ps, const u64* partial, u32 nb) {
-  if (D == 1) ood_finish_kernel<1><<<1, 32, 0, st>>>(ps, partial, nb); else ood_finish_kernel<2><<<1, 32, 0, st>>>(ps, partial, nb);
+  if (D == 1) ood_finish_kernel<1><<<1, 32 * (XFG_TRACE_WIDTH + 1), 0, st>>>(ps, partial, nb); else ood_finish_kernel<2><<<1, 32 * (XFG_TRACE_WIDTH + 2), 0, st>>>(ps, partial, nb);
   XFG_LAUNCHED(1);
 }
 void launch_fri_commit(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u32 layer) {
