@@ -349,7 +349,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,
                 "peak_source": peak_src, "launch_ms": top["ms"], "alg_bytes": top["alg_bytes"],
                 "alu_pipe_busy_ncu": alu_busy,
-                "note": "every heavy kernel of this path is bound by the 32-bit integer ALU pipe (64-bit modular arithmetic, BLAKE3), not by HBM: ncu ALU pipe 74-84 % busy, DRAM 5-14 % (DESIGN.md section 4)",
+                "note": "every heavy kernel of this path is bound by the 32-bit integer ALU pipe (64-bit modular arithmetic, BLAKE3), not by HBM: ncu ALU pipe 64-87 % busy, DRAM 8-20 % (DESIGN.md section 4)",
                 "whole_proof": {"alg_bytes": ab["_total_survey"], "gbps": round(ab["_total_survey"] / times["device_ms"] / 1e6, 1),
                                 "frac": round(ab["_total_survey"] / times["device_ms"] / 1e6 / peak, 4)}}
 
