@@ -62,4 +62,14 @@ enum {
 #define XFG_MAX_QUERIES       255
 #define XFG_MAX_FRI_LAYERS    16
 
+/* ---- generic AIR front-end (xfg_air_desc): limits of this backend ---- */
+#define XFG_AIR_MAX_WIDTH        128   /* one BLAKE3 chunk per row (A.6); winter-air allows 255 */
+#define XFG_AIR_MAX_PUB_INPUTS   120
+#define XFG_AIR_MAX_CONSTANTS    512
+#define XFG_AIR_MAX_INSTR        4096
+#define XFG_AIR_MAX_CONSTRAINTS  256
+#define XFG_AIR_MAX_ASSERTIONS   255
+#define XFG_AIR_MAX_GROUPS       16    /* distinct assertion steps = boundary-constraint divisors */
+#define XFG_AIR_MAX_LIVE         64    /* simultaneously live intermediate values after register allocation */
+
 #endif /* XFG_SPEC_H */

@@ -118,6 +118,44 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn_amount, uint64_t
                                     uint32_t network_id, uint32_t target_chain_id, uint32_t commitment_version, uint32_t n_log2,
                                     const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
 
+/* ---- generic AIR front-end ----
+ * The same pipeline for any main-segment-only AIR whose transition constraints have degree <= 2 (then ce_blowup = 2 and the
+ * composition polynomial is one column) and whose assertions are single-point.  The AIR is a straight-line
+ * program over the evaluation frame: what the body of `Air::evaluate_transition` computes (e.g. the 4-column XfgBurnAir sketch,
+ * src/winterfell_air.rs:87-127, whose constraints are `current[i] - constant`), given as data instead of Rust code.
+ * Value ids: [0, width) = frame.current()[i]; [width, 2*width) = frame.next()[i]; [2*width, 2*width + num_constants) =
+ * constants[i]; 2*width + num_constants + i = result of code[i] (operands must refer to earlier values).
+ * constraint_values[j] is the value id written to result[j].  Assertions are `Assertion::single(column, step, value)`
+ * (`Air::get_assertions`, src/winterfell_air.rs:117-124); they are sorted as winter-air does (step, then column) before the
+ * boundary coefficients are assigned.  pub_inputs are `PublicInputs::to_elements()`, appended to the coin seed (A.4). */
+enum { XFG_OP_ADD = 0, XFG_OP_SUB = 1, XFG_OP_MUL = 2 };
+typedef struct xfg_air_instr { uint32_t op, a, b; } xfg_air_instr;
+typedef struct xfg_assertion { uint32_t column; uint32_t step; uint64_t value; } xfg_assertion;
+typedef struct xfg_air_desc {
+  uint32_t width;               /* 1..XFG_AIR_MAX_WIDTH trace columns */
+  uint32_t num_pub_inputs;      /* <= XFG_AIR_MAX_PUB_INPUTS */
+  uint32_t num_constants;       /* <= XFG_AIR_MAX_CONSTANTS */
+  uint32_t num_instr;           /* <= XFG_AIR_MAX_INSTR */
+  uint32_t num_constraints;     /* 1..XFG_AIR_MAX_CONSTRAINTS transition constraints */
+  uint32_t num_assertions;      /* 1..XFG_AIR_MAX_ASSERTIONS, at most XFG_AIR_MAX_GROUPS distinct steps */
+  const uint64_t* pub_inputs;
+  const uint64_t* constants;
+  const xfg_air_instr* code;
+  const uint32_t* constraint_values;
+  const xfg_assertion* assertions;
+} xfg_air_desc;
+/* limits: XFG_AIR_MAX_* in xfg/spec.h */
+/* like xfg_create, with workspaces sized for traces of up to max_width columns */
+int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t max_width, xfg_ctx** out);
+/* replaces `air.prove(trace)` (winter_prover::Prover::prove) for the AIR described by `air`; trace: column-major, air->width
+ * columns x 2^n_log2 rows, host memory (or device memory for the *_device variant).  Errors: XFG_ERR_BAD_ARGS for a malformed
+ * description, XFG_ERR_UNSUPPORTED_OPTIONS for degree > 2 / too many groups / too many live values,
+ * XFG_ERR_UNSATISFIED_CONSTRAINT when the trace violates a constraint or an assertion. */
+int xfg_prove_air(xfg_ctx* ctx, const xfg_air_desc* air, const uint64_t* trace_colmajor, uint32_t n_log2, const xfg_options* options,
+                  uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
+int xfg_prove_air_device(xfg_ctx* ctx, const xfg_air_desc* air, const uint64_t* d_trace_colmajor, uint32_t n_log2, const xfg_options* options,
+                         uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
+
 /* ---- one wide trace sharded over the GPUs of a box (BASELINE config 5) ----
  * Replaces DefaultTraceLde::new (src/burn_mint_air.rs:513: interpolate_columns + evaluate_polys_over + commit_to_rows +
  * MerkleTree::new) for a W-column x 2^n_log2-row trace: rank r interpolates and extends columns [r*W/G, (r+1)*W/G); the last

@@ -10,6 +10,7 @@
 //   input validation / packing .............. src/burn_mint_prover.rs:74-107, 132-221
 //   ProofOptions + Context (winter-air 0.8.3) SURVEY.md A.2, A.4, A.12
 #pragma once
+#include <algorithm>
 #include <string>
 #include "hash.hpp"
 
@@ -124,20 +125,81 @@ inline std::vector<Assertion> get_assertions(const PublicInputs& pi, const AirCo
           {4, 0, 0}, {5, 0, c.nullifier}, {6, 0, c.commitment}, {4, n - 1, XFG_FINAL_STATE}};
 }
 
+// ---- generic degree-<=2 AIR: a straight-line program over the evaluation frame --------------------
+// Value ids: [0, w) = current row, [w, 2w) = next row, [2w, 2w + C) = constants, 2w + C + i = result of instruction i.
+// This is the role of a user's `Air::evaluate_transition` body (e.g. the 4-column XfgBurnAir sketch, src/winterfell_air.rs:87-127);
+// Winterfell's own rules around it - assertion ordering (A.8), ce_blowup 2 and one composition column for degrees <= 2 (A.3) -
+// are unchanged.
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2 };
+struct Instr { u32 op, a, b; };
+struct AirDef {
+  bool burn_mint = false;                   // the hard-wired normalised BurnMintAir (AirConsts in `ac`), else the program below
+  AirConsts ac{};
+  size_t width = 0, num_transition = 0;
+  std::vector<u64> pub_inputs;              // ToElements order; appended to the coin seed after Context::to_elements
+  std::vector<u64> constants; std::vector<Instr> code; std::vector<u32> outputs;   // outputs[j] = value id of constraint j
+  std::vector<Assertion> assertions;        // Winterfell's sorted order (stride, first_step, column) = (step, column) for single assertions
+};
+inline AirDef burn_mint_air(const PublicInputs& pi, const AirConsts& c, size_t n) {
+  AirDef a; a.burn_mint = true; a.ac = c; a.width = XFG_TRACE_WIDTH; a.num_transition = XFG_NUM_TRANSITION;
+  a.pub_inputs.assign(pi.v, pi.v + XFG_NUM_PUB_INPUTS); a.assertions = get_assertions(pi, c, n); return a;
+}
+// Air::new-style validation of a generic definition; returns "" or the reason (strings follow winter-air's panics where one exists)
+inline std::string validate_air(AirDef& a, size_t n) {
+  if (a.burn_mint) return "";
+  const size_t w = a.width, C = a.constants.size();
+  if (w < 1 || w > 255) return "number of columns must be between 1 and 255";
+  if (a.outputs.empty()) return "at least one transition constraint degree must be specified";
+  if (a.assertions.empty()) return "at least one assertion must be specified";
+  for (u64 c : a.constants) if (c >= P) return "non-canonical constant";
+  for (u64 c : a.pub_inputs) if (c >= P) return "non-canonical public input";
+  std::vector<u32> deg(2 * w + C + a.code.size(), 0);
+  for (size_t i = 0; i < 2 * w; i++) deg[i] = 1;
+  for (size_t i = 0; i < a.code.size(); i++) {
+    const Instr& in = a.code[i]; const size_t id = 2 * w + C + i;
+    if (in.a >= id || in.b >= id || in.op > OP_MUL) return "invalid instruction";
+    deg[id] = in.op == OP_MUL ? deg[in.a] + deg[in.b] : std::max(deg[in.a], deg[in.b]);
+    if (deg[id] > 2) return "transition constraint degree above 2 is not supported";
+  }
+  for (u32 o : a.outputs) { if (o >= deg.size()) return "invalid constraint output"; if (deg[o] == 0) return "transition constraint degree must be at least one"; }
+  std::sort(a.assertions.begin(), a.assertions.end(), [](const Assertion& x, const Assertion& y) { return x.step != y.step ? x.step < y.step : x.column < y.column; });
+  for (size_t i = 0; i < a.assertions.size(); i++) {
+    const Assertion& s = a.assertions[i];
+    if (s.column >= w) return "assertion column out of range";
+    if (s.step >= n) return "assertion step out of range";
+    if (s.value >= P) return "non-canonical assertion value";
+    if (i && a.assertions[i - 1].step == s.step && a.assertions[i - 1].column == s.column) return "duplicate assertion";
+  }
+  a.num_transition = a.outputs.size();
+  return "";
+}
+template <class E> inline void eval_air_transition(const AirDef& a, const E* cur, const E* nxt, E* r) {
+  if (a.burn_mint) { evaluate_transition<E>(cur, nxt, a.ac, r); return; }
+  const size_t w = a.width, C = a.constants.size();
+  std::vector<E> v(2 * w + C + a.code.size());
+  for (size_t i = 0; i < w; i++) { v[i] = cur[i]; v[w + i] = nxt[i]; }
+  for (size_t i = 0; i < C; i++) v[2 * w + i] = E::from_base(a.constants[i]);
+  for (size_t i = 0; i < a.code.size(); i++) {
+    const Instr& in = a.code[i];
+    v[2 * w + C + i] = in.op == OP_ADD ? v[in.a] + v[in.b] : in.op == OP_SUB ? v[in.a] - v[in.b] : v[in.a] * v[in.b];
+  }
+  for (size_t j = 0; j < a.outputs.size(); j++) r[j] = v[a.outputs[j]];
+}
+
 // winter-air Context::to_elements followed by the public inputs = coin seed elements (A.4, D)
-inline std::vector<F1> seed_elements(size_t n, const ProofOptions& o, const PublicInputs& pi) {
+inline std::vector<F1> seed_elements(size_t n, const ProofOptions& o, size_t width, const std::vector<u64>& pub_inputs) {
   std::vector<F1> e;
-  e.push_back(F1((u64)XFG_TRACE_WIDTH << 8));          // (main_width << 8) | num_aux_segments
+  e.push_back(F1((u64)width << 8));                    // (main_width << 8) | num_aux_segments
   e.push_back(F1(P & 0xFFFFFFFFULL)); e.push_back(F1(P >> 32));   // modulus LE bytes, two halves
   for (auto x : o.to_elements()) e.push_back(x);
   e.push_back(F1((u64)(u32)n));
-  for (int i = 0; i < XFG_NUM_PUB_INPUTS; i++) e.push_back(F1(pi.v[i]));
+  for (u64 v : pub_inputs) e.push_back(F1(v));
   return e;
 }
 // winter-air Context::write_into (A.12, D)
-inline void write_context(std::vector<u8>& o, size_t n, const ProofOptions& opt) {
+inline void write_context(std::vector<u8>& o, size_t n, const ProofOptions& opt, size_t width) {
   unsigned lg = 0; while ((size_t(1) << lg) < n) lg++;
-  o.push_back(XFG_TRACE_WIDTH); o.push_back(0); o.push_back(0); o.push_back((u8)lg);
+  o.push_back((u8)width); o.push_back(0); o.push_back(0); o.push_back((u8)lg);
   o.push_back(0); o.push_back(0);        // u16 meta_len = 0
   o.push_back(8); put_u64(o, P);          // modulus
   opt.write_into(o);

@@ -178,4 +178,44 @@ int orc_verify(const u8* proof, size_t len, const u64 pi[12], const u64 consts[4
   } catch (const std::exception& ex) { set_err(err, errcap, ex.what()); return 1; }
 }
 
+// ---- generic degree-<=2 AIR ----
+// desc: width, num_pub, num_const, num_instr, num_out, num_assert; code = 3 u32 per instruction (op, a, b); assertions = 3 u64 each (column, step, value)
+static AirDef air_from(const uint32_t desc[6], const u64* pub, const u64* consts, const uint32_t* code, const uint32_t* outs, const u64* asr) {
+  AirDef a; a.width = desc[0]; a.pub_inputs.assign(pub, pub + desc[1]); a.constants.assign(consts, consts + desc[2]);
+  for (uint32_t i = 0; i < desc[3]; i++) a.code.push_back(Instr{code[3 * i], code[3 * i + 1], code[3 * i + 2]});
+  a.outputs.assign(outs, outs + desc[4]);
+  for (uint32_t i = 0; i < desc[5]; i++) a.assertions.push_back(Assertion{(u32)asr[3 * i], (size_t)asr[3 * i + 1], asr[3 * i + 2]});
+  return a;
+}
+int orc_prove_air(const u64* trace, unsigned n_log2, const uint32_t desc[6], const u64* pub, const u64* consts, const uint32_t* code, const uint32_t* outs,
+                  const u64* asr, const uint32_t o[6], u8* out, size_t cap, size_t* out_len, double* stage_ms, int keep_debug, char* err, size_t errcap) {
+  try {
+    ProofOptions opt = opts_from(o); std::string e = opt.validate(); if (!e.empty()) { set_err(err, errcap, e); return 1; }
+    const size_t n = size_t(1) << n_log2;
+    AirDef air = air_from(desc, pub, consts, code, outs, asr);
+    e = validate_air(air, n); if (!e.empty()) { set_err(err, errcap, e); return 1; }
+    std::vector<std::vector<F1>> t(air.width, std::vector<F1>(n));
+    for (size_t j = 0; j < air.width; j++) for (size_t i = 0; i < n; i++) { if (trace[j * n + i] >= P) { set_err(err, errcap, "non-canonical trace element"); return 1; } t[j][i] = F1(trace[j * n + i]); }
+    StageTimes st; std::vector<u8> bytes;
+    if (opt.ext == XFG_EXT_NONE) bytes = prove<F1>(t, air, opt, &st, keep_debug ? &g_dbg1 : nullptr);
+    else bytes = prove<F2>(t, air, opt, &st, keep_debug ? &g_dbg2 : nullptr);
+    if (keep_debug) g_dbg_ext = opt.ext;
+    if (stage_ms) for (int i = 0; i < ST_COUNT; i++) stage_ms[i] = st.ms[i];
+    *out_len = bytes.size();
+    if (bytes.size() > cap) { set_err(err, errcap, "output buffer too small"); return 2; }
+    std::memcpy(out, bytes.data(), bytes.size());
+    return 0;
+  } catch (const std::exception& ex) { set_err(err, errcap, ex.what()); return 3; }
+}
+int orc_verify_air(const u8* proof, size_t len, const uint32_t desc[6], const u64* pub, const u64* consts, const uint32_t* code, const uint32_t* outs,
+                   const u64* asr, const uint32_t o[6], char* err, size_t errcap) {
+  try {
+    ProofOptions opt = opts_from(o); std::string e = opt.validate(); if (!e.empty()) { set_err(err, errcap, e); return 1; }
+    AirDef air = air_from(desc, pub, consts, code, outs, asr);
+    std::string r = (opt.ext == XFG_EXT_NONE) ? verify<F1>(proof, len, air, opt) : verify<F2>(proof, len, air, opt);
+    if (!r.empty()) { set_err(err, errcap, r); return 1; }
+    return 0;
+  } catch (const std::exception& ex) { set_err(err, errcap, ex.what()); return 1; }
+}
+
 }  // extern "C"

@@ -65,10 +65,10 @@ template <class E> inline E fold_row(const E* row, size_t F, u64 x_inv, E alpha)
 template <class E> struct FriLayerData { std::vector<E> evals; MerkleTree tree; };
 
 template <class E>
-std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const PublicInputs& pi, const AirConsts& ac,
+std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const AirDef& air,
                       const ProofOptions& opt, StageTimes* times = nullptr, ProverDebug<E>* dbg = nullptr) {
-  const size_t W = XFG_TRACE_WIDTH, n = trace[0].size(), b = opt.blowup, N = n * b, c = XFG_CE_BLOWUP, F = opt.folding;
-  if (trace.size() != W) throw std::runtime_error("trace must have 7 columns");
+  const size_t W = air.width, NT = air.num_transition, n = trace[0].size(), b = opt.blowup, N = n * b, c = XFG_CE_BLOWUP, F = opt.folding;
+  if (trace.size() != W) throw std::runtime_error("trace width does not match the AIR");
   if (n < 8 || (n & (n - 1))) throw std::runtime_error("trace length must be a power of two >= 8");
   if (b < c) throw std::runtime_error("blowup factor too small");
   const int T = g_threads; (void)T;
@@ -78,7 +78,7 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const PublicInp
   StageTimes st; Timer tm;
 
   // 0 ----- channel: coin seeded with context + public inputs (A.4)
-  RandomCoin coin(seed_elements(n, opt, pi));
+  RandomCoin coin(seed_elements(n, opt, W, air.pub_inputs));
 
   // 1 ----- extend_execution_trace: interpolate columns, evaluate over the LDE coset (A.7)
   std::vector<std::vector<F1>> polys(trace), lde(W);
@@ -88,38 +88,41 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const PublicInp
   //       compute_execution_trace_commitment: leaf = hash of the 7 real elements of the row (A.7, D)
   std::vector<Digest> leaves(N);
 #pragma omp parallel for num_threads(T) schedule(static)
-  for (size_t i = 0; i < N; i++) { F1 row[W]; for (size_t j = 0; j < W; j++) row[j] = lde[j][i]; leaves[i] = hash_elements(row, W); }
+  for (size_t i = 0; i < N; i++) { std::vector<F1> row(W); for (size_t j = 0; j < W; j++) row[j] = lde[j][i]; leaves[i] = hash_elements(row.data(), W); }
   MerkleTree trace_tree(std::move(leaves));
   coin.reseed(trace_tree.root());
   st.ms[ST_COMMIT_TRACE] = tm.lap();
 
   // 2 ----- evaluate_constraints over the constraint-evaluation domain (A.8)
-  std::vector<E> tcoef(XFG_NUM_TRANSITION), bcoef(XFG_NUM_ASSERTIONS);
+  const std::vector<Assertion>& asr = air.assertions;
+  std::vector<E> tcoef(NT), bcoef(asr.size());
   for (auto& x : tcoef) x = coin.draw<E>();
   for (auto& x : bcoef) x = coin.draw<E>();
-  const std::vector<Assertion> asr = get_assertions(pi, ac, n);
+  // boundary constraint groups: one per distinct divisor (x - g^step) (A.8)
+  std::vector<size_t> gsteps, gof(asr.size());
+  for (size_t k = 0; k < asr.size(); k++) { size_t g = std::find(gsteps.begin(), gsteps.end(), asr[k].step) - gsteps.begin(); if (g == gsteps.size()) gsteps.push_back(asr[k].step); gof[k] = g; }
+  const size_t G = gsteps.size();
   const size_t cn = c * n, lde_shift = b / c;
   const u64 g_last = fpow(g_n, n - 1);                 // exemption point g^(n-1)
   std::vector<u64> xs = power_series(g_ce, cn, offset);
   // divisor inverses: (x^n - 1) is periodic with period c; (x - 1) and (x - g^(n-1)) need a batch inversion
-  std::vector<F1> zt(c), d0(cn), d1(cn);
+  std::vector<F1> zt(c); std::vector<std::vector<F1>> dg(G, std::vector<F1>(cn));
   for (size_t s = 0; s < c; s++) zt[s] = F1(fsub(fpow(xs[s], n), 1));
-  for (size_t s = 0; s < cn; s++) { d0[s] = F1(fsub(xs[s], 1)); d1[s] = F1(fsub(xs[s], g_last)); }
-  zt = batch_inverse(zt); d0 = batch_inverse(d0); d1 = batch_inverse(d1);
+  for (size_t g = 0; g < G; g++) { const u64 pt = fpow(g_n, gsteps[g]); for (size_t s = 0; s < cn; s++) dg[g][s] = F1(fsub(xs[s], pt)); dg[g] = batch_inverse(dg[g]); }
+  zt = batch_inverse(zt);
   std::vector<E> hev(cn);
 #pragma omp parallel for num_threads(T) schedule(static)
   for (size_t s = 0; s < cn; s++) {
     size_t i0 = s * lde_shift, i1 = (i0 + b) % N;      // frame rows (A.8, D)
-    F1 cur[W], nxt[W], r[XFG_NUM_TRANSITION];
+    std::vector<F1> cur(W), nxt(W), r(NT);
     for (size_t j = 0; j < W; j++) { cur[j] = lde[j][i0]; nxt[j] = lde[j][i1]; }
-    evaluate_transition<F1>(cur, nxt, ac, r);
-    E tsum = E::zero(), b0 = E::zero(), b1 = E::zero();
-    for (size_t k = 0; k < XFG_NUM_TRANSITION; k++) tsum = tsum + tcoef[k].mul_base(r[k].v);
-    for (size_t k = 0; k < asr.size(); k++) {
-      E term = bcoef[k].mul_base(fsub(cur[asr[k].column].v, asr[k].value));
-      if (asr[k].step == 0) b0 = b0 + term; else b1 = b1 + term;
-    }
-    hev[s] = tsum.mul_base(fmul(fsub(xs[s], g_last), zt[s % c].v)) + b0.mul_base(d0[s].v) + b1.mul_base(d1[s].v);
+    eval_air_transition<F1>(air, cur.data(), nxt.data(), r.data());
+    E tsum = E::zero(); std::vector<E> bs(G, E::zero());
+    for (size_t k = 0; k < NT; k++) tsum = tsum + tcoef[k].mul_base(r[k].v);
+    for (size_t k = 0; k < asr.size(); k++) bs[gof[k]] = bs[gof[k]] + bcoef[k].mul_base(fsub(cur[asr[k].column].v, asr[k].value));
+    E h = tsum.mul_base(fmul(fsub(xs[s], g_last), zt[s % c].v));
+    for (size_t g = 0; g < G; g++) h = h + bs[g].mul_base(dg[g][s].v);
+    hev[s] = h;
   }
   if (dbg) dbg->ce_evals = hev;
   st.ms[ST_EVAL_CONSTRAINTS] = tm.lap();
@@ -202,7 +205,7 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const PublicInp
 
   // 8 ----- build_proof_object (A.10-A.12)
   std::vector<u8> out;
-  write_context(out, n, opt);
+  write_context(out, n, opt, W);
   out.push_back((u8)positions.size());
   { std::vector<u8> cm; cm.insert(cm.end(), trace_tree.root().begin(), trace_tree.root().end());
     cm.insert(cm.end(), ctree.root().begin(), ctree.root().end());
@@ -238,6 +241,13 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const PublicInp
     dbg->z = z; dbg->hz = hz; dbg->nonce = nonce; dbg->positions = positions;
   }
   return out;
+}
+// the hard-wired normalised BurnMintAir
+template <class E>
+std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const PublicInputs& pi, const AirConsts& ac,
+                      const ProofOptions& opt, StageTimes* times = nullptr, ProverDebug<E>* dbg = nullptr) {
+  if (trace.size() != XFG_TRACE_WIDTH) throw std::runtime_error("trace must have 7 columns");
+  return prove<E>(trace, burn_mint_air(pi, ac, trace[0].size()), opt, times, dbg);
 }
 
 }  // namespace orc

@@ -42,8 +42,8 @@ template <class E> inline E lagrange_eval(const std::vector<E>& xs, const std::v
 
 // returns "" when the proof is accepted, otherwise the reason for rejection
 template <class E>
-std::string verify(const u8* proof, size_t proof_len, const PublicInputs& pi, const AirConsts& ac, const ProofOptions& acceptable) {
-  const size_t W = XFG_TRACE_WIDTH;
+std::string verify(const u8* proof, size_t proof_len, AirDef air, const ProofOptions& acceptable, bool burn_mint_pi = false, const PublicInputs* pi = nullptr) {
+  const size_t W = air.width;
   Reader rd(proof, proof_len);
   // ---- (1) parse (A.12) ----
   if (rd.uint(1) != W || rd.uint(1) != 0 || rd.uint(1) != 0) return "bad trace layout";
@@ -58,6 +58,9 @@ std::string verify(const u8* proof, size_t proof_len, const PublicInputs& pi, co
   if ((int)opt.ext != (E::DEG == 1 ? XFG_EXT_NONE : XFG_EXT_QUADRATIC)) return "field extension mismatch";
   const size_t n = size_t(1) << lg, b = opt.blowup, N = n * b, F = opt.folding;
   const size_t num_layers = opt.num_fri_layers(N);
+  if (burn_mint_pi) air = burn_mint_air(*pi, air.ac, n);      // the burn-mint assertions depend on the trace length
+  else { std::string e = validate_air(air, n); if (!e.empty()) return e; }
+  const size_t NT = air.num_transition;
   size_t num_unique = rd.uint(1);
   std::vector<u8> cm = rd.bytes(rd.uint(2));
   if (!rd.ok || cm.size() != 32 * (3 + num_layers)) return "bad commitments";
@@ -76,9 +79,9 @@ std::string verify(const u8* proof, size_t proof_len, const PublicInputs& pi, co
   if (!rd.ok || rd.pos != proof_len) return "proof length mismatch";
 
   // ---- (2) replay the transcript ----
-  RandomCoin coin(seed_elements(n, opt, pi));
+  RandomCoin coin(seed_elements(n, opt, W, air.pub_inputs));
   coin.reseed(trace_root);
-  std::vector<E> tcoef(XFG_NUM_TRANSITION), bcoef(XFG_NUM_ASSERTIONS);
+  std::vector<E> tcoef(NT), bcoef(air.assertions.size());
   for (auto& x : tcoef) x = coin.draw<E>();
   for (auto& x : bcoef) x = coin.draw<E>();
   coin.reseed(constraint_root);
@@ -92,16 +95,18 @@ std::string verify(const u8* proof, size_t proof_len, const PublicInputs& pi, co
   coin.reseed(hash_elements(frame));
   const u64 g_n = root_of_unity(ilog2(n)), g_last = fpow(g_n, n - 1);
   {
-    E cur[W], nxt[W], r[XFG_NUM_TRANSITION];
+    std::vector<E> cur(W), nxt(W), r(NT);
     for (size_t j = 0; j < W; j++) { cur[j] = frame[2 * j]; nxt[j] = frame[2 * j + 1]; }
-    evaluate_transition<E>(cur, nxt, ac, r);
-    E t = E::zero(); for (size_t k = 0; k < XFG_NUM_TRANSITION; k++) t = t + tcoef[k] * r[k];
+    eval_air_transition<E>(air, cur.data(), nxt.data(), r.data());
+    E t = E::zero(); for (size_t k = 0; k < NT; k++) t = t + tcoef[k] * r[k];
     E zn = epow(z, (u64)n);
     E result = t * (z - E::from_base(g_last)) * (zn - E::one()).inv();
-    std::vector<Assertion> asr = get_assertions(pi, ac, n);
-    E b0 = E::zero(), b1 = E::zero();
-    for (size_t k = 0; k < asr.size(); k++) { E term = bcoef[k] * (cur[asr[k].column] - E::from_base(asr[k].value)); if (asr[k].step == 0) b0 = b0 + term; else b1 = b1 + term; }
-    result = result + b0 * (z - E::one()).inv() + b1 * (z - E::from_base(g_last)).inv();
+    const std::vector<Assertion>& asr = air.assertions;
+    for (size_t k = 0; k < asr.size();) {       // one boundary group per distinct step: sum of its terms over (z - g^step)
+      E bsum = E::zero(); const size_t step = asr[k].step;
+      for (; k < asr.size() && asr[k].step == step; k++) bsum = bsum + bcoef[k] * (cur[asr[k].column] - E::from_base(asr[k].value));
+      result = result + bsum * (z - E::from_base(fpow(g_n, step))).inv();
+    }
     if (result != hz[0]) return "InconsistentOodConstraintEvaluations";
   }
   coin.reseed(hash_elements(hz));
@@ -186,6 +191,12 @@ std::string verify(const u8* proof, size_t proof_len, const PublicInputs& pi, co
     }
   }
   return "";
+}
+// the hard-wired normalised BurnMintAir
+template <class E>
+std::string verify(const u8* proof, size_t proof_len, const PublicInputs& pi, const AirConsts& ac, const ProofOptions& acceptable) {
+  AirDef a; a.burn_mint = true; a.ac = ac; a.width = XFG_TRACE_WIDTH;
+  return verify<E>(proof, proof_len, a, acceptable, true, &pi);
 }
 
 }  // namespace orc

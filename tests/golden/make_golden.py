@@ -22,3 +22,14 @@ for n_log2 in (3, 6, 10, 12):
                              "proof_hex": proof.hex() if n_log2 == 3 and ext == 1 else None})
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "proofs.json"), "w"), indent=1)
 print("wrote", len(out["cases"]), "cases")
+
+# ---- generic AIR front-end: regression pins of the oracle's generic path on the example AIRs of tests/test_air.py
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+import test_air  # noqa: E402
+
+air_out = {"note": "sha256 of oracle proof bytes of the example AIRs of tests/test_air.py::examples(); options (42,8,4,ext,8,31)"}
+for name, (air, trace) in test_air.examples().items():
+    for ext in (1, 2):
+        air_out[f"{name}/ext{ext}"] = hashlib.sha256(orc.prove_air(air.flatten(), trace, (42, 8, 4, ext, 8, 31))).hexdigest()
+json.dump(air_out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "air_proofs.json"), "w"), indent=1)
+print("wrote", len(air_out) - 1, "generic-AIR cases")

@@ -55,6 +55,8 @@ def lib():
         L.orc_validate_options.argtypes = [vp, cp, sz]
         L.orc_prove.argtypes = [vp, C.c_uint, vp, vp, vp, vp, sz, vp, vp, C.c_int, cp, sz]
         L.orc_verify.argtypes = [vp, sz, vp, vp, vp, cp, sz]
+        L.orc_prove_air.argtypes = [vp, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, C.c_int, cp, sz]
+        L.orc_verify_air.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, cp, sz]
         L.orc_debug_get.restype = C.c_long; L.orc_debug_get.argtypes = [cp, vp, sz]
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_fri_fold.argtypes = [vp, sz, C.c_int, sz, vp, vp]
@@ -184,6 +186,37 @@ def verify(proof: bytes, pi, ac, options=DEFAULT_OPTIONS) -> str:
     """Returns '' when accepted, else the rejection reason."""
     err = C.create_string_buffer(256); o = _opts(options)
     rc = lib().orc_verify(proof, len(proof), _p(pi), _p(ac), _p(o), err, len(err))
+    return "" if rc == 0 else (err.value.decode() or "rejected")
+
+
+def _air_arrays(flat):
+    """flat: dict from AirBuilder.flatten() (plain arrays: the AIR as data, no product code involved)."""
+    return (np.ascontiguousarray(flat["desc"], dtype=np.uint32), np.ascontiguousarray(flat["pub"], dtype=np.uint64),
+            np.ascontiguousarray(flat["consts"], dtype=np.uint64), np.ascontiguousarray(flat["code"], dtype=np.uint32),
+            np.ascontiguousarray(flat["outs"], dtype=np.uint32), np.ascontiguousarray(flat["asr"], dtype=np.uint64))
+
+
+def prove_air(flat, trace: np.ndarray, options=DEFAULT_OPTIONS, keep_debug=False, want_times=False):
+    """Generic degree-<=2 AIR.  trace: (width, n) u64 column-major."""
+    desc, pub, consts, code, outs, asr = _air_arrays(flat)
+    t = np.ascontiguousarray(trace, dtype=np.uint64)
+    n_log2 = t.shape[1].bit_length() - 1
+    cap = 1 << 22
+    out = C.create_string_buffer(cap); ln = C.c_size_t(0)
+    ms = np.zeros(len(STAGES), dtype=np.float64); err = C.create_string_buffer(256)
+    o = _opts(options)
+    rc = lib().orc_prove_air(_p(t), n_log2, _p(desc), _p(pub), _p(consts), _p(code), _p(outs), _p(asr), _p(o), out, cap, C.byref(ln), _p(ms),
+                             int(keep_debug), err, len(err))
+    if rc:
+        raise RuntimeError(err.value.decode())
+    proof = out.raw[:ln.value]
+    return (proof, dict(zip(STAGES, ms.tolist()))) if want_times else proof
+
+
+def verify_air(proof: bytes, flat, options=DEFAULT_OPTIONS) -> str:
+    desc, pub, consts, code, outs, asr = _air_arrays(flat)
+    err = C.create_string_buffer(256); o = _opts(options)
+    rc = lib().orc_verify_air(proof, len(proof), _p(desc), _p(pub), _p(consts), _p(code), _p(outs), _p(asr), _p(o), err, len(err))
     return "" if rc == 0 else (err.value.decode() or "rejected")
 
 

@@ -1,0 +1,94 @@
+"""Generic AIR front-end, CPU side: the builder's flattening, the oracle's generic prover / verifier on the
+example AIRs (self-consistency, tamper rejection, unsatisfied traces), and equality of the oracle's generic path with its
+hard-wired burn-mint path on the same AIR."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "air_proofs.json")
+
+
+def examples():
+    from xfg_stark_b200 import air as A
+    return {"burn4": A.xfg_burn_air(0x1234567890ABCDEF, 987654321, 8_000_000, 4, 64), "fib": A.fibonacci_air(128),
+            "wide12": A.wide_quadratic_air(12, 64, seed=3, extra_steps=(5, 32)), "wide40": A.wide_quadratic_air(40, 32, seed=4)}
+
+
+def test_builder_flatten_and_cse():
+    from xfg_stark_b200 import AirBuilder
+    a = AirBuilder(3, pub_inputs=[5, orc.P + 1])
+    x = a.cur(0) * a.cur(1) + 7
+    y = a.cur(0) * a.cur(1) + 7          # same expression: shared instructions
+    a.constraint(a.nxt(2) - x); a.constraint(a.nxt(2) - y)
+    a.assert_single(2, 0, 9)
+    f = a.flatten()
+    assert f["desc"].tolist() == [3, 2, 1, 3, 2, 1]
+    assert f["pub"].tolist() == [5, 1]
+    assert f["code"].tolist() == [[2, 0, 1], [0, 7, 6], [1, 5, 8]]      # mul cur0 cur1 -> v7; add v7 const0(6) -> v8; sub nxt2(5) v8 -> v9
+    assert f["outs"].tolist() == [9, 9]
+
+
+def test_numpy_goldilocks_helpers():
+    from xfg_stark_b200 import air as A
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, A.P, size=500, dtype=np.uint64); b = rng.integers(0, A.P, size=500, dtype=np.uint64)
+    a[:4] = [A.P - 1, A.P - 1, 0, 1 << 63]; b[:4] = [A.P - 1, 1, 5, (1 << 63) + 12345]
+    m, s = A.gl_mul_np(a, b), A.gl_add_np(a, b)
+    assert all(int(m[i]) == int(a[i]) * int(b[i]) % A.P and int(s[i]) == (int(a[i]) + int(b[i])) % A.P for i in range(500))
+
+
+@pytest.mark.parametrize("ext", [1, 2])
+@pytest.mark.parametrize("name", ["burn4", "fib", "wide12", "wide40"])
+def test_oracle_generic_prove_verify(name, ext):
+    air, trace = examples()[name]
+    f = air.flatten(); o = (42, 8, 4, ext, 8, 31)
+    proof = orc.prove_air(f, trace, o)
+    assert proof[0] == air.width
+    assert orc.verify_air(proof, f, o) == ""
+    rng = np.random.default_rng(1)
+    for pos in rng.integers(0, len(proof), size=12):
+        bad = bytearray(proof); bad[pos] ^= 1 << int(rng.integers(0, 8))
+        assert orc.verify_air(bytes(bad), f, o) != ""
+    # a different statement (public input / assertion value) is rejected
+    g = dict(f); g["asr"] = f["asr"].copy(); g["asr"][0, 2] = (int(g["asr"][0, 2]) + 1) % orc.P
+    assert orc.verify_air(proof, g, o) != ""
+    # golden regression pin of the oracle's generic path (tests/golden/make_golden.py)
+    import hashlib
+    gold = json.load(open(GOLDEN))
+    assert hashlib.sha256(proof).hexdigest() == gold[f"{name}/ext{ext}"]
+
+
+def test_oracle_generic_rejects_bad_traces_and_airs():
+    from xfg_stark_b200 import air as A
+    air, trace = A.fibonacci_air(64)
+    f = air.flatten()
+    t2 = trace.copy(); t2[1, 17] = (int(t2[1, 17]) + 1) % orc.P
+    with pytest.raises(RuntimeError, match="UnsatisfiedTransitionConstraintError"):
+        orc.prove_air(f, t2)
+    g = dict(f); g["asr"] = f["asr"].copy(); g["asr"][0, 2] = 5            # wrong assertion value: boundary quotient is not a polynomial
+    with pytest.raises(RuntimeError, match="UnsatisfiedTransitionConstraintError"):
+        orc.prove_air(g, trace)
+    b = A.AirBuilder(1); x = b.cur(0); b.constraint(b.nxt(0) - x * x * x); b.assert_single(0, 0, 2)
+    with pytest.raises(RuntimeError, match="degree above 2"):
+        orc.prove_air(b.flatten(), np.full((1, 8), 1, dtype=np.uint64))
+    b = A.AirBuilder(1); b.constraint(b.nxt(0) - b.cur(0)); b.assert_single(0, 0, 2); b.assert_single(0, 0, 2)
+    with pytest.raises(RuntimeError, match="duplicate assertion"):
+        orc.prove_air(b.flatten(), np.full((1, 8), 2, dtype=np.uint64))
+    b = A.AirBuilder(1); b.constraint(b.nxt(0) - b.cur(0))
+    with pytest.raises(RuntimeError, match="at least one assertion"):
+        orc.prove_air(b.flatten(), np.full((1, 8), 2, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("ext", [1, 2])
+def test_oracle_generic_equals_hardwired_burn_mint(ext):
+    """The burn-mint AIR written as a program goes through the interpreter and the generic boundary groups; the bytes must equal
+    the hard-wired path's (same coefficients order, same divisors)."""
+    from xfg_stark_b200 import air as A
+    tr, pi, ac = orc.synthetic_case(64, 3)
+    o = (42, 8, 4, ext, 8, 31)
+    air = A.burn_mint_air(pi, ac[0], ac[1], ac[2], ac[3], 64)
+    assert orc.prove_air(air.flatten(), tr, o) == orc.prove(tr, pi, ac, o)

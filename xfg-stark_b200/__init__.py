@@ -6,6 +6,7 @@ host-side mirror of the reference's operator surface for that path, used by the 
 * ``ProofOptions``           — winter_air::ProofOptions as built at src/burn_mint_prover.rs:28-35
 * ``XfgBurnMintProver``      — src/burn_mint_prover.rs:18-237 (``new``/``with_options``/``prove_burn_mint``/...)
 * ``XfgBurnMintVerifier`` / ``BatchBurnMintVerifier`` — src/burn_mint_verifier.rs:18-408 over the CUDA batch verifier
+* ``AirBuilder`` / ``Context.prove_air`` — generic AIR front-end: a user-defined ``impl Air`` (src/winterfell_air.rs:87-127) as data
 * ``Context``                — one device + workspaces; stage-level entry points for kernel parity tests
 
 There is no CPU fallback: importing works anywhere (so the CPU test-suite can check the exported symbols), but creating
@@ -15,7 +16,9 @@ a ``Context`` without a CUDA device raises ``XfgError``.  The directory name car
 from ._binding import (WideTrace, Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgBurnMintVerifier, BatchBurnMintVerifier, XfgError, AirConsts, STAGE_NAMES, load_library,
                        library_path, EXPORTED_SYMBOLS, FieldExtension, pack_inputs, build_trace)
 from .synthetic import synthetic_inputs
+from .air import AirBuilder
+from . import air
 from . import multi
 
 __all__ = ["WideTrace", "Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgBurnMintVerifier", "BatchBurnMintVerifier", "XfgError", "AirConsts", "STAGE_NAMES",
-           "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "synthetic_inputs", "multi"]
+           "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "synthetic_inputs", "multi", "AirBuilder", "air"]

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
-                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror"]
+                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -54,6 +54,19 @@ class StageTimes(C.Structure):
         d.update(h2d_ms=float(self.h2d_ms), device_ms=float(self.device_ms), total_ms=float(self.total_ms),
                  kernel_launches=int(self.kernel_launches), h2d_bytes=int(self.h2d_bytes), d2h_bytes=int(self.d2h_bytes))
         return d
+
+
+class _AirInstr(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("a", C.c_uint32), ("b", C.c_uint32)]
+
+
+class _Assertion(C.Structure):
+    _fields_ = [("column", C.c_uint32), ("step", C.c_uint32), ("value", C.c_uint64)]
+
+
+class _AirDesc(C.Structure):      # xfg_air_desc
+    _fields_ = [(n, C.c_uint32) for n in ("width", "num_pub_inputs", "num_constants", "num_instr", "num_constraints", "num_assertions")] + \
+               [("pub_inputs", C.c_void_p), ("constants", C.c_void_p), ("code", C.c_void_p), ("constraint_values", C.c_void_p), ("assertions", C.c_void_p)]
 
 
 class VerifyTimes(C.Structure):
@@ -102,12 +115,15 @@ def load_library():
     L = C.CDLL(_SO)
     vp, u32, u64, sz, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
     L.xfg_create.argtypes = [i, u32, u32, C.POINTER(vp)]
+    L.xfg_create_ex.argtypes = [i, u32, u32, u32, C.POINTER(vp)]
     L.xfg_destroy.argtypes = [vp]; L.xfg_destroy.restype = None
     L.xfg_strerror.argtypes = [i]; L.xfg_strerror.restype = C.c_char_p
     L.xfg_last_error.argtypes = [vp]; L.xfg_last_error.restype = C.c_char_p
     prove_tail = [vp, sz, C.POINTER(sz), C.POINTER(StageTimes)]
     L.xfg_prove_burn_mint.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
     L.xfg_prove_burn_mint_device.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
+    L.xfg_prove_air.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
+    L.xfg_prove_air_device.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
     L.xfg_prove_burn_mint_batch.argtypes = [vp, u32, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options), vp, sz, vp, C.POINTER(C.c_float)]
     inputs = [u64, u64, vp, vp, sz, vp, sz, u32, u32, u32]
     L.xfg_burn_mint_pack_inputs.argtypes = [vp] + inputs + [C.POINTER(AirConsts)]
@@ -170,10 +186,10 @@ def build_trace(air, n_log2):
 class Context:
     """xfg_ctx: one CUDA device, `num_slots` proof workspaces sized for traces of up to 2**max_n_log2 rows."""
 
-    def __init__(self, device=0, max_n_log2=16, num_slots=1):
+    def __init__(self, device=0, max_n_log2=16, num_slots=1, max_width=7):
         self._lib = load_library()
         self._h = C.c_void_p()
-        rc = self._lib.xfg_create(device, max_n_log2, num_slots, C.byref(self._h))
+        rc = self._lib.xfg_create_ex(device, max_n_log2, num_slots, max_width, C.byref(self._h))
         if rc:
             raise XfgError(rc, "xfg_create failed: " + self._lib.xfg_strerror(rc).decode() + " (a CUDA device is required; no CPU fallback)")
         self.device, self.max_n_log2, self.num_slots = device, max_n_log2, num_slots
@@ -220,6 +236,40 @@ class Context:
     def _prove_ptr(self, fn, ptr, n_log2, air, options, want_times):
         out = self._out; ln = C.c_size_t(0); st = StageTimes(); o = options._c()
         self._check(fn(self._h, ptr, n_log2, C.byref(air), C.byref(o), out, len(out), C.byref(ln), C.byref(st) if want_times else None))
+        proof = C.string_at(out, ln.value)
+        return (proof, st.as_dict()) if want_times else proof
+
+    # ---- generic AIR front-end ----
+    @staticmethod
+    def _air_desc(air):
+        """air: an AirBuilder or the dict of its flatten().  -> (xfg_air_desc, arrays kept alive, width)"""
+        f = air.flatten() if hasattr(air, "flatten") else air
+        d = [int(v) for v in f["desc"]]
+        pub = np.ascontiguousarray(f["pub"], dtype=np.uint64); consts = np.ascontiguousarray(f["consts"], dtype=np.uint64)
+        code = np.ascontiguousarray(f["code"], dtype=np.uint32); outs = np.ascontiguousarray(f["outs"], dtype=np.uint32)
+        a = np.asarray(f["asr"], dtype=np.uint64).reshape(-1, 3)
+        asr = (_Assertion * max(1, len(a)))(*[_Assertion(int(r[0]), int(r[1]), int(r[2])) for r in a])
+        desc = _AirDesc(d[0], d[1], d[2], d[3], d[4], d[5], pub.ctypes.data, consts.ctypes.data, code.ctypes.data, outs.ctypes.data, C.addressof(asr))
+        return desc, (pub, consts, code, outs, asr), d[0]
+
+    def prove_air(self, air, trace, options=ProofOptions(), want_times=False):
+        """air: AirBuilder (xfg_air_desc); trace: (width, n) uint64 column-major host array.  Replaces `air.prove(trace)` for a
+        user-defined AIR (e.g. src/winterfell_air.rs:169)."""
+        desc, keep, w = self._air_desc(air)
+        t = np.ascontiguousarray(trace, dtype=np.uint64)
+        if t.ndim != 2 or t.shape[0] != w:
+            raise XfgError(1, "trace width does not match the AIR")
+        out = self._out; ln = C.c_size_t(0); st = StageTimes(); o = options._c()
+        self._check(self._lib.xfg_prove_air(self._h, C.byref(desc), _ptr(t), t.shape[1].bit_length() - 1, C.byref(o), out, len(out), C.byref(ln),
+                                            C.byref(st) if want_times else None))
+        proof = C.string_at(out, ln.value)
+        return (proof, st.as_dict()) if want_times else proof
+
+    def prove_air_device(self, air, device_ptr, n_log2, options=ProofOptions(), want_times=False):
+        desc, keep, w = self._air_desc(air)
+        out = self._out; ln = C.c_size_t(0); st = StageTimes(); o = options._c()
+        self._check(self._lib.xfg_prove_air_device(self._h, C.byref(desc), C.c_void_p(device_ptr), n_log2, C.byref(o), out, len(out), C.byref(ln),
+                                                   C.byref(st) if want_times else None))
         proof = C.string_at(out, ln.value)
         return (proof, st.as_dict()) if want_times else proof
 

@@ -17,6 +17,7 @@
 #include <vector>
 #include "../../include/xfg_stark.h"
 #include "burn_mint_host.hpp"
+#include "generic_air.cuh"
 #include "merkle.cuh"
 #include "ntt.cuh"
 #include "stark_kernels.cuh"
@@ -74,6 +75,9 @@ struct Slot {
   ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
   ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;
   AirParams* d_air = nullptr; AirParams* h_air = nullptr;
+  // generic AIR front-end (xfg_prove_air): compiled program + AIR-sized state; W = trace width of the proof in flight
+  GenProgram* d_prog = nullptr; GenProgram* h_prog = nullptr; GenState* d_gen = nullptr; u64 (*h_ood)[2] = nullptr;
+  bool generic = false; u32 W = XFG_TRACE_WIDTH, seed_count = 8 + XFG_NUM_PUB_INPUTS;
   std::map<GraphKey, cudaGraphExec_t> graphs;            // whole-proof CUDA graphs, one per (plan, extension, options, trace pointer)
   cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
   // in-flight proof (batch mode)
@@ -90,7 +94,7 @@ thread_local unsigned g_xfg_launches = 0;
 struct VerifyBufs { u8* h = nullptr; u8* d = nullptr; size_t cap = 0; };   // grow-only pinned staging + device copy of a verification batch
 
 struct xfg_ctx {
-  int device = 0; u32 max_log = 0;
+  int device = 0; u32 max_log = 0, max_width = XFG_TRACE_WIDTH;
   VerifyBufs vbufs;
   std::vector<Slot> slots;
   u64 *tw_fwd = nullptr, *tw_inv = nullptr;
@@ -187,9 +191,9 @@ int get_plan(xfg_ctx* ctx, u32 ln, u32 rem_max_deg, const Plan** out) {
   *out = &ins.first->second; return XFG_OK;
 }
 
-size_t slab_words_for(u32 ln, int D) {
+size_t slab_words_for(u32 ln, int D, size_t W) {
   const size_t n = size_t(1) << ln, N = 8 * n;
-  size_t w = 7 * n + 7 * n + 7 * N + 8 * N + 2 * D * n + 2 * D * n + D * n + D * N + 8 * N + D * N;
+  size_t w = W * n + W * n + W * N + 8 * N + 2 * D * n + 2 * D * n + D * n + D * N + 8 * N + D * N;
   w += (size_t)D * N / 7 + 64 * MAX_LAYERS;   // FRI layer evaluations l >= 1
   w += 8 * N / 7 + 64 * MAX_LAYERS;           // FRI trees
   w += 2 * (size_t)D * 2048 + 64;             // remainder in / coefficients
@@ -197,9 +201,9 @@ size_t slab_words_for(u32 ln, int D) {
 }
 
 void carve(const Slot& s, const Plan& p, int D, Carve& c) {
-  u64* w = s.slab; const size_t n = p.n, N = p.N;
+  u64* w = s.slab; const size_t n = p.n, N = p.N, W = s.W;
   auto take = [&](size_t k) { u64* r = w; w += (k + 7) & ~size_t(7); return r; };
-  c.trace_in = take(7 * n); c.trace_coef = take(7 * n); c.lde = take(7 * N);
+  c.trace_in = take(W * n); c.trace_coef = take(W * n); c.lde = take(W * N);
   c.trace_tree = reinterpret_cast<Digest*>(take(8 * N));
   c.ce_evals = take(2 * D * n); c.ce_tmp = take(2 * D * n); c.h_coef = take(D * n); c.h_lde = take(D * N);
   c.comp_tree = reinterpret_cast<Digest*>(take(8 * N));
@@ -212,24 +216,24 @@ void carve(const Slot& s, const Plan& p, int D, Carve& c) {
 }
 
 // coin seed elements: Context::to_elements() then the public inputs (A.4)
-void seed_elements(u32 ln, const xfg_options& o, const xfg_air_consts& air, u64 out[8 + XFG_NUM_PUB_INPUTS]) {
+void seed_elements(u32 ln, const xfg_options& o, u32 width, const u64* pub_inputs, u32 num_pub, u64* out) {
   int k = 0;
-  out[k++] = (u64)XFG_TRACE_WIDTH << 8;
+  out[k++] = (u64)width << 8;
   out[k++] = XFG_P & 0xFFFFFFFFull; out[k++] = XFG_P >> 32;
   out[k++] = (u64)o.field_extension << 16 | (u64)o.fri_folding_factor << 8 | o.fri_remainder_max_degree;
   out[k++] = o.grinding_factor; out[k++] = o.blowup_factor; out[k++] = o.num_queries;
   out[k++] = (u64)(u32)(size_t(1) << ln);
-  for (int i = 0; i < XFG_NUM_PUB_INPUTS; i++) out[k++] = air.pub_inputs[i];
+  for (u32 i = 0; i < num_pub; i++) out[k++] = pub_inputs[i];
 }
 
 // layout of the material buffer for this proof; fills the gather tasks
-size_t build_gather(const Plan& p, int D, const xfg_options& o, const Carve& c, GatherTasks& g) {
+size_t build_gather(const Plan& p, int D, u32 W, const xfg_options& o, const Carve& c, GatherTasks& g) {
   const u32 q = o.num_queries; size_t off = 0; u32 t = 0;
   auto add = [&](const u64* src, const Digest* tree, u64 limb_stride, u64 coset_n, u64 R, u64 M, u32 J, u32 limbs, u32 depth, int layer) {
     GatherTask& k = g.t[t++]; k.src = src; k.tree = tree; k.limb_stride = limb_stride; k.coset_n = coset_n; k.R = R; k.M = M; k.J = J; k.limbs = limbs;
     k.depth = depth; k.fri_layer = layer; k.rows_off = off; off += ((size_t)q * J * limbs + 3) & ~size_t(3); k.paths_off = off; off += (size_t)q * depth * 4;
   };
-  add(c.lde, c.trace_tree, p.N, p.n, 0, p.N, 1, XFG_TRACE_WIDTH, p.lN, -1);
+  add(c.lde, c.trace_tree, p.N, p.n, 0, p.N, 1, W, p.lN, -1);
   add(c.h_lde, c.comp_tree, p.N, p.n, 0, p.N, 1, (u32)D, p.lN, -1);
   for (u32 l = 0; l < p.num_layers; l++) {
     const u64 Nl = u64(1) << p.layer_log[l], R = Nl / 8;
@@ -240,7 +244,8 @@ size_t build_gather(const Plan& p, int D, const xfg_options& o, const Carve& c, 
 
 // ---- enqueue the whole proof on the slot's stream (no host synchronisation) ----
 void prepare_inputs(Slot& s, const Plan& p, const xfg_options& o, const xfg_air_consts& air) {
-  seed_elements(p.ln, o, air, s.h_seed);
+  seed_elements(p.ln, o, XFG_TRACE_WIDTH, air.pub_inputs, XFG_NUM_PUB_INPUTS, s.h_seed);
+  s.generic = false; s.W = XFG_TRACE_WIDTH; s.seed_count = 8 + XFG_NUM_PUB_INPUTS;
   AirParams& ap = *s.h_air;
   ap.txn = air.txn_hash; ap.rcpt = air.recipient_hash; ap.nullifier = air.nullifier; ap.commitment = air.commitment;
   ap.assert0[0] = air.pub_inputs[XFG_PI_BURN]; ap.assert0[1] = air.pub_inputs[XFG_PI_MINT]; ap.assert0[2] = air.pub_inputs[XFG_PI_TXN_HASH];
@@ -266,17 +271,19 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
 
   // per-proof inputs (coin seed elements, AIR constants) were written to pinned memory by prepare_inputs(); copying them here keeps
   // the whole launch sequence replayable as a CUDA graph
-  CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (8 + XFG_NUM_PUB_INPUTS) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(s.d_air, s.h_air, sizeof(AirParams), cudaMemcpyHostToDevice, st));
+  const u32 W = s.W; const bool gen = s.generic;
+  CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (size_t)s.seed_count * 8, cudaMemcpyHostToDevice, st));
+  if (gen) CU(cudaMemcpyAsync(s.d_prog, s.h_prog, offsetof(GenProgram, code) + (size_t)s.h_prog->num_instr * sizeof(GenInstr), cudaMemcpyHostToDevice, st));
+  else CU(cudaMemcpyAsync(s.d_air, s.h_air, sizeof(AirParams), cudaMemcpyHostToDevice, st));
   mark();   // ev0: start of device work
-  PROF("transcript", launch_seed(st, s.d_state, s.d_seed, 8 + XFG_NUM_PUB_INPUTS));
+  PROF("transcript", launch_seed(st, s.d_state, s.d_seed, (int)s.seed_count));
   // 1 ---- extend_execution_trace: interpolate the 7 columns, evaluate on the 8 cosets s_k * <w_n>
   // With a split upload the trace goes column by column so that a column's NTTs start as soon as its copy has landed.  (Running
   // the HBM-resident path column by column as well - to keep one column's 64 MB four-step intermediate inside the L2 - was
   // measured: 7x smaller grids cost more (5.88 vs 5.46 ms per proof) than the saved DRAM traffic gains on these ALU-bound kernels.)
   const bool waits = s.split_upload && !d_trace;
   for (int g = 0; g < (waits ? UPLOAD_GROUPS : 1); g++) {
-    const int c0 = waits ? UPLOAD_GROUP_START[g] : 0, per = waits ? UPLOAD_GROUP_START[g + 1] - c0 : XFG_TRACE_WIDTH;
+    const int c0 = waits ? UPLOAD_GROUP_START[g] : 0, per = waits ? UPLOAD_GROUP_START[g + 1] - c0 : (int)W;
     const size_t off = (size_t)c0 * n;
     if (waits) CU(cudaStreamWaitEvent(st, s.col_ev[g], 0));
     PROF("check_canonical", launch_check_canonical(st, trace_src + off, (size_t)per * n, s.d_state));
@@ -287,12 +294,15 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   }
   mark();
   //   ---- compute_execution_trace_commitment
-  PROF("commit_rows.trace", launch_commit_rows(st, c.lde, N, XFG_TRACE_WIDTH, ln, c.trace_tree));
+  if (W == 1 || W == 2 || W == XFG_TRACE_WIDTH) PROF("commit_rows.trace", launch_commit_rows(st, c.lde, N, (int)W, ln, c.trace_tree));
+  else PROF("commit_rows.trace", launch_commit_rows_wide(st, c.lde, N, W, ln, c.trace_tree));
   PROF("tree_upper.trace", merkle_build_upper(st, c.trace_tree, n));
-  PROF("transcript", launch_trace_root(st, D, s.d_state, c.trace_tree));
+  if (gen) PROF("transcript", launch_gen_trace_root(st, D, s.d_state, s.d_gen, s.d_prog, c.trace_tree));
+  else PROF("transcript", launch_trace_root(st, D, s.d_state, c.trace_tree));
   mark();
   // 2 ---- evaluate_constraints
-  PROF("constraints", launch_constraints(st, D, c.lde, ln, s.d_air, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals));
+  if (gen) PROF("constraints", launch_gen_constraints(st, D, c.lde, ln, s.d_prog, s.d_gen, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, p.g_last, c.ce_evals));
+  else PROF("constraints", launch_constraints(st, D, c.lde, ln, s.d_air, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals));
   mark();
   // 3 ---- commit_to_constraint_evaluations: coset interpolation (2 cosets of size n), composition column, LDE, commitment
   { NttJob j{}; j.src = c.ce_evals; j.dst = c.ce_tmp; j.ln = ln; j.batch = 2 * D; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
@@ -311,11 +321,13 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   PROF("transcript", launch_constraint_root(st, D, s.d_state, c.comp_tree, p.g_n));
   mark();
   // 4 ---- build_deep_composition_poly: OOD frame + coefficients
-  PROF("ood", launch_ood(st, D, c.trace_coef, c.h_coef, ln, s.d_state, s.d_partial));
-  PROF("transcript", launch_ood_finish(st, D, s.d_state, s.d_partial, ood_num_blocks(ln)));
+  PROF("ood", launch_ood(st, D, c.trace_coef, c.h_coef, ln, W, s.d_state, s.d_partial));
+  if (gen) PROF("transcript", launch_gen_ood_finish(st, D, s.d_state, s.d_gen, W, s.d_partial, ood_num_blocks(ln)));
+  else PROF("transcript", launch_ood_finish(st, D, s.d_state, s.d_partial, ood_num_blocks(ln)));
   mark();
   // 5 ---- evaluate_deep_composition_poly (pointwise) + leaves of the first FRI layer
-  PROF("deep", launch_deep(st, D, c.lde, c.h_lde, ln, s.d_state, p.ntt.wn_fwd, p.d_sk, c.deep, p.num_layers ? c.fri_tree[0] : nullptr));
+  { const u64* dcoef = gen ? &s.d_gen->dcoef[0][0] : reinterpret_cast<const u64*>(reinterpret_cast<const char*>(s.d_state) + offsetof(ProofState, dcoef));
+    PROF("deep", launch_deep(st, D, c.lde, c.h_lde, ln, s.d_state, dcoef, W, p.ntt.wn_fwd, p.d_sk, c.deep, p.num_layers ? c.fri_tree[0] : nullptr)); }
   mark();
   // 6 ---- compute_fri_layers
   for (u32 l = 0; l < p.num_layers; l++) {
@@ -335,13 +347,14 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   PROF("transcript", launch_positions(st, s.d_state, o.num_queries, p.lN, p.num_layers));
   mark();
   // 8 ---- build_proof_object: gather opened rows + authentication nodes, copy out
-  const size_t mat_words = build_gather(p, D, o, c, s.tasks);
+  const size_t mat_words = build_gather(p, D, s.W, o, c, s.tasks);
   if (mat_words > MATERIAL_WORDS) return fail(ctx, XFG_ERR_INTERNAL, "material buffer too small");
   s.mat_words = mat_words;
   PROF("gather", launch_gather(st, s.tasks, s.d_state, s.d_material));
   mark();   // end of device work
   CU(cudaMemcpyAsync(s.h_state, s.d_state, sizeof(ProofState), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(s.h_material, s.d_material, mat_words * 8, cudaMemcpyDeviceToHost, st));
+  if (gen) CU(cudaMemcpyAsync(s.h_ood, s.d_gen->ood_frame, (size_t)2 * W * 16, cudaMemcpyDeviceToHost, st));
   mark();
   CU(cudaGetLastError());
 #undef PROF
@@ -353,6 +366,7 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
 // when no per-stage timing is requested and the upload is not split, otherwise launch by launch.
 int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const xfg_air_consts& air, const u64* d_trace, bool timed) {
   prepare_inputs(s, p, o, air);
+  { Carve c; carve(s, p, D, c); if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length"); }
   const bool use_graph = ctx->graphs && !timed && !ctx->profiling && !(s.split_upload && !d_trace);
   if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);
   const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor};
@@ -372,7 +386,7 @@ int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options&
     it = s.graphs.emplace(key, exec).first;
     s.graph_launches = g_xfg_launches - before;
   } else {
-    Carve c; carve(s, p, D, c); s.mat_words = build_gather(p, D, o, c, s.tasks);
+    Carve c; carve(s, p, D, c); s.mat_words = build_gather(p, D, s.W, o, c, s.tasks);
     g_xfg_launches += s.graph_launches;
     s.busy = true; s.plan = &p; s.D = D; s.opt = o; s.timed = false; s.prof.clear();
   }
@@ -413,10 +427,10 @@ void batch_paths(const u32* pos, u32 cnt, const u64* paths, u32 depth, u64 M, Ou
 }
 
 // StarkProof::to_bytes (A.12)
-void assemble(const Plan& p, int D, const xfg_options& o, const ProofState& s, const u64* mat, const GatherTasks& g, std::vector<u8>& bytes) {
+void assemble(const Plan& p, int D, u32 W, const u64 (*ood_frame)[2], const xfg_options& o, const ProofState& s, const u64* mat, const GatherTasks& g, std::vector<u8>& bytes) {
   Out out;
   // Context
-  out.u8_(XFG_TRACE_WIDTH); out.u8_(0); out.u8_(0); out.u8_(p.ln); out.u16_(0); out.u8_(8); out.u64_(XFG_P);
+  out.u8_(W); out.u8_(0); out.u8_(0); out.u8_(p.ln); out.u16_(0); out.u8_(8); out.u64_(XFG_P);
   out.u8_(o.num_queries); out.u8_(o.blowup_factor); out.u8_(o.grinding_factor); out.u8_(o.field_extension); out.u8_(o.fri_folding_factor); out.u8_(o.fri_remainder_max_degree);
   out.u8_(s.num_positions);
   // Commitments
@@ -434,8 +448,8 @@ void assemble(const Plan& p, int D, const xfg_options& o, const ProofState& s, c
   queries(g.t[0], s.positions, s.num_positions);
   queries(g.t[1], s.positions, s.num_positions);
   // OodFrame
-  out.u16_(1 + 2 * XFG_TRACE_WIDTH * D * 8); out.u8_(2);
-  for (int i = 0; i < 2 * XFG_TRACE_WIDTH; i++) for (int l = 0; l < D; l++) out.u64_(s.ood_frame[i][l]);
+  out.u16_(1 + 2 * (size_t)W * D * 8); out.u8_(2);
+  for (u32 i = 0; i < 2 * W; i++) for (int l = 0; l < D; l++) out.u64_(ood_frame[i][l]);
   out.u16_(D * 8); for (int l = 0; l < D; l++) out.u64_(s.hz[l]);
   // FriProof
   out.u8_(p.num_layers);
@@ -461,9 +475,9 @@ int finish_proof(xfg_ctx* ctx, Slot& s, u8* out, size_t cap, size_t* out_len, xf
     }
   }
   if (hs.error_flags & ERR_FLAG_NONCANONICAL) return fail(ctx, XFG_ERR_BAD_ARGS, "non-canonical trace element");
-  if (hs.error_flags & ERR_FLAG_DEGREE) return fail(ctx, XFG_ERR_UNSATISFIED_CONSTRAINT, "UnsatisfiedTransitionConstraintError: the trace does not satisfy the burn-mint AIR (composition polynomial degree too high)");
+  if (hs.error_flags & ERR_FLAG_DEGREE) return fail(ctx, XFG_ERR_UNSATISFIED_CONSTRAINT, "UnsatisfiedTransitionConstraintError: the trace does not satisfy the AIR (composition polynomial degree too high)");
   if (hs.error_flags & ERR_FLAG_COIN) return fail(ctx, XFG_ERR_INTERNAL, "FailedToDrawFieldElement");
-  std::vector<u8> bytes; assemble(*s.plan, s.D, s.opt, hs, s.h_material, s.tasks, bytes);
+  std::vector<u8> bytes; assemble(*s.plan, s.D, s.W, s.generic ? s.h_ood : hs.ood_frame, s.opt, hs, s.h_material, s.tasks, bytes);
   if (times && s.timed) {
     for (int i = 0; i < XFG_NUM_STAGES; i++) cudaEventElapsedTime(&times->stage_ms[i], s.ev[i], s.ev[i + 1]);
     cudaEventElapsedTime(&times->device_ms, s.ev[0], s.ev[XFG_NUM_STAGES]);
@@ -491,12 +505,12 @@ int check_air(xfg_ctx* ctx, const xfg_air_consts* air) {
 int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace, bool allow_split) {
   Carve c; carve(s, p, D, c);
   if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length");
-  const size_t bytes = 7 * p.n * 8;
+  const size_t bytes = (size_t)s.W * p.n * 8;
   cudaPointerAttributes at{}; const bool pinned = cudaPointerGetAttributes(&at, h_trace) == cudaSuccess && at.type == cudaMemoryTypeHost;
   cudaGetLastError();   // unregistered host memory may leave a sticky-free error code behind on older drivers
   const u64* src = h_trace;
   if (!pinned) { std::memcpy(s.h_trace, h_trace, bytes); src = s.h_trace; }
-  s.split_upload = allow_split && p.ln >= 17;
+  s.split_upload = allow_split && p.ln >= 17 && !s.generic;
   if (s.split_upload) {      // one copy + event per column group on the copy stream; a group's NTTs start as soon as it has landed
     for (int g = 0; g < UPLOAD_GROUPS; g++) {
       const size_t c0 = UPLOAD_GROUP_START[g], c1 = UPLOAD_GROUP_START[g + 1];
@@ -523,7 +537,7 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1;
   g_xfg_launches = 0;
   if (times) { std::memset(times, 0, sizeof *times); cudaEventRecord(s.ev[XFG_NUM_STAGES + 2], s.st); }
-  s.split_upload = false;
+  s.split_upload = false; s.generic = false; s.W = XFG_TRACE_WIDTH;
   if (h_trace && (rc = upload_trace(ctx, s, *p, D, h_trace, true))) return rc;
   if ((rc = launch_proof(ctx, s, *p, D, *o, *air, d_trace, times != nullptr))) return rc;
   rc = finish_proof(ctx, s, out, cap, out_len, times);
@@ -531,7 +545,7 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
     cudaEventElapsedTime(&times->h2d_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[0]);
     cudaEventElapsedTime(&times->total_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[XFG_NUM_STAGES + 1]);
     times->kernel_launches = g_xfg_launches;
-    times->h2d_bytes = (h_trace ? 7 * p->n * 8 : 0) + (8 + XFG_NUM_PUB_INPUTS) * 8;
+    times->h2d_bytes = (h_trace ? (size_t)s.W * p->n * 8 : 0) + (size_t)s.seed_count * 8;
     times->d2h_bytes = sizeof(ProofState) + s.mat_words * 8;
   }
   return rc;
@@ -579,12 +593,14 @@ const char* xfg_verify_strerror(int code) {
 }
 const char* xfg_last_error(const xfg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
-int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** out) {
-  if (!out || max_n_log2 < MIN_LOG || max_n_log2 > MAX_LOG || num_slots < 1 || num_slots > 64) return XFG_ERR_BAD_ARGS;
+int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** out) { return xfg_create_ex(device, max_n_log2, num_slots, XFG_TRACE_WIDTH, out); }
+int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t max_width, xfg_ctx** out) {
+  if (!out || max_n_log2 < MIN_LOG || max_n_log2 > MAX_LOG || num_slots < 1 || num_slots > 64 || max_width < 1 || max_width > XFG_AIR_MAX_WIDTH) return XFG_ERR_BAD_ARGS;
+  if (max_width < XFG_TRACE_WIDTH) max_width = XFG_TRACE_WIDTH;
   *out = nullptr;
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return XFG_ERR_CUDA;   // no CPU fallback
-  xfg_ctx* ctx = new xfg_ctx; ctx->device = device; ctx->max_log = max_n_log2;
+  xfg_ctx* ctx = new xfg_ctx; ctx->device = device; ctx->max_log = max_n_log2; ctx->max_width = max_width;
   auto bail = [&](int rc) { xfg_destroy(ctx); return rc; };
 #define CUB(call) do { if ((call) != cudaSuccess) return bail(XFG_ERR_CUDA); } while (0)
   CUB(cudaSetDevice(device));
@@ -593,16 +609,18 @@ int xfg_create(int device, uint32_t max_n_log2, uint32_t num_slots, xfg_ctx** ou
     CUB(cudaMalloc(&ctx->tw_fwd, f.size() * 8)); CUB(cudaMalloc(&ctx->tw_inv, b.size() * 8));
     CUB(cudaMemcpy(ctx->tw_fwd, f.data(), f.size() * 8, cudaMemcpyHostToDevice)); CUB(cudaMemcpy(ctx->tw_inv, b.data(), b.size() * 8, cudaMemcpyHostToDevice)); }
   ctx->slots.resize(num_slots);
-  const size_t words = slab_words_for(max_n_log2, 2), trace_words = size_t(7) << max_n_log2;
+  const size_t words = slab_words_for(max_n_log2, 2, max_width), trace_words = size_t(max_width) << max_n_log2;
   for (Slot& s : ctx->slots) {
     CUB(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)); CUB(cudaStreamCreateWithFlags(&s.copy_st, cudaStreamNonBlocking));
     for (auto& e : s.col_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaMalloc(&s.slab, words * 8)); s.slab_words = words;
-    CUB(cudaMalloc(&s.d_state, sizeof(ProofState))); CUB(cudaMalloc(&s.d_seed, 64 * 8));
-    CUB(cudaMalloc(&s.d_partial, (size_t)NUM_OOD_POLYS * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
+    CUB(cudaMalloc(&s.d_state, sizeof(ProofState))); CUB(cudaMalloc(&s.d_seed, 128 * 8));
+    CUB(cudaMalloc(&s.d_partial, (size_t)(XFG_AIR_MAX_WIDTH + 2) * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
     CUB(cudaMallocHost(&s.h_state, sizeof(ProofState))); CUB(cudaMallocHost(&s.h_material, MATERIAL_WORDS * 8));
-    CUB(cudaMallocHost(&s.h_seed, 64 * 8)); CUB(cudaMallocHost(&s.h_trace, trace_words * 8));
+    CUB(cudaMallocHost(&s.h_seed, 128 * 8)); CUB(cudaMallocHost(&s.h_trace, trace_words * 8));
     CUB(cudaMalloc(&s.d_air, sizeof(AirParams))); CUB(cudaMallocHost(&s.h_air, sizeof(AirParams)));
+    CUB(cudaMalloc(&s.d_prog, sizeof(GenProgram))); CUB(cudaMallocHost(&s.h_prog, sizeof(GenProgram))); CUB(cudaMalloc(&s.d_gen, sizeof(GenState)));
+    CUB(cudaMallocHost(&s.h_ood, sizeof(u64) * 2 * 2 * XFG_AIR_MAX_WIDTH));
     for (auto& e : s.ev) CUB(cudaEventCreate(&e));
   }
 #undef CUB
@@ -617,6 +635,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     cudaFree(s.slab); cudaFree(s.d_state); cudaFree(s.d_seed); cudaFree(s.d_partial); cudaFree(s.d_material);
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
     cudaFree(s.d_air); cudaFreeHost(s.h_air);
+    cudaFree(s.d_prog); cudaFreeHost(s.h_prog); cudaFree(s.d_gen); cudaFreeHost(s.h_ood);
     for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
@@ -668,6 +687,7 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
     if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
     if ((rc = check_air(ctx, &airs[i]))) { drain_slots(ctx); return rc; }
     if (!traces[i]) { drain_slots(ctx); return fail(ctx, XFG_ERR_BAD_ARGS, "null trace"); }
+    s.generic = false; s.W = XFG_TRACE_WIDTH;
     if ((rc = upload_trace(ctx, s, *p, D, traces[i], false))) { drain_slots(ctx); return rc; }
     s.proof_index = i;
     if ((rc = launch_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) { drain_slots(ctx); return rc; }
@@ -705,3 +725,4 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn, uint64_t mint, 
 #include "stage_api.inc"
 #include "wide.inc"
 #include "verify_api.inc"
+#include "air_api.inc"

@@ -132,12 +132,12 @@ void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64*
 // Horner pass in z^TOT; block partials are added by the transcript kernel.  partial: [poly][block][point][limb]
 // ------------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln,
+__global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln, u32 width,
                                                    const ProofState* __restrict__ ps, u64* __restrict__ partial) {
   const size_t n = size_t(1) << ln;
   const u32 poly = blockIdx.y, nb = gridDim.x, tid = threadIdx.x;
   const size_t TOT = (size_t)nb * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + tid;
-  const u64* c = poly < XFG_TRACE_WIDTH ? trace_coef + (size_t)poly * n : h_coef + (size_t)(poly - XFG_TRACE_WIDTH) * n;
+  const u64* c = poly < width ? trace_coef + (size_t)poly * n : h_coef + (size_t)(poly - width) * n;
   // powers of the two evaluation points shared by the block: sq[w][b] = pt_w^(2^b), b < 32 (one lane per (w, b) chain would be
   // serial anyway: thread w squares 31 times), then every thread assembles pt^t and pt^TOT from the set bits of t / TOT
   __shared__ u64 sq[2][32][2];
@@ -174,10 +174,10 @@ __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_
   if (tid == 0) for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) partial[(((size_t)poly * nb + blockIdx.x) * 2 + w) * 2 + l] = red[0][w][l];
 }
 u32 ood_num_blocks(u32 ln) { size_t n = size_t(1) << ln; size_t b = n / 256; if (b < 1) b = 1; if (b > OOD_MAX_BLOCKS) b = OOD_MAX_BLOCKS; return (u32)b; }   // 64 x 256 threads per polynomial: Horner chains of n / 16384 steps
-void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, const ProofState* ps, u64* partial) {
-  dim3 grid(ood_num_blocks(ln), XFG_TRACE_WIDTH + D);
-  if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, ps, partial);
-  else ood_kernel<2><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, ps, partial);
+void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, u32 width, const ProofState* ps, u64* partial) {
+  dim3 grid(ood_num_blocks(ln), width + D);
+  if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ps, partial);
+  else ood_kernel<2><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ps, partial);
   XFG_LAUNCHED(1);
 }
 
@@ -214,19 +214,24 @@ template <int D> __device__ __forceinline__ Ext<D> deep_mul_conj(const DeepPoint
 #ifndef XFG_DEEP_MINB
 #define XFG_DEEP_MINB 4   // 122 registers, no spills: measured 0.652 ms; 3 (146 regs) 0.664, unconstrained (152) 0.662, 5 (96 regs, 24 B spilled) 0.740, 6-7: 0.69
 #endif
-template <int D>
+// WC = compile-time trace width (the burn-mint AIR: 7, loops over the columns unrolled) or 0 = run-time width `width_rt` (generic
+// AIR front-end, up to XFG_AIR_MAX_WIDTH columns); dcoef = width + 1 DEEP coefficients of 2 limbs.
+template <int D, int WC>
 __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
+                                                             const u64* __restrict__ dcoef, u32 width_rt,
                                                              PowTable wn, const u64* __restrict__ s_k, u64 w8, u64* __restrict__ deep, Digest* __restrict__ fri_tree0) {
+  constexpr int MAXW = WC ? WC : XFG_AIR_MAX_WIDTH;
+  const int W = WC ? WC : (int)width_rt;
   __shared__ u64 sh[8][D + 2][DEEP_THREADS];          // per point: numerator -> result (D), n_z n_zg, prefix
-  __shared__ u64 sc[2 * (XFG_TRACE_WIDTH + 1) + 8];   // dcoef[8][2], then c1, c2, z, zg
+  __shared__ u64 sc[2 * (MAXW + 1) + 8];              // dcoef[W + 1][2], then (at 2 (MAXW + 1)) c1, c2, z, zg
   const size_t n = size_t(1) << ln, N = 8 * n, n8 = n / 8;
   const u32 k = blockIdx.y, tid = threadIdx.x; const size_t a = (size_t)blockIdx.x * blockDim.x + tid;
-  if (tid < 2 * (XFG_TRACE_WIDTH + 1)) sc[tid] = (&ps->dcoef[0][0])[tid];
-  else if (tid < 2 * (XFG_TRACE_WIDTH + 1) + 8) { const u32 i = tid - 2 * (XFG_TRACE_WIDTH + 1); const u64* src = i < 2 ? ps->deep_c1 : i < 4 ? ps->deep_c2 : i < 6 ? ps->z : ps->zg; sc[tid] = src[i & 1]; }
+  for (u32 i = tid; i < 2u * (W + 1); i += DEEP_THREADS) sc[i] = dcoef[i];
+  if (tid < 8) { const u64* src = tid < 2 ? ps->deep_c1 : tid < 4 ? ps->deep_c2 : tid < 6 ? ps->z : ps->zg; sc[2 * (MAXW + 1) + tid] = src[tid & 1]; }
   __syncthreads();
   if (a >= n8) return;
-  const u64* cc = sc + 2 * (XFG_TRACE_WIDTH + 1);
-  const Ext<D> delta(sc[2 * XFG_TRACE_WIDTH], sc[2 * XFG_TRACE_WIDTH + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]);
+  const u64* cc = sc + 2 * (MAXW + 1);
+  const Ext<D> delta(sc[2 * W], sc[2 * W + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]);
   const DeepPoint<D> pz{cc[4], cc[5], gl_neg(gl_dbl(cc[5])), gl_dbl(gl_sqr(cc[5]))}, pzg{cc[6], cc[7], gl_neg(gl_dbl(cc[7])), gl_dbl(gl_sqr(cc[7]))};
   u64 x = gl_mul(s_k[k], pow_lookup(wn, a)), acc = 1;      // x_j = x_0 * w_8^j  (m = a + j n/8)
 #pragma unroll 1
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
     const size_t idx = (size_t)k * n + a + (size_t)j * n8;
     DotAcc sa[D];     // S_T = sum_c gamma_c T_c(x): un-reduced dot product, one reduction per limb
 #pragma unroll
-    for (int c = 0; c < XFG_TRACE_WIDTH; c++) { const u64 tv = lde[(size_t)c * N + idx]; for (int l = 0; l < D; l++) sa[l].fma(sc[2 * c + l], tv); }
+    for (int c = 0; c < W; c++) { const u64 tv = lde[(size_t)c * N + idx]; for (int l = 0; l < D; l++) sa[l].fma(sc[2 * c + l], tv); }
     Ext<D> st; for (int l = 0; l < D; l++) st.set_limb(l, sa[l].result());
     Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + idx]);
     u64 uz, uzg;
@@ -261,12 +266,15 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
     store_digest(fri_tree0 + n + 8 * a + k, b3_hash_limbs<8 * D>(row));
   }
 }
-void launch_deep(cudaStream_t st, int D, const u64* lde, const u64* hlde, u32 ln, const ProofState* ps, PowTable wn, const u64* s_k,
+void launch_deep(cudaStream_t st, int D, const u64* lde, const u64* hlde, u32 ln, const ProofState* ps, const u64* dcoef, u32 width, PowTable wn, const u64* s_k,
                  u64* deep, Digest* fri_tree0) {
   const size_t n8 = (size_t(1) << ln) / 8; dim3 grid((unsigned)((n8 + DEEP_THREADS - 1) / DEEP_THREADS), 8);
   const u64 w8 = gl_root_of_unity(3);
-  if (D == 1) deep_kernel<1><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, wn, s_k, w8, deep, fri_tree0);
-  else deep_kernel<2><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, wn, s_k, w8, deep, fri_tree0);
+  if (width == XFG_TRACE_WIDTH) {
+    if (D == 1) deep_kernel<1, XFG_TRACE_WIDTH><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
+    else deep_kernel<2, XFG_TRACE_WIDTH><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
+  } else if (D == 1) deep_kernel<1, 0><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
+  else deep_kernel<2, 0><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
   XFG_LAUNCHED(1);
 }
 
