@@ -225,6 +225,86 @@ def run_verify(args, rank, world, local):
     ctx.close(); multi.finalize()
 
 
+def run_air(args, rank, world, local):
+    """one proof of the "wide synthetic AIR" with real constraints through the generic front-end
+    (xfg_prove_air): `air_width` registers, x_j' = x_j * x_(j+1) + c_j (degree 2), 2^n rows.  Replicas across GPUs, as the latency workload."""
+    import numpy as np
+    import torch
+    import xfg_stark_b200 as xs
+    from xfg_stark_b200 import multi, air as A
+    n_log2 = args.n_log2 if args.n_log2 != 20 else 16
+    W = args.air_width
+    opts = xs.ProofOptions(field_extension=args.ext)
+    air, trace = A.wide_quadratic_air(W, 1 << n_log2, seed=1 + rank, extra_steps=(1 << (n_log2 - 1),))
+    ctx = xs.Context(device=local, max_n_log2=n_log2, num_slots=1, max_width=W)
+    h_trace = torch.empty((W, 1 << n_log2), dtype=torch.int64).pin_memory()
+    h_np = h_trace.numpy().view(np.uint64); h_np[:] = trace
+    d_trace = h_trace.cuda(); torch.cuda.synchronize()
+    dev_fn = lambda: ctx.prove_air_device(air, d_trace.data_ptr(), n_log2, opts)
+    e2e_fn = lambda: ctx.prove_air(air, h_np, opts)
+
+    def region(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        multi.barrier(); torch.cuda.synchronize(); e0.record()
+        for _ in range(steps):
+            last = fn()
+        e1.record(); e1.synchronize(); multi.barrier()
+        return multi.max_over_ranks(e0.elapsed_time(e1), device="cuda"), last
+    for _ in range(args.warmup):
+        dev_fn()
+    e2e_fn()
+    sampler = ClockSampler(local); sampler.start()
+    t_end = time.time() + 0.6
+    while time.time() < t_end:
+        dev_fn()
+    dev_ms, proof = region(dev_fn, args.steps)
+    e2e_ms, proof2 = region(e2e_fn, args.steps)
+    clocks = sampler.stop()
+    assert proof == proof2
+    _, times = ctx.prove_air_device(air, d_trace.data_ptr(), n_log2, opts, want_times=True)
+    _, times2 = ctx.prove_air(air, h_np, opts, want_times=True)
+    ctx.set_profiling(True); acc = {}
+    for _ in range(3):
+        ctx.prove_air_device(air, d_trace.data_ptr(), n_log2, opts, want_times=True)
+        for name, ms, launches in ctx.get_profile():
+            a = acc.setdefault(name, [0.0, 0]); a[0] += ms / 3.0; a[1] = launches
+    ctx.set_profiling(False)
+    n = 1 << n_log2; N = 8 * n; e = args.ext
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+    ab = {"ntt.interpolate_trace": 16 * W * n, "ntt.lde_trace": 8 * W * n + 8 * W * N, "commit_rows.trace": 8 * W * N + 32 * N + 96 * (N - N // 8),
+          "constraints": 8 * W * 2 * n + 8 * e * 2 * n, "deep": 8 * W * N + 16 * e * N + 4 * N, "ood": 8 * W * n + 8 * e * n,
+          "commit_rows.comp": 8 * e * N + 32 * N + 96 * (N - N // 8), "ntt.lde_comp": 8 * e * (n + N)}
+    kernels = [{"name": k, "ms": round(ms, 4), "launches": l, "alg_bytes": ab.get(k), "gbps": round(ab[k] / ms / 1e6, 1) if k in ab and ms > 0 else None,
+                "frac": round(ab[k] / ms / 1e6 / peak, 4) if k in ab and ms > 0 else None} for k, (ms, l) in sorted(acc.items(), key=lambda kv: -kv[1][0])]
+    top = kernels[0]
+    out = {"metric": f"generic-AIR proof latency (ms): {W} registers x 2^{n_log2} rows, degree-2 constraints", "value": dev_ms / (args.steps * world), "unit": "ms",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": False, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64 (Goldilocks) + u32 ARX (BLAKE3)", "data": "synthetic",
+           "config": {"workload": f"wide synthetic AIR through the generic front-end (xfg_prove_air): {W} registers, x_j' = x_j x_(j+1) + c_j, 2^{n_log2} rows, blowup 8, "
+                                  f"{'quadratic' if e == 2 else 'no'} extension, 42 queries, {W + 2} assertions on 3 steps", "l2": "working set >> L2 at the default size; no explicit flush"},
+           "proof_bytes": len(proof), "clocks": clocks,
+           "e2e": {"value": e2e_ms / (args.steps * world), "unit": "ms", "h2d_bytes_per_step": times2["h2d_bytes"], "d2h_bytes_per_step": times2["d2h_bytes"]},
+           "gpu_launches": times["kernel_launches"] * args.steps, "device_ms_per_proof": times["device_ms"],
+           "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},
+           "roofline": {"bound": "hbm", "kernel": top["name"], "achieved": top["gbps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": None,
+                        "peak_source": peak_src, "launch_ms": top["ms"], "alg_bytes": top["alg_bytes"],
+                        "note": "integer-pipe bound like the burn-mint path (DESIGN.md section 4)"},
+           "kernels": kernels}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import orc                                                       # CPU baseline leg only
+        cores = orc.max_threads(); orc.set_threads(cores)
+        f = air.flatten(); t0 = time.perf_counter(); ref = orc.prove_air(f, trace, opts.as_tuple()); cpu_ms = (time.perf_counter() - t0) * 1e3
+        orc.set_threads(1)
+        assert ref == proof, "GPU proof differs from the CPU oracle"
+        out["cpu_baseline"] = {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port", "sample": f"the same proof once by the CPU oracle's generic prover, {cores} OpenMP threads (bytes compared with the GPU proof)"}
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close(); multi.finalize()
+
+
 def workload_config(args):
     return {"workload": f"BurnMintAir synthetic trace 2^{args.n_log2} rows x 7 cols, blowup 8, {'quadratic' if args.ext == 2 else 'no'} extension, "
                         f"42 queries, grinding 4, FRI folding 8, remainder max degree 31 (BASELINE config {'3' if args.n_log2 == 20 else '2-like'})",
@@ -243,10 +323,11 @@ def main():
     ap.add_argument("--ext", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-preload", action="store_true", help="skip the 0.6 s untimed load loop before the timed region (deterministic launch count for ncu)")
-    ap.add_argument("--workload", default="latency", choices=["latency", "batch", "wide", "verify"],
+    ap.add_argument("--workload", default="latency", choices=["latency", "batch", "wide", "verify", "air"],
                     help="latency: the headline (one 2^n proof per step); batch: BASELINE config 4, 1024 independent 2^16 proofs sharded over "
                          "the GPUs; wide: BASELINE config 5, one 64-column x 2^24-row trace, column-sharded LDE with the all-to-all fused into the "
                          "last NTT pass, then row hashing (needs --gpus >= 2 for a real exchange)")
+    ap.add_argument("--air-width", type=int, default=64, help="registers of the wide synthetic AIR for --workload air (generic front-end; 2^16 rows unless --n-log2 is given)")
     ap.add_argument("--batch-total", type=int, default=1024)
     ap.add_argument("--slots", type=int, default=16, help="proof workspaces/streams per GPU for --workload batch (1487 / 2148 / 2784 / 3145 proofs/s at 2 / 4 / 8 / 16 on one B200)")
     args = ap.parse_args()
@@ -273,6 +354,8 @@ def main():
         return run_batch(args, rank, world, local)
     if args.workload == "verify":
         return run_verify(args, rank, world, local)
+    if args.workload == "air":
+        return run_air(args, rank, world, local)
     opts = xs.ProofOptions(field_extension=args.ext)
     ctx = xs.Context(device=local, max_n_log2=args.n_log2, num_slots=1)
     n = 1 << args.n_log2
@@ -380,6 +463,8 @@ def main():
         "gpu_launches": times["kernel_launches"] * args.steps,
         "device_ms_per_proof": times["device_ms"],
         "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},
+        "e2e_stages_ms": dict({k: round(v, 4) for k, v in times2.items() if k in xs.STAGE_NAMES}, h2d_until_first_kernel_ms=round(times2["h2d_ms"], 4),
+                              device_ms=round(times2["device_ms"], 4), total_ms=round(times2["total_ms"], 4)),
         "roofline": roofline, "int_pipe": int_pipe, "kernels": kernels,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -33,8 +33,9 @@ void launch_gen_trace_root(cudaStream_t st, int D, ProofState* ps, GenState* gs,
 // The boundary sum is carried as one fraction num/den (num <- num (x - p_g) + B_g den, den <- den (x - p_g)), so a point costs
 // one base-field inversion whatever the number of groups, batched over the thread's points.   out: [limb][k'][m], k' < 2
 // ------------------------------------------------------------------------------------------------------------------
-static constexpr int GCE_PTS = 4, GCE_THREADS = 128;
-template <int D>
+// GCE_PTS = points per thread: 4 for long traces (one inversion per 4 points), 1 when the domain is too small to fill the GPU otherwise.
+static constexpr int GCE_THREADS = 128;
+template <int D, int GCE_PTS>
 __global__ void __launch_bounds__(GCE_THREADS) gen_constraint_kernel(const u64* __restrict__ lde, u32 ln, const GenProgram* __restrict__ prog, const GenState* __restrict__ gs,
                                                                      PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64 g_last, u64* __restrict__ out) {
   __shared__ u64 sh[GCE_PTS][2 * D + 2][GCE_THREADS];      // per point: u (D), num (D), den, prefix
@@ -109,9 +110,12 @@ __global__ void __launch_bounds__(GCE_THREADS) gen_constraint_kernel(const u64* 
 }
 void launch_gen_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const GenProgram* prog, const GenState* gs, PowTable wn,
                             u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64 g_last, u64* out) {
-  const size_t per = (size_t(1) << ln) / GCE_PTS; dim3 grid((unsigned)((per + GCE_THREADS - 1) / GCE_THREADS), 2);
-  if (D == 1) gen_constraint_kernel<1><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
-  else gen_constraint_kernel<2><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
+  const int pts = ln >= 19 ? 4 : 1;
+  const size_t per = (size_t(1) << ln) / pts; dim3 grid((unsigned)((per + GCE_THREADS - 1) / GCE_THREADS), 2);
+  if (D == 1 && pts == 4) gen_constraint_kernel<1, 4><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
+  else if (D == 1) gen_constraint_kernel<1, 1><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
+  else if (pts == 4) gen_constraint_kernel<2, 4><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
+  else gen_constraint_kernel<2, 1><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
   XFG_LAUNCHED(1);
 }
 
@@ -141,8 +145,22 @@ template <int D> __global__ void __launch_bounds__(32 * GOF_WARPS) gen_ood_finis
   Coin c = coin_load(ps);
   for (u32 t = lane; t < 2 * W * D; t += 32) { const u32 l = t % D, w = (t / D) & 1u, j = t / (2 * D); limbs[t] = sums[j][w][l]; }   // interleaved per column (A.9)
   __syncwarp();
+  // hash_elements(frame): up to 4 BLAKE3 chunks of 128 limbs; lane c hashes chunk c, lane 0 merges the chaining values (tree mode)
   Digest d;
-  if (lane == 0) d = b3_hash_limbs_dyn(limbs, (int)(2 * W * D));
+  {
+    const int nl = (int)(2 * W * D), chunks = nl <= 128 ? 1 : (nl + 127) / 128;
+    u32 cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if ((int)lane < chunks) { int cl = nl - (int)lane * 128; if (cl > 128) cl = 128; b3_chunk_dyn(limbs + lane * 128, cl, lane, chunks == 1, cv); }
+    u32 c1[8], c2[8], c3[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c1[i] = __shfl_sync(0xFFFFFFFFu, cv[i], 1); c2[i] = __shfl_sync(0xFFFFFFFFu, cv[i], 2); c3[i] = __shfl_sync(0xFFFFFFFFu, cv[i], 3); }
+    if (lane == 0) {
+      if (chunks == 1) { for (int i = 0; i < 8; i++) d.w[i] = cv[i]; }
+      else if (chunks == 2) b3_parent(cv, c1, true, d.w);
+      else { u32 l[8]; b3_parent(cv, c1, false, l);
+             if (chunks == 3) b3_parent(l, c2, true, d.w); else { u32 r[8]; b3_parent(c2, c3, false, r); b3_parent(l, r, true, d.w); } }
+    }
+  }
   d = bcast_digest(d, 0);
   coin_reseed(c, d);
   // H(z) = P_limb0(z) + phi * P_limb1(z), phi = (0,1): (a0,a1) * phi = (-2 a1, a0 + a1)

@@ -29,11 +29,22 @@ using namespace xfg;
 
 namespace {
 
-// Split upload of a large trace: column groups {0} {1} {2,3} {4,5,6}.  Small groups first so that the NTTs start after one column's
-// copy time; larger groups later, because a one-column launch fills the GPU for 3.5 waves only (tail effect) and the copy
-// of the later columns is hidden behind the earlier groups' NTTs anyway.
-constexpr int UPLOAD_GROUPS = 4;
-constexpr int UPLOAD_GROUP_START[UPLOAD_GROUPS + 1] = {0, 1, 2, 4, XFG_TRACE_WIDTH};
+// Split upload of a large trace: one copy + event per column, the column's NTTs start as soon as it has landed.  A one-column launch
+// fills the GPU for 3.5 waves only (and its interpolation for less than one), so consecutive columns run on different streams and
+// fill each other's partial waves.
+int UPLOAD_GROUPS = 7;
+int UPLOAD_GROUP_START[XFG_TRACE_WIDTH + 1] = {0, 1, 2, 3, 4, 5, 6, XFG_TRACE_WIDTH};
+// XFG_UPLOAD_SPLIT="1,1,2,3" (group sizes, sum 7) overrides the split; XFG_UPLOAD_STREAMS=1 keeps every group on one stream (A/B runs)
+int g_upload_streams = 4;   // measured e2e at 2^20 (ms per proof): one stream {1,1,2,3} 4.95, per column on 1 / 2 / 3 / 4 streams 5.03 / 4.88 / 4.87 / 4.84
+void upload_split_from_env() {
+  static bool done = false; if (done) return; done = true;
+  if (const char* e = getenv("XFG_UPLOAD_STREAMS")) g_upload_streams = std::min(4, std::max(1, atoi(e)));
+  const char* e = getenv("XFG_UPLOAD_SPLIT"); if (!e) return;
+  int start[XFG_TRACE_WIDTH + 1] = {0}, k = 0, sum = 0;
+  for (const char* q = e; *q && k < XFG_TRACE_WIDTH;) { const int v = atoi(q); if (v < 1) return; sum += v; start[++k] = sum; while (*q && *q != ',') q++; if (*q == ',') q++; }
+  if (sum != XFG_TRACE_WIDTH) return;
+  UPLOAD_GROUPS = k; for (int i = 0; i <= k; i++) UPLOAD_GROUP_START[i] = start[i];
+}
 constexpr size_t MATERIAL_WORDS = size_t(1) << 20;   // 8 MiB: opened rows + per-position authentication paths
 constexpr u32 MIN_LOG = 3, MAX_LOG = 24;
 
@@ -68,8 +79,8 @@ struct GraphKey {
 struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 
 struct Slot {
-  cudaStream_t st = nullptr, copy_st = nullptr;         // copy_st: column-wise trace upload overlapped with the first NTTs
-  cudaEvent_t col_ev[XFG_TRACE_WIDTH] = {nullptr};
+  cudaStream_t st = nullptr, copy_st = nullptr, aux_st[3] = {nullptr, nullptr, nullptr};   // copy_st: column-wise trace upload overlapped with the first NTTs; aux_st: every other column group
+  cudaEvent_t col_ev[XFG_TRACE_WIDTH] = {nullptr}, fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
   bool split_upload = false;
   u64* slab = nullptr; size_t slab_words = 0;
   ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
@@ -281,17 +292,23 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   // With a split upload the trace goes column by column so that a column's NTTs start as soon as its copy has landed.  (Running
   // the HBM-resident path column by column as well - to keep one column's 64 MB four-step intermediate inside the L2 - was
   // measured: 7x smaller grids cost more (5.88 vs 5.46 ms per proof) than the saved DRAM traffic gains on these ALU-bound kernels.)
-  const bool waits = s.split_upload && !d_trace;
+  // Consecutive column groups alternate between two streams: a group's launches are 1-3 columns wide (3.5 waves of CTAs per column), and
+  // the partial last wave of one group is filled by the next group's kernels instead of idling.
+  const bool waits = s.split_upload && !d_trace, two = waits && g_upload_streams >= 2 && !profiling;
+  const int nstreams = two ? g_upload_streams : 1;
+  if (two) { CU(cudaEventRecord(s.fork_ev, st)); for (int a = 0; a + 1 < nstreams; a++) CU(cudaStreamWaitEvent(s.aux_st[a], s.fork_ev, 0)); }
   for (int g = 0; g < (waits ? UPLOAD_GROUPS : 1); g++) {
     const int c0 = waits ? UPLOAD_GROUP_START[g] : 0, per = waits ? UPLOAD_GROUP_START[g + 1] - c0 : (int)W;
     const size_t off = (size_t)c0 * n;
-    if (waits) CU(cudaStreamWaitEvent(st, s.col_ev[g], 0));
-    PROF("check_canonical", launch_check_canonical(st, trace_src + off, (size_t)per * n, s.d_state));
+    cudaStream_t gs = (g % nstreams) ? s.aux_st[g % nstreams - 1] : st;
+    if (waits) CU(cudaStreamWaitEvent(gs, s.col_ev[g], 0));
+    PROF("check_canonical", launch_check_canonical(gs, trace_src + off, (size_t)per * n, s.d_state));
     { NttJob j{}; j.src = trace_src + off; j.dst = c.trace_coef + off; j.ln = ln; j.batch = per; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
-      j.inverse = true; j.scale = p.n_inv; PROF("ntt.interpolate_trace", ntt_batch(st, p.ntt, j)); }
+      j.inverse = true; j.scale = p.n_inv; PROF("ntt.interpolate_trace", ntt_batch(gs, p.ntt, j)); }
     { NttJob j{}; j.src = c.trace_coef + off; j.dst = c.lde + off * 8; j.ln = ln; j.batch = per * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
-      j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_trace", ntt_batch(st, p.ntt, j)); }
+      j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_trace", ntt_batch(gs, p.ntt, j)); }
   }
+  for (int a = 0; a + 1 < nstreams; a++) { CU(cudaEventRecord(s.join_ev[a], s.aux_st[a])); CU(cudaStreamWaitEvent(st, s.join_ev[a], 0)); }
   mark();
   //   ---- compute_execution_trace_commitment
   if (W == 1 || W == 2 || W == XFG_TRACE_WIDTH) PROF("commit_rows.trace", launch_commit_rows(st, c.lde, N, (int)W, ln, c.trace_tree));
@@ -401,34 +418,49 @@ struct Out { std::vector<u8> b;
   void raw(const void* p, size_t n) { const u8* q = (const u8*)p; b.insert(b.end(), q, q + n); } };
 
 // BatchMerkleProof::serialize_nodes of MerkleTree::prove_batch(positions) (A.11), built from the per-position sibling paths:
-// path(q, lvl) = tree[((M + pos[q]) >> lvl) ^ 1]
+// path(q, lvl) = tree[((M + pos[q]) >> lvl) ^ 1].  Follows the crate's bookkeeping exactly (norm = sorted unique (index & ~1); at every level
+// `nodes[i]` is indexed by the position i in the current node list), without its BTreeMap: the ancestors (M + pos) >> lvl =
+// (M >> lvl) + (pos >> lvl) are monotone in pos, so the owner of a node is found by binary search over the positions sorted once
+// (any queried leaf below a node yields the same sibling digest).  ~10 us for 42 positions in a 2^23-leaf tree (the linear-search version: 35 us,
+// seven trees per proof).
 void batch_paths(const u32* pos, u32 cnt, const u64* paths, u32 depth, u64 M, Out& out) {
   auto path = [&](u32 q, u32 lvl) { return reinterpret_cast<const u8*>(paths + ((size_t)q * depth + lvl) * 4); };
-  auto owner = [&](u64 heap_index, u32 lvl) -> int { for (u32 q = 0; q < cnt; q++) if (((M + pos[q]) >> lvl) == heap_index) return (int)q; return -1; };
-  std::set<u64> norm; for (u32 q = 0; q < cnt; q++) norm.insert(pos[q] & ~u64(1));
-  std::vector<std::vector<const u8*>> nodes; std::vector<u64> next;
-  for (u64 index : norm) {
-    std::vector<const u8*> v;
-    for (u64 i = index; i < index + 2; i++) if (owner(M + i, 0) < 0) v.push_back(path((u32)owner(M + (i ^ 1), 0), 0));   // unqueried leaf = sibling of its queried partner
-    nodes.push_back(v); next.push_back((index + M) >> 1);
+  u32 ord[256]; for (u32 q = 0; q < cnt; q++) ord[q] = q;
+  std::sort(ord, ord + cnt, [&](u32 a, u32 b) { return pos[a] < pos[b]; });
+  auto owner = [&](u64 heap_index, u32 lvl) -> int {
+    const u64 key = heap_index - (M >> lvl); u32 lo = 0, hi = cnt;
+    while (lo < hi) { const u32 mid = (lo + hi) / 2; if (((u64)pos[ord[mid]] >> lvl) < key) lo = mid + 1; else hi = mid; }
+    return (lo < cnt && ((u64)pos[ord[lo]] >> lvl) == key) ? (int)ord[lo] : -1;
+  };
+  u64 cur[256], next[256]; u32 nn = 0, nnext = 0;
+  static thread_local std::vector<const u8*> flat; flat.resize((size_t)256 * (depth + 2)); u32 ncount[256];
+  const size_t stride = depth + 2;
+  u64 norm[256];
+  for (u32 i = 0; i < cnt; i++) { const u64 v = pos[ord[i]] & ~u64(1); if (!nn || norm[nn - 1] != v) norm[nn++] = v; }
+  for (u32 k = 0; k < nn; k++) {
+    const u64 index = norm[k]; ncount[k] = 0;
+    for (u64 i = index; i < index + 2; i++) if (owner(M + i, 0) < 0) flat[k * stride + ncount[k]++] = path((u32)owner(M + (i ^ 1), 0), 0);
+    next[nnext++] = (index + M) >> 1;
   }
   for (u32 d = 1; d < depth; d++) {
-    std::vector<u64> cur = next; next.clear();
-    size_t i = 0;
-    while (i < cur.size()) {
+    const u32 nc = nnext; for (u32 i = 0; i < nc; i++) cur[i] = next[i];
+    nnext = 0;
+    u32 i = 0;
+    while (i < nc) {
       const u64 sib = cur[i] ^ 1;
-      if (i + 1 < cur.size() && cur[i + 1] == sib) i += 1;
-      else nodes[i].push_back(path((u32)owner(cur[i], d), d));   // indexed by position in `cur`, as the reference crate does
-      next.push_back(sib >> 1); i += 1;
+      if (i + 1 < nc && cur[i + 1] == sib) i += 1;
+      else flat[i * stride + ncount[i]++] = path((u32)owner(cur[i], d), d);
+      next[nnext++] = sib >> 1; i += 1;
     }
   }
-  out.u8_((u32)nodes.size());
-  for (auto& v : nodes) { out.u8_((u32)v.size()); for (const u8* d : v) out.raw(d, 32); }
+  size_t total = 1; for (u32 k = 0; k < nn; k++) total += 1 + 32 * (size_t)ncount[k];
+  const size_t base = out.b.size(); out.b.resize(base + total);
+  u8* w = out.b.data() + base; *w++ = (u8)nn;
+  for (u32 k = 0; k < nn; k++) { *w++ = (u8)ncount[k]; for (u32 j = 0; j < ncount[k]; j++) { std::memcpy(w, flat[k * stride + j], 32); w += 32; } }
 }
-
 // StarkProof::to_bytes (A.12)
 void assemble(const Plan& p, int D, u32 W, const u64 (*ood_frame)[2], const xfg_options& o, const ProofState& s, const u64* mat, const GatherTasks& g, std::vector<u8>& bytes) {
-  Out out;
+  Out out; out.b.reserve(size_t(1) << 18);
   // Context
   out.u8_(W); out.u8_(0); out.u8_(0); out.u8_(p.ln); out.u16_(0); out.u8_(8); out.u64_(XFG_P);
   out.u8_(o.num_queries); out.u8_(o.blowup_factor); out.u8_(o.grinding_factor); out.u8_(o.field_extension); out.u8_(o.fri_folding_factor); out.u8_(o.fri_remainder_max_degree);
@@ -604,6 +636,7 @@ int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t 
   auto bail = [&](int rc) { xfg_destroy(ctx); return rc; };
 #define CUB(call) do { if ((call) != cudaSuccess) return bail(XFG_ERR_CUDA); } while (0)
   CUB(cudaSetDevice(device));
+  upload_split_from_env();
   ntt_init(true);
   { const u64 w = gl_root_of_unity(NTT_TW_LOG); std::vector<u64> f = pow_series(w, 1u << (NTT_TW_LOG - 1)), b = pow_series(gl_inv(w), 1u << (NTT_TW_LOG - 1));
     CUB(cudaMalloc(&ctx->tw_fwd, f.size() * 8)); CUB(cudaMalloc(&ctx->tw_inv, b.size() * 8));
@@ -612,7 +645,9 @@ int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t 
   const size_t words = slab_words_for(max_n_log2, 2, max_width), trace_words = size_t(max_width) << max_n_log2;
   for (Slot& s : ctx->slots) {
     CUB(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)); CUB(cudaStreamCreateWithFlags(&s.copy_st, cudaStreamNonBlocking));
+    for (auto& a : s.aux_st) CUB(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     for (auto& e : s.col_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming)); for (auto& e : s.join_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaMalloc(&s.slab, words * 8)); s.slab_words = words;
     CUB(cudaMalloc(&s.d_state, sizeof(ProofState))); CUB(cudaMalloc(&s.d_seed, 128 * 8));
     CUB(cudaMalloc(&s.d_partial, (size_t)(XFG_AIR_MAX_WIDTH + 2) * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
@@ -640,6 +675,9 @@ void xfg_destroy(xfg_ctx* ctx) {
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
     for (auto& e : s.col_ev) if (e) cudaEventDestroy(e);
+    if (s.fork_ev) cudaEventDestroy(s.fork_ev);
+    for (auto& e : s.join_ev) if (e) cudaEventDestroy(e);
+    for (auto& a : s.aux_st) if (a) cudaStreamDestroy(a);
     if (s.copy_st) cudaStreamDestroy(s.copy_st);
     if (s.st) cudaStreamDestroy(s.st);
   }

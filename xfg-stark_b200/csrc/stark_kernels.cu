@@ -132,12 +132,12 @@ void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64*
 // Horner pass in z^TOT; block partials are added by the transcript kernel.  partial: [poly][block][point][limb]
 // ------------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln, u32 width,
+__global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln, u32 width, u32 polys_per_block,
                                                    const ProofState* __restrict__ ps, u64* __restrict__ partial) {
   const size_t n = size_t(1) << ln;
-  const u32 poly = blockIdx.y, nb = gridDim.x, tid = threadIdx.x;
+  const u32 nb = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t TOT = (size_t)nb * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + tid;
-  const u64* c = poly < width ? trace_coef + (size_t)poly * n : h_coef + (size_t)(poly - width) * n;
+  const u32 P = width + D, p0 = blockIdx.y * polys_per_block, p1 = min(P, p0 + polys_per_block);
   // powers of the two evaluation points shared by the block: sq[w][b] = pt_w^(2^b), b < 32 (one lane per (w, b) chain would be
   // serial anyway: thread w squares 31 times), then every thread assembles pt^t and pt^TOT from the set bits of t / TOT
   __shared__ u64 sq[2][32][2];
@@ -153,31 +153,48 @@ __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_
   const size_t steps = n > TOT ? n / TOT : 1;
   for (size_t i = tid; i < steps; i += blockDim.x) for (int w = 0; w < 2; w++) { const Ext<D> v = pw(w, i * TOT); tab[i][w][0] = v.limb(0); tab[i][w][1] = D == 2 ? v.limb(1) : 0; }
   __syncthreads();
-  Ext<D> acc[2];
-  if (t < n) {
-    DotAcc d[2][D];
-    for (size_t i = 0; i < steps; i++) {
-      const u64 cv = c[t + i * TOT];
-#pragma unroll
-      for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) d[w][l].fma(cv, tab[i][w][l]);
-    }
+  // the powers pt^t of this thread serve every polynomial of the block's group (blockIdx.y): wide traces amortise the set-up above
+  Ext<D> pt[2];
+  if (t < n) { pt[0] = pw(0, t); pt[1] = pw(1, t); }
+  __shared__ u64 red[2][8][4];
 #pragma unroll 1
-    for (int w = 0; w < 2; w++) { Ext<D> a; for (int l = 0; l < D; l++) a.set_limb(l, d[w][l].result()); acc[w] = a * pw(w, t); }
-  }
-  __shared__ u64 red[256][2][2];
-  for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) red[tid][w][l] = l < D ? acc[w].limb(l) : 0;
-  __syncthreads();
-  for (u32 s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (tid < s) for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) red[tid][w][l] = gl_add(red[tid][w][l], red[tid + s][w][l]);
+  for (u32 poly = p0; poly < p1; poly++) {
+    const u64* c = poly < width ? trace_coef + (size_t)poly * n : h_coef + (size_t)(poly - width) * n;
+    u64 r[4] = {0, 0, 0, 0};
+    if (t < n) {
+      DotAcc d[2][D];
+      for (size_t i = 0; i < steps; i++) {
+        const u64 cv = c[t + i * TOT];
+#pragma unroll
+        for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) d[w][l].fma(cv, tab[i][w][l]);
+      }
+#pragma unroll
+      for (int w = 0; w < 2; w++) { Ext<D> a; for (int l = 0; l < D; l++) a.set_limb(l, d[w][l].result()); a = a * pt[w]; for (int l = 0; l < D; l++) r[2 * w + l] = a.limb(l); }
+    }
+    // block sum: shuffles inside the warps, then 8 warp sums per value (exact arithmetic: any order gives the same element)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (D == 1 && (q & 1)) continue;
+      for (int o = 16; o > 0; o >>= 1) r[q] = gl_add(r[q], __shfl_xor_sync(0xFFFFFFFFu, r[q], o));
+    }
+    u64 (*rb)[4] = red[poly & 1];            // double-buffered: one barrier per polynomial
+    if (lane == 0) for (int q = 0; q < 4; q++) rb[warp][q] = r[q];
     __syncthreads();
+    if (tid < 4) {
+      u64 s = 0;
+      for (u32 wv = 0; wv < blockDim.x / 32; wv++) s = gl_add(s, rb[wv][tid]);
+      partial[(((size_t)poly * nb + blockIdx.x) * 2 + (tid >> 1)) * 2 + (tid & 1)] = s;
+    }
   }
-  if (tid == 0) for (int w = 0; w < 2; w++) for (int l = 0; l < 2; l++) partial[(((size_t)poly * nb + blockIdx.x) * 2 + w) * 2 + l] = red[0][w][l];
 }
 u32 ood_num_blocks(u32 ln) { size_t n = size_t(1) << ln; size_t b = n / 256; if (b < 1) b = 1; if (b > OOD_MAX_BLOCKS) b = OOD_MAX_BLOCKS; return (u32)b; }   // 64 x 256 threads per polynomial: Horner chains of n / 16384 steps
 void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, u32 width, const ProofState* ps, u64* partial) {
-  dim3 grid(ood_num_blocks(ln), width + D);
-  if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ps, partial);
-  else ood_kernel<2><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ps, partial);
+  // one polynomial per block while that already gives >= 4 blocks per SM, else groups of polynomials share a block's power tables
+  const u32 nb = ood_num_blocks(ln), P = width + D;
+  u32 ppb = 1; while ((size_t)nb * ((P + ppb - 1) / ppb) > 148 * 4 && ppb < P) ppb++;
+  dim3 grid(nb, (P + ppb - 1) / ppb);
+  if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
+  else ood_kernel<2><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
   XFG_LAUNCHED(1);
 }
 
