@@ -231,6 +231,9 @@ int xfg_field_selftest(xfg_ctx* ctx, uint32_t op, const uint64_t* a, const uint6
 /* measured peak of the 32-bit integer ALU pipe (IADD3 / LOP3 / SHF mix, no memory traffic), 1e9 operations per second: the roofline
  * denominator of the BLAKE3 kernels; replaces nothing in the reference */
 int xfg_int_pipe_peak(xfg_ctx* ctx, double* gops);
+/* the same loop with other instruction mixes (1: IMAD only, 2: 2 ALU + 2 IMAD, 3: 3 ALU + 1 IMAD, 4: IMAD.WIDE only, 5: 3 ALU + 1 IMAD.WIDE, 6: 3-input adds):
+ * thread-level instructions per second (1e9).  Measurement tool behind DESIGN.md section 4 (what the FMA pipe can take off the ALU pipe) */
+int xfg_pipe_probe(xfg_ctx* ctx, int mode, double* gops);
 /* hash_elements of `rows` rows of `limbs` (1, 2, 7, 8 or 16) canonical u64 each, row-major; out = rows x 32 bytes */
 int xfg_hash_rows(xfg_ctx* ctx, const uint64_t* rows_rowmajor, size_t rows, uint32_t limbs, uint8_t* out);
 

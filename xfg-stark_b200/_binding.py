@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
-                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device"]
+                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_pipe_probe"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -140,6 +140,7 @@ def load_library():
     L.xfg_set_profiling.argtypes = [vp, i]
     L.xfg_set_graphs.argtypes = [vp, i]
     L.xfg_int_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.xfg_pipe_probe.argtypes = [vp, i, C.POINTER(C.c_double)]
     L.xfg_wide_create.argtypes = [vp, u32, u32, u32, u32, C.POINTER(vp)]
     L.xfg_wide_destroy.argtypes = [vp]; L.xfg_wide_destroy.restype = None
     L.xfg_wide_recv_ptr.argtypes = [vp]; L.xfg_wide_recv_ptr.restype = vp
@@ -314,6 +315,10 @@ class Context:
     def int_pipe_peak(self):
         """measured 32-bit integer ALU-pipe peak of this device in Gop/s (IADD3 / LOP3 / SHF mix)"""
         g = C.c_double(0); self._check(self._lib.xfg_int_pipe_peak(self._h, C.byref(g))); return float(g.value)
+
+    def pipe_probe(self, mode):
+        """thread-level instructions per second (1e9) of instruction mix `mode` (xfg_pipe_probe)"""
+        g = C.c_double(0); self._check(self._lib.xfg_pipe_probe(self._h, mode, C.byref(g))); return float(g.value)
 
     def set_graphs(self, on=True):
         self._check(self._lib.xfg_set_graphs(self._h, int(on)))

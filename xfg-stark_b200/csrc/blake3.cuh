@@ -20,11 +20,34 @@ XFG_HD u32 b3_rotr(u32 x, int n) {
   return (x >> n) | (x << (32 - n));
 #endif
 }
-#define XFG_B3_G(a, b, c, d, mx, my)            \
-  a = a + b + (mx); d = b3_rotr(d ^ a, 16);     \
-  c = c + d;        b = b3_rotr(b ^ c, 12);     \
-  a = a + b + (my); d = b3_rotr(d ^ a, 8);      \
-  c = c + d;        b = b3_rotr(b ^ c, 7);
+// XFG_B3_IMAD: ptxas already issues the 2-input additions of G (c += d) on the FMA pipe as `IMAD.IADD x, y, 0x1, z` and keeps a + b + m as
+// one ALU-pipe IADD3 (10 ALU + 2 FMA instructions per G; the ALU pipe is the bound of the hashing kernels - xfg_pipe_probe measures
+// 18.5 T instr/s for ALU-only or IMAD-only code, 27.6 T for a 2+2 mix).  1: a + b is computed as IMAD a = b * one + a with an opaque multiplier (a __constant__ word), the
+// message word is added by a 2-input addition that ptxas may place on either pipe (8-9 ALU + 4-6 FMA per G)
+#ifndef XFG_B3_IMAD
+#define XFG_B3_IMAD 1
+#endif
+#if defined(__CUDACC__)
+static __constant__ u32 g_b3_one = 1;     // opaque multiplier: keeps ptxas from folding x*1+y back into an addition it would fuse into IADD3
+#endif
+XFG_HD u32 b3_add3_split(u32 a, u32 b, u32 m) {
+#if defined(__CUDA_ARCH__)
+  u32 t; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(b), "r"(g_b3_one), "r"(a)); return t + m;
+#else
+  return a + b + m;
+#endif
+}
+#define XFG_B3_ADD_CD(c, d) c = c + d
+#if XFG_B3_IMAD == 0
+#define XFG_B3_ADD_ABM(a, b, m) a = a + b + (m)
+#else
+#define XFG_B3_ADD_ABM(a, b, m) a = b3_add3_split(a, b, (m))
+#endif
+#define XFG_B3_G(a, b, c, d, mx, my)                    \
+  XFG_B3_ADD_ABM(a, b, mx); d = b3_rotr(d ^ a, 16);     \
+  XFG_B3_ADD_CD(c, d);      b = b3_rotr(b ^ c, 12);     \
+  XFG_B3_ADD_ABM(a, b, my); d = b3_rotr(d ^ a, 8);      \
+  XFG_B3_ADD_CD(c, d);      b = b3_rotr(b ^ c, 7);
 #define XFG_B3_ROUND(m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11, m12, m13, m14, m15) \
   XFG_B3_G(s0, s4, s8, s12, m0, m1) XFG_B3_G(s1, s5, s9, s13, m2, m3)                      \
   XFG_B3_G(s2, s6, s10, s14, m4, m5) XFG_B3_G(s3, s7, s11, s15, m6, m7)                    \

@@ -11,6 +11,44 @@
 
 namespace xfg {
 
+#ifndef XFG_COMMIT_ROLLED
+#define XFG_COMMIT_ROLLED 1
+#endif
+#if XFG_COMMIT_ROLLED
+// One inlined leaf compression and one inlined node compression, each in a rolled loop: the unrolled kernel (15 compressions, 144 KB of
+// SASS; 8 per iteration after the first rolling, 88 KB) stalled on instruction fetch (ncu: no_instruction was its top stall).  The 8 leaf
+// digests of the thread are staged in shared memory ([slot][word][thread], conflict-free) and reduced in place: node j of a level reads
+// slots 2j, 2j+1 and writes slot j, which the in-order loop has already consumed.
+template <int NL>
+__global__ void __launch_bounds__(128) commit_rows_kernel(const u64* __restrict__ data, size_t limb_stride, u32 ln, Digest* __restrict__ tree) {
+  __shared__ u32 sd[8][8][128];
+  const size_t n = size_t(1) << ln, N = n * 8;
+  const u32 tid = threadIdx.x;
+  const size_t m = (size_t)blockIdx.x * blockDim.x + tid;
+  if (m >= n) return;
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) {
+    u64 limbs[NL];
+#pragma unroll
+    for (int j = 0; j < NL; j++) limbs[j] = data[j * limb_stride + (size_t)k * n + m];
+    const Digest d = b3_hash_limbs<NL>(limbs);
+    store_digest(tree + N + 8 * m + k, d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) sd[k][i][tid] = d.w[i];
+  }
+#pragma unroll 1
+  for (int it = 0; it < 7; it++) {
+    const int lvl = it < 4 ? 0 : it < 6 ? 1 : 2, j = it - (lvl == 0 ? 0 : lvl == 1 ? 4 : 6), cnt = 4 >> lvl;
+    Digest l, r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { l.w[i] = sd[2 * j][i][tid]; r.w[i] = sd[2 * j + 1][i][tid]; }
+    const Digest d = b3_merge(l, r);
+    store_digest(tree + (N >> (lvl + 1)) + (size_t)cnt * m + j, d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) sd[j][i][tid] = d.w[i];
+  }
+}
+#else
 template <int NL>
 __global__ void __launch_bounds__(128) commit_rows_kernel(const u64* __restrict__ data, size_t limb_stride, u32 ln, Digest* __restrict__ tree) {
   const size_t n = size_t(1) << ln, N = n * 8;
@@ -44,6 +82,8 @@ __global__ void __launch_bounds__(128) commit_rows_kernel(const u64* __restrict_
   }
   store_digest(tree + N / 8 + m, b3_merge(top[0], top[1]));
 }
+
+#endif
 
 // Wide rows (config 5: W = 64 columns): same thread shape, but the row is streamed through the BLAKE3 chunk 8 limbs (one
 // 64-byte block) at a time instead of being held in registers.  data[j*limb_stride + k*n + m], num_limbs <= 128.
@@ -84,7 +124,30 @@ void launch_commit_rows_wide(cudaStream_t st, const u64* data, size_t limb_strid
   XFG_LAUNCHED(1);
 }
 
-// level of M nodes at [M, 2M) -> levels M/2, M/4, M/8; one thread per 8 children
+// level of M nodes at [M, 2M) -> levels M/2, M/4, M/8; one thread per 8 children.  One inlined compression in a rolled loop of 7 (see
+// commit_rows_kernel): the first 4 nodes read their children from the heap, the others from the shared-memory staging.
+#if XFG_COMMIT_ROLLED
+__global__ void __launch_bounds__(128) tree_reduce8_kernel(Digest* __restrict__ tree, size_t M) {
+  __shared__ u32 sd[4][8][128];
+  const u32 tid = threadIdx.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + tid;
+  if (t >= M / 8) return;
+#pragma unroll 1
+  for (int it = 0; it < 7; it++) {
+    const int lvl = it < 4 ? 0 : it < 6 ? 1 : 2, j = it - (lvl == 0 ? 0 : lvl == 1 ? 4 : 6), cnt = 4 >> lvl;
+    Digest l, r;
+    if (lvl == 0) { l = load_digest(tree + M + 8 * t + 2 * j); r = load_digest(tree + M + 8 * t + 2 * j + 1); }
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) { l.w[i] = sd[2 * j][i][tid]; r.w[i] = sd[2 * j + 1][i][tid]; }
+    }
+    const Digest d = b3_merge(l, r);
+    store_digest(tree + (M >> (lvl + 1)) + (size_t)cnt * t + j, d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) sd[j][i][tid] = d.w[i];
+  }
+}
+#else
 __global__ void __launch_bounds__(128) tree_reduce8_kernel(Digest* __restrict__ tree, size_t M) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= M / 8) return;
@@ -99,6 +162,8 @@ __global__ void __launch_bounds__(128) tree_reduce8_kernel(Digest* __restrict__ 
   store_digest(tree + M / 4 + 2 * t, a); store_digest(tree + M / 4 + 2 * t + 1, b);
   store_digest(tree + M / 8 + t, b3_merge(a, b));
 }
+
+#endif
 
 // one CTA finishes the tree from a level of M <= 2048 nodes up to the root.  Every level is written to the heap (authentication
 // paths need all nodes) but the next level reads its children from shared memory (ping-pong buffers), so a level costs one

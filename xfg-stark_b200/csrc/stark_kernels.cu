@@ -421,6 +421,46 @@ __global__ void __launch_bounds__(256) int_peak_kernel(const u32* __restrict__ i
   for (int c = 0; c < 8; c++) acc ^= x[c];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
+// ---- pipe probe (xfg_pipe_probe): the same 8-chain loop with other instruction mixes, to see what the FMA pipe (IMAD) can take off the ALU pipe.
+// MODE 1: 4 IMAD; 2: xor, IMAD, shf, IMAD; 3: xor, shf, xor, IMAD; 4: 4 IMAD.WIDE (64-bit accumulate); 5: xor, shf, IMAD.WIDE, xor; 6: 4 IADD3 (3-input adds)
+template <int MODE> __global__ void __launch_bounds__(256) pipe_probe_kernel(const u32* __restrict__ in, u32* __restrict__ out, u32 iters) {
+  u32 x[8], y = in[threadIdx.x & 31] | 1u, z = in[32 + (threadIdx.x & 31)];
+  unsigned long long w[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) { x[c] = in[(threadIdx.x + c) & 63]; w[c] = x[c]; }
+  for (u32 i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (MODE == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;\n\t mad.lo.u32 %0, %0, %2, %1;\n\t mad.lo.u32 %0, %0, %1, %2;\n\t mad.lo.u32 %0, %0, %2, %1;" : "+r"(x[c]) : "r"(y), "r"(z));
+        else if (MODE == 2) asm volatile("xor.b32 %0, %0, %2;\n\t mad.lo.u32 %0, %0, %1, %2;\n\t shf.r.wrap.b32 %0, %0, %0, 7;\n\t mad.lo.u32 %0, %0, %2, %1;" : "+r"(x[c]) : "r"(y), "r"(z));
+        else if (MODE == 3) asm volatile("xor.b32 %0, %0, %2;\n\t shf.r.wrap.b32 %0, %0, %0, 7;\n\t xor.b32 %0, %0, %1;\n\t mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z));
+        else if (MODE == 4) asm volatile("{\n\t .reg .u32 lo, hi;\n\t mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %1, %0;\n\t mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %2, %0;\n\t"
+                                         " mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %1, %0;\n\t mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %2, %0;\n\t}" : "+l"(w[c]) : "r"(y), "r"(z));
+        else if (MODE == 5) { asm volatile("xor.b32 %0, %0, %2;\n\t shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(x[c]) : "r"(y), "r"(z));
+                              asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(x[c]), "r"(z));
+                              asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[c]) : "r"(y)); }
+        else if (MODE == 6) asm volatile("{\n\t .reg .u32 t;\n\t add.u32 t, %0, %1;\n\t add.u32 %0, t, %2;\n\t add.u32 t, %0, %2;\n\t add.u32 %0, t, %1;\n\t add.u32 t, %0, %1;\n\t add.u32 %0, t, %2;\n\t add.u32 t, %0, %2;\n\t add.u32 %0, t, %1;\n\t}" : "+r"(x[c]) : "r"(y), "r"(z));
+      }
+  }
+  u32 acc = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) acc ^= x[c] ^ (u32)w[c] ^ (u32)(w[c] >> 32);
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+void launch_pipe_probe(cudaStream_t st, int mode, const u32* in, u32* out, u32 blocks, u32 iters) {
+  switch (mode) {
+    case 1: pipe_probe_kernel<1><<<blocks, 256, 0, st>>>(in, out, iters); break;
+    case 2: pipe_probe_kernel<2><<<blocks, 256, 0, st>>>(in, out, iters); break;
+    case 3: pipe_probe_kernel<3><<<blocks, 256, 0, st>>>(in, out, iters); break;
+    case 4: pipe_probe_kernel<4><<<blocks, 256, 0, st>>>(in, out, iters); break;
+    case 5: pipe_probe_kernel<5><<<blocks, 256, 0, st>>>(in, out, iters); break;
+    case 6: pipe_probe_kernel<6><<<blocks, 256, 0, st>>>(in, out, iters); break;
+    default: int_peak_kernel<<<blocks, 256, 0, st>>>(in, out, iters); break;
+  }
+  XFG_LAUNCHED(1);
+}
 void launch_int_peak(cudaStream_t st, const u32* in, u32* out, u32 blocks, u32 iters) { int_peak_kernel<<<blocks, 256, 0, st>>>(in, out, iters); XFG_LAUNCHED(1); }
 
 // ---- field self-test (xfg_field_selftest): exercises the canonical and the weak arithmetic on caller-chosen operands ----
