@@ -21,6 +21,34 @@ pub const XFG_ERR_TOO_LARGE: c_int = 9;
 
 #[repr(C)]
 pub struct xfg_ctx { _private: [u8; 0] }
+#[repr(C)]
+pub struct xfg_wide { _private: [u8; 0] }
+
+// ---- generic AIR front-end (xfg_air_desc) ----
+pub const XFG_OP_ADD: u32 = 0;
+pub const XFG_OP_SUB: u32 = 1;
+pub const XFG_OP_MUL: u32 = 2;
+pub const XFG_AIR_MAX_WIDTH: u32 = 128;
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct xfg_air_instr { pub op: u32, pub a: u32, pub b: u32 }
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct xfg_assertion { pub column: u32, pub step: u32, pub value: u64 }
+#[repr(C)]
+pub struct xfg_air_desc {
+    pub width: u32,
+    pub num_pub_inputs: u32,
+    pub num_constants: u32,
+    pub num_instr: u32,
+    pub num_constraints: u32,
+    pub num_assertions: u32,
+    pub pub_inputs: *const u64,
+    pub constants: *const u64,
+    pub code: *const xfg_air_instr,
+    pub constraint_values: *const u32,
+    pub assertions: *const xfg_assertion,
+}
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
@@ -88,6 +116,11 @@ extern "C" {
                                            recipient_len: usize, secret: *const u8, secret_len: usize, network_id: u32, target_chain_id: u32,
                                            commitment_version: u32, n_log2: u32, options: *const xfg_options, out: *mut u8, out_cap: usize,
                                            out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_create_ex(device: c_int, max_n_log2: u32, num_slots: u32, max_width: u32, out: *mut *mut xfg_ctx) -> c_int;
+    pub fn xfg_prove_air(ctx: *mut xfg_ctx, air: *const xfg_air_desc, trace_colmajor: *const u64, n_log2: u32, options: *const xfg_options, out: *mut u8,
+                         out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_prove_air_device(ctx: *mut xfg_ctx, air: *const xfg_air_desc, d_trace_colmajor: *const u64, n_log2: u32, options: *const xfg_options,
+                                out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
     pub fn xfg_verify_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, proofs: *const *const u8, proof_lens: *const usize, air: *const xfg_air_consts,
                                       acceptable: *const xfg_options, results: *mut i32, times: *mut xfg_verify_times) -> c_int;
     pub fn xfg_verify_strerror(code: c_int) -> *const c_char;
@@ -97,5 +130,18 @@ extern "C" {
     pub fn xfg_eval_constraints(ctx: *mut xfg_ctx, lde: *const u64, n_log2: u32, air: *const xfg_air_consts, ext: u32, coeffs: *const u64, out: *mut u64) -> c_int;
     pub fn xfg_fri_fold_layer(ctx: *mut xfg_ctx, evals: *const u64, nl_log2: u32, ext: u32, alpha: *const u64, out: *mut u64) -> c_int;
     pub fn xfg_field_selftest(ctx: *mut xfg_ctx, op: u32, a: *const u64, b: *const u64, n: usize, out: *mut u64) -> c_int;
+    pub fn xfg_int_pipe_peak(ctx: *mut xfg_ctx, gops: *mut f64) -> c_int;
+    pub fn xfg_set_graphs(ctx: *mut xfg_ctx, on: c_int) -> c_int;
+    // one wide trace sharded over the GPUs of a box (BASELINE config 5)
+    pub fn xfg_wide_create(ctx: *mut xfg_ctx, n_log2: u32, total_cols: u32, num_ranks: u32, rank: u32, out: *mut *mut xfg_wide) -> c_int;
+    pub fn xfg_wide_destroy(w: *mut xfg_wide);
+    pub fn xfg_wide_recv_ptr(w: *mut xfg_wide) -> *mut std::os::raw::c_void;
+    pub fn xfg_wide_ipc_handle(w: *mut xfg_wide, out: *mut u8) -> c_int;
+    pub fn xfg_wide_open_peers(w: *mut xfg_wide, handles: *const u8) -> c_int;
+    pub fn xfg_wide_set_peer_ptrs(w: *mut xfg_wide, ptrs: *const *mut std::os::raw::c_void) -> c_int;
+    pub fn xfg_wide_extend(w: *mut xfg_wide, d_cols_local: *const u64, device_ms: *mut f32) -> c_int;
+    pub fn xfg_wide_commit(w: *mut xfg_wide, subtree_root: *mut u8, device_ms: *mut f32) -> c_int;
+    pub fn xfg_wide_read_recv(w: *mut xfg_wide, out: *mut u64) -> c_int;
+    pub fn xfg_pipe_probe(ctx: *mut xfg_ctx, mode: c_int, gops: *mut f64) -> c_int;
     pub fn xfg_hash_rows(ctx: *mut xfg_ctx, rows_rowmajor: *const u64, rows: usize, limbs: u32, out: *mut u8) -> c_int;
 }

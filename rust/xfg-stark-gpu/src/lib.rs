@@ -19,6 +19,13 @@ use xfg_stark_gpu_sys as sys;
 pub struct GpuContext { raw: *mut sys::xfg_ctx }
 
 impl GpuContext {
+    /// workspaces for traces of up to `max_width` columns (generic AIR front-end); `new` sizes them for the 7-column burn-mint trace
+    pub fn with_width(device: i32, max_trace_log2: u32, slots: u32, max_width: u32) -> Result<Self, String> {
+        let mut raw = ptr::null_mut();
+        let rc = unsafe { sys::xfg_create_ex(device, max_trace_log2, slots, max_width, &mut raw) };
+        if rc != sys::XFG_OK { return Err(format!("xfg_create_ex: {}", unsafe { CStr::from_ptr(sys::xfg_strerror(rc)) }.to_string_lossy())); }
+        Ok(Self { raw })
+    }
     pub fn new(device: i32, max_trace_log2: u32, slots: u32) -> Result<Self, String> {
         let mut raw = ptr::null_mut();
         let rc = unsafe { sys::xfg_create(device, max_trace_log2, slots, &mut raw) };
@@ -89,4 +96,74 @@ impl Prover for GpuBurnMintProver {
             _ => panic!("xfg_prove_burn_mint failed ({rc}): {}", self.ctx.last_error()),
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generic AIR front-end: any main-segment AIR with transition degree <= 2 and single-point assertions,
+// e.g. the 4-register `XfgBurnAir` sketch (src/winterfell_air.rs:87-127).  The AIR's `evaluate_transition` body is
+// recorded once as a straight-line program; `prove` then goes through `xfg_prove_air`.
+// ------------------------------------------------------------------------------------------------------------------
+/// A value of the program: frame.current()[i], frame.next()[i], a constant, or the result of an earlier instruction.
+#[derive(Clone, Copy)]
+pub enum Val { Cur(u32), Next(u32), Const(u32), Instr(u32) }
+
+#[derive(Default)]
+pub struct AirProgram {
+    pub width: u32,
+    pub pub_inputs: Vec<u64>,
+    constants: Vec<u64>,
+    code: Vec<(u32, Val, Val)>,
+    outputs: Vec<Val>,
+    assertions: Vec<sys::xfg_assertion>,
+}
+
+impl AirProgram {
+    pub fn new(width: u32, pub_inputs: &[BaseElement]) -> Self { Self { width, pub_inputs: pub_inputs.iter().map(|e| e.as_int()).collect(), ..Default::default() } }
+    pub fn constant(&mut self, v: BaseElement) -> Val { self.constants.push(v.as_int()); Val::Const(self.constants.len() as u32 - 1) }
+    fn emit(&mut self, op: u32, a: Val, b: Val) -> Val { self.code.push((op, a, b)); Val::Instr(self.code.len() as u32 - 1) }
+    pub fn add(&mut self, a: Val, b: Val) -> Val { self.emit(sys::XFG_OP_ADD, a, b) }
+    pub fn sub(&mut self, a: Val, b: Val) -> Val { self.emit(sys::XFG_OP_SUB, a, b) }
+    pub fn mul(&mut self, a: Val, b: Val) -> Val { self.emit(sys::XFG_OP_MUL, a, b) }
+    /// `result[j] = v` for the next j
+    pub fn constraint(&mut self, v: Val) { self.outputs.push(v) }
+    /// `Assertion::single(column, step, value)`
+    pub fn assert_single(&mut self, column: usize, step: usize, value: BaseElement) {
+        self.assertions.push(sys::xfg_assertion { column: column as u32, step: step as u32, value: value.as_int() })
+    }
+    fn id(&self, v: Val) -> u32 {
+        let (w, c) = (self.width, self.constants.len() as u32);
+        match v { Val::Cur(i) => i, Val::Next(i) => w + i, Val::Const(i) => 2 * w + i, Val::Instr(i) => 2 * w + c + i }
+    }
+    /// trace: column-major canonical u64, `width` columns of 2^n_log2 rows
+    pub fn prove(&self, ctx: &GpuContext, trace_colmajor: &[u64], n_log2: u32, options: &ProofOptions) -> Result<StarkProof, ProverError> {
+        let code: Vec<sys::xfg_air_instr> = self.code.iter().map(|&(op, a, b)| sys::xfg_air_instr { op, a: self.id(a), b: self.id(b) }).collect();
+        let outs: Vec<u32> = self.outputs.iter().map(|&v| self.id(v)).collect();
+        let desc = sys::xfg_air_desc {
+            width: self.width, num_pub_inputs: self.pub_inputs.len() as u32, num_constants: self.constants.len() as u32, num_instr: code.len() as u32,
+            num_constraints: outs.len() as u32, num_assertions: self.assertions.len() as u32, pub_inputs: self.pub_inputs.as_ptr(),
+            constants: self.constants.as_ptr(), code: code.as_ptr(), constraint_values: outs.as_ptr(), assertions: self.assertions.as_ptr(),
+        };
+        let opts = options_to_c(options);
+        let mut out = vec![0u8; 1 << 20];
+        let mut len = 0usize;
+        let rc = unsafe { sys::xfg_prove_air(ctx.raw, &desc, trace_colmajor.as_ptr(), n_log2, &opts, out.as_mut_ptr(), out.len(), &mut len, ptr::null_mut()) };
+        match rc {
+            sys::XFG_OK => { out.truncate(len); StarkProof::from_bytes(&out).map_err(|_| ProverError::UnsupportedFieldExtension(0)) }
+            sys::XFG_ERR_UNSATISFIED_CONSTRAINT => Err(ProverError::UnsatisfiedTransitionConstraintError(0)),
+            sys::XFG_ERR_UNSUPPORTED_EXTENSION => Err(ProverError::UnsupportedFieldExtension(3)),
+            _ => panic!("xfg_prove_air failed ({rc}): {}", ctx.last_error()),
+        }
+    }
+}
+
+/// The XfgBurnAir sketch (src/winterfell_air.rs:87-127) as a program: constraint i = current[i] - expected_i, assertions at step 0.
+pub fn xfg_burn_air_program(commitment: BaseElement, nullifier: BaseElement, amount: BaseElement, network_id: BaseElement) -> AirProgram {
+    let mut p = AirProgram::new(4, &[]);
+    for (i, v) in [commitment, nullifier, amount, network_id].into_iter().enumerate() {
+        let c = p.constant(v);
+        let d = p.sub(Val::Cur(i as u32), c);
+        p.constraint(d);
+        p.assert_single(i, 0, v);
+    }
+    p
 }

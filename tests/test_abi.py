@@ -32,6 +32,13 @@ def test_library_exports_every_declared_symbol():
         assert re.search(rf"\bT {name}\b", out), name
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/xfg-stark-gpu-sys (source only: no cargo in the image) must bind every entry point of the header"""
+    rs = open(os.path.join(ROOT, "rust", "xfg-stark-gpu-sys", "src", "lib.rs")).read()
+    missing = [n for n in header_symbols() if not re.search(rf"\bpub fn {n}\(", rs)]
+    assert missing == []
+
+
 def test_library_is_built_for_sm_100a():
     import xfg_stark_b200 as xs
     out = subprocess.run(["cuobjdump", "-lelf", xs.library_path()], capture_output=True, text=True).stdout

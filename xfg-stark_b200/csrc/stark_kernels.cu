@@ -436,8 +436,10 @@ template <int MODE> __global__ void __launch_bounds__(256) pipe_probe_kernel(con
         if (MODE == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;\n\t mad.lo.u32 %0, %0, %2, %1;\n\t mad.lo.u32 %0, %0, %1, %2;\n\t mad.lo.u32 %0, %0, %2, %1;" : "+r"(x[c]) : "r"(y), "r"(z));
         else if (MODE == 2) asm volatile("xor.b32 %0, %0, %2;\n\t mad.lo.u32 %0, %0, %1, %2;\n\t shf.r.wrap.b32 %0, %0, %0, 7;\n\t mad.lo.u32 %0, %0, %2, %1;" : "+r"(x[c]) : "r"(y), "r"(z));
         else if (MODE == 3) asm volatile("xor.b32 %0, %0, %2;\n\t shf.r.wrap.b32 %0, %0, %0, 7;\n\t xor.b32 %0, %0, %1;\n\t mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z));
-        else if (MODE == 4) asm volatile("{\n\t .reg .u32 lo, hi;\n\t mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %1, %0;\n\t mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %2, %0;\n\t"
-                                         " mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %1, %0;\n\t mov.b64 {lo, hi}, %0;\n\t mad.wide.u32 %0, lo, %2, %0;\n\t}" : "+l"(w[c]) : "r"(y), "r"(z));
+        else if (MODE == 4) {       // w[c] += lo(w[c ^ 1]) * y : the multiplicand varies, nothing to hoist; 4 per group like the other modes
+          asm volatile("{\n\t .reg .u32 lo, hi;\n\t mov.b64 {lo, hi}, %1;\n\t mad.wide.u32 %0, lo, %2, %0;\n\t mad.wide.u32 %0, hi, %3, %0;\n\t mad.wide.u32 %0, lo, %3, %0;\n\t mad.wide.u32 %0, hi, %2, %0;\n\t}"
+                       : "+l"(w[c]) : "l"(w[c ^ 1]), "r"(y), "r"(z));
+        }
         else if (MODE == 5) { asm volatile("xor.b32 %0, %0, %2;\n\t shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(x[c]) : "r"(y), "r"(z));
                               asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(x[c]), "r"(z));
                               asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[c]) : "r"(y)); }
