@@ -30,9 +30,15 @@ template <int K> __device__ __forceinline__ void batch_inv(u64 (&v)[K]) {
 //   H(x) = T(x) (x - g^(n-1)) / (x^n - 1) + B0(x) / (x - 1) + B1(x) / (x - g^(n-1))      (A.8)
 // out: [limb][k'][m], k' < 2
 // ------------------------------------------------------------------------------------------------------------------
-static constexpr int CE_PTS = 4, CE_THREADS = 128;
+#ifndef XFG_CE_PTS
+#define XFG_CE_PTS 8      // 8 points per thread share one inversion (30 % of the 4-point kernel was the inversion): 0.210 -> 0.188 ms at 2^20
+#endif
+#ifndef XFG_CE_THREADS
+#define XFG_CE_THREADS 64
+#endif
+static constexpr int CE_PTS = XFG_CE_PTS, CE_THREADS = XFG_CE_THREADS;
 #ifndef XFG_CE_MINB
-#define XFG_CE_MINB 4
+#define XFG_CE_MINB 8
 #endif
 // The loops over the CE_PTS points are NOT unrolled and the per-point intermediates live in shared memory ([point][word][thread],
 // conflict-free): the fully unrolled version was 160 KB of SASS and stalled on instruction fetch (ncu: no_instruction).
