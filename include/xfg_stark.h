@@ -226,7 +226,7 @@ int xfg_eval_constraints(xfg_ctx* ctx, const uint64_t* lde, uint32_t n_log2, con
  * alpha = ext limbs; out = 2^(nl_log2-3) x ext limbs */
 int xfg_fri_fold_layer(xfg_ctx* ctx, const uint64_t* evals, uint32_t nl_log2, uint32_t ext, const uint64_t* alpha, uint64_t* out);
 /* element-wise field self-test of the device arithmetic (winter-math f64::BaseElement): op 0 mul, 1 weak mul,
- * 2 weak add, 3 weak sub, 4 add, 5 sub, 6 inv, 7/8 weak +- b*2^32, 100+S multiply by 2^S; out[i] = canonical result */
+ * 2 weak add, 3 weak sub, 4 add, 5 sub, 6 inv, 7/8 weak +- b*2^32, 9 un-reduced dot product, 10 weak inversion, 100+S multiply by 2^S; out[i] = canonical result */
 int xfg_field_selftest(xfg_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
 /* measured peak of the 32-bit integer ALU pipe (IADD3 / LOP3 / SHF mix, no memory traffic), 1e9 operations per second: the roofline
  * denominator of the BLAKE3 kernels; replaces nothing in the reference */

@@ -37,7 +37,7 @@ def _operands(rng, canonical_b):
     return a, b
 
 
-@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9] + [100 + s for s in (0, 1, 12, 24, 31, 32, 33, 36, 48, 60, 63, 64, 65, 72, 84, 95)])
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10] + [100 + s for s in (0, 1, 12, 24, 31, 32, 33, 36, 48, 60, 63, 64, 65, 72, 84, 95)])
 def test_field_arithmetic_exact(ctx, op):
     """device field arithmetic (incl. the weak forms used inside NTT butterflies) against Python big integers, on every pair
     of edge values: 0, 1, p-1, the non-canonical aliases p..2^64-1, values around 2^32 and 2^63."""
@@ -51,7 +51,7 @@ def test_field_arithmetic_exact(ctx, op):
     if op in (0, 1): exp = [(x * y) % P for x, y in zip(ai, bi)]
     elif op in (2, 4): exp = [(x + y) % P for x, y in zip(ai, bi)]
     elif op in (3, 5): exp = [(x - y) % P for x, y in zip(ai, bi)]
-    elif op == 6: exp = [pow(x, P - 2, P) for x in ai]
+    elif op in (6, 10): exp = [pow(x, P - 2, P) for x in ai]           # 10: inversion over weak products, any u64 operand
     elif op == 7: exp = [(x + ((y & 0xFFFFFFFF) << 32)) % P for x, y in zip(ai, bi)]
     elif op == 8: exp = [(x - ((y & 0xFFFFFFFF) << 32)) % P for x, y in zip(ai, bi)]
     elif op == 9: exp = [(37 * x * y + y * y) % P for x, y in zip(ai, bi)]

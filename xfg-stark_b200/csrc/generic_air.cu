@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(GCE_THREADS) gen_constraint_kernel(const u64* 
     sh[q][2 * D][tid] = den; sh[q][2 * D + 1][tid] = acc;
     acc = gl_mul(acc, den);
   }
-  acc = gl_inv(acc);
+  acc = w_inv(acc);
 #pragma unroll 1
   for (int q = GCE_PTS - 1; q >= 0; q--) {
     const size_t m = t + q * per;
