@@ -347,7 +347,12 @@ def main():
     import xfg_stark_b200 as xs
     from xfg_stark_b200 import multi
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("XFG_NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL writes its banner / debug output to stdout unless told otherwise
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    if "XFG_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["XFG_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
     torch.cuda.set_device(local)
     multi.init("nccl", torch.device("cuda", local))
     if args.workload == "batch":
@@ -432,14 +437,15 @@ def main():
     roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,
                 "peak_source": peak_src, "launch_ms": top["ms"], "alg_bytes": top["alg_bytes"],
                 "alu_pipe_busy_ncu": alu_busy,
-                "note": "every heavy kernel of this path is bound by the 32-bit integer ALU pipe (64-bit modular arithmetic, BLAKE3), not by HBM: ncu ALU pipe 64-87 % busy, DRAM 8-20 % (DESIGN.md section 4)",
+                "note": "every heavy kernel of this path is bound by the 32-bit integer pipes (64-bit modular arithmetic, BLAKE3), not by HBM: ncu ALU pipe 56-93 % busy, DRAM 8-25 % (DESIGN.md section 4)",
                 "whole_proof": {"alg_bytes": ab["_total_survey"], "gbps": round(ab["_total_survey"] / times["device_ms"] / 1e6, 1),
                                 "frac": round(ab["_total_survey"] / times["device_ms"] / 1e6 / peak, 4)}}
 
     # integer-pipe roofline of the BLAKE3 kernels: measured ALU-pipe peak (LOP3/SHF microbenchmark, no memory
-    # traffic) against compressions/s x 570 ALU-pipe instructions per compression (SASS count of commit_rows_kernel<7>: 8551 / 15)
+    # traffic) against compressions/s x 458 ALU-pipe instructions per compression (SASS of the compression loop of commit_rows_kernel: 8 per G x 56 G + 10;
+    # the 4 additions of G run on the FMA pipe as IMAD)
     int_peak = ctx.int_pipe_peak()
-    n_rows = 1 << args.n_log2; ALU_PER_COMPRESSION = 570
+    n_rows = 1 << args.n_log2; ALU_PER_COMPRESSION = 458
     fri_leaves = []; nl = 8 * n_rows
     while nl > 256:
         fri_leaves.append(nl // 8); nl //= 8

@@ -18,7 +18,11 @@ def run(n_log2, W, steps=1, check=False, seed=1234):
     import torch.distributed as dist
     import xfg_stark_b200 as xs
     from xfg_stark_b200 import multi
-    os.environ["NCCL_DEBUG"] = os.environ.get("XFG_NCCL_DEBUG", "WARN")
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"          # NCCL's banner must not pollute the JSON line on stdout
+    if "XFG_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["XFG_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
     rank, world, local = multi.rank_world()
     torch.cuda.set_device(local)
     multi.init("nccl", torch.device("cuda", local))
