@@ -156,6 +156,11 @@ int xfg_prove_air(xfg_ctx* ctx, const xfg_air_desc* air, const uint64_t* trace_c
 int xfg_prove_air_device(xfg_ctx* ctx, const xfg_air_desc* air, const uint64_t* d_trace_colmajor, uint32_t n_log2, const xfg_options* options,
                          uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
 
+/* `count` independent proofs of equal trace length (descriptions may differ: other constants, assertion values, public inputs, even other
+ * programs), pipelined over the context's slots like xfg_prove_burn_mint_batch; traces[i]: host memory, airs[i].width columns x 2^n_log2 rows */
+int xfg_prove_air_batch(xfg_ctx* ctx, uint32_t count, const xfg_air_desc* airs, const uint64_t* const* traces, uint32_t n_log2,
+                        const xfg_options* options, uint8_t* out, size_t out_stride, size_t* out_lens, float* total_ms);
+
 /* ---- one wide trace sharded over the GPUs of a box (BASELINE config 5) ----
  * Replaces DefaultTraceLde::new (src/burn_mint_air.rs:513: interpolate_columns + evaluate_polys_over + commit_to_rows +
  * MerkleTree::new) for a W-column x 2^n_log2-row trace: rank r interpolates and extends columns [r*W/G, (r+1)*W/G); the last

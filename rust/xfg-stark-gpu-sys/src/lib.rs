@@ -121,6 +121,8 @@ extern "C" {
                          out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
     pub fn xfg_prove_air_device(ctx: *mut xfg_ctx, air: *const xfg_air_desc, d_trace_colmajor: *const u64, n_log2: u32, options: *const xfg_options,
                                 out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_prove_air_batch(ctx: *mut xfg_ctx, count: u32, airs: *const xfg_air_desc, traces: *const *const u64, n_log2: u32, options: *const xfg_options,
+                               out: *mut u8, out_stride: usize, out_lens: *mut usize, total_ms: *mut f32) -> c_int;
     pub fn xfg_verify_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, proofs: *const *const u8, proof_lens: *const usize, air: *const xfg_air_consts,
                                       acceptable: *const xfg_options, results: *mut i32, times: *mut xfg_verify_times) -> c_int;
     pub fn xfg_verify_strerror(code: c_int) -> *const c_char;

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
-                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_pipe_probe"]
+                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_pipe_probe"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -124,6 +124,7 @@ def load_library():
     L.xfg_prove_burn_mint_device.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
     L.xfg_prove_air.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
     L.xfg_prove_air_device.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
+    L.xfg_prove_air_batch.argtypes = [vp, u32, vp, vp, u32, C.POINTER(_Options), vp, sz, vp, C.POINTER(C.c_float)]
     L.xfg_prove_burn_mint_batch.argtypes = [vp, u32, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options), vp, sz, vp, C.POINTER(C.c_float)]
     inputs = [u64, u64, vp, vp, sz, vp, sz, u32, u32, u32]
     L.xfg_burn_mint_pack_inputs.argtypes = [vp] + inputs + [C.POINTER(AirConsts)]
@@ -273,6 +274,21 @@ class Context:
                                                    C.byref(st) if want_times else None))
         proof = C.string_at(out, ln.value)
         return (proof, st.as_dict()) if want_times else proof
+
+    def prove_air_batch(self, airs, traces, options=ProofOptions(), out_stride=1 << 17):
+        """airs: list of AirBuilder (one per proof); traces: list of (width, n) uint64 arrays of equal n.  -> (list of proof bytes, device wall ms)"""
+        cnt = len(traces)
+        if cnt == 0:
+            return [], 0.0
+        descs, keep = [], []
+        for a in airs:
+            d, k, _ = self._air_desc(a); descs.append(d); keep.append(k)
+        ts = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+        n_log2 = ts[0].shape[1].bit_length() - 1
+        darr = (_AirDesc * cnt)(*descs); ptrs = (C.c_void_p * cnt)(*[t.ctypes.data for t in ts])
+        out = np.empty(cnt * out_stride, dtype=np.uint8); lens = np.zeros(cnt, dtype=np.uint64); ms = C.c_float(0); o = options._c()
+        self._check(self._lib.xfg_prove_air_batch(self._h, cnt, darr, ptrs, n_log2, C.byref(o), _ptr(out), out_stride, _ptr(lens), C.byref(ms)))
+        return [out[i * out_stride:i * out_stride + int(lens[i])].tobytes() for i in range(cnt)], float(ms.value)
 
     def prove_batch(self, traces, airs, options=ProofOptions(), out_stride=1 << 17):
         """traces: list of (7, n) uint64 arrays; airs: list of AirConsts.  Returns (list of proof bytes, device wall ms)."""
