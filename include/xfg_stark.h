@@ -161,6 +161,12 @@ int xfg_prove_air_device(xfg_ctx* ctx, const xfg_air_desc* air, const uint64_t* 
 int xfg_prove_air_batch(xfg_ctx* ctx, uint32_t count, const xfg_air_desc* airs, const uint64_t* const* traces, uint32_t n_log2,
                         const xfg_options* options, uint8_t* out, size_t out_stride, size_t* out_lens, float* total_ms);
 
+/* host-only (no device needed): validates and compiles `air` exactly as xfg_prove_air does and reports the compiled size; with cur / next / out
+ * non-NULL it also runs the COMPILED register program on that one frame (canonical elements; out = num_constraints results).  A self-test of the
+ * front-end's compiler for CPU-only boxes; the proving path never evaluates constraints on the host. */
+int xfg_air_compile_check(const xfg_air_desc* air, uint32_t n_log2, uint32_t* num_instr, uint32_t* num_slots, uint32_t* num_groups,
+                          const uint64_t* cur, const uint64_t* next, uint64_t* out);
+
 /* ---- one wide trace sharded over the GPUs of a box (BASELINE config 5) ----
  * Replaces DefaultTraceLde::new (src/burn_mint_air.rs:513: interpolate_columns + evaluate_polys_over + commit_to_rows +
  * MerkleTree::new) for a W-column x 2^n_log2-row trace: rank r interpolates and extends columns [r*W/G, (r+1)*W/G); the last

@@ -123,6 +123,8 @@ extern "C" {
                                 out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
     pub fn xfg_prove_air_batch(ctx: *mut xfg_ctx, count: u32, airs: *const xfg_air_desc, traces: *const *const u64, n_log2: u32, options: *const xfg_options,
                                out: *mut u8, out_stride: usize, out_lens: *mut usize, total_ms: *mut f32) -> c_int;
+    pub fn xfg_air_compile_check(air: *const xfg_air_desc, n_log2: u32, num_instr: *mut u32, num_slots: *mut u32, num_groups: *mut u32,
+                                 cur: *const u64, next: *const u64, out: *mut u64) -> c_int;
     pub fn xfg_verify_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, proofs: *const *const u8, proof_lens: *const usize, air: *const xfg_air_consts,
                                       acceptable: *const xfg_options, results: *mut i32, times: *mut xfg_verify_times) -> c_int;
     pub fn xfg_verify_strerror(code: c_int) -> *const c_char;

@@ -92,3 +92,69 @@ def test_oracle_generic_equals_hardwired_burn_mint(ext):
     o = (42, 8, 4, ext, 8, 31)
     air = A.burn_mint_air(pi, ac[0], ac[1], ac[2], ac[3], 64)
     assert orc.prove_air(air.flatten(), tr, o) == orc.prove(tr, pi, ac, o)
+
+
+# ---- the front-end's host-side compiler (validation, dead-code elimination, slot allocation), checked without a GPU ----
+def test_compiler_matches_source_program_on_random_frames():
+    """xfg_air_compile_check runs the COMPILED register program on one frame; it must equal the builder's own evaluation of the source
+    expressions (Python integers) for programs with shared sub-expressions, dead code and many live values"""
+    import xfg_stark_b200 as xs
+    from xfg_stark_b200 import air as A
+    import test_gpu_air as T
+    rng = np.random.default_rng(7)
+    for seed in range(8):
+        width = [1, 2, 3, 5, 8, 13, 21, 34][seed]
+        air, trace = T.random_air(300 + seed, width, 8)
+        dead = air.cur(0) * air.cur(0) + 5                      # never used by a constraint: must be eliminated
+        assert dead is not None
+        outs = [A.Expr(air, v) for v in air._outs]
+        for _ in range(5):
+            cur = rng.integers(0, orc.P, size=width, dtype=np.uint64); nxt = rng.integers(0, orc.P, size=width, dtype=np.uint64)
+            r = xs.air_compile_check(air, 3, cur, nxt)
+            exp = [air.evaluate(e, [int(x) for x in cur], [int(x) for x in nxt]) for e in outs]
+            assert [int(x) for x in r["results"]] == exp
+        assert r["num_groups"] == 2 and r["num_slots"] <= 64
+        assert r["num_instr"] <= len(air._code) - 2 + len(air._outs)      # the two dead instructions are gone
+    # on a satisfying trace every constraint vanishes on consecutive rows
+    air, trace = A.wide_quadratic_air(9, 16, seed=5)
+    for i in range(15):
+        assert not xs.air_compile_check(air, 4, trace[:, i], trace[:, i + 1])["results"].any()
+
+
+def test_compiler_validation_codes():
+    import xfg_stark_b200 as xs
+    from xfg_stark_b200 import air as A
+
+    def code(b, n_log2=3):
+        with pytest.raises(xs.XfgError) as e:
+            xs.air_compile_check(b, n_log2)
+        return e.value.code
+    b = A.AirBuilder(1); x = b.cur(0); b.constraint(b.nxt(0) - x * x * x); b.assert_single(0, 0, 1)
+    assert code(b) == 3                                          # degree 3: XFG_ERR_UNSUPPORTED_OPTIONS
+    b = A.AirBuilder(1); b.constraint(b.nxt(0) - b.cur(0))
+    assert code(b) == 1                                          # no assertion
+    b = A.AirBuilder(1); b.assert_single(0, 0, 1)
+    assert code(b) == 1                                          # no constraint
+    b = A.AirBuilder(1); b.constraint(b.const(5) + 1); b.assert_single(0, 0, 1)
+    assert code(b) == 1                                          # degree-0 constraint
+    b = A.AirBuilder(1); b.constraint(b.nxt(0) - b.cur(0)); b.assert_single(0, 0, 1); b.assert_single(0, 0, 2)
+    assert code(b) == 1                                          # duplicate assertion
+    b = A.AirBuilder(1); b.constraint(b.nxt(0) - b.cur(0)); b.assert_single(0, 8, 1)
+    assert code(b) == 1                                          # step out of range for 2^3 rows
+    b = A.AirBuilder(2); b.constraint(b.nxt(0) - b.cur(0)); b.assert_single(2, 0, 1)
+    assert code(b) == 1                                          # column out of range
+    b = A.AirBuilder(129); b.constraint(b.nxt(0) - b.cur(0)); b.assert_single(0, 0, 1)
+    assert code(b) == 1                                          # wider than XFG_AIR_MAX_WIDTH
+    b = A.AirBuilder(2); b.constraint(b.nxt(0) - b.cur(0))
+    for s in range(17):
+        b.assert_single(0, s, 1)
+    assert code(b, 5) == 3                                       # 17 distinct assertion steps
+    b = A.AirBuilder(2); vals = [b.cur(0) + (i + 1) for i in range(80)]
+    acc = vals[0] * b.cur(1)
+    for v in vals[1:]:
+        acc = acc + v * b.cur(1)
+    b.constraint(b.nxt(1) - acc); b.assert_single(0, 0, 1)
+    assert code(b) == 3                                          # 80 values alive at once > XFG_AIR_MAX_LIVE
+    ok = A.AirBuilder(2); ok.constraint(ok.nxt(0) - ok.cur(0) * ok.cur(1)); ok.constraint(ok.cur(1) - 3); ok.assert_single(0, 0, 1); ok.assert_single(1, 7, 3)
+    r = xs.air_compile_check(ok, 3)
+    assert r["num_groups"] == 2 and r["num_instr"] == 5 and r["num_slots"] >= 1       # mul, sub, OUT, sub, OUT

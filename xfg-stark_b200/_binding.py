@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
-                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_pipe_probe"]
+                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_air_compile_check", "xfg_pipe_probe"]
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -124,6 +124,7 @@ def load_library():
     L.xfg_prove_burn_mint_device.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
     L.xfg_prove_air.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
     L.xfg_prove_air_device.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
+    L.xfg_air_compile_check.argtypes = [C.POINTER(_AirDesc), u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), vp, vp, vp]
     L.xfg_prove_air_batch.argtypes = [vp, u32, vp, vp, u32, C.POINTER(_Options), vp, sz, vp, C.POINTER(C.c_float)]
     L.xfg_prove_burn_mint_batch.argtypes = [vp, u32, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options), vp, sz, vp, C.POINTER(C.c_float)]
     inputs = [u64, u64, vp, vp, sz, vp, sz, u32, u32, u32]
@@ -183,6 +184,25 @@ def build_trace(air, n_log2):
     if rc:
         raise XfgError(rc, "bad arguments")
     return t
+
+
+def air_compile_check(air, n_log2, cur=None, nxt=None):
+    """Host-only (no GPU): validate + compile an AirBuilder as xfg_prove_air would.  -> dict(num_instr, num_slots, num_groups[, results]); results =
+    the compiled program's constraint values on the frame (cur, nxt) when given.  Raises XfgError with the library's code otherwise."""
+    L = load_library()
+    desc, keep, w = Context._air_desc(air)
+    ni, ns, ng = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    out = None; pc = pn = po = None
+    if cur is not None:
+        c = np.ascontiguousarray(cur, dtype=np.uint64); n = np.ascontiguousarray(nxt, dtype=np.uint64); out = np.zeros(desc.num_constraints, dtype=np.uint64)
+        pc, pn, po = _ptr(c), _ptr(n), _ptr(out)
+    rc = L.xfg_air_compile_check(C.byref(desc), n_log2, C.byref(ni), C.byref(ns), C.byref(ng), pc, pn, po)
+    if rc:
+        raise XfgError(rc, L.xfg_strerror(rc).decode())
+    r = dict(num_instr=ni.value, num_slots=ns.value, num_groups=ng.value)
+    if out is not None:
+        r["results"] = out
+    return r
 
 
 class Context:
