@@ -73,10 +73,13 @@ struct Carve {   // device pointers of one proof, carved from the slot slab for 
   size_t words;
 };
 
-struct GraphKey {
-  const void* plan; const void* trace; int D; u32 q, g;
-  bool operator<(const GraphKey& o) const { return std::tie(plan, trace, D, q, g) < std::tie(o.plan, o.trace, o.D, o.q, o.g); }
+struct GraphKey {      // everything that is baked into the captured launch sequence (kernel arguments, grids, copy sizes)
+  const void* plan; const void* trace; int D; u32 q, g; u32 width, seed_count, prog_instr;   // prog_instr: 0 = burn-mint kernels, else generic program length + 1
+  bool operator<(const GraphKey& o) const {
+    return std::tie(plan, trace, D, q, g, width, seed_count, prog_instr) < std::tie(o.plan, o.trace, o.D, o.q, o.g, o.width, o.seed_count, o.prog_instr);
+  }
 };
+struct GraphEntry { cudaGraphExec_t exec; unsigned launches; };
 struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 
 struct Slot {
@@ -90,11 +93,11 @@ struct Slot {
   // generic AIR front-end (xfg_prove_air): compiled program + AIR-sized state; W = trace width of the proof in flight
   GenProgram* d_prog = nullptr; GenProgram* h_prog = nullptr; GenState* d_gen = nullptr; u64 (*h_ood)[2] = nullptr;
   bool generic = false; u32 W = XFG_TRACE_WIDTH, seed_count = 8 + XFG_NUM_PUB_INPUTS;
-  std::map<GraphKey, cudaGraphExec_t> graphs;            // whole-proof CUDA graphs, one per (plan, extension, options, trace pointer)
+  std::map<GraphKey, GraphEntry> graphs;            // whole-proof CUDA graphs, one per (plan, extension, options, trace pointer)
   cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
   // in-flight proof (batch mode)
   bool busy = false; const Plan* plan = nullptr; int D = 1; xfg_options opt{}; u32 proof_index = 0; bool timed = false;
-  GatherTasks tasks{}; size_t mat_words = 0; unsigned graph_launches = 0;
+  GatherTasks tasks{}; size_t mat_words = 0;
   // optional per-kernel-family timing (xfg_set_profiling): events around each launcher call on this slot's stream
   std::vector<cudaEvent_t> pev; std::vector<ProfRec> prof; size_t pev_used = 0;
 };
@@ -382,15 +385,15 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
 
 // Runs the proof's launch sequence: as a cached CUDA graph (captured on first use per plan / extension / options / trace pointer)
 // when no per-stage timing is requested and the upload is not split, otherwise launch by launch.
-int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const xfg_air_consts& air, const u64* d_trace, bool timed) {
-  prepare_inputs(s, p, o, air);
+// the slot's per-proof inputs (seed elements, AIR constants or compiled program, width) have been prepared in its pinned mirrors
+int launch_prepared(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const u64* d_trace, bool timed) {
   { Carve c; carve(s, p, D, c); if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length"); }
   const bool use_graph = ctx->graphs && !timed && !ctx->profiling && !(s.split_upload && !d_trace);
   if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);
-  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor};
+  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor, s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0};
   auto it = s.graphs.find(key);
   if (it == s.graphs.end()) {
-    if (s.graphs.size() >= 16) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second); s.graphs.clear(); }   // bounded cache (callers that keep changing the device trace pointer)
+    if (s.graphs.size() >= 16) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec); s.graphs.clear(); }   // bounded cache (callers that keep changing the device trace pointer)
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
     const unsigned before = g_xfg_launches;
@@ -401,15 +404,18 @@ int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options&
     cudaGraphExec_t exec = nullptr;
     CU(cudaGraphInstantiate(&exec, graph, 0));
     cudaGraphDestroy(graph);
-    it = s.graphs.emplace(key, exec).first;
-    s.graph_launches = g_xfg_launches - before;
+    it = s.graphs.emplace(key, GraphEntry{exec, g_xfg_launches - before}).first;
   } else {
     Carve c; carve(s, p, D, c); s.mat_words = build_gather(p, D, s.W, o, c, s.tasks);
-    g_xfg_launches += s.graph_launches;
+    g_xfg_launches += it->second.launches;
     s.busy = true; s.plan = &p; s.D = D; s.opt = o; s.timed = false; s.prof.clear();
   }
-  CU(cudaGraphLaunch(it->second, s.st));
+  CU(cudaGraphLaunch(it->second.exec, s.st));
   return XFG_OK;
+}
+int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const xfg_air_consts& air, const u64* d_trace, bool timed) {
+  prepare_inputs(s, p, o, air);
+  return launch_prepared(ctx, s, p, D, o, d_trace, timed);
 }
 
 // ---- host serialisation ----
@@ -672,7 +678,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
     cudaFree(s.d_air); cudaFreeHost(s.h_air);
     cudaFree(s.d_prog); cudaFreeHost(s.h_prog); cudaFree(s.d_gen); cudaFreeHost(s.h_ood);
-    for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
     for (auto& e : s.col_ev) if (e) cudaEventDestroy(e);
