@@ -476,6 +476,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ms, cores, sample = cpu_reference_ms(args.n_log2, args.ext, budget_s=30.0, steps=1)
         out["cpu_baseline"] = {"value": ms[0], "unit": "ms", "cores": cores, "kind": "port", "sample": sample}
+        # the reference's actual build is single-threaded: one thread on a 2^16-row proof, scaled n log n
+        import orc
+        orc.set_threads(1)
+        tr, pi, ac = orc.synthetic_case(1 << 16, 0)
+        t0 = time.perf_counter(); orc.prove(tr, pi, ac, (42, 8, 4, args.ext, 8, 31)); t1 = (time.perf_counter() - t0) * 1e3
+        scale = (1 << (args.n_log2 - 16)) * args.n_log2 / 16.0 if args.n_log2 > 16 else 1.0
+        out["cpu_baseline"]["single_thread"] = {"value": t1 * scale, "unit": "ms", "cores": 1,
+                                                "sample": (f"2^16-row proof on one thread ({t1:.0f} ms)" + (f", scaled x{scale:.1f} (n log n) to 2^{args.n_log2}" if scale != 1.0 else ""))}
     if rank == 0:
         print(json.dumps(out))
     ctx.close()
