@@ -108,6 +108,23 @@ def test_invalid_trace_is_rejected(ctx):
     assert ctx.prove(trace, air) == orc.prove(*orc.synthetic_case(256, 2))   # the context stays usable
 
 
+@pytest.mark.parametrize("n_log2", [3, 6, 11, 12, 13, 15, 16, 17])
+def test_non_canonical_trace_element_is_rejected_at_every_size(n_log2):
+    """the canonicity check is fused into the first load of the interpolation: every NTT kernel shape (single pass, radix-2 four-step,
+    register-radix four-step, split upload) must report an element >= p, wherever it sits, and accept the largest canonical value"""
+    import xfg_stark_b200 as xs
+    from test_gpu_stages import big_ctx
+    c = big_ctx()
+    air, trace = gpu_case(xs, 1, n_log2)
+    n = 1 << n_log2
+    for col, row, val in ((0, 0, orc.P), (6, n - 1, (1 << 64) - 1), (3, n // 2 + 1, orc.P + 5)):
+        bad = trace.copy(); bad[col, row] = val
+        with pytest.raises(xs.XfgError) as e:
+            c.prove(bad, air)
+        assert e.value.code == 1 and "non-canonical" in e.value.message
+    assert c.prove(trace, air) == orc.prove(*orc.synthetic_case(n, 1))
+
+
 def test_output_buffer_too_small_and_empty_batch(ctx):
     import ctypes as C
     import xfg_stark_b200 as xs

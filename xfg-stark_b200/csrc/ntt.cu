@@ -38,13 +38,16 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(NttPass p) {
   // ---- load (bit-reversed row placement), optional pre-scale by s^(global index) ----
   const u64 col0 = (u64)tile << p.Tlog;
   PowTable pre; pre.lo = p.pre_lo ? p.pre_lo + (size_t)coset * POW_LO : nullptr; pre.hi = p.pre_hi ? p.pre_hi + (size_t)coset * p.pre_hi_stride : nullptr;
+  bool bad = false;
   for (u32 e = tid; e < L * T; e += NTT_THREADS) {
     u32 c = e & (T - 1), r = e >> p.Tlog;
     u64 gi = (u64)r * p.in_row_stride + col0 + c;
     u64 v = src[gi];
+    bad |= v >= GL_P;
     if (pre.lo) v = gl_mul(v, pow_lookup(pre, gi));
     S[bitrev(r, p.Llog) * TP + c] = v;
   }
+  if (p.canon_flag && bad) atomicOr(p.canon_flag, p.canon_bit);
   __syncthreads();
 
   // ---- radix-2 DIT stages ----
@@ -198,6 +201,12 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
         u64 v[CH];
 #pragma unroll
         for (int i = 0; i < CH; i++) v[i] = sp[(h + i) * step];
+        if (p.canon_flag) {
+          bool bad = false;
+#pragma unroll
+          for (int i = 0; i < CH; i++) bad |= v[i] >= GL_P;
+          if (bad) atomicOr(p.canon_flag, p.canon_bit);
+        }
         if (pr) {
 #pragma unroll
           for (int i = 0; i < CH; i++) v[i] = w_mul(v[i], __ldg(pr + (h + i) * rstep));      // weak product: the butterflies accept any u64 residue
@@ -352,6 +361,7 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   p.pre_lo = job.pre_lo; p.pre_hi = job.pre_hi; p.pre_hi_stride = job.pre_hi_stride;
   p.post_div = job.post_div ? job.post_div : 1;
   p.coset_map = job.coset_map; p.dst_cosets = job.dst_cosets;
+  p.canon_flag = job.canon_flag; p.canon_bit = job.canon_bit;
   if (ln <= NTT_SINGLE_MAX_LOG) {
     p.src = job.src; p.dst = job.dst; p.Llog = ln; p.Tlog = 0; p.in_row_stride = 1; p.out_row_stride = 1;
     p.store_transposed = 0; p.scale = job.scale;
@@ -378,7 +388,7 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
   else { ntt_pass<<<dim3((1u << l1) >> Tlog, job.batch), NTT_THREADS, ntt_pass_smem(l2, Tlog), st>>>(p); XFG_LAUNCHED(1); }
   // pass B (in place on dst)
   p.src = job.dst; p.dst = job.dst; p.src_is_dst = 1;                      // pass B: in place on the slot pass A wrote
-  p.pre_lo = nullptr; p.pre_hi = nullptr; p.pre_row = nullptr; p.it_tab = nullptr;
+  p.pre_lo = nullptr; p.pre_hi = nullptr; p.pre_row = nullptr; p.it_tab = nullptr; p.canon_flag = nullptr;
   p.Llog = l1; p.in_row_stride = u64(1) << l2; p.out_row_stride = u64(1) << l2; p.store_transposed = 0; p.scale = job.scale;
   p.post_lo = job.post_lo; p.post_hi = job.post_hi; p.post_hi_stride = job.post_hi_stride;
   if (dir_inv) {   // 1/n already applied by d_it_inv

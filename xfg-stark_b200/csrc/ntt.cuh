@@ -29,6 +29,9 @@ struct NttPass {
   // direct (one 8-byte load per element) twiddle tables of a four-step transform, see NttTables; they replace pre_*, it_*, post_*
   const u64* pre_row; const u64* it_tab; u64 it_tstride; const u64* post_tab; u64 post_tstride;
   u32 grp_fast;   // ntt_pass_r16: blockIdx.y = sub * groups + group instead of group * src_div + sub
+  // input validation fused into the first load of a transform: if non-null, *canon_flag |= canon_bit when an input element is >= p
+  // (the prover's check that every trace element is a canonical field element; saves a separate pass over the trace)
+  u32* canon_flag; u32 canon_bit;
 };
 
 // device tables owned by a plan (one per trace length)
@@ -63,6 +66,7 @@ struct NttJob {
   const u64* post_lo; const u64* post_hi; u32 post_hi_stride; u32 post_div;
   u64* peer[NTT_MAX_PEERS]; u32 peer_log;   // see NttPass
   u32 coset_map, dst_cosets;                // optional subset of cosets, see ntt_pass
+  u32* canon_flag; u32 canon_bit;           // see NttPass (applies to the pass that reads `src`)
 };
 
 void ntt_init(bool force);

@@ -306,8 +306,9 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
     const size_t off = (size_t)c0 * n;
     cudaStream_t gs = (g % nstreams) ? s.aux_st[g % nstreams - 1] : st;
     if (waits) CU(cudaStreamWaitEvent(gs, s.col_ev[g], 0));
-    PROF("check_canonical", launch_check_canonical(gs, trace_src + off, (size_t)per * n, s.d_state));
+    // every trace element must be a canonical field element: checked by the pass of the interpolation that reads the trace
     { NttJob j{}; j.src = trace_src + off; j.dst = c.trace_coef + off; j.ln = ln; j.batch = per; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
+      j.canon_flag = &s.d_state->error_flags; j.canon_bit = ERR_FLAG_NONCANONICAL;
       j.inverse = true; j.scale = p.n_inv; PROF("ntt.interpolate_trace", ntt_batch(gs, p.ntt, j)); }
     { NttJob j{}; j.src = c.trace_coef + off; j.dst = c.lde + off * 8; j.ln = ln; j.batch = per * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
       j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_trace", ntt_batch(gs, p.ntt, j)); }

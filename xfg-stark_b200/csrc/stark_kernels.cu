@@ -397,17 +397,6 @@ void launch_coset_to_natural(cudaStream_t st, const u64* src, u64* dst, u32 ln, 
   coset_to_natural_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(src, dst, ln, D, src_limb_stride, dst_limb_stride); XFG_LAUNCHED(1);
 }
 
-// every trace element must be a canonical field element (< p); the boundary takes `BaseElement::as_int()` values
-__global__ void __launch_bounds__(256) check_canonical_kernel(const u64* __restrict__ v, size_t count, ProofState* ps) {
-  bool bad = false;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) bad |= v[i] >= GL_P;
-  if (bad) atomicOr(&ps->error_flags, ERR_FLAG_NONCANONICAL);
-}
-void launch_check_canonical(cudaStream_t st, const u64* v, size_t count, ProofState* ps) {
-  size_t blocks = (count + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-  check_canonical_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, count, ps); XFG_LAUNCHED(1);
-}
-
 // ---- 32-bit integer-pipe peak (xfg_int_pipe_peak): 8 independent chains per thread of the BLAKE3 operation mix
 // (LOP3 xor, IADD3, SHF rotate - all ALU-pipe instructions; 4 per group, checked in SASS), no memory traffic: the roofline denominator of the hashing kernels
 __global__ void __launch_bounds__(256) int_peak_kernel(const u32* __restrict__ in, u32* __restrict__ out, u32 iters) {
