@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_
 u32 ood_num_blocks(u32 ln) { size_t n = size_t(1) << ln; size_t b = n / 256; if (b < 1) b = 1; if (b > OOD_MAX_BLOCKS) b = OOD_MAX_BLOCKS; return (u32)b; }   // 64 x 256 threads per polynomial: Horner chains of n / 16384 steps
 void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, u32 width, const ProofState* ps, u64* partial) {
   // one polynomial per block while that already gives >= 4 blocks per SM, else groups of polynomials share a block's power tables
+  // (sharing more - 2 polynomials per block at width 7 - was measured slower, 0.097 -> 0.118 ms: the kernel is latency-bound and wants blocks)
   const u32 nb = ood_num_blocks(ln), P = width + D;
   u32 ppb = 1; while ((size_t)nb * ((P + ppb - 1) / ppb) > 148 * 4 && ppb < P) ppb++;
   dim3 grid(nb, (P + ppb - 1) / ppb);
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
     for (int l = 0; l < D; l++) { DotAcc m; m.fma(pc.limb(l), nzg); m.fma(qc.limb(l), nz); sh[j][l][tid] = m.result(); }
     const u64 den = gl_mul(nz, nzg);
     sh[j][D][tid] = den; sh[j][D + 1][tid] = acc;
-    acc = gl_mul(acc, den); x = gl_mul(x, w8);
+    acc = gl_mul(acc, den); x = gl_mul_pow2<24>(x);      // x_j = x_0 * w_8^j, w_8 = 2^24
   }
   acc = w_inv(acc);
 #pragma unroll 1

@@ -2,26 +2,39 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "state.cuh"
+#if defined(__CUDACC__)
+#include "field_weak.cuh"
+#endif
 
 namespace xfg {
 
 struct FriConsts { u64 w8i[4]; u64 inv8; u64 inv7; };   // w_8^-1 powers 0..3, 8^-1, 7^-1
 #if defined(__CUDACC__)
+// x * 2^S (S < 96) and x * (-2^S) for a canonical x, canonical result: shifts and carry fix-ups instead of a 64x64-bit multiplication
+template <int S> __device__ __forceinline__ u64 gl_mul_pow2(u64 x) { return w_canon(w_mul_pow2<S>(x)); }
+template <int S, int D> __device__ __forceinline__ Ext<D> ext_mul_neg_pow2(Ext<D> a) {
+  Ext<D> r;
+#pragma unroll
+  for (int l = 0; l < D; l++) r.set_limb(l, gl_neg(gl_mul_pow2<S>(a.limb(l))));
+  return r;
+}
 // P(beta * x_r) for the polynomial P of degree < 8 interpolating v[j] at x_r * w_8^j, i.e. apply_drp's fold with beta = alpha / x_r
 // (shared by the prover's FRI layers and the verifier's per-query fold check)
 template <int D>
 __device__ __forceinline__ Ext<D> fold8(const Ext<D> (&v)[8], const FriConsts& fc, Ext<D> beta) {
-  // radix-2 DIT inverse DFT of size 8 (input bit-reversed), twiddles w_8^-j
+  // radix-2 DIT inverse DFT of size 8 (input bit-reversed), twiddles w_8^-j.  w_8 = 2^24 and 2^96 = -1, so w_8^-j = -2^(96 - 24 j): powers of two
   Ext<D> a[8] = {v[0], v[4], v[2], v[6], v[1], v[5], v[3], v[7]};
 #pragma unroll
   for (int i = 0; i < 8; i += 2) { Ext<D> u = a[i], w = a[i + 1]; a[i] = u + w; a[i + 1] = u - w; }
 #pragma unroll
   for (int i = 0; i < 8; i += 4) {
     Ext<D> u = a[i], w = a[i + 2]; a[i] = u + w; a[i + 2] = u - w;
-    u = a[i + 1]; w = mul_base(a[i + 3], fc.w8i[2]); a[i + 1] = u + w; a[i + 3] = u - w;
+    u = a[i + 1]; w = ext_mul_neg_pow2<48, D>(a[i + 3]); a[i + 1] = u + w; a[i + 3] = u - w;      // w_8^-2 = -2^48
   }
-#pragma unroll
-  for (int j = 0; j < 4; j++) { Ext<D> u = a[j], w = j ? mul_base(a[j + 4], fc.w8i[j]) : a[j + 4]; a[j] = u + w; a[j + 4] = u - w; }
+  { Ext<D> u = a[0], w = a[4]; a[0] = u + w; a[4] = u - w; }
+  { Ext<D> u = a[1], w = ext_mul_neg_pow2<72, D>(a[5]); a[1] = u + w; a[5] = u - w; }               // w_8^-1 = -2^72
+  { Ext<D> u = a[2], w = ext_mul_neg_pow2<48, D>(a[6]); a[2] = u + w; a[6] = u - w; }               // w_8^-2
+  { Ext<D> u = a[3], w = ext_mul_neg_pow2<24, D>(a[7]); a[3] = u + w; a[7] = u - w; }               // w_8^-3 = -2^24
   Ext<D> r = a[7];
 #pragma unroll
   for (int kk = 6; kk >= 0; kk--) r = r * beta + a[kk];
