@@ -75,8 +75,9 @@ struct Carve {   // device pointers of one proof, carved from the slot slab for 
 
 struct GraphKey {      // everything that is baked into the captured launch sequence (kernel arguments, grids, copy sizes)
   const void* plan; const void* trace; int D; u32 q, g; u32 width, seed_count, prog_instr;   // prog_instr: 0 = burn-mint kernels, else generic program length + 1
+  const void* host_src;                                                                      // split upload: the column copies are part of the graph
   bool operator<(const GraphKey& o) const {
-    return std::tie(plan, trace, D, q, g, width, seed_count, prog_instr) < std::tie(o.plan, o.trace, o.D, o.q, o.g, o.width, o.seed_count, o.prog_instr);
+    return std::tie(plan, trace, D, q, g, width, seed_count, prog_instr, host_src) < std::tie(o.plan, o.trace, o.D, o.q, o.g, o.width, o.seed_count, o.prog_instr, o.host_src);
   }
 };
 struct GraphEntry { cudaGraphExec_t exec; unsigned launches; };
@@ -84,8 +85,8 @@ struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 
 struct Slot {
   cudaStream_t st = nullptr, copy_st = nullptr, aux_st[3] = {nullptr, nullptr, nullptr};   // copy_st: column-wise trace upload overlapped with the first NTTs; aux_st: every other column group
-  cudaEvent_t col_ev[XFG_TRACE_WIDTH] = {nullptr}, fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
-  bool split_upload = false;
+  cudaEvent_t col_ev[XFG_TRACE_WIDTH] = {nullptr}, fork_ev = nullptr, fork2_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+  bool split_upload = false; const u64* up_src = nullptr;   // split upload: the (pinned) host trace the column copies read, issued inside enqueue_proof
   u64* slab = nullptr; size_t slab_words = 0;
   ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
   ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;
@@ -287,6 +288,14 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   // per-proof inputs (coin seed elements, AIR constants) were written to pinned memory by prepare_inputs(); copying them here keeps
   // the whole launch sequence replayable as a CUDA graph
   const u32 W = s.W; const bool gen = s.generic;
+  if (s.split_upload && !d_trace) {   // one copy + event per column on the copy stream (forked here so that the whole sequence is capturable as a
+    CU(cudaEventRecord(s.fork_ev, st)); CU(cudaStreamWaitEvent(s.copy_st, s.fork_ev, 0));      // CUDA graph); a column's NTTs start as soon as it has landed
+    for (int g = 0; g < UPLOAD_GROUPS; g++) {
+      const size_t c0 = UPLOAD_GROUP_START[g], c1 = UPLOAD_GROUP_START[g + 1];
+      CU(cudaMemcpyAsync(c.trace_in + c0 * n, s.up_src + c0 * n, (c1 - c0) * n * 8, cudaMemcpyHostToDevice, s.copy_st));
+      CU(cudaEventRecord(s.col_ev[g], s.copy_st));
+    }
+  }
   CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (size_t)s.seed_count * 8, cudaMemcpyHostToDevice, st));
   if (gen) CU(cudaMemcpyAsync(s.d_prog, s.h_prog, offsetof(GenProgram, code) + (size_t)s.h_prog->num_instr * sizeof(GenInstr), cudaMemcpyHostToDevice, st));
   else CU(cudaMemcpyAsync(s.d_air, s.h_air, sizeof(AirParams), cudaMemcpyHostToDevice, st));
@@ -300,7 +309,7 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   // the partial last wave of one group is filled by the next group's kernels instead of idling.
   const bool waits = s.split_upload && !d_trace, two = waits && g_upload_streams >= 2 && !profiling;
   const int nstreams = two ? g_upload_streams : 1;
-  if (two) { CU(cudaEventRecord(s.fork_ev, st)); for (int a = 0; a + 1 < nstreams; a++) CU(cudaStreamWaitEvent(s.aux_st[a], s.fork_ev, 0)); }
+  if (two) { CU(cudaEventRecord(s.fork2_ev, st)); for (int a = 0; a + 1 < nstreams; a++) CU(cudaStreamWaitEvent(s.aux_st[a], s.fork2_ev, 0)); }
   for (int g = 0; g < (waits ? UPLOAD_GROUPS : 1); g++) {
     const int c0 = waits ? UPLOAD_GROUP_START[g] : 0, per = waits ? UPLOAD_GROUP_START[g + 1] - c0 : (int)W;
     const size_t off = (size_t)c0 * n;
@@ -389,9 +398,10 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
 // the slot's per-proof inputs (seed elements, AIR constants or compiled program, width) have been prepared in its pinned mirrors
 int launch_prepared(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const u64* d_trace, bool timed) {
   { Carve c; carve(s, p, D, c); if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length"); }
-  const bool use_graph = ctx->graphs && !timed && !ctx->profiling && !(s.split_upload && !d_trace);
+  const bool use_graph = ctx->graphs && !timed && !ctx->profiling;
   if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);
-  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor, s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0};
+  const bool split = s.split_upload && !d_trace;
+  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor, s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0, split ? s.up_src : nullptr};
   auto it = s.graphs.find(key);
   if (it == s.graphs.end()) {
     if (s.graphs.size() >= 16) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec); s.graphs.clear(); }   // bounded cache (callers that keep changing the device trace pointer)
@@ -551,12 +561,8 @@ int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace
   const u64* src = h_trace;
   if (!pinned) { std::memcpy(s.h_trace, h_trace, bytes); src = s.h_trace; }
   s.split_upload = allow_split && p.ln >= 17 && !s.generic;
-  if (s.split_upload) {      // one copy + event per column group on the copy stream; a group's NTTs start as soon as it has landed
-    for (int g = 0; g < UPLOAD_GROUPS; g++) {
-      const size_t c0 = UPLOAD_GROUP_START[g], c1 = UPLOAD_GROUP_START[g + 1];
-      CU(cudaMemcpyAsync(c.trace_in + c0 * p.n, src + c0 * p.n, (c1 - c0) * p.n * 8, cudaMemcpyHostToDevice, s.copy_st));
-      CU(cudaEventRecord(s.col_ev[g], s.copy_st));
-    }
+  if (s.split_upload) {      // the column copies are issued by enqueue_proof (copy stream forked from the proof's stream), so that the
+    s.up_src = src;          // whole end-to-end sequence can be captured and replayed as one CUDA graph
   } else {
     CU(cudaMemcpyAsync(c.trace_in, src, bytes, cudaMemcpyHostToDevice, s.st));
   }
@@ -655,7 +661,7 @@ int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t 
     CUB(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)); CUB(cudaStreamCreateWithFlags(&s.copy_st, cudaStreamNonBlocking));
     for (auto& a : s.aux_st) CUB(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     for (auto& e : s.col_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUB(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming)); for (auto& e : s.join_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming)); CUB(cudaEventCreateWithFlags(&s.fork2_ev, cudaEventDisableTiming)); for (auto& e : s.join_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaMalloc(&s.slab, words * 8)); s.slab_words = words;
     CUB(cudaMalloc(&s.d_state, sizeof(ProofState))); CUB(cudaMalloc(&s.d_seed, 128 * 8));
     CUB(cudaMalloc(&s.d_partial, (size_t)(XFG_AIR_MAX_WIDTH + 2) * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
@@ -684,6 +690,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
     for (auto& e : s.col_ev) if (e) cudaEventDestroy(e);
     if (s.fork_ev) cudaEventDestroy(s.fork_ev);
+    if (s.fork2_ev) cudaEventDestroy(s.fork2_ev);
     for (auto& e : s.join_ev) if (e) cudaEventDestroy(e);
     for (auto& a : s.aux_st) if (a) cudaStreamDestroy(a);
     if (s.copy_st) cudaStreamDestroy(s.copy_st);
