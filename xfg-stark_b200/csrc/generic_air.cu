@@ -37,7 +37,7 @@ void launch_gen_trace_root(cudaStream_t st, int D, ProofState* ps, GenState* gs,
 static constexpr int GCE_THREADS = 128;
 template <int D, int GCE_PTS>
 __global__ void __launch_bounds__(GCE_THREADS) gen_constraint_kernel(const u64* __restrict__ lde, u32 ln, const GenProgram* __restrict__ prog, const GenState* __restrict__ gs,
-                                                                     PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64 g_last, u64* __restrict__ out) {
+                                                                     PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64 g_last, u64* __restrict__ out, size_t out_tstride) {
   __shared__ u64 sh[GCE_PTS][2 * D + 2][GCE_THREADS];      // per point: u (D), num (D), den, prefix
   __shared__ u64 sc[(GEN_MAX_CONSTRAINTS + GEN_MAX_ASSERTIONS) * 2];
   const size_t n = size_t(1) << ln, N = 8 * n;
@@ -105,17 +105,17 @@ __global__ void __launch_bounds__(GCE_THREADS) gen_constraint_kernel(const u64* 
     const size_t m = t + q * per;
     const u64 dinv = gl_mul(sh[q][2 * D + 1][tid], acc); acc = gl_mul(acc, sh[q][2 * D][tid]);
 #pragma unroll
-    for (int l = 0; l < D; l++) out[(size_t)l * 2 * n + (size_t)kp * n + m] = gl_add(sh[q][l][tid], gl_mul(sh[q][D + l][tid], dinv));
+    for (int l = 0; l < D; l++) out[(size_t)(l * 2 + kp) * out_tstride + m] = gl_add(sh[q][l][tid], gl_mul(sh[q][D + l][tid], dinv));
   }
 }
 void launch_gen_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const GenProgram* prog, const GenState* gs, PowTable wn,
-                            u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64 g_last, u64* out) {
+                            u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64 g_last, u64* out, size_t out_tstride) {
   const int pts = ln >= 19 ? 4 : 1;
   const size_t per = (size_t(1) << ln) / pts; dim3 grid((unsigned)((per + GCE_THREADS - 1) / GCE_THREADS), 2);
-  if (D == 1 && pts == 4) gen_constraint_kernel<1, 4><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
-  else if (D == 1) gen_constraint_kernel<1, 1><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
-  else if (pts == 4) gen_constraint_kernel<2, 4><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
-  else gen_constraint_kernel<2, 1><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out);
+  if (D == 1 && pts == 4) gen_constraint_kernel<1, 4><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out, out_tstride);
+  else if (D == 1) gen_constraint_kernel<1, 1><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out, out_tstride);
+  else if (pts == 4) gen_constraint_kernel<2, 4><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out, out_tstride);
+  else gen_constraint_kernel<2, 1><<<grid, GCE_THREADS, 0, st>>>(lde, ln, prog, gs, wn, s_k0, s_k1, zinv0, zinv1, g_last, out, out_tstride);
   XFG_LAUNCHED(1);
 }
 

@@ -332,21 +332,21 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   else PROF("transcript", launch_trace_root(st, D, s.d_state, c.trace_tree));
   mark();
   // 2 ---- evaluate_constraints
-  if (gen) PROF("constraints", launch_gen_constraints(st, D, c.lde, ln, s.d_prog, s.d_gen, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, p.g_last, c.ce_evals));
-  else PROF("constraints", launch_constraints(st, D, c.lde, ln, s.d_air, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.ce_evals));
+  // The constraint-evaluation domain is cosets 0 and 4 of the LDE domain, so the evaluations are written where the composition LDE needs them:
+  // limb l, coset 4k' of h_lde = transform 2l + k' at stride 4n (no copy after the interpolation has verified the degree)
+  if (gen) PROF("constraints", launch_gen_constraints(st, D, c.lde, ln, s.d_prog, s.d_gen, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, p.g_last, c.h_lde, 4 * n));
+  else PROF("constraints", launch_constraints(st, D, c.lde, ln, s.d_air, s.d_state, p.ntt.wn_fwd, p.s_k[0], p.s_k[4], p.zinv0, p.zinv1, c.h_lde, 4 * n));
   mark();
   // 3 ---- commit_to_constraint_evaluations: coset interpolation (2 cosets of size n), composition column, LDE, commitment
-  { NttJob j{}; j.src = c.ce_evals; j.dst = c.ce_tmp; j.ln = ln; j.batch = 2 * D; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
+  { NttJob j{}; j.src = c.h_lde; j.dst = c.ce_tmp; j.ln = ln; j.batch = 2 * D; j.src_tstride = 4 * n; j.dst_tstride = n; j.src_div = 1;
     j.inverse = true; j.scale = p.n_inv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 2; PROF("ntt.interpolate_comp", ntt_batch(st, p.ntt, j)); }
   PROF("combine", launch_combine(st, c.ce_tmp, ln, D, p.inv2, c.h_coef, s.d_state));
   // composition LDE: cosets 0 and 4 of the LDE domain ARE the constraint-evaluation domain, and once combine_kernel has verified
-  // that the 2n-point interpolant has degree < n the polynomial's values there are the evaluations already computed - copy them,
-  // compute only cosets 1,2,3,5,6,7
+  // that the 2n-point interpolant has degree < n the polynomial's values there are the evaluations the constraint kernel already
+  // wrote into those slots of h_lde - compute only cosets 1,2,3,5,6,7
   { NttJob j{}; j.src = c.h_coef; j.dst = c.h_lde; j.ln = ln; j.batch = D * 6; j.src_tstride = n; j.dst_tstride = n; j.src_div = 6;
     j.coset_map = 0x765321; j.dst_cosets = 8;
-    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_comp", ntt_batch(st, p.ntt, j));
-    for (int l = 0; l < D; l++) for (int kp = 0; kp < 2; kp++)
-      CU(cudaMemcpyAsync(c.h_lde + ((size_t)l * 8 + 4 * kp) * n, c.ce_evals + ((size_t)l * 2 + kp) * n, n * 8, cudaMemcpyDeviceToDevice, st)); }
+    j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_comp", ntt_batch(st, p.ntt, j)); }
   PROF("commit_rows.comp", launch_commit_rows(st, c.h_lde, N, D, ln, c.comp_tree));
   PROF("tree_upper.comp", merkle_build_upper(st, c.comp_tree, n));
   PROF("transcript", launch_constraint_root(st, D, s.d_state, c.comp_tree, p.g_n));

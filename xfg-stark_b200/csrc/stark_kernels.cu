@@ -44,7 +44,7 @@ static constexpr int CE_PTS = XFG_CE_PTS, CE_THREADS = XFG_CE_THREADS;
 // conflict-free): the fully unrolled version was 160 KB of SASS and stalled on instruction fetch (ncu: no_instruction).
 template <int D>
 __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(const u64* __restrict__ lde, u32 ln, const AirParams* __restrict__ airp, const ProofState* __restrict__ ps,
-                                                                 PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out) {
+                                                                 PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out, size_t out_tstride) {
   __shared__ u64 sh[CE_PTS][2 * D + 2][CE_THREADS];      // per point: u (D), w (D), d, prefix
   __shared__ u64 sc[(XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS) * 2];
   const AirParams air = *airp;                            // AIR constants live in device memory so that the launch is CUDA-graph replayable
@@ -100,15 +100,15 @@ __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(con
     const size_t m = t + q * per;
     const u64 dinv = gl_mul(sh[q][2 * D + 1][tid], acc); acc = gl_mul(acc, sh[q][2 * D][tid]);
 #pragma unroll
-    for (int l = 0; l < D; l++) out[(size_t)l * 2 * n + (size_t)kp * n + m] = gl_add(sh[q][l][tid], gl_mul(sh[q][D + l][tid], dinv));
+    for (int l = 0; l < D; l++) out[(size_t)(l * 2 + kp) * out_tstride + m] = gl_add(sh[q][l][tid], gl_mul(sh[q][D + l][tid], dinv));
   }
 }
 
 void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams* air, const ProofState* ps, PowTable wn,
-                        u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out) {
+                        u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out, size_t out_tstride) {
   const size_t per = (size_t(1) << ln) / CE_PTS; dim3 grid((unsigned)((per + CE_THREADS - 1) / CE_THREADS), 2);
-  if (D == 1) constraint_kernel<1><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
-  else constraint_kernel<2><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out);
+  if (D == 1) constraint_kernel<1><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out, out_tstride);
+  else constraint_kernel<2><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out, out_tstride);
   XFG_LAUNCHED(1);
 }
 

@@ -42,7 +42,7 @@ __device__ __forceinline__ Ext<D> fold8(const Ext<D> (&v)[8], const FriConsts& f
 }
 #endif
 void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams* d_air, const ProofState* ps, PowTable wn,
-                        u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out);
+                        u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out, size_t out_tstride);   // evaluation (limb l, coset k') at out + (2l + k') * out_tstride
 void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64* h, ProofState* ps);
 u32 ood_num_blocks(u32 ln);
 void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, u32 width, const ProofState* ps, u64* partial);
