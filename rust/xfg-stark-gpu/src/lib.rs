@@ -32,6 +32,18 @@ impl GpuContext {
         if rc != sys::XFG_OK { return Err(format!("xfg_create: {}", unsafe { CStr::from_ptr(sys::xfg_strerror(rc)) }.to_string_lossy())); }
         Ok(Self { raw })
     }
+    /// `XfgBurnMintProver`'s input half (validation, public-input packing, Keccak scalars: src/burn_mint_prover.rs:74-107, 132-221) through
+    /// the library's host mirror `xfg_burn_mint_pack_inputs`
+    #[allow(clippy::too_many_arguments)]
+    pub fn pack_inputs(&self, burn: u64, mint: u64, tx_prefix_hash: &[u8], recipient: &[u8], secret: &[u8], network_id: u32, target_chain_id: u32,
+                       commitment_version: u32) -> Result<sys::xfg_air_consts, String> {
+        assert_eq!(tx_prefix_hash.len(), 32);
+        let mut air = sys::xfg_air_consts::default();
+        let rc = unsafe { sys::xfg_burn_mint_pack_inputs(self.raw, burn, mint, tx_prefix_hash.as_ptr(), recipient.as_ptr(), recipient.len(), secret.as_ptr(),
+                                                         secret.len(), network_id, target_chain_id, commitment_version, &mut air) };
+        if rc != sys::XFG_OK { return Err(self.last_error()); }
+        Ok(air)
+    }
     fn last_error(&self) -> String { unsafe { CStr::from_ptr(sys::xfg_last_error(self.raw)) }.to_string_lossy().into_owned() }
 }
 impl Drop for GpuContext { fn drop(&mut self) { unsafe { sys::xfg_destroy(self.raw) } } }
@@ -55,6 +67,18 @@ pub struct GpuBurnMintProver {
     pub nullifier: BaseElement,
     pub commitment: BaseElement,
     pub options: ProofOptions,
+}
+
+impl GpuBurnMintProver {
+    /// from the packed statement (`GpuContext::pack_inputs`): the 12 public-input elements in `ToElements` order plus the two AIR scalars
+    pub fn from_parts(ctx: GpuContext, air: &sys::xfg_air_consts, options: ProofOptions) -> Self {
+        let e = |i: usize| BaseElement::new(air.pub_inputs[i]);
+        let public_inputs = BurnMintPublicInputs {
+            burn_amount: e(0), mint_amount: e(1), txn_hash: e(2), recipient_hash: e(3), state: e(4), tx_prefix_hash_0: e(5), tx_prefix_hash_1: e(6),
+            tx_prefix_hash_2: e(7), tx_prefix_hash_3: e(8), network_id: e(9), target_chain_id: e(10), commitment_version: e(11),
+        };
+        Self { ctx, public_inputs, nullifier: BaseElement::new(air.nullifier), commitment: BaseElement::new(air.commitment), options }
+    }
 }
 
 impl Prover for GpuBurnMintProver {

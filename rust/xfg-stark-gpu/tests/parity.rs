@@ -7,7 +7,7 @@
 //! Appendix B.2, which is what the GPU backend and the oracle implement.
 use winterfell::{math::fields::f64::BaseElement, FieldExtension, ProofOptions, Prover};
 
-mod normalised_air;   // B.2 AIR + default CPU `Prover` impl (kept next to this test; omitted from the source-only drop)
+mod normalised_air;   // B.2 AIR + default CPU `Prover` impl + synthetic cases (tests/normalised_air/mod.rs)
 
 #[test]
 fn gpu_bytes_equal_winterfell_bytes() {
