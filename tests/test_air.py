@@ -158,3 +158,44 @@ def test_compiler_validation_codes():
     ok = A.AirBuilder(2); ok.constraint(ok.nxt(0) - ok.cur(0) * ok.cur(1)); ok.constraint(ok.cur(1) - 3); ok.assert_single(0, 0, 1); ok.assert_single(1, 7, 3)
     r = xs.air_compile_check(ok, 3)
     assert r["num_groups"] == 2 and r["num_instr"] == 5 and r["num_slots"] >= 1       # mul, sub, OUT, sub, OUT
+
+
+def test_compiler_survives_hostile_descriptions():
+    """random, mostly malformed xfg_air_desc arrays (indices out of range, absurd counts, non-canonical values) must come back with an error
+    code or a valid compilation - never a crash; whatever compiles must evaluate like the straight-line source"""
+    import ctypes as C
+    import xfg_stark_b200 as xs
+    from xfg_stark_b200._binding import _AirDesc, _Assertion, load_library
+    L = load_library()
+    rng = np.random.default_rng(11)
+    ok = bad = 0
+    for _ in range(400):
+        w = int(rng.integers(0, 140)); nc = int(rng.integers(0, 6)); ni = int(rng.integers(0, 40)); no = int(rng.integers(0, 6)); na = int(rng.integers(0, 6))
+        hi = 2 * max(w, 1) + nc + ni + 3
+        consts = rng.integers(0, 1 << 64, size=max(nc, 1), dtype=np.uint64, endpoint=False) if rng.integers(0, 4) == 0 else rng.integers(0, orc.P, size=max(nc, 1), dtype=np.uint64)
+        code = np.stack([rng.integers(0, 4, size=max(ni, 1)), rng.integers(0, hi, size=max(ni, 1)), rng.integers(0, hi, size=max(ni, 1))], axis=1).astype(np.uint32)
+        outs = rng.integers(0, hi, size=max(no, 1)).astype(np.uint32)
+        asr = (_Assertion * max(na, 1))(*[_Assertion(int(rng.integers(0, max(w, 1) + 2)), int(rng.integers(0, 20)), int(rng.integers(0, orc.P, dtype=np.uint64))) for _ in range(max(na, 1))])
+        if _ % 2 and 1 <= w <= 128 and ni and no and na:      # every other case: structurally valid (operands refer to earlier values, mostly linear operations)
+            first = 2 * w + nc
+            code = np.array([[int(rng.choice([0, 0, 1, 1, 2])), int(rng.integers(0, first + i)), int(rng.integers(0, first + i))] for i in range(ni)], dtype=np.uint32)
+            outs = rng.integers(first, first + ni, size=no).astype(np.uint32)
+            asr = (_Assertion * na)(*[_Assertion(int(rng.integers(0, w)), k, int(rng.integers(0, orc.P, dtype=np.uint64))) for k in range(na)])
+        pub = rng.integers(0, orc.P, size=3, dtype=np.uint64)
+        d = _AirDesc(w, 3, nc, ni, no, na, pub.ctypes.data, consts.ctypes.data, code.ctypes.data, outs.ctypes.data, C.addressof(asr))
+        n1, n2, n3 = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        cur = rng.integers(0, orc.P, size=max(w, 1), dtype=np.uint64); nxt = rng.integers(0, orc.P, size=max(w, 1), dtype=np.uint64)
+        res = np.zeros(max(no, 1), dtype=np.uint64)
+        rc = L.xfg_air_compile_check(C.byref(d), 4, C.byref(n1), C.byref(n2), C.byref(n3), cur.ctypes.data, nxt.ctypes.data, res.ctypes.data)
+        assert rc in (0, 1, 3)
+        if rc:
+            bad += 1
+            continue
+        ok += 1
+        vals = [int(x) for x in cur] + [int(x) for x in nxt] + [int(x) for x in consts[:nc]]
+        for op, a, b in code[:ni]:
+            x, y = vals[int(a)], vals[int(b)]
+            vals.append((x + y) % orc.P if op == 0 else (x - y) % orc.P if op == 1 else x * y % orc.P)
+        assert [int(v) for v in res[:no]] == [vals[int(o)] for o in outs[:no]]
+        assert n1.value <= ni + no and n2.value <= 64 and 1 <= n3.value <= 16
+    assert bad > 150 and ok > 30, (ok, bad)
