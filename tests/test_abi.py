@@ -39,6 +39,17 @@ def test_rust_sys_crate_declares_every_symbol():
     assert missing == []
 
 
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """include/xfg_stark.h must be consumable by a C compiler (cgo / FFI generators read it as C) and the library must link from C"""
+    import xfg_stark_b200 as xs
+    exe = str(tmp_path / "abi_example")
+    libdir = os.path.dirname(xs.library_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "abi_example.c"),
+                           "-o", exe, "-L", libdir, "-lxfgstark", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "ABI_EXAMPLE_OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_library_is_built_for_sm_100a():
     import xfg_stark_b200 as xs
     out = subprocess.run(["cuobjdump", "-lelf", xs.library_path()], capture_output=True, text=True).stdout
