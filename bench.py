@@ -60,6 +60,18 @@ def algorithmic_bytes(n_log2, e):
     }
 
 
+def ntt_gbps_from(acc, n_log2, ext):
+    """BASELINE.json's third metric, "NTT GB/s" = 16 B x elements / time of one batched transform, per NTT family of the proof.
+    acc: {family: [ms, launches]} from the per-kernel profile."""
+    n = 1 << n_log2
+    out = {}
+    for name, transforms in (("ntt.interpolate_trace", W_COLS), ("ntt.lde_trace", W_COLS * BLOWUP), ("ntt.interpolate_comp", CE * ext), ("ntt.lde_comp", 6 * ext)):
+        ms = acc.get(name, [0.0, 0])[0]
+        if ms > 0:
+            out[name] = {"transforms": transforms, "gbps": round(16.0 * transforms * n / ms / 1e6, 1)}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -473,6 +485,10 @@ def main():
                               device_ms=round(times2["device_ms"], 4), total_ms=round(times2["total_ms"], 4)),
         "roofline": roofline, "int_pipe": int_pipe, "kernels": kernels,
     }
+    try:
+        out["ntt_gbps"] = ntt_gbps_from(acc, args.n_log2, args.ext)
+    except Exception as e:          # reporting only: never lose the bench line over it
+        out["ntt_gbps"] = {"error": str(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ms, cores, sample = cpu_reference_ms(args.n_log2, args.ext, budget_s=30.0, steps=1)
         out["cpu_baseline"] = {"value": ms[0], "unit": "ms", "cores": cores, "kind": "port", "sample": sample}

@@ -29,3 +29,14 @@ def test_cli_flags_of_the_contract():
         assert flag in out
     for w in ("latency", "batch", "wide", "verify", "air"):
         assert w in out
+
+
+def test_ntt_gbps_metric():
+    sys.path.insert(0, ROOT)
+    import bench
+    acc = {"ntt.lde_trace": [1.1409, 2], "ntt.interpolate_trace": [0.1595, 2], "deep": [0.63, 1]}
+    r = bench.ntt_gbps_from(acc, 20, 2)
+    assert set(r) == {"ntt.lde_trace", "ntt.interpolate_trace"}
+    assert r["ntt.lde_trace"] == {"transforms": 56, "gbps": round(16 * 56 * (1 << 20) / 1.1409 / 1e6, 1)}
+    assert 700 < r["ntt.interpolate_trace"]["gbps"] < 760
+    assert bench.ntt_gbps_from({}, 16, 1) == {}
