@@ -113,25 +113,29 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """Host threads the CPU arm uses: every core this process may run on, regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_ms(n_log2, ext, budget_s, steps=1):
-    """Times the CPU oracle (all host threads) on a bounded sample of the workload.  Returns (ms per 2^n_log2 proof, cores, sample text)."""
+    """Times the CPU oracle on the FULL workload (one complete 2^n_log2-row proof per step, never a smaller trace) with every host core.
+    The budget only bounds HOW MANY proofs are timed.  Returns (ms per proof list, cores, sample text)."""
     import orc
-    cores = orc.max_threads(); orc.set_threads(cores)
+    cores = host_cores(); orc.set_threads(cores)
     opts = (42, 8, 4, ext, 8, 31)
-    tr, pi, ac = orc.synthetic_case(1 << 16, 0)
-    t0 = time.perf_counter(); orc.prove(tr, pi, ac, opts); t16 = time.perf_counter() - t0
-    est_full = t16 * (1 << (n_log2 - 16)) * n_log2 / 16.0
-    sample_log = n_log2
-    while sample_log > 16 and est_full * steps > budget_s:
-        est_full /= 2.0 * sample_log / (sample_log - 1); sample_log -= 1
-    tr, pi, ac = orc.synthetic_case(1 << sample_log, 0)
-    ts = []
-    for _ in range(steps):
+    tr, pi, ac = orc.synthetic_case(1 << n_log2, 0)
+    ts = []; t_start = time.perf_counter()
+    for k in range(max(1, steps)):
         t0 = time.perf_counter(); orc.prove(tr, pi, ac, opts); ts.append(time.perf_counter() - t0)
-    scale = (1 << (n_log2 - sample_log)) * n_log2 / float(sample_log)
-    txt = (f"one full 2^{n_log2}-row proof per step" if sample_log == n_log2 else
-           f"2^{sample_log}-row proof per step, scaled x{scale:.2f} (n log n) to 2^{n_log2}") + f", ext degree {ext}, {cores} OpenMP threads, oracle restatement (not Winterfell)"
-    return [t * 1e3 * scale for t in ts], cores, txt
+        if time.perf_counter() - t_start + ts[-1] > budget_s:
+            break
+    txt = (f"{len(ts)} full 2^{n_log2}-row proof(s), one per step, ext degree {ext}, {cores} OpenMP threads (all host cores; OMP_NUM_THREADS ignored), "
+           "oracle restatement of the reference's Winterfell path (the Rust crate cannot be built here)")
+    return [t * 1e3 for t in ts], cores, txt
 
 
 def run_reference(args, rank, world):
@@ -150,9 +154,10 @@ def run_reference(args, rank, world):
     }))
 
 
-def run_batch(args, rank, world, local):
+def measure_batch(args, rank, world, local):
     """BASELINE config 4: `batch_total` independent 2^16-row proofs (no extension), proof i on GPU i mod G, each GPU pipelining
-    its share over `slots` streams through xfg_prove_burn_mint_batch (host traces in, proof bytes out).  Strong scaling."""
+    its share over `slots` streams through xfg_prove_burn_mint_batch (host traces in, proof bytes out).  Strong scaling.
+    Returns the result dict (every rank)."""
     import numpy as np
     import torch
     import xfg_stark_b200 as xs
@@ -172,7 +177,7 @@ def run_batch(args, rank, world, local):
     tl = [traces[i % distinct] for i in range(len(mine))]; al = [airs[i % distinct] for i in range(len(mine))]
     ctx.prove_batch(tl[:8], al[:8], opts)                            # warm-up
     best = None
-    for _ in range(max(1, args.steps)):
+    for _ in range(max(1, min(args.steps, 3))):
         multi.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         proofs, dev_ms = ctx.prove_batch(tl, al, opts)
@@ -180,11 +185,19 @@ def run_batch(args, rank, world, local):
         ms = multi.max_over_ranks((time.perf_counter() - t0) * 1e3, device="cuda")
         best = ms if best is None else min(best, ms)
     assert all(len(p) > 1000 for p in proofs)
+    ctx.close()
+    return {"metric": "burn-mint proofs/s (1024 x 2^16-row proofs)", "value": args.batch_total / (best / 1e3), "unit": "proofs/s", "n_gpus": world,
+            "higher_is_better": True, "scaling": "strong", "batch_total": args.batch_total, "wall_ms": best, "slots": args.slots,
+            "h2d_bytes_per_proof": 7 * 8 << n_log2, "proof_bytes": len(proofs[0]),
+            "config": {"workload": "1024 independent BurnMintAir proofs, 2^16 rows, blowup 8, no extension (BASELINE config 4), host traces in / proof bytes out"}}
+
+
+def run_batch(args, rank, world, local):
+    from xfg_stark_b200 import multi
+    out = measure_batch(args, rank, world, local)
     if rank == 0:
-        print(json.dumps({"metric": "burn-mint proofs/s (1024 x 2^16-row proofs)", "value": args.batch_total / (best / 1e3), "unit": "proofs/s", "n_gpus": world,
-                          "higher_is_better": True, "scaling": "strong", "batch_total": args.batch_total, "wall_ms": best, "slots": args.slots,
-                          "config": {"workload": "1024 independent BurnMintAir proofs, 2^16 rows, blowup 8, no extension (BASELINE config 4), host traces in / proof bytes out"}}))
-    ctx.close(); multi.finalize()
+        print(json.dumps(out))
+    multi.finalize()
 
 
 def run_verify(args, rank, world, local):
@@ -339,6 +352,8 @@ def main():
                     help="latency: the headline (one 2^n proof per step); batch: BASELINE config 4, 1024 independent 2^16 proofs sharded over "
                          "the GPUs; wide: BASELINE config 5, one 64-column x 2^24-row trace, column-sharded LDE with the all-to-all fused into the "
                          "last NTT pass, then row hashing (needs --gpus >= 2 for a real exchange)")
+    ap.add_argument("--headline-only", action="store_true", help="latency workload: skip the batch (config 4) and wide (config 5, N >= 2) measurements that ride on the same JSON line")
+    ap.add_argument("--wide-log2", type=int, default=24); ap.add_argument("--wide-check-log2", type=int, default=20)
     ap.add_argument("--air-width", type=int, default=64, help="registers of the wide synthetic AIR for --workload air (generic front-end; 2^16 rows unless --n-log2 is given)")
     ap.add_argument("--batch-total", type=int, default=1024)
     ap.add_argument("--slots", type=int, default=16, help="proof workspaces/streams per GPU for --workload batch (1487 / 2148 / 2784 / 3145 proofs/s at 2 / 4 / 8 / 16 on one B200)")
@@ -360,11 +375,7 @@ def main():
     from xfg_stark_b200 import multi
 
     # keep stdout to the one JSON line: NCCL writes its banner / debug output to stdout unless told otherwise
-    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
-    if "XFG_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["XFG_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL_DEBUG itself is left as the caller set it (the driver reads the rank count from its log)
     torch.cuda.set_device(local)
     multi.init("nccl", torch.device("cuda", local))
     if args.workload == "batch":
@@ -413,8 +424,36 @@ def main():
         dev_fn()
     dev_ms, proof = timed_region(dev_fn, args.steps)
     e2e_ms, proof2 = timed_region(e2e_fn, args.steps)
+    # the reference's real callers (SURVEY.md 8b / src/burn_mint_prover.rs:62-129), same timed-region rules:
+    #  from_inputs : the 8-argument entry, trace built on the device (0 B of trace upload)
+    #  mont_cols   : seven registered column buffers in Montgomery form (TraceTable::get_column memory), no conversion pass
+    #  pageable    : the contiguous canonical trace in ordinary (pageable) host memory, staged by the library
+    inp = (s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"], s["version"])
+    fi_fn = lambda: ctx.prove_from_inputs(*inp, n_log2=args.n_log2, options=opts)
+    pg_np = np.array(h_np, copy=True)
+    pg_fn = lambda: ctx.prove(pg_np, air, opts)
+    R = (1 << 64) % xs.P
+    mont = [np.full(n, (int(h_np[c, 0]) * R) % xs.P, dtype=np.uint64) if c != 4 else
+            np.array([(v * R) % xs.P for v in range(4)], dtype=np.uint64)[h_np[4].astype(np.int64)] for c in range(7)]
+    for a in mont:
+        ctx.host_register(a)
+    mc_fn = lambda: ctx.prove_cols(mont, air, opts, form=1)
+    callers = {}
+    for name, fn in (("from_inputs", fi_fn), ("mont_cols", mc_fn), ("pageable", pg_fn)):
+        fn()
+        ms_c, pr = timed_region(fn, args.steps)
+        assert pr == proof, f"{name}: proof differs"
+        callers[name] = ms_c / (args.steps * world)
+    for a in mont:
+        ctx.host_unregister(a)
     clocks = sampler.stop()
     assert proof == proof2, "device-resident and host-buffer proofs differ"
+    # sustained: >= 2.5 s of back-to-back proofs with its own clock samples (thermal / power behaviour of a long batch of large proofs)
+    sus_steps = max(args.steps, int(2500.0 / max(dev_ms / args.steps, 1e-3)))
+    sampler2 = ClockSampler(local); sampler2.start()
+    sus_ms, proof_s = timed_region(dev_fn, sus_steps)
+    sus_clocks = sampler2.stop()
+    assert proof_s == proof
     proof3, times = dev_fn_timed()
     _, times2 = ctx.prove(h_np, air, opts, want_times=True)
     assert proof3 == proof
@@ -476,8 +515,12 @@ def main():
         "dtype": "u64 (Goldilocks) + u32 ARX (BLAKE3)", "data": "synthetic", "config": workload_config(args),
         "proofs_per_s": args.steps * world / (dev_ms / 1e3), "proof_bytes": len(proof),
         "clocks": clocks,
+        "sustained": {"ms_per_proof": sus_ms / (sus_steps * world), "ms_per_step": sus_ms / sus_steps, "steps": sus_steps, "seconds": sus_ms / 1e3, "clocks": sus_clocks},
         "e2e": {"value": e2e_ms / (args.steps * world), "unit": "ms", "h2d_bytes_per_step": times2["h2d_bytes"], "d2h_bytes_per_step": times2["d2h_bytes"],
                 "proofs_per_s": args.steps * world / (e2e_ms / 1e3)},
+        "e2e_callers_ms": {"pinned_contiguous_canonical": e2e_ms / (args.steps * world), "from_inputs_device_built_trace": callers["from_inputs"],
+                           "registered_montgomery_columns": callers["mont_cols"], "pageable_contiguous_canonical": callers["pageable"],
+                           "note": "same proof bytes on every path (asserted); from_inputs uploads 160 B, the others the 7 x n x 8 B trace"},
         "gpu_launches": times["kernel_launches"] * args.steps,
         "device_ms_per_proof": times["device_ms"],
         "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},
@@ -500,9 +543,25 @@ def main():
         scale = (1 << (args.n_log2 - 16)) * args.n_log2 / 16.0 if args.n_log2 > 16 else 1.0
         out["cpu_baseline"]["single_thread"] = {"value": t1 * scale, "unit": "ms", "cores": 1,
                                                 "sample": (f"2^16-row proof on one thread ({t1:.0f} ms)" + (f", scaled x{scale:.1f} (n log n) to 2^{args.n_log2}" if scale != 1.0 else ""))}
+    ctx.close()
+    # BASELINE's other two configurations ride on the same line so that the driver's per-N records carry them: config 4 (1024 x 2^16 batch,
+    # every N) and, where a real exchange exists (N >= 2), config 5 (64 x 2^24 wide trace; checked against the oracle at 64 x 2^20 first)
+    if not args.headline_only:
+        try:
+            out["batch"] = measure_batch(args, rank, world, local)
+        except Exception as e:
+            out["batch"] = {"error": repr(e)}
+        if world >= 2:
+            import wide_worker
+            try:
+                chk = wide_worker.measure(args.wide_check_log2, 64, steps=1, check=True)
+                w = wide_worker.measure(args.wide_log2, 64, steps=2)
+                w["check"] = chk["check"]; w["check_workload"] = chk["config"]["workload"]; w["check_root"] = chk["root"]; w["check_ms"] = chk["value"]
+                out["wide"] = w
+            except Exception as e:
+                out["wide"] = {"error": repr(e), "check": False}
     if rank == 0:
         print(json.dumps(out))
-    ctx.close()
     multi.finalize()
 
 

@@ -97,9 +97,23 @@ int xfg_prove_burn_mint(xfg_ctx* ctx, const uint64_t* trace_colmajor, uint32_t n
 /* same, trace already resident in device memory of ctx's device (d_trace is a device pointer) */
 int xfg_prove_burn_mint_device(xfg_ctx* ctx, const uint64_t* d_trace_colmajor, uint32_t n_log2, const xfg_air_consts* air,
                                const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
+/* same, the trace given as seven separate column buffers exactly as the reference holds them: `TraceTable::get_column(i)` of the
+ * table built at src/burn_mint_air.rs:475 is a `Vec<BaseElement>`, i.e. n u64 words in MONTGOMERY form (x * 2^64 mod p, winter-math 0.8
+ * f64::BaseElement).  form = XFG_FORM_MONTGOMERY reads that memory as it is (the factor 2^-64 is folded into the 1/n of the interpolation:
+ * no conversion pass, no `as_int()` loop, no copy on the caller's side); XFG_FORM_CANONICAL expects integers < p.  Columns registered with
+ * xfg_host_register (or otherwise page-locked) are DMA-ed straight from the caller's memory, pageable columns are staged by the library. */
+#define XFG_FORM_CANONICAL  0u
+#define XFG_FORM_MONTGOMERY 1u
+int xfg_prove_burn_mint_cols(xfg_ctx* ctx, const uint64_t* const cols[XFG_TRACE_WIDTH], uint32_t form, uint32_t n_log2, const xfg_air_consts* air,
+                             const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
+/* page-locks / releases a caller buffer (cudaHostRegister, read-only + portable) so that traces in it upload without staging */
+int xfg_host_register(xfg_ctx* ctx, const void* ptr, size_t bytes);
+int xfg_host_unregister(xfg_ctx* ctx, const void* ptr);
 /* `count` independent proofs of equal size, pipelined over the context's slots (BASELINE config 4; replaces the sequential
  * loops of examples/winterfell_burn_mint_production.rs:187-195).  traces[i], airs[i] as above; proof i is written at
- * out + i*out_stride (out_stride >= the largest proof) and its length to out_lens[i]. */
+ * out + i*out_stride (out_stride >= the largest proof) and its length to out_lens[i].
+ * Errors: the return value is the FIRST error met; a proof that failed (unsatisfied trace, non-canonical element, ...) or was
+ * never started has out_lens[i] == 0, every proof with out_lens[i] > 0 is complete and valid. */
 int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* const* traces, uint32_t n_log2,
                               const xfg_air_consts* airs, const xfg_options* options, uint8_t* out, size_t out_stride,
                               size_t* out_lens, float* total_ms);

@@ -1,7 +1,7 @@
 //! Raw bindings, one item per declaration of `include/xfg_stark.h` (kept in the same order).
 //! The product crate `xfg-stark` has `#![deny(unsafe_code)]` (src/lib.rs:17), hence this separate `-sys` crate.
 #![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_int};
+use std::os::raw::{c_char, c_int, c_void};
 
 pub const XFG_NUM_PUB_INPUTS: usize = 12;
 pub const XFG_NUM_STAGES: usize = 9;
@@ -94,6 +94,8 @@ pub struct xfg_verify_times {
     pub d2h_bytes: u64,
 }
 pub const XFG_VERIFY_OK: i32 = 0;
+pub const XFG_FORM_CANONICAL: u32 = 0;
+pub const XFG_FORM_MONTGOMERY: u32 = 1;
 
 extern "C" {
     pub fn xfg_create(device: c_int, max_n_log2: u32, num_slots: u32, out: *mut *mut xfg_ctx) -> c_int;
@@ -106,6 +108,11 @@ extern "C" {
                                out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
     pub fn xfg_prove_burn_mint_device(ctx: *mut xfg_ctx, d_trace_colmajor: *const u64, n_log2: u32, air: *const xfg_air_consts,
                                       options: *const xfg_options, out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    /// cols: seven column pointers (`TraceTable::get_column(i).as_ptr()`); form: XFG_FORM_CANONICAL / XFG_FORM_MONTGOMERY
+    pub fn xfg_prove_burn_mint_cols(ctx: *mut xfg_ctx, cols: *const *const u64, form: u32, n_log2: u32, air: *const xfg_air_consts,
+                                    options: *const xfg_options, out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    pub fn xfg_host_register(ctx: *mut xfg_ctx, ptr: *const c_void, bytes: usize) -> c_int;
+    pub fn xfg_host_unregister(ctx: *mut xfg_ctx, ptr: *const c_void) -> c_int;
     pub fn xfg_prove_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, traces: *const *const u64, n_log2: u32, airs: *const xfg_air_consts,
                                      options: *const xfg_options, out: *mut u8, out_stride: usize, out_lens: *mut usize, total_ms: *mut f32) -> c_int;
     pub fn xfg_burn_mint_pack_inputs(ctx: *mut xfg_ctx, burn_amount: u64, mint_amount: u64, tx_prefix_hash: *const u8, recipient_address: *const u8,

@@ -97,11 +97,12 @@ impl Prover for GpuBurnMintProver {
     fn new_evaluator<'a, E: FieldElement<BaseField = BaseElement>>(&self, air: &'a XfgBurnMintAir, aux: AuxTraceRandElements<E>,
         coeffs: ConstraintCompositionCoefficients<E>) -> Self::ConstraintEvaluator<'a, E> { DefaultConstraintEvaluator::new(air, aux, coeffs) }
 
-    /// Whole-proof override: trace columns -> canonical u64 (`as_int`) -> xfg_prove_burn_mint -> `StarkProof::from_bytes`.
+    /// Whole-proof override: the seven `TraceTable` columns are handed to the library where they lie - `BaseElement` is a transparent
+    /// `u64` holding the Montgomery form x * 2^64 mod p (winter-math 0.8 f64), which `xfg_prove_burn_mint_cols` reads as it is
+    /// (XFG_FORM_MONTGOMERY): no `as_int()` pass, no `collect()`, no copy on this side.  -> `StarkProof::from_bytes`.
     fn prove(&self, trace: Self::Trace) -> Result<StarkProof, ProverError> {
         let n = trace.length();
-        let mut cols: Vec<u64> = Vec::with_capacity(7 * n);
-        for c in 0..7 { cols.extend(trace.get_column(c).iter().map(|e| e.as_int())); }
+        let cols: [*const u64; 7] = core::array::from_fn(|c| trace.get_column(c).as_ptr() as *const u64);
         let pi = self.public_inputs.to_elements();
         let mut air = sys::xfg_air_consts::default();
         for (d, s) in air.pub_inputs.iter_mut().zip(pi.iter()) { *d = s.as_int(); }
@@ -112,7 +113,7 @@ impl Prover for GpuBurnMintProver {
         let opts = options_to_c(&self.options);
         let mut out = vec![0u8; 1 << 20];
         let mut len = 0usize;
-        let rc = unsafe { sys::xfg_prove_burn_mint(self.ctx.raw, cols.as_ptr(), n.trailing_zeros(), &air, &opts, out.as_mut_ptr(), out.len(), &mut len, ptr::null_mut()) };
+        let rc = unsafe { sys::xfg_prove_burn_mint_cols(self.ctx.raw, cols.as_ptr(), sys::XFG_FORM_MONTGOMERY, n.trailing_zeros(), &air, &opts, out.as_mut_ptr(), out.len(), &mut len, ptr::null_mut()) };
         match rc {
             sys::XFG_OK => { out.truncate(len); StarkProof::from_bytes(&out).map_err(|_| ProverError::UnsupportedFieldExtension(0)) }
             sys::XFG_ERR_UNSATISFIED_CONSTRAINT => Err(ProverError::UnsatisfiedTransitionConstraintError(0)),

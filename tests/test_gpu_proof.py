@@ -72,6 +72,68 @@ def test_reference_entry_point_64_rows(ctx):
     assert e.value.code == 8 and "Burn amount must be exactly" in e.value.message
 
 
+@pytest.mark.parametrize("n_log2,ext", [(3, 1), (6, 2), (11, 1), (17, 2)])
+def test_from_inputs_builds_the_trace_on_the_device(n_log2, ext):
+    """the 8-argument entry (src/burn_mint_prover.rs:62-72) uploads no trace: build_trace (src/burn_mint_air.rs:442-476) is a device kernel;
+    bytes equal the oracle's proof of the host-built trace, and the only host->device bytes are the coin seed elements"""
+    import xfg_stark_b200 as xs
+    s = orc.synthetic_inputs(n_log2)
+    opts = xs.ProofOptions(field_extension=ext)
+    with xs.Context(device=0, max_n_log2=n_log2) as c:
+        for _ in range(2):          # second call replays the cached CUDA graph
+            proof, times = c.prove_from_inputs(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"],
+                                               s["version"], n_log2=n_log2, options=opts, want_times=True)
+            tr, pi, ac = orc.synthetic_case(1 << n_log2, n_log2)
+            assert proof == orc.prove(tr, pi, ac, opts.as_tuple())
+            assert times["h2d_bytes"] == 20 * 8
+            proof_b = c.prove_from_inputs(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"],
+                                          s["version"], n_log2=n_log2, options=opts)
+            assert proof_b == proof
+
+
+def to_montgomery(col):
+    """x -> x * 2^64 mod p: the in-memory representation of winter-math 0.8 f64::BaseElement (SURVEY.md A.1)"""
+    return np.array([(int(v) << 64) % orc.P for v in col], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("n_log2,ext", [(5, 1), (10, 2), (17, 1)])
+def test_montgomery_form_columns(n_log2, ext):
+    """xfg_prove_burn_mint_cols: seven separate column buffers in Montgomery form (TraceTable::get_column memory, src/burn_mint_air.rs:475),
+    pageable and registered, give the bytes of the canonical contiguous trace"""
+    import xfg_stark_b200 as xs
+    opts = xs.ProofOptions(field_extension=ext)
+    air, trace = gpu_case(xs, 3, n_log2)
+    consts = {c: (int(trace[c, 0]) << 64) % orc.P for c in range(7)}
+    cols = []
+    for c in range(7):
+        if c == 4:
+            lut = np.array([(v << 64) % orc.P for v in range(4)], dtype=np.uint64); cols.append(lut[trace[4].astype(np.int64)].copy())
+        else:
+            cols.append(np.full(1 << n_log2, consts[c], dtype=np.uint64))
+    assert (cols[0][:3] == to_montgomery(trace[0][:3])).all() and (cols[4][-3:] == to_montgomery(trace[4][-3:])).all()
+    with xs.Context(device=0, max_n_log2=n_log2) as c:
+        expect = c.prove(trace, air, opts)
+        assert c.prove_cols(cols, air, opts, form=1) == expect                          # pageable columns, staged by the library
+        assert c.prove_cols([trace[k].copy() for k in range(7)], air, opts, form=0) == expect
+        for a in cols:
+            c.host_register(a)
+        try:
+            p1, t = c.prove_cols(cols, air, opts, form=1, want_times=True)              # DMA straight from the caller's columns
+            assert p1 == expect and c.prove_cols(cols, air, opts, form=1) == expect
+            assert t["h2d_bytes"] == 7 * 8 * (1 << n_log2) + 20 * 8
+        finally:
+            for a in cols:
+                c.host_unregister(a)
+        bad = cols[2].copy(); bad[7] = orc.P + 3                                         # non-canonical Montgomery word
+        with pytest.raises(xs.XfgError) as e:
+            c.prove_cols(cols[:2] + [bad] + cols[3:], air, opts, form=1)
+        assert e.value.code == 1
+        with pytest.raises(xs.XfgError):
+            c.prove_cols(cols, air, opts, form=7)
+    tr, pi, ac = orc.synthetic_case(1 << n_log2, 3)
+    assert expect == orc.prove(tr, pi, ac, opts.as_tuple())
+
+
 def test_device_resident_trace_and_times(ctx):
     import torch
     import xfg_stark_b200 as xs
@@ -218,6 +280,17 @@ def test_batch_error_leaves_context_usable(ctx):
     with pytest.raises(xs.XfgError) as e:
         ctx.prove_batch(traces[:2] + [bad_trace] + traces[3:], airs)
     assert e.value.code == 5
+    # the failed proof has length 0, every other proof of the batch is complete and valid (out_lens contract of the header)
+    part = e.value.partial
+    assert len(part) == 5 and part[2] == b""
+    for i in (0, 1, 3, 4):
+        assert part[i] == orc.prove(*orc.synthetic_case(1 << 9, i))
+    with pytest.raises(xs.XfgError):                                # malformed inputs never reach the C side
+        ctx.prove(traces[0][:4], airs[0])
+    with pytest.raises(xs.XfgError):
+        ctx.prove_batch(traces[:2] + [traces[2][:, :256]], airs[:3])
+    with pytest.raises(xs.XfgError):
+        ctx.prove_batch(traces[:3], airs[:2])
     proofs, _ = ctx.prove_batch(traces, airs)
     for i, (air, trace) in enumerate(cases):
         assert proofs[i] == orc.prove(*orc.synthetic_case(1 << 9, i))

@@ -13,25 +13,29 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-def run(n_log2, W, steps=1, check=False, seed=1234):
+def make_columns(n, W, world, rank, seed, torch):
+    """Synthetic wide trace: uniformly random canonical elements (values < 2^63 < p) generated on the device.  Seeded per GLOBAL
+    column, so the trace - and therefore the commitment - is the same for every number of ranks."""
+    wl = W // world
+    cols = torch.empty((wl, n), dtype=torch.int64, device="cuda")
+    g = torch.Generator(device="cuda")
+    for c in range(wl):
+        g.manual_seed(seed + rank * wl + c)
+        cols[c] = torch.randint(0, (1 << 63) - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    return cols
+
+
+def measure(n_log2, W, steps=1, check=False, seed=1234):
+    """Config 5 on the already initialised process group (one process per GPU); returns the result dict on every rank."""
     import torch
     import torch.distributed as dist
     import xfg_stark_b200 as xs
     from xfg_stark_b200 import multi
-    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"          # NCCL's banner must not pollute the JSON line on stdout
-    if "XFG_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["XFG_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
     rank, world, local = multi.rank_world()
-    torch.cuda.set_device(local)
-    multi.init("nccl", torch.device("cuda", local))
     n = 1 << n_log2; wl = W // world
     ctx = xs.Context(device=local, max_n_log2=min(n_log2, 16), num_slots=1)
     wide = xs.WideTrace(ctx, n_log2, W, world, rank)
-    # synthetic wide trace: uniformly random canonical elements (values < 2^63 < p), generated on the device, seeded per column block
-    g = torch.Generator(device="cuda"); g.manual_seed(seed + rank)
-    cols = torch.randint(0, (1 << 63) - 1, (wl, n), dtype=torch.int64, device="cuda", generator=g)
+    cols = make_columns(n, W, world, rank, seed, torch)
     # exchange IPC handles of the receive buffers (bytes over NCCL), then map the peers
     h = torch.frombuffer(bytearray(wide.ipc_handle()), dtype=torch.uint8).cuda()
     allh = [torch.empty_like(h) for _ in range(world)]
@@ -60,27 +64,48 @@ def run(n_log2, W, steps=1, check=False, seed=1234):
             best = (ms, ext, com)
     ok = None
     if check:
-        import orc
         full = [torch.empty_like(cols) for _ in range(world)]
         if world > 1:
             dist.all_gather(full, cols)
         else:
             full = [cols]
-        trace = torch.cat(full).cpu().numpy().view(np.uint64)
-        lde = np.stack([orc.lde(orc.ntt(trace[c], 1, 1)) for c in range(W)])
-        exp_root, _ = orc.merkle(orc.hash_rows(lde))
-        ok = exp_root == final
-        assert ok, "sharded commitment differs from the oracle"
+        if rank == 0:
+            import orc
+            orc.set_threads(max(1, len(os.sched_getaffinity(0))))
+            trace = torch.cat(full).cpu().numpy().view(np.uint64)
+            lde = np.stack([orc.lde(orc.ntt(trace[c], 1, 1)) for c in range(W)])
+            exp_root, _ = orc.merkle(orc.hash_rows(lde))
+            ok = bool(exp_root == final)
+        flag = torch.tensor([1 if (ok or rank != 0) else 0], device="cuda")
+        if world > 1:
+            dist.broadcast(flag, 0)
+        ok = bool(flag.item())
+    N = 8 * n
+    sent = (world - 1) / world * W * N * 8 / world                      # bytes each rank stores into OTHER ranks' buffers
+    out = {"metric": "wide-trace LDE + row commitment (ms)", "value": best[0], "unit": "ms", "n_gpus": world, "higher_is_better": False,
+           "extend_ms": best[1], "commit_ms": best[2], "ntt_gbps_per_gpu": 16.0 * wl * n * 9 / best[1] / 1e6,
+           "peer_store_gbps_per_gpu": sent / best[1] / 1e6, "root": final.hex(), "check": ok, "seed": seed,
+           "config": {"workload": f"one {W}-column x 2^{n_log2}-row random trace (seeded per global column: same root for any number of GPUs), blowup 8, "
+                                  f"columns sharded over {world} GPUs, all-to-all fused into the last NTT pass (peer stores), BLAKE3 row hashing + Merkle (BASELINE config 5)"}}
+    wide.close(); ctx.close()
+    del cols; torch.cuda.empty_cache()
+    return out
+
+
+def run(n_log2, W, steps=1, check=False, seed=1234):
+    import torch
+    from xfg_stark_b200 import multi
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")          # NCCL's log must not pollute the JSON line on stdout; NCCL_DEBUG itself is left alone
+    rank, world, local = multi.rank_world()
+    torch.cuda.set_device(local)
+    multi.init("nccl", torch.device("cuda", local))
+    out = measure(n_log2, W, steps, check, seed)
+    if check:
+        assert out["check"], "sharded commitment differs from the oracle"
     if rank == 0:
-        N = 8 * n
-        sent = (world - 1) / world * W * N * 8 / world                      # bytes each rank stores into OTHER ranks' buffers
-        print(json.dumps({"metric": "wide-trace LDE + row commitment (ms)", "value": best[0], "unit": "ms", "n_gpus": world, "higher_is_better": False,
-                          "extend_ms": best[1], "commit_ms": best[2], "ntt_gbps_per_gpu": 16.0 * wl * n * 9 / best[1] / 1e6,
-                          "peer_store_gbps_per_gpu": sent / best[1] / 1e6, "root": final.hex(), "check": ok,
-                          "config": {"workload": f"one {W}-column x 2^{n_log2}-row random trace, blowup 8, columns sharded over {world} GPUs, "
-                                                 "all-to-all fused into the last NTT pass (peer stores), BLAKE3 row hashing + Merkle (BASELINE config 5)"}}))
+        print(json.dumps(out))
         print("WIDE_OK")
-    wide.close(); ctx.close(); multi.finalize()
+    multi.finalize()
 
 
 if __name__ == "__main__":

@@ -14,11 +14,11 @@ a ``Context`` without a CUDA device raises ``XfgError``.  The directory name car
 ``xfg_stark_b200`` shim at the repo root.
 """
 from ._binding import (WideTrace, Context, ProofOptions, StageTimes, XfgBurnMintProver, XfgBurnMintVerifier, BatchBurnMintVerifier, XfgError, AirConsts, STAGE_NAMES, load_library,
-                       library_path, EXPORTED_SYMBOLS, FieldExtension, pack_inputs, build_trace, air_compile_check)
+                       library_path, EXPORTED_SYMBOLS, FieldExtension, pack_inputs, build_trace, air_compile_check, P)
 from .synthetic import synthetic_inputs
 from .air import AirBuilder
 from . import air
 from . import multi
 
 __all__ = ["WideTrace", "Context", "ProofOptions", "StageTimes", "XfgBurnMintProver", "XfgBurnMintVerifier", "BatchBurnMintVerifier", "XfgError", "AirConsts", "STAGE_NAMES",
-           "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "air_compile_check", "synthetic_inputs", "multi", "AirBuilder", "air"]
+           "load_library", "library_path", "EXPORTED_SYMBOLS", "FieldExtension", "pack_inputs", "build_trace", "air_compile_check", "synthetic_inputs", "multi", "AirBuilder", "air", "P"]

@@ -17,7 +17,11 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
-                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_air_compile_check", "xfg_pipe_probe"]
+                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_air_compile_check", "xfg_pipe_probe",
+                    "xfg_prove_burn_mint_cols", "xfg_host_register", "xfg_host_unregister"]
+
+
+P = 0xFFFFFFFF00000001          # the Winterfell base field modulus 2^64 - 2^32 + 1
 
 
 class FieldExtension:           # winterfell::FieldExtension discriminants
@@ -122,6 +126,8 @@ def load_library():
     prove_tail = [vp, sz, C.POINTER(sz), C.POINTER(StageTimes)]
     L.xfg_prove_burn_mint.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
     L.xfg_prove_burn_mint_device.argtypes = [vp, vp, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
+    L.xfg_prove_burn_mint_cols.argtypes = [vp, vp, u32, u32, C.POINTER(AirConsts), C.POINTER(_Options)] + prove_tail
+    L.xfg_host_register.argtypes = [vp, vp, sz]; L.xfg_host_unregister.argtypes = [vp, vp]
     L.xfg_prove_air.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
     L.xfg_prove_air_device.argtypes = [vp, C.POINTER(_AirDesc), vp, u32, C.POINTER(_Options)] + prove_tail
     L.xfg_air_compile_check.argtypes = [C.POINTER(_AirDesc), u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), vp, vp, vp]
@@ -245,11 +251,45 @@ class Context:
     def build_trace(self, air, n_log2):
         return build_trace(air, n_log2)
 
+    @staticmethod
+    def _trace_array(trace, width, n_log2=None):
+        """(width, n) uint64, C-contiguous, n a power of two (and equal to 2^n_log2 when given); anything else would make the C side
+        read past the end of the buffer, so it is rejected here with the prover's own error code."""
+        t = np.ascontiguousarray(trace, dtype=np.uint64)
+        if t.ndim != 2 or t.shape[0] != width or t.shape[1] < 1 or (t.shape[1] & (t.shape[1] - 1)):
+            raise XfgError(1, f"trace must be a ({width}, 2^k) uint64 array, got shape {tuple(t.shape)}")
+        if n_log2 is not None and t.shape[1] != (1 << n_log2):
+            raise XfgError(1, "all traces of a batch must have the same length")
+        return t
+
     # ---- whole proof ----
     def prove(self, trace, air, options=ProofOptions(), want_times=False):
         """trace: (7, n) uint64 column-major host array (numpy; a pinned torch tensor's numpy view is uploaded without staging)."""
-        t = np.ascontiguousarray(trace, dtype=np.uint64)
+        t = self._trace_array(trace, 7)
         return self._prove_ptr(self._lib.xfg_prove_burn_mint, _ptr(t), t.shape[1].bit_length() - 1, air, options, want_times)
+
+    def prove_cols(self, cols, air, options=ProofOptions(), form=0, want_times=False):
+        """cols: seven 1-D uint64 arrays (one per trace column, as `TraceTable::get_column` hands them out); form: 0 = canonical integers,
+        1 = Montgomery form (winter-math BaseElement's in-memory representation, read without conversion)."""
+        if len(cols) != 7:
+            raise XfgError(1, "seven columns are required")
+        arrs = [np.ascontiguousarray(c, dtype=np.uint64) for c in cols]
+        n = arrs[0].shape[0]
+        if any(a.ndim != 1 or a.shape[0] != n for a in arrs) or n < 1 or (n & (n - 1)):
+            raise XfgError(1, "columns must be 1-D uint64 arrays of one power-of-two length")
+        ptrs = (C.c_void_p * 7)(*[a.ctypes.data for a in arrs])
+        out = self._out; ln = C.c_size_t(0); st = StageTimes(); o = options._c()
+        self._check(self._lib.xfg_prove_burn_mint_cols(self._h, ptrs, form, n.bit_length() - 1, C.byref(air), C.byref(o), out, len(out), C.byref(ln),
+                                                       C.byref(st) if want_times else None))
+        proof = C.string_at(out, ln.value)
+        return (proof, st.as_dict()) if want_times else proof
+
+    def host_register(self, array):
+        """page-locks a caller-owned numpy array so that traces in it upload without staging (xfg_host_register)"""
+        self._check(self._lib.xfg_host_register(self._h, C.c_void_p(array.ctypes.data), array.nbytes))
+
+    def host_unregister(self, array):
+        self._check(self._lib.xfg_host_unregister(self._h, C.c_void_p(array.ctypes.data)))
 
     def prove_device(self, device_ptr, n_log2, air, options=ProofOptions(), want_times=False):
         """device_ptr: integer device address of a (7, n) uint64 column-major buffer on this context's device."""
@@ -278,9 +318,7 @@ class Context:
         """air: AirBuilder (xfg_air_desc); trace: (width, n) uint64 column-major host array.  Replaces `air.prove(trace)` for a
         user-defined AIR (e.g. src/winterfell_air.rs:169)."""
         desc, keep, w = self._air_desc(air)
-        t = np.ascontiguousarray(trace, dtype=np.uint64)
-        if t.ndim != 2 or t.shape[0] != w:
-            raise XfgError(1, "trace width does not match the AIR")
+        t = self._trace_array(trace, w)
         out = self._out; ln = C.c_size_t(0); st = StageTimes(); o = options._c()
         self._check(self._lib.xfg_prove_air(self._h, C.byref(desc), _ptr(t), t.shape[1].bit_length() - 1, C.byref(o), out, len(out), C.byref(ln),
                                             C.byref(st) if want_times else None))
@@ -300,11 +338,13 @@ class Context:
         cnt = len(traces)
         if cnt == 0:
             return [], 0.0
-        descs, keep = [], []
+        if len(airs) != cnt:
+            raise XfgError(1, "one AIR description per trace is required")
+        descs, keep, widths = [], [], []
         for a in airs:
-            d, k, _ = self._air_desc(a); descs.append(d); keep.append(k)
-        ts = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
-        n_log2 = ts[0].shape[1].bit_length() - 1
+            d, k, w = self._air_desc(a); descs.append(d); keep.append(k); widths.append(w)
+        n_log2 = np.asarray(traces[0]).shape[-1].bit_length() - 1
+        ts = [self._trace_array(t, w, n_log2) for t, w in zip(traces, widths)]
         darr = (_AirDesc * cnt)(*descs); ptrs = (C.c_void_p * cnt)(*[t.ctypes.data for t in ts])
         out = np.empty(cnt * out_stride, dtype=np.uint8); lens = np.zeros(cnt, dtype=np.uint64); ms = C.c_float(0); o = options._c()
         self._check(self._lib.xfg_prove_air_batch(self._h, cnt, darr, ptrs, n_log2, C.byref(o), _ptr(out), out_stride, _ptr(lens), C.byref(ms)))
@@ -315,13 +355,22 @@ class Context:
         cnt = len(traces)
         if cnt == 0:
             return [], 0.0
-        ts = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
-        n_log2 = ts[0].shape[1].bit_length() - 1
+        if len(airs) != cnt:
+            raise XfgError(1, "one AirConsts per trace is required")
+        n_log2 = np.asarray(traces[0]).shape[-1].bit_length() - 1
+        ts = [self._trace_array(t, 7, n_log2) for t in traces]
         ptrs = (C.c_void_p * cnt)(*[t.ctypes.data for t in ts])
         air_arr = (AirConsts * cnt)(*airs)
         out = np.empty(cnt * out_stride, dtype=np.uint8); lens = np.zeros(cnt, dtype=np.uint64); ms = C.c_float(0); o = options._c()
-        self._check(self._lib.xfg_prove_burn_mint_batch(self._h, cnt, ptrs, n_log2, air_arr, C.byref(o), _ptr(out), out_stride, _ptr(lens), C.byref(ms)))
-        return [out[i * out_stride:i * out_stride + int(lens[i])].tobytes() for i in range(cnt)], float(ms.value)
+        rc = self._lib.xfg_prove_burn_mint_batch(self._h, cnt, ptrs, n_log2, air_arr, C.byref(o), _ptr(out), out_stride, _ptr(lens), C.byref(ms))
+        proofs = [out[i * out_stride:i * out_stride + int(lens[i])].tobytes() for i in range(cnt)]
+        if rc:      # first error of the batch; proofs with a non-zero length are complete and valid (XfgError.partial)
+            try:
+                self._check(rc)
+            except XfgError as e:
+                e.partial = proofs
+                raise
+        return proofs, float(ms.value)
 
     def verify_batch(self, proofs, airs, options=ProofOptions(), want_times=False):
         """proofs: list of proof bytes; airs: list of AirConsts (public inputs + AIR constants of each proof).

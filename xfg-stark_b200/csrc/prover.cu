@@ -6,6 +6,7 @@
 // opened rows / authentication nodes runs on the device as one dependent chain of launches on the slot's stream; the host
 // only serialises (`StarkProof::to_bytes`, `BatchMerkleProof::serialize_nodes`).
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -31,21 +32,10 @@ using namespace xfg;
 namespace {
 
 // Split upload of a large trace: one copy + event per column, the column's NTTs start as soon as it has landed.  A one-column launch
-// fills the GPU for 3.5 waves only (and its interpolation for less than one), so consecutive columns run on different streams and
-// fill each other's partial waves.
-int UPLOAD_GROUPS = 7;
-int UPLOAD_GROUP_START[XFG_TRACE_WIDTH + 1] = {0, 1, 2, 3, 4, 5, 6, XFG_TRACE_WIDTH};
-// XFG_UPLOAD_SPLIT="1,1,2,3" (group sizes, sum 7) overrides the split; XFG_UPLOAD_STREAMS=1 keeps every group on one stream (A/B runs)
-int g_upload_streams = 4;   // measured e2e at 2^20 (ms per proof): one stream {1,1,2,3} 4.95, per column on 1 / 2 / 3 / 4 streams 5.03 / 4.88 / 4.87 / 4.84
-void upload_split_from_env() {
-  static bool done = false; if (done) return; done = true;
-  if (const char* e = getenv("XFG_UPLOAD_STREAMS")) g_upload_streams = std::min(4, std::max(1, atoi(e)));
-  const char* e = getenv("XFG_UPLOAD_SPLIT"); if (!e) return;
-  int start[XFG_TRACE_WIDTH + 1] = {0}, k = 0, sum = 0;
-  for (const char* q = e; *q && k < XFG_TRACE_WIDTH;) { const int v = atoi(q); if (v < 1) return; sum += v; start[++k] = sum; while (*q && *q != ',') q++; if (*q == ',') q++; }
-  if (sum != XFG_TRACE_WIDTH) return;
-  UPLOAD_GROUPS = k; for (int i = 0; i <= k; i++) UPLOAD_GROUP_START[i] = start[i];
-}
+// fills the GPU for 3.5 waves only (and its interpolation for less than one), so consecutive columns run on UPLOAD_STREAMS different
+// streams and fill each other's partial waves (measured e2e at 2^20, ms per proof: one stream with {1,1,2,3}-column groups 4.95, per
+// column on 1 / 2 / 3 / 4 streams 5.03 / 4.88 / 4.87 / 4.84).
+constexpr int UPLOAD_STREAMS = 4;
 constexpr size_t MATERIAL_WORDS = size_t(1) << 20;   // 8 MiB: opened rows + per-position authentication paths
 constexpr u32 MIN_LOG = 3, MAX_LOG = 24;
 
@@ -75,9 +65,10 @@ struct Carve {   // device pointers of one proof, carved from the slot slab for 
 
 struct GraphKey {      // everything that is baked into the captured launch sequence (kernel arguments, grids, copy sizes)
   const void* plan; const void* trace; int D; u32 q, g; u32 width, seed_count, prog_instr;   // prog_instr: 0 = burn-mint kernels, else generic program length + 1
-  const void* host_src;                                                                      // split upload: the column copies are part of the graph
+  std::array<const void*, XFG_TRACE_WIDTH> host_src;                                         // split upload: the column copies are part of the graph
+  bool fill;                                                                                 // trace built on the device from the AIR constants
   bool operator<(const GraphKey& o) const {
-    return std::tie(plan, trace, D, q, g, width, seed_count, prog_instr, host_src) < std::tie(o.plan, o.trace, o.D, o.q, o.g, o.width, o.seed_count, o.prog_instr, o.host_src);
+    return std::tie(plan, trace, D, q, g, width, seed_count, prog_instr, host_src, fill) < std::tie(o.plan, o.trace, o.D, o.q, o.g, o.width, o.seed_count, o.prog_instr, o.host_src, o.fill);
   }
 };
 struct GraphEntry { cudaGraphExec_t exec; unsigned launches; };
@@ -86,7 +77,9 @@ struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 struct Slot {
   cudaStream_t st = nullptr, copy_st = nullptr, aux_st[3] = {nullptr, nullptr, nullptr};   // copy_st: column-wise trace upload overlapped with the first NTTs; aux_st: every other column group
   cudaEvent_t col_ev[XFG_TRACE_WIDTH] = {nullptr}, fork_ev = nullptr, fork2_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
-  bool split_upload = false; const u64* up_src = nullptr;   // split upload: the (pinned) host trace the column copies read, issued inside enqueue_proof
+  bool fill_trace = false;                                  // burn-mint trace generated on the device (xfg_prove_burn_mint_from_inputs): no upload
+  bool split_upload = false; const u64* up_cols[XFG_TRACE_WIDTH] = {nullptr};   // split upload: the (pinned) host columns the copies read, issued inside enqueue_proof
+  u64 in_scale = 1;                                         // 1 for canonical input, R^-1 = 2^-64 for Montgomery-form columns: folded into the 1/n of the interpolation
   u64* slab = nullptr; size_t slab_words = 0;
   ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
   ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;
@@ -200,6 +193,9 @@ int get_plan(xfg_ctx* ctx, u32 ln, u32 rem_max_deg, const Plan** out) {
         CU(cudaDeviceSynchronize());
       }
     } }
+  // the table uploads above are synchronous copies from pageable memory, which may return before the DMA has landed; the consumers run on
+  // non-blocking streams that are not ordered against the legacy stream, so order them here once per plan
+  CU(cudaDeviceSynchronize());
   const u64 w8i = gl_inv(gl_root_of_unity(3));
   p.fc.w8i[0] = 1; for (int i = 1; i < 4; i++) p.fc.w8i[i] = gl_mul(p.fc.w8i[i - 1], w8i);
   p.fc.inv8 = gl_inv(8); p.fc.inv7 = gl_inv(XFG_GENERATOR);
@@ -290,9 +286,8 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   const u32 W = s.W; const bool gen = s.generic;
   if (s.split_upload && !d_trace) {   // one copy + event per column on the copy stream (forked here so that the whole sequence is capturable as a
     CU(cudaEventRecord(s.fork_ev, st)); CU(cudaStreamWaitEvent(s.copy_st, s.fork_ev, 0));      // CUDA graph); a column's NTTs start as soon as it has landed
-    for (int g = 0; g < UPLOAD_GROUPS; g++) {
-      const size_t c0 = UPLOAD_GROUP_START[g], c1 = UPLOAD_GROUP_START[g + 1];
-      CU(cudaMemcpyAsync(c.trace_in + c0 * n, s.up_src + c0 * n, (c1 - c0) * n * 8, cudaMemcpyHostToDevice, s.copy_st));
+    for (int g = 0; g < XFG_TRACE_WIDTH; g++) {
+      CU(cudaMemcpyAsync(c.trace_in + (size_t)g * n, s.up_cols[g], n * 8, cudaMemcpyHostToDevice, s.copy_st));
       CU(cudaEventRecord(s.col_ev[g], s.copy_st));
     }
   }
@@ -300,6 +295,7 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   if (gen) CU(cudaMemcpyAsync(s.d_prog, s.h_prog, offsetof(GenProgram, code) + (size_t)s.h_prog->num_instr * sizeof(GenInstr), cudaMemcpyHostToDevice, st));
   else CU(cudaMemcpyAsync(s.d_air, s.h_air, sizeof(AirParams), cudaMemcpyHostToDevice, st));
   mark();   // ev0: start of device work
+  if (s.fill_trace && !d_trace && !gen) PROF("trace_fill", launch_trace_fill(st, c.trace_in, s.d_air, ln));
   PROF("transcript", launch_seed(st, s.d_state, s.d_seed, (int)s.seed_count));
   // 1 ---- extend_execution_trace: interpolate the 7 columns, evaluate on the 8 cosets s_k * <w_n>
   // With a split upload the trace goes column by column so that a column's NTTs start as soon as its copy has landed.  (Running
@@ -307,18 +303,18 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   // measured: 7x smaller grids cost more (5.88 vs 5.46 ms per proof) than the saved DRAM traffic gains on these ALU-bound kernels.)
   // Consecutive column groups alternate between two streams: a group's launches are 1-3 columns wide (3.5 waves of CTAs per column), and
   // the partial last wave of one group is filled by the next group's kernels instead of idling.
-  const bool waits = s.split_upload && !d_trace, two = waits && g_upload_streams >= 2 && !profiling;
-  const int nstreams = two ? g_upload_streams : 1;
+  const bool waits = s.split_upload && !d_trace, two = waits && !profiling;
+  const int nstreams = two ? UPLOAD_STREAMS : 1;
   if (two) { CU(cudaEventRecord(s.fork2_ev, st)); for (int a = 0; a + 1 < nstreams; a++) CU(cudaStreamWaitEvent(s.aux_st[a], s.fork2_ev, 0)); }
-  for (int g = 0; g < (waits ? UPLOAD_GROUPS : 1); g++) {
-    const int c0 = waits ? UPLOAD_GROUP_START[g] : 0, per = waits ? UPLOAD_GROUP_START[g + 1] - c0 : (int)W;
+  for (int g = 0; g < (waits ? XFG_TRACE_WIDTH : 1); g++) {
+    const int c0 = waits ? g : 0, per = waits ? 1 : (int)W;
     const size_t off = (size_t)c0 * n;
     cudaStream_t gs = (g % nstreams) ? s.aux_st[g % nstreams - 1] : st;
     if (waits) CU(cudaStreamWaitEvent(gs, s.col_ev[g], 0));
     // every trace element must be a canonical field element: checked by the pass of the interpolation that reads the trace
     { NttJob j{}; j.src = trace_src + off; j.dst = c.trace_coef + off; j.ln = ln; j.batch = per; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
       j.canon_flag = &s.d_state->error_flags; j.canon_bit = ERR_FLAG_NONCANONICAL;
-      j.inverse = true; j.scale = p.n_inv; PROF("ntt.interpolate_trace", ntt_batch(gs, p.ntt, j)); }
+      j.inverse = true; j.scale = gen ? p.n_inv : gl_mul(p.n_inv, s.in_scale); PROF("ntt.interpolate_trace", ntt_batch(gs, p.ntt, j)); }
     { NttJob j{}; j.src = c.trace_coef + off; j.dst = c.lde + off * 8; j.ln = ln; j.batch = per * 8; j.src_tstride = n; j.dst_tstride = n; j.src_div = 8;
       j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_trace", ntt_batch(gs, p.ntt, j)); }
   }
@@ -401,7 +397,8 @@ int launch_prepared(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_optio
   const bool use_graph = ctx->graphs && !timed && !ctx->profiling;
   if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);
   const bool split = s.split_upload && !d_trace;
-  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor, s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0, split ? s.up_src : nullptr};
+  std::array<const void*, XFG_TRACE_WIDTH> srcs{}; if (split) for (int c = 0; c < XFG_TRACE_WIDTH; c++) srcs[c] = s.up_cols[c];
+  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor + (s.in_scale != 1 ? 256u : 0u), s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0, srcs, s.fill_trace && !d_trace};
   auto it = s.graphs.find(key);
   if (it == s.graphs.end()) {
     if (s.graphs.size() >= 16) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec); s.graphs.clear(); }   // bounded cache (callers that keep changing the device trace pointer)
@@ -512,6 +509,7 @@ void assemble(const Plan& p, int D, u32 W, const u64 (*ood_frame)[2], const xfg_
 }
 
 int finish_proof(xfg_ctx* ctx, Slot& s, u8* out, size_t cap, size_t* out_len, xfg_stage_times* times) {
+  *out_len = 0;   // every failure below leaves a defined (empty) result for this proof
   CU(cudaStreamSynchronize(s.st));
   s.busy = false;
   const ProofState& hs = *s.h_state;
@@ -550,28 +548,47 @@ int check_air(xfg_ctx* ctx, const xfg_air_consts* air) {
   return XFG_OK;
 }
 
-// trace upload: straight from the caller's buffer when it is page-locked (cudaHostAlloc / cudaHostRegister), otherwise staged
-// through the slot's pinned buffer.  Canonicity (< p) is checked on the device.
-int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace, bool allow_split) {
+// trace upload: straight from the caller's buffers when they are page-locked (cudaHostAlloc / cudaHostRegister / xfg_host_register), otherwise
+// staged through the slot's pinned buffer (large columns by one host thread each).  Canonicity (< p) is checked on the device.
+// cols[c]: column c of the trace (W columns of n elements; for a contiguous column-major trace cols[c] = trace + c * n).
+int upload_cols(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* const* cols, bool allow_split) {
   Carve c; carve(s, p, D, c);
   if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length");
-  const size_t bytes = (size_t)s.W * p.n * 8;
-  cudaPointerAttributes at{}; const bool pinned = cudaPointerGetAttributes(&at, h_trace) == cudaSuccess && at.type == cudaMemoryTypeHost;
-  cudaGetLastError();   // unregistered host memory may leave a sticky-free error code behind on older drivers
-  const u64* src = h_trace;
-  if (!pinned) { std::memcpy(s.h_trace, h_trace, bytes); src = s.h_trace; }
+  const size_t n = p.n, W = s.W;
+  const u64* src[XFG_AIR_MAX_WIDTH]; bool contiguous = true, stage_any = false;
+  for (size_t k = 0; k < W; k++) {
+    cudaPointerAttributes at{}; const bool pinned = cudaPointerGetAttributes(&at, cols[k]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // unregistered host memory may leave a sticky-free error code behind on older drivers
+    src[k] = pinned ? cols[k] : nullptr; stage_any |= !pinned;
+    if (k && cols[k] != cols[0] + k * n) contiguous = false;
+    if (k && pinned != (src[0] != nullptr)) contiguous = false;
+  }
+  if (stage_any) {
+    auto stage = [&](size_t k) { if (!src[k]) { std::memcpy(s.h_trace + k * n, cols[k], n * 8); src[k] = s.h_trace + k * n; } };
+    if (n * 8 >= (size_t(1) << 20)) { std::vector<std::thread> th; for (size_t k = 0; k < W; k++) if (!src[k]) th.emplace_back(stage, k); for (auto& t : th) t.join(); }
+    else for (size_t k = 0; k < W; k++) stage(k);
+  }
   s.split_upload = allow_split && p.ln >= 17 && !s.generic;
   if (s.split_upload) {      // the column copies are issued by enqueue_proof (copy stream forked from the proof's stream), so that the
-    s.up_src = src;          // whole end-to-end sequence can be captured and replayed as one CUDA graph
+    for (size_t k = 0; k < W; k++) s.up_cols[k] = src[k];   // whole end-to-end sequence can be captured and replayed as one CUDA graph
+  } else if (contiguous) {
+    CU(cudaMemcpyAsync(c.trace_in, src[0], W * n * 8, cudaMemcpyHostToDevice, s.st));
   } else {
-    CU(cudaMemcpyAsync(c.trace_in, src, bytes, cudaMemcpyHostToDevice, s.st));
+    for (size_t k = 0; k < W; k++) CU(cudaMemcpyAsync(c.trace_in + k * n, src[k], n * 8, cudaMemcpyHostToDevice, s.st));
   }
   return XFG_OK;
 }
+int upload_trace(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const u64* h_trace, bool allow_split) {
+  const u64* cols[XFG_AIR_MAX_WIDTH];
+  for (size_t k = 0; k < s.W; k++) cols[k] = h_trace + k * p.n;
+  return upload_cols(ctx, s, p, D, cols, allow_split);
+}
 
 int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log2, const xfg_air_consts* air, const xfg_options* o,
-                 u8* out, size_t cap, size_t* out_len, xfg_stage_times* times) {
-  if (!ctx || !air || !o || !out_len || (!h_trace && !d_trace) || (!out && cap)) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+                 u8* out, size_t cap, size_t* out_len, xfg_stage_times* times, bool fill = false, const u64* const* h_cols = nullptr, u32 form = XFG_FORM_CANONICAL) {
+  if (!ctx || !air || !o || !out_len || (!h_trace && !d_trace && !fill && !h_cols) || (!out && cap)) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+  if (form != XFG_FORM_CANONICAL && form != XFG_FORM_MONTGOMERY) return fail(ctx, XFG_ERR_BAD_ARGS, "unknown element form");
+  if (h_cols) for (int c = 0; c < XFG_TRACE_WIDTH; c++) if (!h_cols[c]) return fail(ctx, XFG_ERR_BAD_ARGS, "null column");
   if (n_log2 < MIN_LOG || n_log2 > MAX_LOG) return fail(ctx, XFG_ERR_BAD_ARGS, "trace length must be 2^3 .. 2^24");
   if (n_log2 > ctx->max_log) return fail(ctx, XFG_ERR_TOO_LARGE, "trace longer than the context was created for");
   int rc;
@@ -583,15 +600,19 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1;
   g_xfg_launches = 0;
   if (times) { std::memset(times, 0, sizeof *times); cudaEventRecord(s.ev[XFG_NUM_STAGES + 2], s.st); }
-  s.split_upload = false; s.generic = false; s.W = XFG_TRACE_WIDTH;
+  s.split_upload = false; s.generic = false; s.W = XFG_TRACE_WIDTH; s.fill_trace = fill;
+  // Montgomery-form input (x * 2^64 mod p, what winter-math's BaseElement holds in memory): the interpolation is linear, so the factor
+  // 2^-64 rides on its 1/n scale (2^64 = 2^32 - 1 mod p) and costs nothing
+  s.in_scale = form == XFG_FORM_MONTGOMERY ? gl_inv(0xFFFFFFFFull) : 1;
   if (h_trace && (rc = upload_trace(ctx, s, *p, D, h_trace, true))) return rc;
+  if (h_cols && (rc = upload_cols(ctx, s, *p, D, h_cols, true))) return rc;
   if ((rc = launch_proof(ctx, s, *p, D, *o, *air, d_trace, times != nullptr))) return rc;
   rc = finish_proof(ctx, s, out, cap, out_len, times);
   if (times) {
     cudaEventElapsedTime(&times->h2d_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[0]);
     cudaEventElapsedTime(&times->total_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[XFG_NUM_STAGES + 1]);
     times->kernel_launches = g_xfg_launches;
-    times->h2d_bytes = (h_trace ? (size_t)s.W * p->n * 8 : 0) + (size_t)s.seed_count * 8;
+    times->h2d_bytes = ((h_trace || h_cols) ? (size_t)s.W * p->n * 8 : 0) + (size_t)s.seed_count * 8;
     times->d2h_bytes = sizeof(ProofState) + s.mat_words * 8;
   }
   return rc;
@@ -650,11 +671,11 @@ int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t 
   auto bail = [&](int rc) { xfg_destroy(ctx); return rc; };
 #define CUB(call) do { if ((call) != cudaSuccess) return bail(XFG_ERR_CUDA); } while (0)
   CUB(cudaSetDevice(device));
-  upload_split_from_env();
   ntt_init(true);
   { const u64 w = gl_root_of_unity(NTT_TW_LOG); std::vector<u64> f = pow_series(w, 1u << (NTT_TW_LOG - 1)), b = pow_series(gl_inv(w), 1u << (NTT_TW_LOG - 1));
     CUB(cudaMalloc(&ctx->tw_fwd, f.size() * 8)); CUB(cudaMalloc(&ctx->tw_inv, b.size() * 8));
-    CUB(cudaMemcpy(ctx->tw_fwd, f.data(), f.size() * 8, cudaMemcpyHostToDevice)); CUB(cudaMemcpy(ctx->tw_inv, b.data(), b.size() * 8, cudaMemcpyHostToDevice)); }
+    CUB(cudaMemcpy(ctx->tw_fwd, f.data(), f.size() * 8, cudaMemcpyHostToDevice)); CUB(cudaMemcpy(ctx->tw_inv, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
+    CUB(cudaDeviceSynchronize()); }
   ctx->slots.resize(num_slots);
   const size_t words = slab_words_for(max_n_log2, 2, max_width), trace_words = size_t(max_width) << max_n_log2;
   for (Slot& s : ctx->slots) {
@@ -721,6 +742,25 @@ int xfg_prove_burn_mint_device(xfg_ctx* ctx, const uint64_t* d_trace, uint32_t n
   return prove_common(ctx, nullptr, d_trace, n_log2, air, o, out, cap, out_len, times);
 }
 
+int xfg_prove_burn_mint_cols(xfg_ctx* ctx, const uint64_t* const cols[XFG_TRACE_WIDTH], uint32_t form, uint32_t n_log2, const xfg_air_consts* air,
+                             const xfg_options* o, uint8_t* out, size_t cap, size_t* out_len, xfg_stage_times* times) {
+  if (!cols) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+  return prove_common(ctx, nullptr, nullptr, n_log2, air, o, out, cap, out_len, times, false, cols, form);
+}
+int xfg_host_register(xfg_ctx* ctx, const void* ptr, size_t bytes) {
+  if (!ctx || !ptr || !bytes) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly));
+  return XFG_OK;
+}
+int xfg_host_unregister(xfg_ctx* ctx, const void* ptr) {
+  if (!ctx || !ptr) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  for (Slot& s : ctx->slots) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec); s.graphs.clear(); }   // cached graphs may hold copies from this buffer
+  CU(cudaHostUnregister(const_cast<void*>(ptr)));
+  return XFG_OK;
+}
+
 int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* const* traces, uint32_t n_log2, const xfg_air_consts* airs,
                               const xfg_options* o, uint8_t* out, size_t out_stride, size_t* out_lens, float* total_ms) {
   if (!ctx || !traces || !airs || !o || !out || !out_lens) return fail(ctx, XFG_ERR_BAD_ARGS, "null argument");
@@ -732,6 +772,7 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
   const Plan* p; if ((rc = get_plan(ctx, n_log2, o->fri_remainder_max_degree, &p))) return rc;
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1; const size_t S = ctx->slots.size();
   g_xfg_launches = 0;
+  for (uint32_t i = 0; i < count; i++) out_lens[i] = 0;   // a proof that fails (or is never started) keeps length 0
   cudaEvent_t e0 = ctx->slots[0].ev[XFG_NUM_STAGES + 2], e1 = ctx->slots[0].ev[XFG_NUM_STAGES + 1];
   if (total_ms) { CU(cudaDeviceSynchronize()); CU(cudaEventRecord(e0, ctx->slots[0].st)); }
   int first_err = XFG_OK;
@@ -740,7 +781,7 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
     if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
     if ((rc = check_air(ctx, &airs[i]))) { drain_slots(ctx); return rc; }
     if (!traces[i]) { drain_slots(ctx); return fail(ctx, XFG_ERR_BAD_ARGS, "null trace"); }
-    s.generic = false; s.W = XFG_TRACE_WIDTH;
+    s.generic = false; s.W = XFG_TRACE_WIDTH; s.fill_trace = false; s.in_scale = 1;
     if ((rc = upload_trace(ctx, s, *p, D, traces[i], false))) { drain_slots(ctx); return rc; }
     s.proof_index = i;
     if ((rc = launch_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) { drain_slots(ctx); return rc; }
@@ -768,9 +809,8 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn, uint64_t mint, 
   if (n_log2 < MIN_LOG || n_log2 > ctx->max_log) return fail(ctx, XFG_ERR_TOO_LARGE, "trace longer than the context was created for");
   xfg_air_consts air; int rc = xfg_burn_mint_pack_inputs(ctx, burn, mint, txp, rcpt, rcpt_len, secret, secret_len, network_id, target_chain_id, version, &air);
   if (rc) return rc;
-  std::vector<u64> trace((size_t)7 << n_log2);
-  burn_mint_build_trace(&air, n_log2, trace.data());
-  return xfg_prove_burn_mint(ctx, trace.data(), n_log2, &air, o, out, cap, out_len, times);
+  // build_trace (src/burn_mint_air.rs:442-476) runs on the device: six constant columns and the state step function need no upload
+  return prove_common(ctx, nullptr, nullptr, n_log2, &air, o, out, cap, out_len, times, true);
 }
 
 }  // extern "C"

@@ -398,6 +398,22 @@ void launch_coset_to_natural(cudaStream_t st, const u64* src, u64* dst, u32 ln, 
   coset_to_natural_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(src, dst, ln, D, src_limb_stride, dst_limb_stride); XFG_LAUNCHED(1);
 }
 
+// build_trace on the device (src/burn_mint_air.rs:442-476 with the state column of SURVEY B.2): columns 0-3, 5, 6 are the constants the step-0
+// assertions pin (AirParams::assert0), column 4 is floor(4 i / n).  The 8-argument entry point (xfg_prove_burn_mint_from_inputs) therefore
+// uploads no trace at all.  Two u64 per thread, 16-byte stores.
+__global__ void __launch_bounds__(256) trace_fill_kernel(u64* __restrict__ t, const AirParams* __restrict__ air, u32 ln) {
+  const size_t half = size_t(1) << (ln - 1), i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half) return;
+  const u32 c = blockIdx.y;
+  ulonglong2 v;
+  if (c == 4) { v.x = (8 * i) >> ln; v.y = (8 * i + 4) >> ln; } else { v.x = v.y = air->assert0[c]; }
+  reinterpret_cast<ulonglong2*>(t + ((size_t)c << ln))[i] = v;
+}
+void launch_trace_fill(cudaStream_t st, u64* trace, const AirParams* d_air, u32 ln) {
+  const size_t half = size_t(1) << (ln - 1);
+  trace_fill_kernel<<<dim3((unsigned)((half + 255) / 256), XFG_TRACE_WIDTH), 256, 0, st>>>(trace, d_air, ln); XFG_LAUNCHED(1);
+}
+
 // ---- 32-bit integer-pipe peak (xfg_int_pipe_peak): 8 independent chains per thread of the BLAKE3 operation mix
 // (LOP3 xor, IADD3, SHF rotate - all ALU-pipe instructions; 4 per group, checked in SASS), no memory traffic: the roofline denominator of the hashing kernels
 __global__ void __launch_bounds__(256) int_peak_kernel(const u32* __restrict__ in, u32* __restrict__ out, u32 iters) {

@@ -53,6 +53,7 @@ void launch_fri_fold(cudaStream_t st, int D, const u64* src, size_t src_limb_str
 void launch_int_peak(cudaStream_t st, const u32* in, u32* out, u32 blocks, u32 iters);
 void launch_pipe_probe(cudaStream_t st, int mode, const u32* in, u32* out, u32 blocks, u32 iters);
 void launch_field_selftest(cudaStream_t st, u32 op, const u64* a, const u64* b, size_t n, u64* out);
+void launch_trace_fill(cudaStream_t st, u64* trace, const AirParams* d_air, u32 ln);   // burn-mint build_trace on the device
 void launch_coset_to_natural(cudaStream_t st, const u64* src, u64* dst, u32 ln, int D, size_t src_limb_stride, size_t dst_limb_stride);
 
 }  // namespace xfg
