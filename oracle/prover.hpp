@@ -230,7 +230,7 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const AirDef& a
       domain /= F;
     } }
   { std::vector<u8> rb; put_elems(rb, remainder); put_u16(out, rb.size()); put_bytes(out, rb); }
-  out.push_back(1);           // num_partitions
+  out.push_back(0);           // FriProof::num_partitions is serialised as log2(partitions): 0 for the single partition of a serial prover (pinned by running the reference binary, tests/golden/reference_proofs.json)
   put_u64(out, nonce);
   st.ms[ST_BUILD_PROOF] = tm.lap();
 

@@ -74,7 +74,7 @@ std::string verify(const u8* proof, size_t proof_len, AirDef air, const ProofOpt
   std::vector<std::vector<u8>> fl_vals(num_layers), fl_paths(num_layers);
   for (size_t l = 0; l < num_layers; l++) { fl_vals[l] = rd.bytes(rd.uint(4)); fl_paths[l] = rd.bytes(rd.uint(4)); }
   std::vector<u8> rem_bytes = rd.bytes(rd.uint(2));
-  if (rd.uint(1) != 1) return "bad partition count";
+  if (rd.uint(1) != 0) return "bad partition count";   // log2(num_partitions), one partition
   u64 nonce = rd.uint(8);
   if (!rd.ok || rd.pos != proof_len) return "proof length mismatch";
 

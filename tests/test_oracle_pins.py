@@ -122,7 +122,7 @@ def test_wire_format_examples_from_the_survey():
     q = orc.prove(tr, pi, ac, (42, 8, 4, 2, 8, 31))
     assert q[:21].hex() == "07000006000008010000" "00ffffffff2a080402081f"
     assert proof[22:24] == (32 * 4).to_bytes(2, "little")                               # commitments: trace, constraint, 1 FRI layer, remainder
-    assert proof[-8:] == int(orc_nonce(tr, pi, ac)).to_bytes(8, "little") and proof[-9] == 1   # ... num_partitions = 1, pow_nonce
+    assert proof[-8:] == int(orc_nonce(tr, pi, ac)).to_bytes(8, "little") and proof[-9] == 0   # ... log2(num_partitions) = 0, pow_nonce
 
 
 def orc_nonce(tr, pi, ac, opts=orc.DEFAULT_OPTIONS):

@@ -181,7 +181,7 @@ def wide_quadratic_air(width, n, seed=1, extra_steps=()):
     return air, t
 
 
-def burn_mint_air(pub_inputs, txn, rcpt, nullifier, commitment, n):
+def burn_mint_air(pub_inputs, txn, rcpt, nullifier, commitment, n, last_step=None):
     """The normalised XfgBurnMintAir (src/burn_mint_air.rs:356-377 constraints, :383-394 assertions, :54-71 public inputs) written
     with the builder: the generic pipeline must emit the same proof bytes as the hand-written burn-mint kernels."""
     pi = [int(v) for v in pub_inputs]
@@ -197,5 +197,6 @@ def burn_mint_air(pub_inputs, txn, rcpt, nullifier, commitment, n):
     air.constraint(c[6] - int(commitment))
     for col, v in enumerate([pi[0], pi[1], pi[2], pi[3], 0, int(nullifier), int(commitment)]):
         air.assert_single(col, 0, v)
-    air.assert_single(4, n - 1, 3)
+    # last_step: the reference source pins the final state at step 63 whatever the trace length (src/burn_mint_air.rs:393); the normalised AIR uses n - 1
+    air.assert_single(4, n - 1 if last_step is None else last_step, 3)
     return air

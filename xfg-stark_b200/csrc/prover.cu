@@ -503,7 +503,7 @@ void assemble(const Plan& p, int D, u32 W, const u64 (*ood_frame)[2], const xfg_
   for (u32 l = 0; l < p.num_layers; l++) queries(g.t[2 + l], s.fri_positions[l], s.fri_num_positions[l]);
   out.u16_((size_t)s.remainder_len * D * 8);
   for (u32 i = 0; i < s.remainder_len; i++) for (int l = 0; l < D; l++) out.u64_(s.remainder[i][l]);
-  out.u8_(1);
+  out.u8_(0);   // FriProof::num_partitions as log2 (one partition), pinned against the reference binary
   out.u64_(s.nonce);
   bytes.swap(out.b);
 }
