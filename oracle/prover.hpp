@@ -6,9 +6,10 @@
 // like Winterfell (coefficient-domain DEEP with synthetic division, whole-vector FRI folding) so that the GPU
 // product - which computes the same values pointwise - is checked by an independently shaped computation.
 //
-// PARITY STATUS: the upstream crates are not in /root/reference and cannot be built here, and the reference holds
-// no golden vectors for this path: proof-byte parity with real Winterfell is UNPINNED.  What is
-// pinned: BLAKE3 (Python blake3), Keccak (src/lib.rs:141-148 KAT), field/NTT algebra (big-int), context bytes (A.12).
+// PARITY STATUS: PINNED.  The upstream crates are not in /root/reference, but the reference's shipped arm64 binary
+// (test-dist/xfg-stark-cli, winterfell 0.8.3 linked in) is executed here by oracle/a64emu; the proofs its prover emits
+// (tests/golden/reference_proofs.json) are byte-equal to this file's output on the same statement, trace and options
+// (tests/test_reference_binary_pins.py).  Also pinned: BLAKE3 (Python blake3), Keccak (src/lib.rs:141-148 KAT), field/NTT algebra (big-int).
 #pragma once
 #include <algorithm>
 #include <chrono>

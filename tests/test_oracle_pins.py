@@ -1,7 +1,8 @@
 """CPU tests (-m "not gpu"): pin the oracle (oracle/, test infrastructure) against every independent source available here:
 Python `blake3`, the reference's Keccak KAT (src/lib.rs:141-148), Python big integers for the field / extension / NTT algebra,
 the wire-format examples of SURVEY.md Appendix A, and the committed regression fixture tests/golden/proofs.json.
-Proof-byte parity with real Winterfell 0.8.3 is UNPINNED (no golden vectors in the reference, crates not buildable here)."""
+Proof-byte parity with real Winterfell 0.8.3 is pinned separately, against proofs emitted by the reference's own binary
+(tests/test_reference_binary_pins.py, tests/golden/reference_proofs.json)."""
 import hashlib
 import json
 import os
