@@ -520,7 +520,7 @@ def main():
                 "proofs_per_s": args.steps * world / (e2e_ms / 1e3)},
         "e2e_callers_ms": {"pinned_contiguous_canonical": e2e_ms / (args.steps * world), "from_inputs_device_built_trace": callers["from_inputs"],
                            "registered_montgomery_columns": callers["mont_cols"], "pageable_contiguous_canonical": callers["pageable"],
-                           "note": "same proof bytes on every path (asserted); from_inputs uploads 160 B, the others the 7 x n x 8 B trace"},
+                           "note": "same proof bytes on every path (asserted); from_inputs uploads only the 1 KB init block of the proof state, the others also the 7 x n x 8 B trace"},
         "gpu_launches": times["kernel_launches"] * args.steps,
         "device_ms_per_proof": times["device_ms"],
         "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},

@@ -9,7 +9,7 @@
 // coalesced loads of LDE columns, and the random linear combination is accumulated un-reduced (DotAcc).
 #include "../../include/xfg_stark.h"
 #include "generic_air.cuh"
-#include "coin.cuh"
+#include "b3_rolled.cuh"
 #include "field_weak.cuh"
 #include "launch.cuh"
 
@@ -17,8 +17,9 @@ namespace xfg {
 
 // after the trace commitment: draw the transition then the boundary coefficients (A.8)
 template <int D> __global__ void __launch_bounds__(32) gen_trace_root_kernel(ProofState* ps, GenState* gs, const GenProgram* __restrict__ prog, const Digest* __restrict__ tree) {
-  Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
-  const bool ok = coin_draw_many<D>(c, prog->num_constraints + prog->num_assertions, gs->coef);
+  Coin c; c.seed = r_hash_limbs(ps->seed_limbs, (int)ps->seed_count); c.counter = 0;      // coin seed (A.4), see trace_root_kernel
+  const Digest root = tree[1]; r_reseed(c, root);
+  const bool ok = r_draw_many<D>(c, prog->num_constraints + prog->num_assertions, gs->coef);
   if (lane_id() == 0) { ps->trace_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
   coin_store(ps, c);
 }
@@ -145,30 +146,24 @@ template <int D> __global__ void __launch_bounds__(32 * GOF_WARPS) gen_ood_finis
   Coin c = coin_load(ps);
   for (u32 t = lane; t < 2 * W * D; t += 32) { const u32 l = t % D, w = (t / D) & 1u, j = t / (2 * D); limbs[t] = sums[j][w][l]; }   // interleaved per column (A.9)
   __syncwarp();
-  // hash_elements(frame): up to 4 BLAKE3 chunks of 128 limbs; lane c hashes chunk c, lane 0 merges the chaining values (tree mode)
+  // hash_elements(frame): up to 4 BLAKE3 chunks of 128 limbs; lane c hashes chunk c, then every lane merges the chaining values (tree mode)
   Digest d;
   {
     const int nl = (int)(2 * W * D), chunks = nl <= 128 ? 1 : (nl + 127) / 128;
-    u32 cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if ((int)lane < chunks) { int cl = nl - (int)lane * 128; if (cl > 128) cl = 128; b3_chunk_dyn(limbs + lane * 128, cl, lane, chunks == 1, cv); }
-    u32 c1[8], c2[8], c3[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { c1[i] = __shfl_sync(0xFFFFFFFFu, cv[i], 1); c2[i] = __shfl_sync(0xFFFFFFFFu, cv[i], 2); c3[i] = __shfl_sync(0xFFFFFFFFu, cv[i], 3); }
-    if (lane == 0) {
-      if (chunks == 1) { for (int i = 0; i < 8; i++) d.w[i] = cv[i]; }
-      else if (chunks == 2) b3_parent(cv, c1, true, d.w);
-      else { u32 l[8]; b3_parent(cv, c1, false, l);
-             if (chunks == 3) b3_parent(l, c2, true, d.w); else { u32 r[8]; b3_parent(c2, c3, false, r); b3_parent(l, r, true, d.w); } }
-    }
+    Digest cv = iv_digest();
+    { const int cc = (int)lane < chunks ? (int)lane : 0; int cl = nl - cc * 128; if (cl > 128) cl = 128; cv = r_chunk(limbs + cc * 128, cl, (u32)cc, chunks == 1); }
+    const Digest c0 = bcast_digest(cv, 0), c1 = bcast_digest(cv, 1), c2 = bcast_digest(cv, 2), c3 = bcast_digest(cv, 3);
+    if (chunks == 1) d = c0;
+    else if (chunks == 2) d = r_parent(c0, c1, true);
+    else { const Digest l = r_parent(c0, c1, false); d = chunks == 3 ? r_parent(l, c2, true) : r_parent(l, r_parent(c2, c3, false), true); }
   }
-  d = bcast_digest(d, 0);
-  coin_reseed(c, d);
+  r_reseed(c, d);
   // H(z) = P_limb0(z) + phi * P_limb1(z), phi = (0,1): (a0,a1) * phi = (-2 a1, a0 + a1)
   Ext<D> hz = ldx<D>(sums[W][0]);
   if (D == 2) { const u64 a0 = sums[W + 1][0][0], a1 = sums[W + 1][0][1]; hz = hz + Ext<D>(gl_neg(gl_dbl(a1)), gl_add(a0, a1)); }
   u64 hl[2] = {hz.limb(0), hz.limb(1)};
-  coin_reseed(c, b3_hash_limbs<D>(hl));
-  const bool ok = coin_draw_many<D>(c, W + 1, gs->dcoef);      // width trace coefficients, then 1 composition column
+  r_reseed(c, r_hash_limbs(hl, D));
+  const bool ok = r_draw_many<D>(c, W + 1, gs->dcoef);      // width trace coefficients, then 1 composition column
   __syncwarp();
   Ext<D> c1, c2;
   for (u32 j = lane; j < W; j += 32) { const Ext<D> g = ldx<D>(gs->dcoef[j]); c1 = c1 + g * ldx<D>(sums[j][0]); c2 = c2 + g * ldx<D>(sums[j][1]); }

@@ -77,12 +77,13 @@ struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 struct Slot {
   cudaStream_t st = nullptr, copy_st = nullptr, aux_st[3] = {nullptr, nullptr, nullptr};   // copy_st: column-wise trace upload overlapped with the first NTTs; aux_st: every other column group
   cudaEvent_t col_ev[XFG_TRACE_WIDTH] = {nullptr}, fork_ev = nullptr, fork2_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+  u32 tail_threads = 1024;                                  // block size of the fused FRI tail kernel: 1024 for one proof at a time, 256 when proofs are pipelined over the slots
   bool fill_trace = false;                                  // burn-mint trace generated on the device (xfg_prove_burn_mint_from_inputs): no upload
   bool split_upload = false; const u64* up_cols[XFG_TRACE_WIDTH] = {nullptr};   // split upload: the (pinned) host columns the copies read, issued inside enqueue_proof
   u64 in_scale = 1;                                         // 1 for canonical input, R^-1 = 2^-64 for Montgomery-form columns: folded into the 1/n of the interpolation
   u64* slab = nullptr; size_t slab_words = 0;
-  ProofState* d_state = nullptr; u64* d_seed = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
-  ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;
+  ProofState* d_state = nullptr; u64* d_partial = nullptr; u64* d_material = nullptr;
+  ProofState* h_state = nullptr; u64* h_material = nullptr; u64* h_seed = nullptr; u64* h_trace = nullptr;   // h_seed: pinned mirror of the init block of ProofState
   AirParams* d_air = nullptr; AirParams* h_air = nullptr;
   // generic AIR front-end (xfg_prove_air): compiled program + AIR-sized state; W = trace width of the proof in flight
   GenProgram* d_prog = nullptr; GenProgram* h_prog = nullptr; GenState* d_gen = nullptr; u64 (*h_ood)[2] = nullptr;
@@ -291,12 +292,13 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
       CU(cudaEventRecord(s.col_ev[g], s.copy_st));
     }
   }
-  CU(cudaMemcpyAsync(s.d_seed, s.h_seed, (size_t)s.seed_count * 8, cudaMemcpyHostToDevice, st));
+  // init block of the proof state (coin seed elements, their count, cleared error flags, unset nonce) in one copy: no seeding kernel.  The pinned
+  // mirror is completed by launch_prepared for EVERY proof (a replayed graph reads it at execution time)
+  CU(cudaMemcpyAsync(s.d_state, s.h_seed, PROOF_INIT_BYTES, cudaMemcpyHostToDevice, st));
   if (gen) CU(cudaMemcpyAsync(s.d_prog, s.h_prog, offsetof(GenProgram, code) + (size_t)s.h_prog->num_instr * sizeof(GenInstr), cudaMemcpyHostToDevice, st));
   else CU(cudaMemcpyAsync(s.d_air, s.h_air, sizeof(AirParams), cudaMemcpyHostToDevice, st));
   mark();   // ev0: start of device work
   if (s.fill_trace && !d_trace && !gen) PROF("trace_fill", launch_trace_fill(st, c.trace_in, s.d_air, ln));
-  PROF("transcript", launch_seed(st, s.d_state, s.d_seed, (int)s.seed_count));
   // 1 ---- extend_execution_trace: interpolate the 7 columns, evaluate on the 8 cosets s_k * <w_n>
   // With a split upload the trace goes column by column so that a column's NTTs start as soon as its copy has landed.  (Running
   // the HBM-resident path column by column as well - to keep one column's 64 MB four-step intermediate inside the L2 - was
@@ -356,8 +358,11 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   { const u64* dcoef = gen ? &s.d_gen->dcoef[0][0] : reinterpret_cast<const u64*>(reinterpret_cast<const char*>(s.d_state) + offsetof(ProofState, dcoef));
     PROF("deep", launch_deep(st, D, c.lde, c.h_lde, ln, s.d_state, dcoef, W, p.ntt.wn_fwd, p.d_sk, c.deep, p.num_layers ? c.fri_tree[0] : nullptr)); }
   mark();
-  // 6 ---- compute_fri_layers
-  for (u32 l = 0; l < p.num_layers; l++) {
+  // 6 ---- compute_fri_layers: one tree / commit / fold launch set per large layer; every layer of <= 2^14 evaluations, the remainder, the
+  //   ---- grinding nonce and the query positions (7) run in ONE single-CTA launch (fri_tail.cu)
+  u32 first_tail = p.num_layers;
+  while (first_tail > 0 && p.layer_log[first_tail - 1] <= FRI_TAIL_MAX_LOG) first_tail--;
+  for (u32 l = 0; l < first_tail; l++) {
     PROF("fri.tree", merkle_build_upper(st, c.fri_tree[l], size_t(1) << (p.layer_log[l] - 3)));
     PROF("transcript", launch_fri_commit(st, D, s.d_state, c.fri_tree[l], l));
     PROF("fri.fold", launch_fri_fold(st, D, c.fri_evals[l], l == 0 ? N : (size_t(1) << p.layer_log[l]), l == 0, p.layer_log[l], l, s.d_state, p.wN_inv, p.lN, p.fc,
@@ -365,13 +370,19 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   }
   { const u64* rin = c.fri_evals[p.num_layers]; const size_t Rm = size_t(1) << p.rem_log;
     if (p.num_layers == 0) { launch_coset_to_natural(st, c.deep, c.rem_in, ln, D, N, Rm); rin = c.rem_in; }
-    NttJob j{}; j.src = rin; j.dst = c.rem_coef; j.ln = p.rem_log; j.batch = D; j.src_tstride = Rm; j.dst_tstride = Rm; j.src_div = 1;
-    j.inverse = true; j.scale = p.rem_ninv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 1; PROF("fri.remainder", ntt_batch(st, p.ntt, j));
-    PROF("transcript", launch_remainder(st, D, s.d_state, c.rem_coef, Rm, p.rem_len)); }
-  mark();
-  // 7 ---- determine_query_positions
-  PROF("grind", launch_grind(st, s.d_state, o.grinding_factor));
-  PROF("transcript", launch_positions(st, s.d_state, o.num_queries, p.lN, p.num_layers));
+    FriTailArgs ta{}; ta.first_layer = first_tail; ta.num_layers = p.num_layers;
+    for (u32 l = 0; l <= p.num_layers; l++) { ta.layer_log[l] = p.layer_log[l]; ta.evals[l] = c.fri_evals[l]; ta.limb_stride[l] = l == 0 ? N : (u64(1) << p.layer_log[l]); }
+    for (u32 l = 0; l < p.num_layers; l++) ta.tree[l] = c.fri_tree[l];
+    ta.rem_in = rin; ta.rem_stride = Rm; ta.rem_log = p.rem_log; ta.rem_len = p.rem_len; ta.rem_ninv = p.rem_ninv;
+    ta.tw_inv = p.ntt.tw_inv; ta.un_lo = p.un_lo; ta.wN_inv = p.wN_inv; ta.lN = p.lN; ta.fc = p.fc;
+    ta.grinding = o.grinding_factor; ta.num_queries = o.num_queries; ta.do_grind = o.grinding_factor <= FRI_TAIL_MAX_GRIND;
+    PROF("fri.tail", launch_fri_tail(st, D, ta, s.d_state, s.tail_threads));
+    mark();
+    // 7 ---- determine_query_positions (inside the tail kernel unless the grinding factor needs the whole chip)
+    if (!ta.do_grind) {
+      PROF("grind", launch_grind(st, s.d_state, o.grinding_factor));
+      PROF("transcript", launch_positions(st, s.d_state, o.num_queries, p.lN, p.num_layers));
+    } }
   mark();
   // 8 ---- build_proof_object: gather opened rows + authentication nodes, copy out
   const size_t mat_words = build_gather(p, D, s.W, o, c, s.tasks);
@@ -393,12 +404,13 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
 // when no per-stage timing is requested and the upload is not split, otherwise launch by launch.
 // the slot's per-proof inputs (seed elements, AIR constants or compiled program, width) have been prepared in its pinned mirrors
 int launch_prepared(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const u64* d_trace, bool timed) {
+  { u32* tail = reinterpret_cast<u32*>(s.h_seed + MAX_SEED_LIMBS); tail[0] = s.seed_count; tail[1] = 0; tail[2] = tail[3] = 0xFFFFFFFFu; }   // seed_count, error_flags = 0, nonce = ~0
   { Carve c; carve(s, p, D, c); if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length"); }
   const bool use_graph = ctx->graphs && !timed && !ctx->profiling;
   if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);
   const bool split = s.split_upload && !d_trace;
   std::array<const void*, XFG_TRACE_WIDTH> srcs{}; if (split) for (int c = 0; c < XFG_TRACE_WIDTH; c++) srcs[c] = s.up_cols[c];
-  const GraphKey key{&p, d_trace, D, o.num_queries, o.grinding_factor + (s.in_scale != 1 ? 256u : 0u), s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0, srcs, s.fill_trace && !d_trace};
+  const GraphKey key{&p, d_trace, D, o.num_queries + (s.tail_threads << 16), o.grinding_factor + (s.in_scale != 1 ? 256u : 0u), s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0, srcs, s.fill_trace && !d_trace};
   auto it = s.graphs.find(key);
   if (it == s.graphs.end()) {
     if (s.graphs.size() >= 16) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec); s.graphs.clear(); }   // bounded cache (callers that keep changing the device trace pointer)
@@ -600,7 +612,7 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1;
   g_xfg_launches = 0;
   if (times) { std::memset(times, 0, sizeof *times); cudaEventRecord(s.ev[XFG_NUM_STAGES + 2], s.st); }
-  s.split_upload = false; s.generic = false; s.W = XFG_TRACE_WIDTH; s.fill_trace = fill;
+  s.split_upload = false; s.generic = false; s.W = XFG_TRACE_WIDTH; s.fill_trace = fill; s.tail_threads = 1024;
   // Montgomery-form input (x * 2^64 mod p, what winter-math's BaseElement holds in memory): the interpolation is linear, so the factor
   // 2^-64 rides on its 1/n scale (2^64 = 2^32 - 1 mod p) and costs nothing
   s.in_scale = form == XFG_FORM_MONTGOMERY ? gl_inv(0xFFFFFFFFull) : 1;
@@ -612,7 +624,7 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
     cudaEventElapsedTime(&times->h2d_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[0]);
     cudaEventElapsedTime(&times->total_ms, s.ev[XFG_NUM_STAGES + 2], s.ev[XFG_NUM_STAGES + 1]);
     times->kernel_launches = g_xfg_launches;
-    times->h2d_bytes = ((h_trace || h_cols) ? (size_t)s.W * p->n * 8 : 0) + (size_t)s.seed_count * 8;
+    times->h2d_bytes = ((h_trace || h_cols) ? (size_t)s.W * p->n * 8 : 0) + PROOF_INIT_BYTES;
     times->d2h_bytes = sizeof(ProofState) + s.mat_words * 8;
   }
   return rc;
@@ -684,10 +696,10 @@ int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t 
     for (auto& e : s.col_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming)); CUB(cudaEventCreateWithFlags(&s.fork2_ev, cudaEventDisableTiming)); for (auto& e : s.join_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaMalloc(&s.slab, words * 8)); s.slab_words = words;
-    CUB(cudaMalloc(&s.d_state, sizeof(ProofState))); CUB(cudaMalloc(&s.d_seed, 128 * 8));
+    CUB(cudaMalloc(&s.d_state, sizeof(ProofState)));
     CUB(cudaMalloc(&s.d_partial, (size_t)(XFG_AIR_MAX_WIDTH + 2) * OOD_MAX_BLOCKS * 4 * 8)); CUB(cudaMalloc(&s.d_material, MATERIAL_WORDS * 8));
     CUB(cudaMallocHost(&s.h_state, sizeof(ProofState))); CUB(cudaMallocHost(&s.h_material, MATERIAL_WORDS * 8));
-    CUB(cudaMallocHost(&s.h_seed, 128 * 8)); CUB(cudaMallocHost(&s.h_trace, trace_words * 8));
+    CUB(cudaMallocHost(&s.h_seed, PROOF_INIT_BYTES)); CUB(cudaMallocHost(&s.h_trace, trace_words * 8));
     CUB(cudaMalloc(&s.d_air, sizeof(AirParams))); CUB(cudaMallocHost(&s.h_air, sizeof(AirParams)));
     CUB(cudaMalloc(&s.d_prog, sizeof(GenProgram))); CUB(cudaMallocHost(&s.h_prog, sizeof(GenProgram))); CUB(cudaMalloc(&s.d_gen, sizeof(GenState)));
     CUB(cudaMallocHost(&s.h_ood, sizeof(u64) * 2 * 2 * XFG_AIR_MAX_WIDTH));
@@ -702,7 +714,7 @@ void xfg_destroy(xfg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (Slot& s : ctx->slots) {
     if (s.st) cudaStreamSynchronize(s.st);
-    cudaFree(s.slab); cudaFree(s.d_state); cudaFree(s.d_seed); cudaFree(s.d_partial); cudaFree(s.d_material);
+    cudaFree(s.slab); cudaFree(s.d_state); cudaFree(s.d_partial); cudaFree(s.d_material);
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
     cudaFree(s.d_air); cudaFreeHost(s.h_air);
     cudaFree(s.d_prog); cudaFreeHost(s.h_prog); cudaFree(s.d_gen); cudaFreeHost(s.h_ood);
@@ -781,7 +793,7 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
     if (s.busy) { rc = finish_proof(ctx, s, out + (size_t)s.proof_index * out_stride, out_stride, &out_lens[s.proof_index], nullptr); if (rc && !first_err) first_err = rc; }
     if ((rc = check_air(ctx, &airs[i]))) { drain_slots(ctx); return rc; }
     if (!traces[i]) { drain_slots(ctx); return fail(ctx, XFG_ERR_BAD_ARGS, "null trace"); }
-    s.generic = false; s.W = XFG_TRACE_WIDTH; s.fill_trace = false; s.in_scale = 1;
+    s.generic = false; s.W = XFG_TRACE_WIDTH; s.fill_trace = false; s.in_scale = 1; s.tail_threads = 256;
     if ((rc = upload_trace(ctx, s, *p, D, traces[i], false))) { drain_slots(ctx); return rc; }
     s.proof_index = i;
     if ((rc = launch_proof(ctx, s, *p, D, *o, airs[i], nullptr, false))) { drain_slots(ctx); return rc; }

@@ -53,6 +53,19 @@ void launch_fri_fold(cudaStream_t st, int D, const u64* src, size_t src_limb_str
 void launch_int_peak(cudaStream_t st, const u32* in, u32* out, u32 blocks, u32 iters);
 void launch_pipe_probe(cudaStream_t st, int mode, const u32* in, u32* out, u32 blocks, u32 iters);
 void launch_field_selftest(cudaStream_t st, u32 op, const u64* a, const u64* b, size_t n, u64* out);
+// fri_tail.cu: the FRI layers of at most 2^FRI_TAIL_MAX_LOG evaluations, the remainder, the grinding nonce and the query positions in one launch
+static constexpr u32 FRI_TAIL_MAX_LOG = 14, FRI_TAIL_MAX_GRIND = 12, NTT_TW_LOG_TAIL = 12;
+struct FriTailArgs {
+  u32 first_layer, num_layers, layer_log[MAX_LAYERS + 1];      // layers [first_layer, num_layers) are folded here
+  u64* evals[MAX_LAYERS + 1]; u64 limb_stride[MAX_LAYERS + 1]; // evaluations of layer l: natural order [limb][i] (layer 0: coset-major DEEP evaluations)
+  Digest* tree[MAX_LAYERS];                                    // heap-ordered trees; the leaves of tree[first_layer] are already hashed
+  const u64* rem_in; u64 rem_stride; u32 rem_log, rem_len; u64 rem_ninv;   // remainder: evaluations of the last layer, natural order
+  const u64* tw_inv; const u64* un_lo;                         // w_4096^-i (i < 2048); 7^-j (j < 4096)
+  PowTable wN_inv; u32 lN; FriConsts fc;
+  u32 grinding, num_queries, do_grind;                         // do_grind = 0: stop after the remainder (grind / positions kernels follow)
+  u32 limbs_off;                                               // set by the launcher: shared-memory offset (words) of the remainder limbs
+};
+void launch_fri_tail(cudaStream_t st, int D, FriTailArgs a, ProofState* ps, u32 threads);
 void launch_trace_fill(cudaStream_t st, u64* trace, const AirParams* d_air, u32 ln);   // burn-mint build_trace on the device
 void launch_coset_to_natural(cudaStream_t st, const u64* src, u64* dst, u32 ln, int D, size_t src_limb_stride, size_t dst_limb_stride);
 

@@ -20,7 +20,12 @@ static constexpr int NUM_OOD_POLYS = XFG_TRACE_WIDTH + 2;   // 7 trace polys + u
 
 enum : u32 { ERR_FLAG_DEGREE = 1u, ERR_FLAG_COIN = 2u, ERR_FLAG_NONCANONICAL = 4u };
 
+static constexpr int MAX_SEED_LIMBS = 8 + XFG_AIR_MAX_PUB_INPUTS;   // Context::to_elements (8) + public inputs
+
 struct ProofState {
+  // ---- per-proof inputs: this block is written by ONE host->device copy from the slot's pinned mirror at the start of every proof (no
+  // seeding kernel): the coin seed elements (A.4), and the reset values of the error flags and of the grinding nonce
+  u64 seed_limbs[MAX_SEED_LIMBS]; u32 seed_count; u32 error_flags; unsigned long long nonce;   // nonce: ~0 until the grinding search has found it
   // coin
   Digest seed; u64 counter;
   // commitments
@@ -34,12 +39,12 @@ struct ProofState {
   u64 deep_c1[2], deep_c2[2];              // sum_j gamma_j T_j(z) + delta H(z)   and   sum_j gamma_j T_j(zg)
   u64 alphas[MAX_LAYERS][2];
   u64 remainder[MAX_REMAINDER][2]; u32 remainder_len;
-  // queries
-  unsigned long long nonce;
+  // queries (the grinding nonce lives in the init block above)
   u32 num_positions; u32 positions[MAX_Q];
   u32 fri_num_positions[MAX_LAYERS]; u32 fri_positions[MAX_LAYERS][MAX_Q];
-  u32 error_flags;
 };
+static constexpr size_t PROOF_INIT_BYTES = sizeof(u64) * MAX_SEED_LIMBS + 16;
+static_assert(PROOF_INIT_BYTES == offsetof(ProofState, seed), "init block layout");
 
 // AIR constants and boundary values (src/burn_mint_air.rs:335-395), passed by value to the constraint kernel
 struct AirParams {

@@ -7,31 +7,24 @@
 // `ConstraintCommitment::query`, `FriProver::build_proof` (A.4, A.5, A.9-A.11).
 // The serial steps are single-warp kernels (lanes hash candidate counters in parallel) so the proof needs no host round trip.
 #include "transcript.cuh"
-#include "coin.cuh"
+#include "b3_rolled.cuh"
 #include "launch.cuh"
 
 namespace xfg {
 
-// coin = hash_elements(context elements || public inputs)  (A.4)
-__global__ void __launch_bounds__(32) seed_kernel(ProofState* ps, const u64* __restrict__ seed_limbs, int count) {
-  if (lane_id() == 0) {
-    u64 l[8 + XFG_NUM_PUB_INPUTS];
-#pragma unroll
-    for (int i = 0; i < 8 + XFG_NUM_PUB_INPUTS; i++) l[i] = seed_limbs[i];
-    ps->seed = count == 8 + XFG_NUM_PUB_INPUTS ? b3_hash_limbs<8 + XFG_NUM_PUB_INPUTS>(l) : b3_hash_limbs_dyn(seed_limbs, count);
-    ps->counter = 0; ps->error_flags = 0; ps->nonce = ~0ull;
-  }
-}
+// coin = hash_elements(context elements || public inputs) (A.4), computed here from the seed elements the host copied into the proof state (no
+// separate seeding launch); then commit_trace: reseed with the root, draw the constraint composition coefficients
 template <int D> __global__ void __launch_bounds__(32) trace_root_kernel(ProofState* ps, const Digest* __restrict__ tree) {
-  Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
+  Coin c; c.seed = r_hash_limbs(ps->seed_limbs, (int)ps->seed_count); c.counter = 0;
+  const Digest root = tree[1]; r_reseed(c, root);
   // transition coefficients first, then boundary (A.8): tcoef[7] and bcoef[8] are contiguous in ProofState
-  const bool ok = coin_draw_many<D>(c, XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS, ps->tcoef);
+  const bool ok = r_draw_many<D>(c, XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS, ps->tcoef);
   if (lane_id() == 0) { ps->trace_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
   coin_store(ps, c);
 }
 template <int D> __global__ void __launch_bounds__(32) constraint_root_kernel(ProofState* ps, const Digest* __restrict__ tree, u64 g_n) {
-  Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
-  const bool ok = coin_draw_many<D>(c, 1, &ps->z);
+  Coin c = coin_load(ps); const Digest root = tree[1]; r_reseed(c, root);
+  const bool ok = r_draw_many<D>(c, 1, &ps->z);
   if (lane_id() == 0) { ps->constraint_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; stx<D>(ps->zg, mul_base(ldx<D>(ps->z), g_n)); }
   coin_store(ps, c);
 }
@@ -67,13 +60,13 @@ template <int D> __global__ void __launch_bounds__(32 * NUM_OOD_POLYS) ood_finis
     for (int w = 0; w < 2; w++)
 #pragma unroll
       for (int l = 0; l < D; l++) limbs[(2 * j + w) * D + l] = sums[j][w][l];   // interleaved per column (A.9)
-  coin_reseed(c, b3_hash_limbs<2 * XFG_TRACE_WIDTH * D>(limbs));
+  r_reseed(c, r_hash_limbs(limbs, 2 * XFG_TRACE_WIDTH * D));
   // H(z) = P_limb0(z) + phi * P_limb1(z), phi = (0,1): (a0,a1) * phi = (-2 a1, a0 + a1)
   Ext<D> hz = ldx<D>(sums[XFG_TRACE_WIDTH][0]);
   if (D == 2) { const u64 a0 = sums[XFG_TRACE_WIDTH + 1][0][0], a1 = sums[XFG_TRACE_WIDTH + 1][0][1]; hz = hz + Ext<D>(gl_neg(gl_dbl(a1)), gl_add(a0, a1)); }
   u64 hl[2] = {hz.limb(0), hz.limb(1)};
-  coin_reseed(c, b3_hash_limbs<D>(hl));
-  const bool ok = coin_draw_many<D>(c, XFG_TRACE_WIDTH + 1, ps->dcoef);      // 7 trace coefficients, then 1 composition column
+  r_reseed(c, r_hash_limbs(hl, D));
+  const bool ok = r_draw_many<D>(c, XFG_TRACE_WIDTH + 1, ps->dcoef);      // 7 trace coefficients, then 1 composition column
   __syncwarp();
   // C1 = sum_j gamma_j T_j(z) + delta H(z), C2 = sum_j gamma_j T_j(zg): lane (w, j) computes one product, lane 0 adds them up
   if (lane_id() < 2 * (XFG_TRACE_WIDTH + 1)) {
@@ -95,8 +88,8 @@ template <int D> __global__ void __launch_bounds__(32 * NUM_OOD_POLYS) ood_finis
   coin_store(ps, c);
 }
 template <int D> __global__ void __launch_bounds__(32) fri_commit_kernel(ProofState* ps, const Digest* __restrict__ tree, u32 layer) {
-  Coin c = coin_load(ps); const Digest root = tree[1]; coin_reseed(c, root);
-  const bool ok = coin_draw_many<D>(c, 1, &ps->alphas[layer]);
+  Coin c = coin_load(ps); const Digest root = tree[1]; r_reseed(c, root);
+  const bool ok = r_draw_many<D>(c, 1, &ps->alphas[layer]);
   if (lane_id() == 0) { ps->fri_roots[layer] = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
   coin_store(ps, c);
 }
@@ -109,10 +102,8 @@ template <int D> __global__ void __launch_bounds__(32) remainder_kernel(ProofSta
     ps->remainder[i][l] = v; if (l < (u32)D) limbs[i * D + l] = v;
   }
   __syncwarp();
-  Digest d;
-  if (lane_id() == 0) d = b3_hash_limbs_dyn(limbs, len * D);
-  d = bcast_digest(d, 0);
-  coin_reseed(c, d);
+  const Digest d = r_hash_limbs(limbs, (int)(len * D));     // every lane computes the same digest
+  r_reseed(c, d);
   if (lane_id() == 0) { ps->remainder_len = len; ps->remainder_commitment = d; }
   coin_store(ps, c);
 }
@@ -136,9 +127,9 @@ __global__ void __launch_bounds__(32) positions_kernel(ProofState* ps, u32 num_q
   __shared__ u32 raw[256], srt[256], cur[256], nxt[256];
   __shared__ u32 s_cnt;
   Coin c = coin_load(ps);
-  c.seed = b3_merge_int(c.seed, ps->nonce); c.counter = 0;
+  c.seed = r_merge_int(c.seed, ps->nonce); c.counter = 0;
   const u64 mask = (1ull << lN) - 1; const u32 lane = lane_id();
-  for (u32 i = lane; i < num_queries; i += 32) { const Digest d = b3_merge_int(c.seed, (u64)i + 1); raw[i] = (u32)(((u64)d.w[0] | ((u64)d.w[1] << 32)) & mask); }
+  for (u32 i = lane; i < num_queries; i += 32) { const Digest d = r_merge_int(c.seed, (u64)i + 1); raw[i] = (u32)(((u64)d.w[0] | ((u64)d.w[1] << 32)) & mask); }
   c.counter = num_queries;
   __syncwarp();
   for (u32 i = lane; i < num_queries; i += 32) {       // stable rank sort
@@ -199,7 +190,6 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherTasks tasks, const Pr
   }
 }
 
-void launch_seed(cudaStream_t st, ProofState* ps, const u64* seed_limbs, int count) { seed_kernel<<<1, 32, 0, st>>>(ps, seed_limbs, count); XFG_LAUNCHED(1); }
 void launch_trace_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree) {
   if (D == 1) trace_root_kernel<1><<<1, 32, 0, st>>>(ps, tree); else trace_root_kernel<2><<<1, 32, 0, st>>>(ps, tree);
   XFG_LAUNCHED(1);

@@ -15,7 +15,6 @@ struct GatherTask {
 };
 struct GatherTasks { GatherTask t[2 + MAX_LAYERS]; u32 count; };
 
-void launch_seed(cudaStream_t st, ProofState* ps, const u64* seed_limbs, int count);
 void launch_trace_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree);
 void launch_constraint_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u64 g_n);
 void launch_ood_finish(cudaStream_t st, int D, ProofState* ps, const u64* partial, u32 nb);
