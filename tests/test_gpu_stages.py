@@ -132,6 +132,23 @@ def test_lde_commit_matches_oracle(ctx, n_log2, cols):
     assert (c0[:n] == orc.ntt(tr[0], 1, 1)).all() and not c0[n:].any()
 
 
+def test_lde_three_pass_plan_2p24_matches_oracle():
+    """2^24 points run as three passes of 2^8-point tiles (16 columns, 128-byte runs) instead of two passes of 2^12-point tiles: the
+    interpolation and all eight coset transforms of one column equal the oracle's, element by element (config 5's transform size)"""
+    import xfg_stark_b200 as xs
+    n_log2 = 24; n = 1 << n_log2
+    rng = np.random.default_rng(24)
+    col = rand_elems(rng, (1, n))
+    orc.set_threads(orc.max_threads())
+    coef = orc.ntt(col[0], 1, 1)
+    with xs.Context(device=0, max_n_log2=n_log2, num_slots=1) as c:
+        lde, _ = c.lde_commit(col)
+    exp = orc.lde(coef)
+    orc.set_threads(1)
+    assert lde.shape == (1, 8 * n)
+    assert (lde[0] == exp).all()
+
+
 @pytest.mark.parametrize("ext", [1, 2])
 @pytest.mark.parametrize("n_log2", [3, 6, 11])
 def test_eval_constraints_matches_oracle(ctx, ext, n_log2):

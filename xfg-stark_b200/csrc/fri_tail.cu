@@ -28,7 +28,14 @@ template <int D>
 __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailArgs a, ProofState* ps) {
   extern __shared__ u64 sm[];                        // tree nodes of the current layer / remainder interpolation (2^rem_log x D); then the remainder limbs
   const u32 TAIL_THREADS = blockDim.x;
-  __shared__ u32 raw[256], srt[256], cur[256], nxt[256];
+#ifdef XFG_TAIL_CLOCKS
+  int ck = 0;
+#define TCK() do { if (threadIdx.x == 0 && ck < 48) { ps->dbg_clk[ck++] = clock64(); } } while (0)
+#else
+#define TCK() do {} while (0)
+#endif
+  TCK();
+  __shared__ u32 raw[256], srt[256], cur[256];
   __shared__ unsigned long long s_nonce;
   const u32 tid = threadIdx.x, lane = tid & 31;
   // ---- FRI layers first .. num_layers-1 (A.10) ----
@@ -44,6 +51,7 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
       }
       __syncthreads();
     }
+    TCK();
     if (tid < 32) {                                  // commit_fri_layer + draw_fri_alpha
       Coin c = coin_load(ps); const Digest root = load_digest(snode + 1); c.seed = r_merge(c.seed, root); c.counter = 0;
       const bool ok = r_draw_many<D>(c, 1, &ps->alphas[l]);
@@ -51,6 +59,7 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
       coin_store(ps, c);
     }
     __syncthreads();
+    TCK();
     // apply_drp: next[r] = P_r(alpha), P_r interpolating row r = values at r + j R over x_r w_8^j, x_r = 7 w_Nl^r
     const Ext<D> alpha = ld_ext<D>(ps->alphas, l);
     const u64* src = a.evals[l]; u64* dst = a.evals[l + 1];
@@ -70,6 +79,7 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
       for (int q = 0; q < D; q++) dst[(size_t)q * dstride + r] = w.limb(q);
     }
     __syncthreads();
+    TCK();
     if (l + 1 < a.num_layers) {                      // hash_values: leaves of the next layer's tree, row i' = values at i' + q Rn
       Digest* nt = a.tree[l + 1];
       for (size_t ip = tid; ip < Rn; ip += TAIL_THREADS) {
@@ -82,6 +92,7 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
       }
       __syncthreads();
     }
+    TCK();
   }
   // ---- remainder: coset interpolation (offset 7) of the last layer's evaluations, first rem_len coefficients (A.10) ----
   {
@@ -98,6 +109,7 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
       }
       __syncthreads();
     }
+    TCK();
     // c_j = X_j / L * 7^-j ; limbs interleaved per coefficient for hash_elements
     u64* limbs = sm + a.limbs_off;
     for (u32 e = tid; e < a.rem_len * 2; e += TAIL_THREADS) {
@@ -116,6 +128,7 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
     }
     if (tid == 0) s_nonce = ~0ull;
     __syncthreads();
+    TCK();
   }
   if (!a.do_grind) return;                           // large grinding factors: the multi-CTA grind kernel and positions_kernel follow
   // ---- grinding: smallest nonce >= 1 whose hash has `grinding` trailing zero bits (A.5); candidates in rounds of 1024 ----
@@ -131,21 +144,13 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
       __syncthreads();
     }
     if (tid == 0) ps->nonce = s_nonce;
+    TCK();
   }
-  if (tid >= 32) return;
-  // ---- draw_integers(q, N, nonce) -> sort -> dedup, then fold_positions per layer (one warp, as positions_kernel) ----
-  Coin c = coin_load(ps);
-  c.seed = r_merge_int(c.seed, s_nonce); c.counter = 0;
+  // ---- draw_integers(q, N, nonce) -> sort -> dedup (warp 0), then fold_positions per layer (A.5, A.10).  The folded list of layer l is the
+  // order-preserving dedup of (previous list mod N_l/8); a value dropped at an earlier layer is a duplicate at every later one too, so it equals
+  // the order-preserving dedup of (sorted unique positions mod N_l/8) and the layers are independent: warp l folds layer l.
+  __shared__ u32 s_cnt;
   const u32 num_queries = a.num_queries; const u64 pmask = (1ull << a.lN) - 1;
-  for (u32 i = lane; i < num_queries; i += 32) { const Digest d = r_merge_int(c.seed, (u64)i + 1); raw[i] = (u32)(((u64)d.w[0] | ((u64)d.w[1] << 32)) & pmask); }
-  c.counter = num_queries;
-  __syncwarp();
-  for (u32 i = lane; i < num_queries; i += 32) {
-    const u32 v = raw[i]; u32 r = 0;
-    for (u32 j = 0; j < num_queries; j++) r += (raw[j] < v) || (raw[j] == v && j < i);
-    srt[r] = v;
-  }
-  __syncwarp();
   auto compact = [&](const u32* in, u32 n, u32 vmask, bool sorted_input, u32* out) -> u32 {
     u32 base = 0;
     for (u32 i0 = 0; i0 < n; i0 += 32) {
@@ -162,18 +167,31 @@ __global__ void __launch_bounds__(TAIL_MAX_THREADS, 1) fri_tail_kernel(FriTailAr
     __syncwarp();
     return base;
   };
-  u32 cnt = compact(srt, num_queries, 0xFFFFFFFFu, true, cur);
-  for (u32 i = lane; i < cnt; i += 32) ps->positions[i] = cur[i];
-  if (lane == 0) ps->num_positions = cnt;
-  u32 lNl = a.lN; u32* pa = cur; u32* pb = nxt;
-  for (u32 l = 0; l < a.num_layers; l++) {
-    const u32 fcn = compact(pa, cnt, (1u << (lNl - 3)) - 1, false, pb);
-    for (u32 i = lane; i < fcn; i += 32) ps->fri_positions[l][i] = pb[i];
-    if (lane == 0) ps->fri_num_positions[l] = fcn;
-    cnt = fcn; u32* t = pa; pa = pb; pb = t; lNl -= 3;
+  if (tid < 32) {
+    Coin c = coin_load(ps);
+    c.seed = r_merge_int(c.seed, s_nonce); c.counter = 0;
+    for (u32 i = lane; i < num_queries; i += 32) { const Digest d = r_merge_int(c.seed, (u64)i + 1); raw[i] = (u32)(((u64)d.w[0] | ((u64)d.w[1] << 32)) & pmask); }
+    c.counter = num_queries;
     __syncwarp();
+    for (u32 i = lane; i < num_queries; i += 32) {       // stable rank sort
+      const u32 v = raw[i]; u32 r = 0;
+      for (u32 j = 0; j < num_queries; j++) r += (raw[j] < v) || (raw[j] == v && j < i);
+      srt[r] = v;
+    }
+    __syncwarp();
+    const u32 cnt = compact(srt, num_queries, 0xFFFFFFFFu, true, cur);
+    for (u32 i = lane; i < cnt; i += 32) ps->positions[i] = cur[i];
+    if (lane == 0) { ps->num_positions = cnt; s_cnt = cnt; }
+    coin_store(ps, c);
   }
-  coin_store(ps, c);
+  __syncthreads();
+  const u32 nwarps = TAIL_THREADS >> 5, warp = tid >> 5;
+  for (u32 l = warp; l < a.num_layers; l += nwarps) {
+    u32* outp = ps->fri_positions[l];                      // written in place: lanes only read `cur`
+    const u32 fcn = compact(cur, s_cnt, (1u << (a.lN - 3 * (l + 1))) - 1, false, outp);
+    if (lane == 0) ps->fri_num_positions[l] = fcn;
+  }
+  TCK();
 }
 
 }  // namespace

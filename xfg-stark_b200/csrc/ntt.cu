@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
   const u32 coset = p.coset_map ? (u32)((p.coset_map >> (4 * sub)) & 15) : sub;
   u64* dst = p.dst + (p.coset_map ? (size_t)grp * p.dst_cosets + coset : (size_t)tr) * p.dst_tstride;
   const u64* src = p.src_is_dst ? dst : p.src + (size_t)grp * p.src_tstride;
-  const u64 col0 = (u64)tile << Tlog;
+  // first column of the tile: plain tile * T, or (three-pass plans) split into a slow and a fast part with their own strides
+  const u32 thi = p.tile_lo_log ? tile >> p.tile_lo_log : 0u, tlo = p.tile_lo_log ? tile & ((1u << p.tile_lo_log) - 1) : tile;
+  const u64 col0 = (u64)thi * p.in_hi_stride + ((u64)tlo << Tlog), col0_out = (u64)thi * p.out_hi_stride + ((u64)tlo << Tlog);
 
   // ---- load: CH global loads of a thread are issued before their first use (the plain loop over shared-memory stores would
   // serialise them: the compiler cannot prove that `src` does not alias shared memory) ----
@@ -230,6 +232,8 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
   // ---- store ----
   if (p.store_transposed) {
     // Y[(col0 + c) * L + k] = S[k][c] * w_n^((col0 + c) * k)
+    // three-pass plans store column lo + 2^swap_lo_log * hi at row hi + 2^swap_hi_log * lo (so that the two later passes run in place)
+    auto out_col = [&](u64 col) -> u64 { return p.swap_lo_log ? (col >> p.swap_lo_log) | ((col & ((u64(1) << p.swap_lo_log) - 1)) << p.swap_hi_log) : col; };
     if (p.it_tab) {
       const u64* itab = p.it_tab + (size_t)coset * p.it_tstride;
 #pragma unroll
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
 #pragma unroll
         for (int i = 0; i < CH; i++) {
           const u32 e = tid + (h + i) * nthreads, k = e & (L - 1), c = e >> Llog;
-          dst[(col0 + c) * (u64)L + k] = w_canon(w_mul(S[k * TP + c], w[i]));
+          dst[out_col(col0 + c) * (u64)L + k] = w_canon(w_mul(S[k * TP + c], w[i]));
         }
       }
     } else {
@@ -251,12 +255,12 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
         u64 v = S[k * TP + c];
         const u64 ex = (col0 + c) * (u64)k;
         v = w_canon(ex ? w_mul(v, w_pow_lookup(it, ex)) : v);
-        dst[(col0 + c) * (u64)L + k] = v;
+        dst[out_col(col0 + c) * (u64)L + k] = v;
       }
     }
   } else {
     const u32 c = tid & (T - 1), k0 = tid >> Tlog, kstep = nthreads >> Tlog;
-    const u64 g0 = (u64)k0 * p.out_row_stride + col0 + c, gstep = (u64)kstep * p.out_row_stride;
+    const u64 g0 = (u64)k0 * p.out_row_stride + col0_out + c, gstep = (u64)kstep * p.out_row_stride;
     if (p.post_lo || p.scale != 1) {   // two-level power lookups / separate scale (no direct tables for this length): rolled
       PowTable post; post.lo = p.post_lo ? p.post_lo + (size_t)(tr % p.post_div) * POW_LO : nullptr;
       post.hi = p.post_hi ? p.post_hi + (size_t)(tr % p.post_div) * p.post_hi_stride : nullptr;
@@ -271,10 +275,14 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
       }
     } else {
       const u64* pt = p.post_tab ? p.post_tab + (size_t)(tr % p.post_div) * p.post_tstride + g0 : nullptr;
+      const u64* rt = p.row_tw;         // three-pass plans: row k of this tile is multiplied by row_tw[hi * k] (one value per row, shared by the T columns)
 #pragma unroll
       for (int h = 0; h < EPT; h += CH) {
         u64 w[CH];
-        if (pt) {
+        if (rt) {
+#pragma unroll
+          for (int i = 0; i < CH; i++) w[i] = __ldg(rt + (size_t)thi * (k0 + (h + i) * kstep));
+        } else if (pt) {
 #pragma unroll
           for (int i = 0; i < CH; i++) w[i] = __ldg(pt + (h + i) * gstep);
         }
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
         for (int i = 0; i < CH; i++) {
           u64 x = S[(k0 + (h + i) * kstep) * TP + c];
           const u64 go = g0 + (h + i) * gstep;
-          x = w_canon(pt ? w_mul(x, w[i]) : x);
+          x = w_canon((pt || rt) ? w_mul(x, w[i]) : x);
           if (p.peer_log) p.peer[go >> p.peer_log][(size_t)tr * (u64(1) << p.peer_log) + (go & ((u64(1) << p.peer_log) - 1))] = x;   // fused all-to-all: store to the row owner
           else dst[go] = x;
         }
@@ -370,13 +378,38 @@ void ntt_batch(cudaStream_t st, const NttTables& tb, const NttJob& job) {
     ntt_pass<<<dim3(1, job.batch), NTT_THREADS, ntt_pass_smem(ln, 0), st>>>(p); XFG_LAUNCHED(1);
     return;
   }
-  // four-step: n = n1 * n2 with n2 = 2^l2 (pass A length), n1 = 2^l1 (pass B length)
-  const u32 l2 = ln / 2, l1 = ln - l2;
-  const bool fast = l2 >= 8;            // register-radix Stockham tiles (2^8 .. 2^12 points)
+  // four-step: n = n1 * n2 with n2 = 2^l2 (pass A length), n1 = 2^l1 (pass B length);
+  // three-pass (from 2^24 points, needs the direct tables): n = n1 n2 n3 with n3 = 2^(ln-16) (pass A), n2 = n1 = 2^8 (two in-place passes)
   // direct twiddle tables (NttTables): picked when the job's lookup tables are the ones the direct tables were built from
-  const bool have_direct = fast && tb.d_ln == ln;
-  const bool dir_coset = have_direct && !job.inverse && job.scale == 1 && job.pre_lo && job.pre_lo == tb.d_pre_id && !job.post_lo;
-  const bool dir_inv = have_direct && job.inverse && !job.pre_lo && job.scale == tb.d_scale && (!job.post_lo || job.post_lo == tb.d_post_id);
+  const bool tab_coset = tb.d_ln == ln && !job.inverse && job.scale == 1 && job.pre_lo && job.pre_lo == tb.d_pre_id && !job.post_lo;
+  const bool tab_inv = tb.d_ln == ln && job.inverse && !job.pre_lo && job.scale == tb.d_scale && (!job.post_lo || job.post_lo == tb.d_post_id);
+  const bool three = ln >= NTT_THREE_PASS_MIN_LOG && (tab_coset || tab_inv) && tb.d_rtw_fwd && tb.d_l2 == ntt_pass_a_log(ln);
+  const u32 l2 = three ? ntt_pass_a_log(ln) : ln / 2, l1 = ln - l2;   // jobs the direct tables do not cover keep the four-step plan with the two-level lookups
+  const bool fast = l2 >= 8;            // register-radix Stockham tiles (2^8 .. 2^12 points)
+  const bool have_direct = fast && tb.d_ln == ln && tb.d_l2 == l2;
+  const bool dir_coset = have_direct && tab_coset, dir_inv = have_direct && tab_inv;
+  if (three) {
+    // j = j1 + 2^8 j2 + 2^16 j3, k = k3 + n3 k2 + 2^8 n3 k1.
+    // A : rows j3 (stride 2^16), T consecutive columns c = j1 + 2^8 j2; x w_n^(c k3) (and the coset / 1/n factors); stored at (j2 + 2^8 j1) n3 + k3
+    p.src = job.src; p.dst = job.dst; p.Llog = l2; p.in_row_stride = u64(1) << 16; p.out_row_stride = 0; p.store_transposed = 1; p.scale = 1;
+    p.swap_lo_log = 8; p.swap_hi_log = 8;
+    if (dir_coset) { p.pre_row = tb.d_pre_row; p.it_tab = tb.d_it_coset; p.it_tstride = u64(1) << ln; p.grp_fast = 1; }
+    else { p.it_tab = tb.d_it_inv; p.it_tstride = 0; }
+    p.Tlog = r16_tlog(l2); launch_r16(st, p, job.inverse, (1u << 16) >> p.Tlog, job.batch);
+    // B1: fixed j1 (hi), rows j2 (stride n3), T consecutive k3, in place; x w_65536^(j1 k2)
+    p.src = job.dst; p.src_is_dst = 1; p.pre_lo = nullptr; p.pre_hi = nullptr; p.pre_row = nullptr; p.it_tab = nullptr; p.canon_flag = nullptr;
+    p.swap_lo_log = 0; p.swap_hi_log = 0; p.store_transposed = 0; p.scale = 1; p.post_lo = nullptr; p.post_hi = nullptr;
+    p.Llog = 8; p.Tlog = r16_tlog(8);
+    p.tile_lo_log = l2 - p.Tlog; p.in_hi_stride = p.out_hi_stride = u64(1) << (l2 + 8); p.in_row_stride = p.out_row_stride = u64(1) << l2;
+    p.row_tw = job.inverse ? tb.d_rtw_inv : tb.d_rtw_fwd;
+    launch_r16(st, p, job.inverse, 256u << p.tile_lo_log, job.batch);
+    // B2: fixed k2 (hi), rows j1 (stride 2^8 n3), T consecutive k3, in place: output index k3 + n3 k2 + 2^8 n3 k1 (natural order)
+    p.row_tw = nullptr; p.in_hi_stride = p.out_hi_stride = u64(1) << l2; p.in_row_stride = p.out_row_stride = u64(1) << (l2 + 8);
+    if (dir_inv && job.post_lo) { p.post_tab = tb.d_post; p.post_tstride = u64(1) << ln; }
+    p.peer_log = job.peer_log; for (int i = 0; i < NTT_MAX_PEERS; i++) p.peer[i] = job.peer[i];
+    launch_r16(st, p, job.inverse, 256u << p.tile_lo_log, job.batch);
+    return;
+  }
   const u32 Tlog = l1 > 11 ? 2 : 3;     // 2^12-point tiles only fit 4 columns
   // pass A
   p.src = job.src; p.dst = job.dst; p.Llog = l2; p.Tlog = Tlog; p.in_row_stride = u64(1) << l1; p.out_row_stride = 0;
@@ -415,13 +448,13 @@ __global__ void fill_pow_kernel(u64* __restrict__ out, size_t count, u32 shift, 
 }
 size_t ntt_direct_words(u32 ln, u32 cosets, u32 posts) {
   if (ln < NTT_DIRECT_MIN_LOG || ln > NTT_DIRECT_MAX_LOG) return 0;
-  const size_t n = size_t(1) << ln, n2 = size_t(1) << (ln / 2);
-  return n + cosets * n + cosets * n2 + posts * n;
+  const size_t n = size_t(1) << ln, n2 = size_t(1) << ntt_pass_a_log(ln);
+  return n + cosets * n + cosets * n2 + posts * n + (ln >= NTT_THREE_PASS_MIN_LOG ? (size_t(2) << 16) : 0);
 }
 void ntt_build_direct(NttTables& tb, u32 ln, u64* storage, u64 scale, const u64* pre_lo, const u64* pre_hi, u32 pre_hi_stride, u32 cosets,
                       const u64* post_lo, const u64* post_hi, u32 post_hi_stride, u32 posts) {
   if (!ntt_direct_words(ln, cosets, posts)) return;
-  const size_t n = size_t(1) << ln; const u32 l2 = ln / 2, l1 = ln - l2; const size_t n2 = size_t(1) << l2;
+  const size_t n = size_t(1) << ln; const u32 l2 = ntt_pass_a_log(ln), l1 = ln - l2; const size_t n2 = size_t(1) << l2;
   const unsigned blocks = (unsigned)(n / 256);
   u64* it_inv = storage; u64* it_coset = it_inv + n; u64* pre_row = it_coset + cosets * n; u64* post = pre_row + cosets * n2;
   fill_it_kernel<<<blocks, 256>>>(it_inv, ln, l2, tb.wn_inv, scale, PowTable{nullptr, nullptr});
@@ -433,7 +466,13 @@ void ntt_build_direct(NttTables& tb, u32 ln, u64* storage, u64 scale, const u64*
   for (u32 c = 0; c < posts; c++)
     fill_pow_kernel<<<blocks, 256>>>(post + (size_t)c * n, n, 0, PowTable{post_lo + (size_t)c * POW_LO, post_hi + (size_t)c * post_hi_stride});
   tb.d_it_inv = it_inv; tb.d_it_coset = it_coset; tb.d_pre_row = pre_row; tb.d_post = posts ? post : nullptr;
-  tb.d_pre_id = pre_lo; tb.d_post_id = posts ? post_lo : nullptr; tb.d_scale = scale; tb.d_ln = ln;
+  tb.d_pre_id = pre_lo; tb.d_post_id = posts ? post_lo : nullptr; tb.d_scale = scale; tb.d_ln = ln; tb.d_l2 = l2;
+  if (ln >= NTT_THREE_PASS_MIN_LOG) {   // w_65536^(+-e) = w_n^(+-e * n / 65536), e < 2^16: the twiddles between the two in-place passes
+    u64* rf = post + (size_t)posts * n; u64* ri = rf + (size_t(1) << 16);
+    fill_pow_kernel<<<256, 256>>>(rf, size_t(1) << 16, ln - 16, tb.wn_fwd);
+    fill_pow_kernel<<<256, 256>>>(ri, size_t(1) << 16, ln - 16, tb.wn_inv);
+    tb.d_rtw_fwd = rf; tb.d_rtw_inv = ri;
+  }
 }
 
 }  // namespace xfg

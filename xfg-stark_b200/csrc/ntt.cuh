@@ -29,6 +29,11 @@ struct NttPass {
   // direct (one 8-byte load per element) twiddle tables of a four-step transform, see NttTables; they replace pre_*, it_*, post_*
   const u64* pre_row; const u64* it_tab; u64 it_tstride; const u64* post_tab; u64 post_tstride;
   u32 grp_fast;   // ntt_pass_r16: blockIdx.y = sub * groups + group instead of group * src_div + sub
+  // three-pass transforms (n = n1 n2 n3, 2^24 points and up: 2^12-point tiles would run one 1024-thread CTA per SM and leave 32-byte runs):
+  //   tile t -> (hi, lo) = (t >> tile_lo_log, t mod 2^tile_lo_log); first column of the tile = hi * in_hi_stride + lo * T (out_hi_stride for the store)
+  //   row_tw: non-transposed store multiplies output row k by row_tw[hi * k] (the twiddle between the two in-place passes)
+  //   swap_lo_log / swap_hi_log: the transposed store of pass A writes column c = lo + 2^swap_lo_log * hi at (hi + 2^swap_hi_log * lo) * L
+  u32 tile_lo_log; u64 in_hi_stride, out_hi_stride; const u64* row_tw; u32 swap_lo_log, swap_hi_log;
   // input validation fused into the first load of a transform: if non-null, *canon_flag |= canon_bit when an input element is >= p
   // (the prover's check that every trace element is a canonical field element; saves a separate pass over the trace)
   u32* canon_flag; u32 canon_bit;
@@ -47,9 +52,14 @@ struct NttTables {
   //   d_post     [posts][n]     output j:                 post_base_c^j                      inverse coset transforms (post table == d_post_id)
   const u64* d_it_inv = nullptr; const u64* d_it_coset = nullptr; const u64* d_pre_row = nullptr; const u64* d_post = nullptr;
   const u64* d_pre_id = nullptr; const u64* d_post_id = nullptr; u64 d_scale = 0; u32 d_ln = 0;
+  u32 d_l2 = 0;                                            // length (log2) of pass A the d_it_* / d_pre_row tables were built for
+  const u64* d_rtw_fwd = nullptr; const u64* d_rtw_inv = nullptr;   // three-pass plans: w_65536^(+-e), e < 2^16
 };
 // words of device memory ntt_build_direct needs / fill the tables (synchronous on stream 0); direct tables exist for 16 <= ln <= NTT_DIRECT_MAX_LOG
+static constexpr u32 NTT_THREE_PASS_MIN_LOG = 24;
 static constexpr u32 NTT_DIRECT_MIN_LOG = 16, NTT_DIRECT_MAX_LOG = 24;   // 1.4 GB of tables at 2^24 (falls back to the lookups when the allocation fails)
+// length (log2) of pass A: half of ln for the four-step plan; ln - 16 for the three-pass plan (2^(ln-16) x 2^8 x 2^8) used from 2^24 points up
+static inline u32 ntt_pass_a_log(u32 ln) { return ln >= NTT_THREE_PASS_MIN_LOG ? ln - 16 : ln / 2; }
 size_t ntt_direct_words(u32 ln, u32 cosets, u32 posts);
 void ntt_build_direct(NttTables& tb, u32 ln, u64* storage, u64 scale, const u64* pre_lo, const u64* pre_hi, u32 pre_hi_stride, u32 cosets,
                       const u64* post_lo, const u64* post_hi, u32 post_hi_stride, u32 posts);

@@ -42,6 +42,9 @@ struct ProofState {
   // queries (the grinding nonce lives in the init block above)
   u32 num_positions; u32 positions[MAX_Q];
   u32 fri_num_positions[MAX_LAYERS]; u32 fri_positions[MAX_LAYERS][MAX_Q];
+#ifdef XFG_TAIL_CLOCKS
+  long long dbg_clk[48];   // phase timestamps of the fused tail kernel (debug builds only)
+#endif
 };
 static constexpr size_t PROOF_INIT_BYTES = sizeof(u64) * MAX_SEED_LIMBS + 16;
 static_assert(PROOF_INIT_BYTES == offsetof(ProofState, seed), "init block layout");
