@@ -1,13 +1,13 @@
 """Per-kernel time of the timed region from an ncu launch list (ncu --metrics gpu__time_duration.sum --csv --log-file ...).
 python tools/launch_table.py gpurun_out/v4_launches.csv [out_subset.csv]
-Proofs are delimited by seed_kernel launches; with `bench.py --steps 2 --warmup 3 --no-preload` proofs 1-3 are the warm-up, 4 the e2e
-warm-up (split upload), 5-6 the timed HBM-resident region (44 launches each, replayed from the whole-proof CUDA graph)."""
+A proof ends with its gather_kernel launch; with `bench.py --steps 2 --warmup 3 --no-preload --headline-only` proofs 1-3 are the warm-up, 4 the e2e
+warm-up (split upload), 5-6 the timed HBM-resident region (33 launches each at 2^20 rows, replayed from the whole-proof CUDA graph)."""
 import csv, sys, re, collections
 rows = [r for r in csv.reader(open(sys.argv[1], errors="ignore")) if len(r) > 14 and r[0].isdigit()]
 names = [re.sub(r"\(.*", "", r[4]).replace("void ", "") for r in rows]
 us = [float(r[14]) / 1e3 for r in rows]
-starts = [i for i, n in enumerate(names) if n.startswith("seed_kernel")] + [len(rows)]
-proofs = [(starts[k], starts[k + 1]) for k in range(len(starts) - 1)]
+ends = [i + 1 for i, n in enumerate(names) if "gather_kernel" in n]
+proofs = [(a, b) for a, b in zip([0] + ends[:-1], ends)]
 print("proofs (launch counts):", [b - a for a, b in proofs])
 sel = proofs[4:6]
 agg = collections.OrderedDict()
