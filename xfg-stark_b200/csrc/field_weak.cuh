@@ -15,23 +15,48 @@ namespace xfg {
 
 __device__ __forceinline__ u64 w_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
 
-// weak -> canonical.  x >= p  <=>  x + EPS carries out of bit 64, and then x - p = x + EPS (mod 2^64): add, select on the carry (4 instructions)
+// XFG_WEAK_MADFIX (A/B switch, default 0): the "+ EPS when bit 64 was carried out" fix-up as one `mad.wide  r = c * EPS + r` (c = the carry)
+// instead of mask-select + two-word addition, i.e. 2-3 ALU-pipe instructions traded for FMA-pipe work.  MEASURED SLOWER on B200 (2^20 rows,
+// quadratic): ntt.lde_trace 1.154 -> 1.254 ms, deep 0.631 -> 0.649, constraints 0.195 -> 0.199 - ptxas expands the multiplication by 2^32 - 1 into
+// IMAD.HI + IMAD + extra moves (IMAD.HI 86 -> 311 per NTT kernel) and the heavy half of the FMA pipe (IMAD.WIDE / IMAD.HI, 7.6 T instr/s against
+// 18.5 T for 32-bit IMAD) is already as loaded as the ALU pipe.  Kept for the record; the select form stays the product path.
+#ifndef XFG_WEAK_MADFIX
+#define XFG_WEAK_MADFIX 0
+#endif
+// r + c * EPS for c in {0, 1} (mod 2^64)
+__device__ __forceinline__ u64 w_fix_eps(u32 c, u64 r) { u64 o; asm("mad.wide.u32 %0, %1, 0xffffffff, %2;" : "=l"(o) : "r"(c), "l"(r)); return o; }
+
+// weak -> canonical.  x >= p  <=>  x + EPS carries out of bit 64, and then x - p = x + EPS (mod 2^64)
 __device__ __forceinline__ u64 w_canon(u64 x) {
+#if XFG_WEAK_MADFIX
+  u32 c;
+  asm("{\n\t .reg .u32 t0, t1;\n\t add.cc.u32 t0, %1, 0xffffffff;\n\t addc.cc.u32 t1, %2, 0;\n\t addc.u32 %0, 0, 0;\n\t}"
+      : "=r"(c) : "r"((u32)x), "r"((u32)(x >> 32)));
+  return w_fix_eps(c, x);
+#else
   u32 r0, r1;
   asm("{\n\t .reg .pred p; .reg .u32 c, t0, t1;\n\t add.cc.u32 t0, %2, 0xffffffff;\n\t addc.cc.u32 t1, %3, 0;\n\t addc.u32 c, 0, 0;\n\t setp.ne.u32 p, c, 0;\n\t"
       "selp.b32 %0, t0, %2, p;\n\t selp.b32 %1, t1, %3, p;\n\t}"
       : "=r"(r0), "=r"(r1) : "r"((u32)x), "r"((u32)(x >> 32)));
   return w_pack(r0, r1);
+#endif
 }
 
 // a (weak) + b (canonical) -> weak.  a + b < 2^64 + p, so after a carry the wrapped sum is < p and adding EPS cannot carry again.
-// The carry mask is built as setp/selp so that ptxas keeps it one SEL on the carry predicate (5 instructions in all).
 __device__ __forceinline__ u64 w_add_c(u64 a, u64 b) {
+#if XFG_WEAK_MADFIX
+  u32 s0, s1, c;
+  asm("{\n\t add.cc.u32 %0, %3, %5;\n\t addc.cc.u32 %1, %4, %6;\n\t addc.u32 %2, 0, 0;\n\t}"
+      : "=&r"(s0), "=&r"(s1), "=&r"(c) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  return w_fix_eps(c, w_pack(s0, s1));
+#else
+  // The carry mask is built as setp/selp so that ptxas keeps it one SEL on the carry predicate (5 instructions in all).
   u32 s0, s1;
   asm("{\n\t .reg .pred p; .reg .u32 c, m;\n\t add.cc.u32 %0, %2, %4;\n\t addc.cc.u32 %1, %3, %5;\n\t addc.u32 c, 0, 0;\n\t setp.ne.u32 p, c, 0;\n\t"
       "selp.b32 m, 0xffffffff, 0, p;\n\t add.cc.u32 %0, %0, m;\n\t addc.u32 %1, %1, 0;\n\t}"
       : "=&r"(s0), "=&r"(s1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
   return w_pack(s0, s1);
+#endif
 }
 // a (weak) - b (canonical) -> weak.  After a borrow the wrapped difference is >= 2^64 - (p-1) >= EPS, so subtracting EPS cannot borrow again.
 __device__ __forceinline__ u64 w_sub_c(u64 a, u64 b) {
@@ -46,11 +71,19 @@ __device__ __forceinline__ u64 w_mul_eps(u32 a) { u64 r; asm("mul.wide.u32 %0, %
 // a * EPS is at most 2^32 - 2, so bit 64 was carried out exactly when the sum's high word is below b1 (one 32-bit compare); the
 // wrapped sum is then <= 2^64 - 2^33, so + EPS cannot carry again.
 __device__ __forceinline__ u64 w_eps_madd(u32 a, u32 b0, u32 b1) {
+#if XFG_WEAK_MADFIX
+  u64 r; u32 c;
+  asm("{\n\t .reg .u64 b; .reg .pred p; .reg .u32 h;\n\t mov.b64 b, {%3, %4};\n\t mad.wide.u32 %0, %2, 0xffffffff, b;\n\t mov.b64 {_, h}, %0;\n\t"
+      "setp.lt.u32 p, h, %4;\n\t selp.u32 %1, 1, 0, p;\n\t}"
+      : "=&l"(r), "=&r"(c) : "r"(a), "r"(b0), "r"(b1));
+  return w_fix_eps(c, r);
+#else
   u32 r0, r1;
   asm("{\n\t .reg .u64 r, b; .reg .pred p; .reg .u32 m;\n\t mov.b64 b, {%3, %4};\n\t mad.wide.u32 r, %2, 0xffffffff, b;\n\t mov.b64 {%0, %1}, r;\n\t"
       "setp.lt.u32 p, %1, %4;\n\t selp.b32 m, 0xffffffff, 0, p;\n\t add.cc.u32 %0, %0, m;\n\t addc.u32 %1, %1, 0;\n\t}"
       : "=&r"(r0), "=&r"(r1) : "r"(a), "r"(b0), "r"(b1));
   return w_pack(r0, r1);
+#endif
 }
 // r (weak) + c * 2^32, c < 2^32 -> weak
 __device__ __forceinline__ u64 w_add_hi32(u64 r, u32 c) { return w_add_c(r, w_pack(0u, c)); }   // c * 2^32 <= 2^64 - 2^32 < p: canonical
