@@ -262,6 +262,13 @@ int xfg_pipe_probe(xfg_ctx* ctx, int mode, double* gops);
 /* hash_elements of `rows` rows of `limbs` (1, 2, 7, 8 or 16) canonical u64 each, row-major; out = rows x 32 bytes */
 int xfg_hash_rows(xfg_ctx* ctx, const uint64_t* rows_rowmajor, size_t rows, uint32_t limbs, uint8_t* out);
 
+/* ---- debug: workspace guard zones.  Every region of a proof's workspace is followed by a guard zone no kernel may write; _fill paints slot 0's
+ * slab, _check counts damaged guard words after proofs of the given shape (memory-safety evidence where compute-sanitizer is unavailable) ---- */
+int xfg_debug_guard_fill(xfg_ctx* ctx);
+int xfg_debug_guard_check(xfg_ctx* ctx, uint32_t n_log2, uint32_t field_extension, uint32_t width, uint32_t fri_remainder_max_degree,
+                          uint64_t* violations, int32_t* first_region);
+int xfg_debug_poke_guard(xfg_ctx* ctx, uint32_t n_log2);   /* self-test of the checker: damages the first guard zone */
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,10 @@ extern "C" {
     /// cols: seven column pointers (`TraceTable::get_column(i).as_ptr()`); form: XFG_FORM_CANONICAL / XFG_FORM_MONTGOMERY
     pub fn xfg_prove_burn_mint_cols(ctx: *mut xfg_ctx, cols: *const *const u64, form: u32, n_log2: u32, air: *const xfg_air_consts,
                                     options: *const xfg_options, out: *mut u8, out_cap: usize, out_len: *mut usize, times: *mut xfg_stage_times) -> c_int;
+    /// debug: workspace guard zones (memory-safety check where compute-sanitizer is unavailable)
+    pub fn xfg_debug_guard_fill(ctx: *mut xfg_ctx) -> c_int;
+    pub fn xfg_debug_guard_check(ctx: *mut xfg_ctx, n_log2: u32, field_extension: u32, width: u32, fri_remainder_max_degree: u32, violations: *mut u64, first_region: *mut i32) -> c_int;
+    pub fn xfg_debug_poke_guard(ctx: *mut xfg_ctx, n_log2: u32) -> c_int;
     pub fn xfg_host_register(ctx: *mut xfg_ctx, ptr: *const c_void, bytes: usize) -> c_int;
     pub fn xfg_host_unregister(ctx: *mut xfg_ctx, ptr: *const c_void) -> c_int;
     pub fn xfg_prove_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, traces: *const *const u64, n_log2: u32, airs: *const xfg_air_consts,

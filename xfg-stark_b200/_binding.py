@@ -18,7 +18,8 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
                     "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_air_compile_check", "xfg_pipe_probe",
-                    "xfg_prove_burn_mint_cols", "xfg_host_register", "xfg_host_unregister"]
+                    "xfg_prove_burn_mint_cols", "xfg_host_register", "xfg_host_unregister",
+                    "xfg_debug_guard_fill", "xfg_debug_guard_check", "xfg_debug_poke_guard"]
 
 
 P = 0xFFFFFFFF00000001          # the Winterfell base field modulus 2^64 - 2^32 + 1
@@ -283,6 +284,18 @@ class Context:
                                                        C.byref(st) if want_times else None))
         proof = C.string_at(out, ln.value)
         return (proof, st.as_dict()) if want_times else proof
+
+    def guard_fill(self):
+        """paints slot 0's workspace; see guard_check"""
+        self._lib.xfg_debug_guard_fill.argtypes = [C.c_void_p]
+        self._check(self._lib.xfg_debug_guard_fill(self._h))
+
+    def guard_check(self, n_log2, options=ProofOptions(), width=7):
+        """-> (damaged guard words, index of the first damaged zone) after proofs of that shape since guard_fill()"""
+        v = C.c_uint64(0); r = C.c_int32(-1)
+        self._lib.xfg_debug_guard_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        self._check(self._lib.xfg_debug_guard_check(self._h, n_log2, options.field_extension, width, options.fri_remainder_max_degree, C.byref(v), C.byref(r)))
+        return int(v.value), int(r.value)
 
     def host_register(self, array):
         """page-locks a caller-owned numpy array so that traces in it upload without staging (xfg_host_register)"""

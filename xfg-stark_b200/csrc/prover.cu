@@ -36,6 +36,7 @@ namespace {
 // streams and fill each other's partial waves (measured e2e at 2^20, ms per proof: one stream with {1,1,2,3}-column groups 4.95, per
 // column on 1 / 2 / 3 / 4 streams 5.03 / 4.88 / 4.87 / 4.84).
 constexpr int UPLOAD_STREAMS = 4;
+constexpr size_t GUARD_WORDS = 64;
 constexpr size_t MATERIAL_WORDS = size_t(1) << 20;   // 8 MiB: opened rows + per-position authentication paths
 constexpr u32 MIN_LOG = 3, MAX_LOG = 24;
 
@@ -210,12 +211,16 @@ size_t slab_words_for(u32 ln, int D, size_t W) {
   w += (size_t)D * N / 7 + 64 * MAX_LAYERS;   // FRI layer evaluations l >= 1
   w += 8 * N / 7 + 64 * MAX_LAYERS;           // FRI trees
   w += 2 * (size_t)D * 2048 + 64;             // remainder in / coefficients
+  w += (size_t)GUARD_WORDS * (16 + 2 * MAX_LAYERS);   // guard zones between the regions (see carve)
   return w;
 }
 
-void carve(const Slot& s, const Plan& p, int D, Carve& c) {
+// Every region of the workspace is followed by a guard zone of GUARD_WORDS words that no kernel may touch: compute-sanitizer is not
+// available on this GPU pool, so out-of-bounds writes are hunted with xfg_debug_guard_fill / xfg_debug_guard_check (tests/test_gpu_guards.py):
+// fill the slab with a pattern, prove, and require every guard zone (and the slack behind the last region) to be intact.
+void carve(const Slot& s, const Plan& p, int D, Carve& c, std::vector<std::pair<size_t, size_t>>* guards = nullptr) {
   u64* w = s.slab; const size_t n = p.n, N = p.N, W = s.W;
-  auto take = [&](size_t k) { u64* r = w; w += (k + 7) & ~size_t(7); return r; };
+  auto take = [&](size_t k) { u64* r = w; w += (k + 7) & ~size_t(7); if (guards) guards->push_back({(size_t)(w - s.slab), (size_t)GUARD_WORDS}); w += GUARD_WORDS; return r; };
   c.trace_in = take(W * n); c.trace_coef = take(W * n); c.lde = take(W * N);
   c.trace_tree = reinterpret_cast<Digest*>(take(8 * N));
   c.ce_evals = take(2 * D * n); c.ce_tmp = take(2 * D * n); c.h_coef = take(D * n); c.h_lde = take(D * N);
