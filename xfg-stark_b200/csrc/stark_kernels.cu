@@ -137,6 +137,9 @@ void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64*
 // out-of-domain evaluation: poly p (base-field coefficients) at z and z*g.  Thread t sums c[t + i*TOT] z^(t + i*TOT) by a
 // Horner pass in z^TOT; block partials are added by the transcript kernel.  partial: [poly][block][point][limb]
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef XFG_OOD_MLP
+#define XFG_OOD_MLP 4
+#endif
 template <int D>
 __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln, u32 width, u32 polys_per_block,
                                                    const ProofState* __restrict__ ps, u64* __restrict__ partial) {
@@ -169,7 +172,19 @@ __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_
     u64 r[4] = {0, 0, 0, 0};
     if (t < n) {
       DotAcc d[2][D];
-      for (size_t i = 0; i < steps; i++) {      // (8 loads in flight per thread were tried: 78 registers, 0.097 -> 0.123 ms)
+      // XFG_OOD_MLP coefficient loads are issued before their products: the loop is bound by the latency of its dependent global loads, not by
+      // bandwidth (75 MB in 0.097 ms) - (8 in flight were tried in round 1: 78 registers, 0.123 ms)
+      size_t i = 0;
+      for (; i + XFG_OOD_MLP <= steps; i += XFG_OOD_MLP) {
+        u64 cv[XFG_OOD_MLP];
+#pragma unroll
+        for (int q = 0; q < XFG_OOD_MLP; q++) cv[q] = c[t + (i + q) * TOT];
+#pragma unroll
+        for (int q = 0; q < XFG_OOD_MLP; q++)
+#pragma unroll
+          for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) d[w][l].fma(cv[q], tab[i + q][w][l]);
+      }
+      for (; i < steps; i++) {
         const u64 cv = c[t + i * TOT];
 #pragma unroll
         for (int w = 0; w < 2; w++) for (int l = 0; l < D; l++) d[w][l].fma(cv, tab[i][w][l]);
