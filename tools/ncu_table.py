@@ -1,7 +1,7 @@
 """Prints one line per profiled kernel of an .ncu-rep (ncu --set full): time, DRAM bytes, occupancy, pipe utilisation, top stalls."""
 import csv, subprocess, sys
 rep = sys.argv[1]
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep, errors="ignore").read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines())); hdr = rows[0]
 want = [('Kernel Name', 'kernel'), ('launch__grid_size', 'grid'), ('launch__block_size', 'blk'), ('gpu__time_duration.sum', 'us'), ('dram__bytes_read.sum', 'rdMB'), ('dram__bytes_write.sum', 'wrMB'),
         ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram%'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ%'), ('launch__registers_per_thread', 'regs'),

@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Regenerates profiles/ncu_traffic.json from an `ncu --set full` capture of one proof (tools/profile_round.sh):
-    python tools/ncu_traffic.py gpurun_out/r02_prof.ncu-rep [git-head]
+    python tools/ncu_traffic.py gpurun_out/r02_prof.ncu-rep|r02_ncu_raw.csv [git-head]
 Per kernel family of bench.py: DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, summed over the family's launches), and the ALU / FMA
 pipe utilisation (time-weighted).  Families are assigned by kernel name and launch order within the proof (the capture filters the heavy kernels)."""
 import csv, json, subprocess, sys, os
 
 rep = sys.argv[1]; head = sys.argv[2] if len(sys.argv) > 2 else subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep, errors="ignore").read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines())); hdr = rows[0]
 col = lambda n: hdr.index(n)
 def num(r, n):
