@@ -165,7 +165,8 @@ def main():
                     ("n64_q64_g1_rem63", (64, 8, 1, 2, 8, 63))):
         add(name, 6, o, k, False); k += 1
     for n_log2, ext, o in ((7, 1, (42, 8, 4, 1, 8, 31)), (8, 2, (42, 8, 4, 2, 8, 31)), (9, 1, (30, 8, 3, 1, 8, 7)), (10, 2, (42, 8, 4, 2, 8, 31)),
-                           (11, 1, (42, 8, 4, 1, 8, 15)), (12, 2, (60, 8, 6, 2, 8, 31)), (13, 1, (42, 8, 4, 1, 8, 31))):
+                           (11, 1, (42, 8, 4, 1, 8, 15)), (12, 2, (60, 8, 6, 2, 8, 31)), (13, 1, (42, 8, 4, 1, 8, 31)),
+                           (16, 1, (42, 8, 4, 1, 8, 31))):      # 2^16 rows, no extension: the trace size of BASELINE configs 2 and 4 (4 FRI layers; ~6 G guest instructions)
         add(f"n2p{n_log2}_ext{ext}", n_log2, o, k, True); k += 1
     out["air_context_calls_seen"] = sorted(set(ref.ctx_calls))
     path = os.path.join(ROOT, "tests", "golden", "reference_proofs.json")
