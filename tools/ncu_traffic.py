@@ -18,8 +18,11 @@ seen = {"ntt1": 0, "ntt0": 0, "commit": 0}
 agg = {}
 for r in rows[2:]:
     name = r[col("Kernel Name")]
-    if "ntt_pass_r16<1" in name or "ntt_pass_r16<(bool)1" in name: k = "ntt1"; fam = fam_seq[k][min(seen[k], 3)]; seen[k] += 1
-    elif "ntt_pass_r16" in name: k = "ntt0"; fam = fam_seq[k][min(seen[k], 3)]; seen[k] += 1
+    if "ntt_pass_r16<1" in name or "ntt_pass_r16<(bool)1" in name or "ntt_pass_r16" in name:
+        k = "ntt1" if ("ntt_pass_r16<1" in name or "ntt_pass_r16<(bool)1" in name) else "ntt0"
+        seen[k] += 1
+        if seen[k] > 4: continue          # launches of the next proof that the capture window still caught
+        fam = fam_seq[k][seen[k] - 1]
     elif "commit_rows_kernel" in name: fam = "commit_rows.trace" if seen["commit"] == 0 else "commit_rows.comp"; seen["commit"] += 1
     elif "constraint_kernel" in name: fam = "constraints"
     elif "deep_kernel" in name: fam = "deep"
@@ -43,6 +46,8 @@ res = {"_comment": f"per kernel family at 2^20 rows / quadratic extension, from 
 for k, v in agg.items():
     res[k] = round(v["bytes"] * scale)
 for key, f in (("_alu_pipe_busy", "alu"), ("_fma_pipe_busy", "fma"), ("_fmaheavy_pipe_busy", "fmah"), ("_issue_active", "issue")):
-    res[key] = {k: round(v[f] / v["t"], 3) for k, v in agg.items() if v["t"] > 0}
+    vals = {k: round(v[f] / v["t"], 3) for k, v in agg.items() if v["t"] > 0}
+    if any(vals.values()):
+        res[key] = vals
 json.dump(res, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json"), "w"), indent=1)
 print(json.dumps(res, indent=1))

@@ -149,7 +149,10 @@ __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __
 
 // tile shape and radix plan of ntt_pass_r16 as functions of the tile length (shared by the host launcher and the specialised kernels):
 // 4096 elements per CTA (more with 2^11, 2^12-point tiles), 16 per thread: 8:(4,4) 9:(4,3,2) 10:(4,4,2) 11:(4,4,3) 12:(4,4,4)
-__host__ __device__ constexpr u32 r16_tlog_c(u32 Llog) { return Llog >= 10 ? 2 : 12 - Llog; }
+#ifndef XFG_R16_T10LOG
+#define XFG_R16_T10LOG 2      // log2 columns of a 2^10-point tile (A/B switch): 2 = 4 columns, 4096 elements, 256 threads, 4 CTAs/SM; 3 = 8 columns, 512 threads, 2 CTAs/SM
+#endif
+__host__ __device__ constexpr u32 r16_tlog_c(u32 Llog) { return Llog == 10 ? XFG_R16_T10LOG : Llog >= 10 ? 2 : 12 - Llog; }
 __host__ __device__ constexpr u32 r16_radix_count_c(u32 Llog) { return Llog == 8 ? 2 : 3; }
 __host__ __device__ constexpr u32 r16_radix_packed_c(u32 Llog) {
   return Llog == 8 ? 0x44u : Llog == 9 ? 0x234u : Llog == 10 ? 0x244u : Llog == 11 ? 0x344u : 0x444u;
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
 
 static size_t r16_smem(u32 Llog, u32 Tlog) { const size_t L = size_t(1) << Llog, TP = (size_t(1) << Tlog) + 1; return (L * TP + L) * sizeof(u64); }
 // 4 columns per 2^10-point tile: measured 1.36 ms for the 2^20 trace LDE, against 1.84 ms with 2 columns (half-used sectors) and 1.33 ms with 8 (2 CTAs/SM)
-static u32 r16_tlog(u32 Llog) { return Llog >= 10 ? 2 : 12 - Llog; }                       // 4096 elements per CTA (more with 2^11, 2^12-point tiles): 4+ CTAs per SM
+static u32 r16_tlog(u32 Llog) { return r16_tlog_c(Llog); }                       // 4096 elements per CTA (more with 2^11, 2^12-point tiles): 4+ CTAs per SM
 // Elements per thread: 16.  A 32-element variant (radix-32 passes, 1024 = 32 x 32, one pass fewer) was measured and is slower
 // (136 registers -> 12 warps/SM: LDE of the trace 2.41 ms vs 1.76 ms), so only EPT = 16 is instantiated.
 static int r16_ept() { return 16; }
@@ -353,8 +356,8 @@ void ntt_init(bool force) {
   cudaFuncSetAttribute(ntt_pass_r16<true, 16, 1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(12, 2));
   cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
   cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(11, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(10, 2));
-  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(10, 2));
+  cudaFuncSetAttribute(ntt_pass_r16<false, 16, 512, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(10, r16_tlog_c(10)));
+  cudaFuncSetAttribute(ntt_pass_r16<true, 16, 512, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r16_smem(10, r16_tlog_c(10)));
   done = true;
 }
 
