@@ -99,6 +99,33 @@ def test_live_reference_run_reproduces_the_fixture_and_the_oracle(ref, name):
 
 
 @have_binary
+def test_declared_degrees_up_to_2_do_not_change_the_proof(ref):
+    """SURVEY.md A.3 / VERDICT r1: the source declares every transition degree as 1 although two constraints have degree 2; the Rust harness
+    (rust/xfg-stark-gpu/tests/normalised_air) declares [2,1,1,1,2,1,1].  Executed in the reference binary: any declaration with degrees <= 2 gives
+    the SAME bytes (ce_blowup 2, one composition column); degree 3 does not (two composition columns - outside this backend, which rejects it)."""
+    c = next(x for x in refvec.cases() if x["name"] == "n64_default_ext2")
+    tx, rcpt, secret = bytes.fromhex(c["tx_prefix_hash"]), bytes.fromhex(c["recipient"]), bytes.fromhex(c["secret"])
+    ctx_new = ref.rb.m.find(r"AirContext<B>::new::", 0)
+
+    def with_degrees(degs):
+        def fix(r):
+            cap, ptr, ln = r.u64s(r.x[1], 3)
+            entry = r.read(ptr, 32)                                            # TransitionConstraintDegree { cycles: Vec (3 words), base }
+            r.write(r.x[1], struct.pack("<QQQ", 7, r.put(b"".join(entry[:24] + struct.pack("<Q", d) for d in degs)), 7)); r.x[2] = 8
+            return "continue"
+        ref.rb.hook(ctx_new, fix)
+        try:
+            return ref.prove64(tx, rcpt, secret, tuple(c["options"]))[0]
+        finally:
+            ref.rb.hook(ctx_new, ref._fix_ctx)
+    want = refvec.proof_bytes(c)
+    assert with_degrees([2, 1, 1, 1, 2, 1, 1]) == want
+    assert with_degrees([2] * 7) == want
+    deg3 = with_degrees([3, 1, 1, 1, 1, 1, 1])
+    assert deg3 != want and len(deg3) > len(want)                              # a second composition column appears in the openings and the OOD frame
+
+
+@have_binary
 def test_shipped_binary_cannot_prove_without_the_intervention():
     """SURVEY.md B.1: `Air::new` declares 6 assertions, `get_assertions` returns 8 -> winter-air panics before any proof exists"""
     sys.path.insert(0, os.path.join(ROOT, "oracle", "a64emu"))
