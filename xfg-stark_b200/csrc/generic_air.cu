@@ -15,18 +15,7 @@
 
 namespace xfg {
 
-// after the trace commitment: draw the transition then the boundary coefficients (A.8)
-template <int D> __global__ void __launch_bounds__(32) gen_trace_root_kernel(ProofState* ps, GenState* gs, const GenProgram* __restrict__ prog, const Digest* __restrict__ tree) {
-  Coin c; c.seed = r_hash_limbs(ps->seed_limbs, (int)ps->seed_count); c.counter = 0;      // coin seed (A.4), see trace_root_kernel
-  const Digest root = tree[1]; r_reseed(c, root);
-  const bool ok = r_draw_many<D>(c, prog->num_constraints + prog->num_assertions, gs->coef);
-  if (lane_id() == 0) { ps->trace_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
-  coin_store(ps, c);
-}
-void launch_gen_trace_root(cudaStream_t st, int D, ProofState* ps, GenState* gs, const GenProgram* prog, const Digest* tree) {
-  if (D == 1) gen_trace_root_kernel<1><<<1, 32, 0, st>>>(ps, gs, prog, tree); else gen_trace_root_kernel<2><<<1, 32, 0, st>>>(ps, gs, prog, tree);
-  XFG_LAUNCHED(1);
-}
+// (the trace-root step - coin seed, commit_trace, transition then boundary coefficients, A.8 - runs inside the tree kernel: merkle.cu RootStep)
 
 // ------------------------------------------------------------------------------------------------------------------
 // evaluate_constraints for a compiled program: thread t evaluates GCE_PTS points of constraint-evaluation coset k' (LDE coset 4k')

@@ -41,7 +41,6 @@ struct GenState {
   u64 coef[GEN_MAX_CONSTRAINTS + GEN_MAX_ASSERTIONS][2];        // transition coefficients, then boundary coefficients (A.8 draw order)
 };
 
-void launch_gen_trace_root(cudaStream_t st, int D, ProofState* ps, GenState* gs, const GenProgram* prog, const Digest* tree);
 void launch_gen_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const GenProgram* prog, const GenState* gs, PowTable wn,
                             u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64 g_last, u64* out, size_t out_tstride);
 void launch_gen_ood_finish(cudaStream_t st, int D, ProofState* ps, GenState* gs, u32 width, const u64* partial, u32 nb);

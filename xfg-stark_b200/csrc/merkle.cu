@@ -7,6 +7,7 @@
 // trace step (8 leaves = one complete 3-level subtree in the coset-major layout) and reduces them itself; the levels above
 // are reduced 8 -> 1 per thread as well, never by a shrinking tree inside a warp.
 #include "merkle.cuh"
+#include "b3_rolled.cuh"
 #include "launch.cuh"
 
 namespace xfg {
@@ -165,10 +166,35 @@ __global__ void __launch_bounds__(128) tree_reduce8_kernel(Digest* __restrict__ 
 
 #endif
 
+// warp 0 of the CTA that has just written the root (tree[1]): the transcript step that consumes it (see RootStep)
+static __device__ void root_step(const RootStep& rs, const Digest* tree) {
+  if (rs.kind == 0 || threadIdx.x >= 32) return;
+  __syncwarp();
+  const Digest root = load_digest(tree + 1);
+  ProofState* ps = rs.ps;
+  Coin c;
+  if (rs.kind == 1) { c.seed = r_hash_limbs(ps->seed_limbs, (int)ps->seed_count); c.counter = 0; }      // coin = hash_elements(context || public inputs)
+  else c = coin_load(ps);
+  r_reseed(c, root);
+  bool ok;
+  if (rs.kind == 1) ok = rs.D == 2 ? r_draw_many<2>(c, rs.count, rs.out) : r_draw_many<1>(c, rs.count, rs.out);
+  else if (rs.kind == 2) ok = rs.D == 2 ? r_draw_many<2>(c, 1, &ps->z) : r_draw_many<1>(c, 1, &ps->z);
+  else ok = rs.D == 2 ? r_draw_many<2>(c, 1, &ps->alphas[rs.layer]) : r_draw_many<1>(c, 1, &ps->alphas[rs.layer]);
+  if (lane_id() == 0) {
+    if (rs.kind == 1) ps->trace_root = root;
+    else if (rs.kind == 2) {
+      ps->constraint_root = root;
+      if (rs.D == 2) stx<2>(ps->zg, mul_base(ldx<2>(ps->z), rs.g_n)); else stx<1>(ps->zg, mul_base(ldx<1>(ps->z), rs.g_n));
+    } else ps->fri_roots[rs.layer] = root;
+    if (!ok) ps->error_flags |= ERR_FLAG_COIN;
+  }
+  coin_store(ps, c);
+}
+
 // one CTA finishes the tree from a level of M <= 2048 nodes up to the root.  Every level is written to the heap (authentication
 // paths need all nodes) but the next level reads its children from shared memory (ping-pong buffers), so a level costs one
 // compression latency + a barrier instead of a global-memory round trip; the last levels run inside one warp.
-__global__ void __launch_bounds__(1024) tree_top_kernel(Digest* __restrict__ tree, u32 M) {
+__global__ void __launch_bounds__(1024) tree_top_kernel(Digest* __restrict__ tree, u32 M, RootStep rs) {
   __shared__ Digest bufA[1024], bufB[512];
   Digest* out = bufA; Digest* in = nullptr;
   for (u32 lvl = M / 2; lvl >= 1; lvl >>= 1) {
@@ -180,6 +206,7 @@ __global__ void __launch_bounds__(1024) tree_top_kernel(Digest* __restrict__ tre
     if (lvl > 16) __syncthreads(); else __syncwarp();     // levels of <= 16 nodes are produced and consumed by warp 0 only
     in = out; out = (out == bufA) ? bufB : bufA;
   }
+  root_step(rs, tree);
 }
 
 // hash_elements of row-major rows (stage entry point xfg_hash_rows; the pipeline hashes rows inside its fused kernels)
@@ -238,7 +265,7 @@ __device__ __forceinline__ void smem_tree_levels(Digest* __restrict__ tree, size
     in = out; out = (out == bufA) ? bufB : bufA;
   }
 }
-__global__ void __launch_bounds__(512) tree_upper_fused_kernel(Digest* __restrict__ tree, size_t M) {
+__global__ void __launch_bounds__(512) tree_upper_fused_kernel(Digest* __restrict__ tree, size_t M, RootStep rs) {
   __shared__ Digest bufA[512], bufB[256];
   __shared__ bool is_last;
   smem_tree_levels(tree, M / 2, (size_t)blockIdx.x * 512, 1024, bufA, bufB);     // -> node M/1024 + blockIdx.x
@@ -254,9 +281,11 @@ __global__ void __launch_bounds__(512) tree_upper_fused_kernel(Digest* __restric
   __threadfence();
   const u32 roots = (u32)(M / 1024);                                              // <= 1024
   smem_tree_levels(tree, roots / 2, 0, roots, bufA, bufB);
+  root_step(rs, tree);
 }
 
-void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M) {
+void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M, const RootStep* step) {
+  RootStep rs{}; if (step) rs = *step;
   // big levels: 8 -> 1 per thread (every lane busy for 7 compressions); from 2^17 nodes down: one fused launch
   while (M > (size_t(1) << 17)) {
     const size_t t = M / 8;
@@ -266,10 +295,10 @@ void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M) {
   }
   if (M > 2048) {
     cudaMemsetAsync(tree, 0, sizeof(unsigned), st);
-    tree_upper_fused_kernel<<<(unsigned)(M / 1024), 512, 0, st>>>(tree, M); XFG_LAUNCHED(1);
+    tree_upper_fused_kernel<<<(unsigned)(M / 1024), 512, 0, st>>>(tree, M, rs); XFG_LAUNCHED(1);
     return;
   }
-  if (M >= 2) { tree_top_kernel<<<1, 1024, 0, st>>>(tree, (u32)M); XFG_LAUNCHED(1); }
+  if (M >= 2) { tree_top_kernel<<<1, 1024, 0, st>>>(tree, (u32)M, rs); XFG_LAUNCHED(1); }
 }
 
 }  // namespace xfg

@@ -1,9 +1,17 @@
 // merkle.cuh — interface of the row-hashing / Merkle-tree kernels (see merkle.cu).
 #pragma once
 #include <cuda_runtime.h>
-#include "blake3.cuh"
+#include "state.cuh"
 
 namespace xfg {
+
+// Fiat-Shamir step fused into the tree kernel: the CTA that computes the root continues (warp 0) with what winter-prover does with a commitment
+// (`commit_trace` / `commit_constraints` / `commit_fri_layer`: reseed the coin with the root, then the draws that follow it), instead of a
+// dependent single-warp launch per tree.
+struct RootStep {
+  int kind;                 // 0 none; 1 trace root: coin seed (A.4), reseed, `count` coefficients -> out; 2 constraint root: z, z g; 3 FRI layer `layer`: alpha
+  int D; ProofState* ps; u64 (*out)[2]; u32 count; u64 g_n; u32 layer;
+};
 
 // Heap layout of a tree over M leaves: tree[M + i] = leaf i, tree[i] = BLAKE3(tree[2i] || tree[2i+1]) for 1 <= i < M,
 // tree[1] = root (winter-crypto MerkleTree::new keeps the same `nodes` numbering, A.7).
@@ -16,7 +24,7 @@ void launch_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, in
 void launch_commit_rows_wide(cudaStream_t st, const u64* data, size_t limb_stride, u32 num_limbs, u32 ln, Digest* tree);
 void merkle_commit_rows(cudaStream_t st, const u64* data, size_t limb_stride, int num_limbs, u32 ln, Digest* tree);
 // Completes the tree above a fully written level of M nodes (heap range [M, 2M)).
-void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M);
+void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M, const RootStep* step = nullptr);
 // hash_elements of `count` row-major rows of `limbs` (1, 2, 7, 8, 16) elements
 void launch_hash_rows(cudaStream_t st, const u64* rows, size_t count, int limbs, Digest* out);
 

@@ -68,8 +68,9 @@ struct GraphKey {      // everything that is baked into the captured launch sequ
   const void* plan; const void* trace; int D; u32 q, g; u32 width, seed_count, prog_instr;   // prog_instr: 0 = burn-mint kernels, else generic program length + 1
   std::array<const void*, XFG_TRACE_WIDTH> host_src;                                         // split upload: the column copies are part of the graph
   bool fill;                                                                                 // trace built on the device from the AIR constants
+  u32 ncoef;                                                                                 // constraint + assertion count (baked into the trace-root step of the tree kernel)
   bool operator<(const GraphKey& o) const {
-    return std::tie(plan, trace, D, q, g, width, seed_count, prog_instr, host_src, fill) < std::tie(o.plan, o.trace, o.D, o.q, o.g, o.width, o.seed_count, o.prog_instr, o.host_src, o.fill);
+    return std::tie(plan, trace, D, q, g, width, seed_count, prog_instr, host_src, fill, ncoef) < std::tie(o.plan, o.trace, o.D, o.q, o.g, o.width, o.seed_count, o.prog_instr, o.host_src, o.fill, o.ncoef);
   }
 };
 struct GraphEntry { cudaGraphExec_t exec; unsigned launches; };
@@ -330,9 +331,11 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   //   ---- compute_execution_trace_commitment
   if (W == 1 || W == 2 || W == XFG_TRACE_WIDTH) PROF("commit_rows.trace", launch_commit_rows(st, c.lde, N, (int)W, ln, c.trace_tree));
   else PROF("commit_rows.trace", launch_commit_rows_wide(st, c.lde, N, W, ln, c.trace_tree));
-  PROF("tree_upper.trace", merkle_build_upper(st, c.trace_tree, n));
-  if (gen) PROF("transcript", launch_gen_trace_root(st, D, s.d_state, s.d_gen, s.d_prog, c.trace_tree));
-  else PROF("transcript", launch_trace_root(st, D, s.d_state, c.trace_tree));
+  // commit_trace + the constraint composition coefficients run on the CTA that computes the root (RootStep): no separate transcript launch
+  { RootStep rs{}; rs.kind = 1; rs.D = D; rs.ps = s.d_state;
+    if (gen) { rs.out = reinterpret_cast<u64(*)[2]>(reinterpret_cast<char*>(s.d_gen) + offsetof(GenState, coef)); rs.count = s.h_prog->num_constraints + s.h_prog->num_assertions; }
+    else { rs.out = reinterpret_cast<u64(*)[2]>(reinterpret_cast<char*>(s.d_state) + offsetof(ProofState, tcoef)); rs.count = XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS; }
+    PROF("tree_upper.trace", merkle_build_upper(st, c.trace_tree, n, &rs)); }
   mark();
   // 2 ---- evaluate_constraints
   // The constraint-evaluation domain is cosets 0 and 4 of the LDE domain, so the evaluations are written where the composition LDE needs them:
@@ -351,8 +354,8 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
     j.coset_map = 0x765321; j.dst_cosets = 8;
     j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_comp", ntt_batch(st, p.ntt, j)); }
   PROF("commit_rows.comp", launch_commit_rows(st, c.h_lde, N, D, ln, c.comp_tree));
-  PROF("tree_upper.comp", merkle_build_upper(st, c.comp_tree, n));
-  PROF("transcript", launch_constraint_root(st, D, s.d_state, c.comp_tree, p.g_n));
+  { RootStep rs{}; rs.kind = 2; rs.D = D; rs.ps = s.d_state; rs.g_n = p.g_n;      // commit_constraints, draw z, z g
+    PROF("tree_upper.comp", merkle_build_upper(st, c.comp_tree, n, &rs)); }
   mark();
   // 4 ---- build_deep_composition_poly: OOD frame + coefficients
   PROF("ood", launch_ood(st, D, c.trace_coef, c.h_coef, ln, W, s.d_state, s.d_partial));
@@ -368,8 +371,8 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   u32 first_tail = p.num_layers;
   while (first_tail > 0 && p.layer_log[first_tail - 1] <= FRI_TAIL_MAX_LOG) first_tail--;
   for (u32 l = 0; l < first_tail; l++) {
-    PROF("fri.tree", merkle_build_upper(st, c.fri_tree[l], size_t(1) << (p.layer_log[l] - 3)));
-    PROF("transcript", launch_fri_commit(st, D, s.d_state, c.fri_tree[l], l));
+    { RootStep rs{}; rs.kind = 3; rs.D = D; rs.ps = s.d_state; rs.layer = l;     // commit_fri_layer, draw alpha
+      PROF("fri.tree", merkle_build_upper(st, c.fri_tree[l], size_t(1) << (p.layer_log[l] - 3), &rs)); }
     PROF("fri.fold", launch_fri_fold(st, D, c.fri_evals[l], l == 0 ? N : (size_t(1) << p.layer_log[l]), l == 0, p.layer_log[l], l, s.d_state, p.wN_inv, p.lN, p.fc,
                     c.fri_evals[l + 1], size_t(1) << p.layer_log[l + 1], l + 1 < p.num_layers ? c.fri_tree[l + 1] : nullptr));
   }
@@ -415,7 +418,8 @@ int launch_prepared(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_optio
   if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);
   const bool split = s.split_upload && !d_trace;
   std::array<const void*, XFG_TRACE_WIDTH> srcs{}; if (split) for (int c = 0; c < XFG_TRACE_WIDTH; c++) srcs[c] = s.up_cols[c];
-  const GraphKey key{&p, d_trace, D, o.num_queries + (s.tail_threads << 16), o.grinding_factor + (s.in_scale != 1 ? 256u : 0u), s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0, srcs, s.fill_trace && !d_trace};
+  const GraphKey key{&p, d_trace, D, o.num_queries + (s.tail_threads << 16), o.grinding_factor + (s.in_scale != 1 ? 256u : 0u), s.W, s.seed_count, s.generic ? s.h_prog->num_instr + 1 : 0, srcs, s.fill_trace && !d_trace,
+                     s.generic ? s.h_prog->num_constraints + s.h_prog->num_assertions : 0u};
   auto it = s.graphs.find(key);
   if (it == s.graphs.end()) {
     if (s.graphs.size() >= 16) { for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec); s.graphs.clear(); }   // bounded cache (callers that keep changing the device trace pointer)

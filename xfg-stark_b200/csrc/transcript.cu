@@ -12,22 +12,8 @@
 
 namespace xfg {
 
-// coin = hash_elements(context elements || public inputs) (A.4), computed here from the seed elements the host copied into the proof state (no
-// separate seeding launch); then commit_trace: reseed with the root, draw the constraint composition coefficients
-template <int D> __global__ void __launch_bounds__(32) trace_root_kernel(ProofState* ps, const Digest* __restrict__ tree) {
-  Coin c; c.seed = r_hash_limbs(ps->seed_limbs, (int)ps->seed_count); c.counter = 0;
-  const Digest root = tree[1]; r_reseed(c, root);
-  // transition coefficients first, then boundary (A.8): tcoef[7] and bcoef[8] are contiguous in ProofState
-  const bool ok = r_draw_many<D>(c, XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS, ps->tcoef);
-  if (lane_id() == 0) { ps->trace_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
-  coin_store(ps, c);
-}
-template <int D> __global__ void __launch_bounds__(32) constraint_root_kernel(ProofState* ps, const Digest* __restrict__ tree, u64 g_n) {
-  Coin c = coin_load(ps); const Digest root = tree[1]; r_reseed(c, root);
-  const bool ok = r_draw_many<D>(c, 1, &ps->z);
-  if (lane_id() == 0) { ps->constraint_root = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; stx<D>(ps->zg, mul_base(ldx<D>(ps->z), g_n)); }
-  coin_store(ps, c);
-}
+// The root-consuming steps (commit_trace / commit_constraints / commit_fri_layer and the draws that follow them) run inside the tree kernels
+// (merkle.cu: RootStep); the remainder commitment, grinding and positions of ordinary proofs inside fri_tail.cu.
 // sums the OOD partials, sends the frame and H(z) to the coin, draws the DEEP coefficients (A.9)
 // Block of (7 + D) warps: warp p first sums the partials of polynomial p (all loads of a lane issued together: one memory latency
 // instead of one per sum), then warp 0 alone continues with the transcript.
@@ -85,26 +71,6 @@ template <int D> __global__ void __launch_bounds__(32 * NUM_OOD_POLYS) ood_finis
     for (int j = 0; j <= XFG_TRACE_WIDTH; j++) { c1 = c1 + ldx<D>(cpart[0][j]); c2 = c2 + ldx<D>(cpart[1][j]); }
     stx<D>(ps->deep_c1, c1); stx<D>(ps->deep_c2, c2);
   }
-  coin_store(ps, c);
-}
-template <int D> __global__ void __launch_bounds__(32) fri_commit_kernel(ProofState* ps, const Digest* __restrict__ tree, u32 layer) {
-  Coin c = coin_load(ps); const Digest root = tree[1]; r_reseed(c, root);
-  const bool ok = r_draw_many<D>(c, 1, &ps->alphas[layer]);
-  if (lane_id() == 0) { ps->fri_roots[layer] = root; if (!ok) ps->error_flags |= ERR_FLAG_COIN; }
-  coin_store(ps, c);
-}
-// remainder = first `len` coefficients; commitment = hash_elements(remainder); reseed (A.10)
-template <int D> __global__ void __launch_bounds__(32) remainder_kernel(ProofState* ps, const u64* __restrict__ coef, size_t limb_stride, u32 len) {
-  __shared__ u64 limbs[MAX_REMAINDER * 2];
-  Coin c = coin_load(ps);
-  for (u32 t = lane_id(); t < len * 2; t += 32) {
-    const u32 i = t >> 1, l = t & 1; const u64 v = l < (u32)D ? coef[(size_t)l * limb_stride + i] : 0;
-    ps->remainder[i][l] = v; if (l < (u32)D) limbs[i * D + l] = v;
-  }
-  __syncwarp();
-  const Digest d = r_hash_limbs(limbs, (int)(len * D));     // every lane computes the same digest
-  r_reseed(c, d);
-  if (lane_id() == 0) { ps->remainder_len = len; ps->remainder_commitment = d; }
   coin_store(ps, c);
 }
 // grinding: smallest nonce >= 1 with trailing_zeros(LE head of BLAKE3(seed || nonce)) >= grinding_factor (A.5).
@@ -190,24 +156,8 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherTasks tasks, const Pr
   }
 }
 
-void launch_trace_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree) {
-  if (D == 1) trace_root_kernel<1><<<1, 32, 0, st>>>(ps, tree); else trace_root_kernel<2><<<1, 32, 0, st>>>(ps, tree);
-  XFG_LAUNCHED(1);
-}
-void launch_constraint_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u64 g_n) {
-  if (D == 1) constraint_root_kernel<1><<<1, 32, 0, st>>>(ps, tree, g_n); else constraint_root_kernel<2><<<1, 32, 0, st>>>(ps, tree, g_n);
-  XFG_LAUNCHED(1);
-}
 void launch_ood_finish(cudaStream_t st, int D, ProofState* ps, const u64* partial, u32 nb) {
   if (D == 1) ood_finish_kernel<1><<<1, 32 * (XFG_TRACE_WIDTH + 1), 0, st>>>(ps, partial, nb); else ood_finish_kernel<2><<<1, 32 * (XFG_TRACE_WIDTH + 2), 0, st>>>(ps, partial, nb);
-  XFG_LAUNCHED(1);
-}
-void launch_fri_commit(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u32 layer) {
-  if (D == 1) fri_commit_kernel<1><<<1, 32, 0, st>>>(ps, tree, layer); else fri_commit_kernel<2><<<1, 32, 0, st>>>(ps, tree, layer);
-  XFG_LAUNCHED(1);
-}
-void launch_remainder(cudaStream_t st, int D, ProofState* ps, const u64* coef, size_t limb_stride, u32 len) {
-  if (D == 1) remainder_kernel<1><<<1, 32, 0, st>>>(ps, coef, limb_stride, len); else remainder_kernel<2><<<1, 32, 0, st>>>(ps, coef, limb_stride, len);
   XFG_LAUNCHED(1);
 }
 void launch_grind(cudaStream_t st, ProofState* ps, u32 grinding) {

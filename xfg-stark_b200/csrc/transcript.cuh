@@ -15,11 +15,7 @@ struct GatherTask {
 };
 struct GatherTasks { GatherTask t[2 + MAX_LAYERS]; u32 count; };
 
-void launch_trace_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree);
-void launch_constraint_root(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u64 g_n);
 void launch_ood_finish(cudaStream_t st, int D, ProofState* ps, const u64* partial, u32 nb);
-void launch_fri_commit(cudaStream_t st, int D, ProofState* ps, const Digest* tree, u32 layer);
-void launch_remainder(cudaStream_t st, int D, ProofState* ps, const u64* coef, size_t limb_stride, u32 len);
 void launch_grind(cudaStream_t st, ProofState* ps, u32 grinding);
 void launch_positions(cudaStream_t st, ProofState* ps, u32 num_queries, u32 lN, u32 num_layers);
 void launch_gather(cudaStream_t st, const GatherTasks& tasks, const ProofState* ps, u64* out);
