@@ -85,7 +85,7 @@ def test_from_inputs_builds_the_trace_on_the_device(n_log2, ext):
                                                s["version"], n_log2=n_log2, options=opts, want_times=True)
             tr, pi, ac = orc.synthetic_case(1 << n_log2, n_log2)
             assert proof == orc.prove(tr, pi, ac, opts.as_tuple())
-            assert times["h2d_bytes"] == 128 * 8 + 16        # the init block of the proof state (seed elements, flags): no trace bytes
+            assert times["h2d_bytes"] == 128 * 8 + 16 + 64        # the init block of the proof state (seed elements, flags): no trace bytes
             proof_b = c.prove_from_inputs(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"],
                                           s["version"], n_log2=n_log2, options=opts)
             assert proof_b == proof
@@ -120,7 +120,7 @@ def test_montgomery_form_columns(n_log2, ext):
         try:
             p1, t = c.prove_cols(cols, air, opts, form=1, want_times=True)              # DMA straight from the caller's columns
             assert p1 == expect and c.prove_cols(cols, air, opts, form=1) == expect
-            assert t["h2d_bytes"] == 7 * 8 * (1 << n_log2) + 128 * 8 + 16
+            assert t["h2d_bytes"] == 7 * 8 * (1 << n_log2) + 128 * 8 + 16 + 64
         finally:
             for a in cols:
                 c.host_unregister(a)

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(512) tree_upper_fused_kernel(Digest* __restric
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned* ticket = reinterpret_cast<unsigned*>(tree);
+    unsigned* ticket = rs.ticket ? rs.ticket : reinterpret_cast<unsigned*>(tree);
     is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     if (is_last) *ticket = 0;
   }
@@ -294,7 +294,7 @@ void merkle_build_upper(cudaStream_t st, Digest* tree, size_t M, const RootStep*
     M /= 8;
   }
   if (M > 2048) {
-    cudaMemsetAsync(tree, 0, sizeof(unsigned), st);
+    if (!rs.ticket) cudaMemsetAsync(tree, 0, sizeof(unsigned), st);
     tree_upper_fused_kernel<<<(unsigned)(M / 1024), 512, 0, st>>>(tree, M, rs); XFG_LAUNCHED(1);
     return;
   }

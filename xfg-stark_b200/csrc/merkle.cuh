@@ -11,6 +11,7 @@ namespace xfg {
 struct RootStep {
   int kind;                 // 0 none; 1 trace root: coin seed (A.4), reseed, `count` coefficients -> out; 2 constraint root: z, z g; 3 FRI layer `layer`: alpha
   int D; ProofState* ps; u64 (*out)[2]; u32 count; u64 g_n; u32 layer;
+  unsigned* ticket;         // zero-initialised "last CTA" counter for the fused upper-tree kernel (null: heap slot 0 of the tree, cleared by a memset)
 };
 
 // Heap layout of a tree over M leaves: tree[M + i] = leaf i, tree[i] = BLAKE3(tree[2i] || tree[2i+1]) for 1 <= i < M,

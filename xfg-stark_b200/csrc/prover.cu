@@ -332,7 +332,8 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   if (W == 1 || W == 2 || W == XFG_TRACE_WIDTH) PROF("commit_rows.trace", launch_commit_rows(st, c.lde, N, (int)W, ln, c.trace_tree));
   else PROF("commit_rows.trace", launch_commit_rows_wide(st, c.lde, N, W, ln, c.trace_tree));
   // commit_trace + the constraint composition coefficients run on the CTA that computes the root (RootStep): no separate transcript launch
-  { RootStep rs{}; rs.kind = 1; rs.D = D; rs.ps = s.d_state;
+  auto ticket = [&](int i) -> unsigned* { return i < 16 ? reinterpret_cast<unsigned*>(reinterpret_cast<char*>(s.d_state) + offsetof(ProofState, tickets)) + i : nullptr; };
+  { RootStep rs{}; rs.kind = 1; rs.D = D; rs.ps = s.d_state; rs.ticket = ticket(0);
     if (gen) { rs.out = reinterpret_cast<u64(*)[2]>(reinterpret_cast<char*>(s.d_gen) + offsetof(GenState, coef)); rs.count = s.h_prog->num_constraints + s.h_prog->num_assertions; }
     else { rs.out = reinterpret_cast<u64(*)[2]>(reinterpret_cast<char*>(s.d_state) + offsetof(ProofState, tcoef)); rs.count = XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS; }
     PROF("tree_upper.trace", merkle_build_upper(st, c.trace_tree, n, &rs)); }
@@ -354,7 +355,7 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
     j.coset_map = 0x765321; j.dst_cosets = 8;
     j.inverse = false; j.scale = 1; j.pre_lo = p.pre_lo; j.pre_hi = p.pre_hi; j.pre_hi_stride = p.pre_hi_stride; PROF("ntt.lde_comp", ntt_batch(st, p.ntt, j)); }
   PROF("commit_rows.comp", launch_commit_rows(st, c.h_lde, N, D, ln, c.comp_tree));
-  { RootStep rs{}; rs.kind = 2; rs.D = D; rs.ps = s.d_state; rs.g_n = p.g_n;      // commit_constraints, draw z, z g
+  { RootStep rs{}; rs.kind = 2; rs.D = D; rs.ps = s.d_state; rs.g_n = p.g_n; rs.ticket = ticket(1);      // commit_constraints, draw z, z g
     PROF("tree_upper.comp", merkle_build_upper(st, c.comp_tree, n, &rs)); }
   mark();
   // 4 ---- build_deep_composition_poly: OOD frame + coefficients
@@ -371,7 +372,7 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   u32 first_tail = p.num_layers;
   while (first_tail > 0 && p.layer_log[first_tail - 1] <= FRI_TAIL_MAX_LOG) first_tail--;
   for (u32 l = 0; l < first_tail; l++) {
-    { RootStep rs{}; rs.kind = 3; rs.D = D; rs.ps = s.d_state; rs.layer = l;     // commit_fri_layer, draw alpha
+    { RootStep rs{}; rs.kind = 3; rs.D = D; rs.ps = s.d_state; rs.layer = l; rs.ticket = ticket(2 + (int)l);     // commit_fri_layer, draw alpha
       PROF("fri.tree", merkle_build_upper(st, c.fri_tree[l], size_t(1) << (p.layer_log[l] - 3), &rs)); }
     PROF("fri.fold", launch_fri_fold(st, D, c.fri_evals[l], l == 0 ? N : (size_t(1) << p.layer_log[l]), l == 0, p.layer_log[l], l, s.d_state, p.wN_inv, p.lN, p.fc,
                     c.fri_evals[l + 1], size_t(1) << p.layer_log[l + 1], l + 1 < p.num_layers ? c.fri_tree[l + 1] : nullptr));
@@ -412,7 +413,8 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
 // when no per-stage timing is requested and the upload is not split, otherwise launch by launch.
 // the slot's per-proof inputs (seed elements, AIR constants or compiled program, width) have been prepared in its pinned mirrors
 int launch_prepared(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options& o, const u64* d_trace, bool timed) {
-  { u32* tail = reinterpret_cast<u32*>(s.h_seed + MAX_SEED_LIMBS); tail[0] = s.seed_count; tail[1] = 0; tail[2] = tail[3] = 0xFFFFFFFFu; }   // seed_count, error_flags = 0, nonce = ~0
+  { u32* tail = reinterpret_cast<u32*>(s.h_seed + MAX_SEED_LIMBS); tail[0] = s.seed_count; tail[1] = 0; tail[2] = tail[3] = 0xFFFFFFFFu;    // seed_count, error_flags = 0, nonce = ~0
+    for (int i = 0; i < 16; i++) tail[4 + i] = 0; }                                                                                       // tree tickets
   { Carve c; carve(s, p, D, c); if (c.words > s.slab_words) return fail(ctx, XFG_ERR_TOO_LARGE, "workspace too small for this trace length"); }
   const bool use_graph = ctx->graphs && !timed && !ctx->profiling;
   if (!use_graph) return enqueue_proof(ctx, s, p, D, o, d_trace, timed);

@@ -26,6 +26,7 @@ struct ProofState {
   // ---- per-proof inputs: this block is written by ONE host->device copy from the slot's pinned mirror at the start of every proof (no
   // seeding kernel): the coin seed elements (A.4), and the reset values of the error flags and of the grinding nonce
   u64 seed_limbs[MAX_SEED_LIMBS]; u32 seed_count; u32 error_flags; unsigned long long nonce;   // nonce: ~0 until the grinding search has found it
+  u32 tickets[16];          // "last CTA finishes the tree" counters of the upper-tree kernels (one per tree of the proof), zeroed by the same copy
   // coin
   Digest seed; u64 counter;
   // commitments
@@ -46,7 +47,7 @@ struct ProofState {
   long long dbg_clk[48];   // phase timestamps of the fused tail kernel (debug builds only)
 #endif
 };
-static constexpr size_t PROOF_INIT_BYTES = sizeof(u64) * MAX_SEED_LIMBS + 16;
+static constexpr size_t PROOF_INIT_BYTES = sizeof(u64) * MAX_SEED_LIMBS + 16 + 64;
 static_assert(PROOF_INIT_BYTES == offsetof(ProofState, seed), "init block layout");
 
 // AIR constants and boundary values (src/burn_mint_air.rs:335-395), passed by value to the constraint kernel
