@@ -140,6 +140,9 @@ void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64*
 #ifndef XFG_OOD_MLP
 #define XFG_OOD_MLP 4
 #endif
+#ifndef XFG_OOD_SHARE
+#define XFG_OOD_SHARE 0
+#endif
 template <int D>
 __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln, u32 width, u32 polys_per_block,
                                                    const ProofState* __restrict__ ps, u64* __restrict__ partial) {
@@ -214,6 +217,11 @@ void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef
   // (sharing more - 2 polynomials per block at width 7 - was measured slower, 0.097 -> 0.118 ms: the kernel is latency-bound and wants blocks)
   const u32 nb = ood_num_blocks(ln), P = width + D;
   u32 ppb = 1; while ((size_t)nb * ((P + ppb - 1) / ppb) > 148 * 4 && ppb < P) ppb++;
+#if XFG_OOD_SHARE
+  // A/B switch: every block evaluates ALL polynomials on its slice of exponents, so the per-thread power set-up (pt^t) is paid once instead of once per
+  // polynomial.  MEASURED SLOWER at 2^20 rows (round 2): 0.089 ms -> 0.140 / 0.111 / 0.130 ms with 128 / 256 / 512 blocks: the kernel wants its 576 short blocks.
+  ppb = P;
+#endif
   dim3 grid(nb, (P + ppb - 1) / ppb);
   if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
   else ood_kernel<2><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
