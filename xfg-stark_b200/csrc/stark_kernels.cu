@@ -236,6 +236,11 @@ void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef
 // batched inversion, writes them coset-major and hashes the row into the layer-0 FRI tree.
 // ------------------------------------------------------------------------------------------------------------------
 static constexpr int DEEP_THREADS = 128;
+#ifndef XFG_DEEP_UNROLL
+#define XFG_DEEP_UNROLL 1   // points of the first loop interleaved per iteration (A/B switch).  Measured at 2^20 rows / quadratic (round 2): 1 -> 0.633 ms, 2 -> 0.676, 4 -> 0.692
+                            // (128 registers, no spills in all three: the larger loop body costs instruction-cache hits, as the fully unrolled kernel of round 1 did)
+#endif
+static constexpr int DEEP_UNROLL = XFG_DEEP_UNROLL;
 // 1 / (x - w) for a base-field x and an extension point w = (w0, w1):  (x - w)^-1 = conj / norm with
 //   u = x - w0,  conj = (u - w1, w1),  norm = u (u - w1) + 2 w1^2           (degree 2; one multiplication)
 //   conj = 1,    norm = x - w0                                              (degree 1)
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
   const Ext<D> delta(sc[2 * W], sc[2 * W + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]);
   const DeepPoint<D> pz{cc[4], cc[5], gl_neg(gl_dbl(cc[5])), gl_dbl(gl_sqr(cc[5]))}, pzg{cc[6], cc[7], gl_neg(gl_dbl(cc[7])), gl_dbl(gl_sqr(cc[7]))};
   u64 x = gl_mul(s_k[k], pow_lookup(wn, a)), acc = 1;      // x_j = x_0 * w_8^j  (m = a + j n/8)
-#pragma unroll 1
+#pragma unroll DEEP_UNROLL
   for (int j = 0; j < 8; j++) {
     const size_t idx = (size_t)k * n + a + (size_t)j * n8;
     DotAcc sa[D];     // S_T = sum_c gamma_c T_c(x): un-reduced dot product, one reduction per limb
