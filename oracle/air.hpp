@@ -31,7 +31,7 @@ struct ProofOptions {
     if (!pow2(folding)) return "FRI folding factor must be a power of 2";
     if (folding < 2 || folding > 16) return "FRI folding factor out of range";
     if (rem_max_deg > 255 || !pow2(rem_max_deg + 1)) return "FRI polynomial remainder degree must be one less than a power of two";
-    if (ext != XFG_EXT_NONE && ext != XFG_EXT_QUADRATIC) return "UnsupportedFieldExtension";
+    if (ext != XFG_EXT_NONE && ext != XFG_EXT_QUADRATIC && ext != XFG_EXT_CUBIC) return "UnsupportedFieldExtension";
     return "";
   }
   // ProofOptions::to_elements (A.2, D)

@@ -14,7 +14,7 @@ namespace orc { int g_threads = 1; }
 using namespace orc;
 
 namespace {
-ProverDebug<F1> g_dbg1; ProverDebug<F2> g_dbg2; int g_dbg_ext = 0;
+ProverDebug<F1> g_dbg1; ProverDebug<F2> g_dbg2; ProverDebug<F3> g_dbg3; int g_dbg_ext = 0;
 ProofOptions opts_from(const uint32_t o[6]) { ProofOptions p; p.num_queries = o[0]; p.blowup = o[1]; p.grinding = o[2]; p.ext = o[3]; p.folding = o[4]; p.rem_max_deg = o[5]; return p; }
 PublicInputs pi_from(const u64* v) { PublicInputs p; for (int i = 0; i < XFG_NUM_PUB_INPUTS; i++) p.v[i] = v[i]; return p; }
 AirConsts ac_from(const u64* c) { return {c[0], c[1], c[2], c[3]}; }
@@ -42,6 +42,8 @@ u64 orc_fpow(u64 a, u64 e) { return fpow(a, e); }
 u64 orc_root_of_unity(unsigned k) { return root_of_unity(k); }
 void orc_f2_mul(const u64 a[2], const u64 b[2], u64 o[2]) { F2 r = F2(a[0], a[1]) * F2(b[0], b[1]); o[0] = r.a0; o[1] = r.a1; }
 void orc_f2_inv(const u64 a[2], u64 o[2]) { F2 r = F2(a[0], a[1]).inv(); o[0] = r.a0; o[1] = r.a1; }
+void orc_f3_mul(const u64 a[3], const u64 b[3], u64 o[3]) { F3 r = F3(a[0], a[1], a[2]) * F3(b[0], b[1], b[2]); for (int i = 0; i < 3; i++) o[i] = r.a[i]; }
+void orc_f3_inv(const u64 a[3], u64 o[3]) { F3 r = F3(a[0], a[1], a[2]).inv(); for (int i = 0; i < 3; i++) o[i] = r.a[i]; }
 
 // data: n elements of `deg` limbs each (interleaved limbs). mode 0: forward NTT; 1: interpolate_poly (scaled inverse);
 // 2: naive O(n^2) forward DFT
@@ -119,6 +121,7 @@ int orc_prove(const u64* trace, unsigned n_log2, const u64 pi[12], const u64 con
     for (size_t j = 0; j < XFG_TRACE_WIDTH; j++) for (size_t i = 0; i < n; i++) { if (trace[j * n + i] >= P) { set_err(err, errcap, "non-canonical trace element"); return 1; } t[j][i] = F1(trace[j * n + i]); }
     StageTimes st; std::vector<u8> bytes;
     if (opt.ext == XFG_EXT_NONE) bytes = prove<F1>(t, pi_from(pi), ac_from(consts), opt, &st, keep_debug ? &g_dbg1 : nullptr);
+    else if (opt.ext == XFG_EXT_CUBIC) bytes = prove<F3>(t, pi_from(pi), ac_from(consts), opt, &st, keep_debug ? &g_dbg3 : nullptr);
     else bytes = prove<F2>(t, pi_from(pi), ac_from(consts), opt, &st, keep_debug ? &g_dbg2 : nullptr);
     if (keep_debug) g_dbg_ext = opt.ext;
     if (stage_ms) for (int i = 0; i < ST_COUNT; i++) stage_ms[i] = st.ms[i];
@@ -151,7 +154,7 @@ long orc_debug_get(const char* name, u64* out, size_t cap) {
     else return false;
     return true;
   };
-  bool ok = (g_dbg_ext == XFG_EXT_QUADRATIC) ? fill(g_dbg2) : fill(g_dbg1);
+  bool ok = (g_dbg_ext == XFG_EXT_QUADRATIC) ? fill(g_dbg2) : (g_dbg_ext == XFG_EXT_CUBIC) ? fill(g_dbg3) : fill(g_dbg1);
   if (!ok || v.size() > cap) return -1;
   std::memcpy(out, v.data(), v.size() * 8); return (long)v.size();
 }
@@ -172,7 +175,8 @@ int orc_verify(const u8* proof, size_t len, const u64 pi[12], const u64 consts[4
   try {
     ProofOptions opt = opts_from(o); std::string e = opt.validate(); if (!e.empty()) { set_err(err, errcap, e); return 1; }
     std::string r = (opt.ext == XFG_EXT_NONE) ? verify<F1>(proof, len, pi_from(pi), ac_from(consts), opt)
-                                              : verify<F2>(proof, len, pi_from(pi), ac_from(consts), opt);
+                  : (opt.ext == XFG_EXT_CUBIC) ? verify<F3>(proof, len, pi_from(pi), ac_from(consts), opt)
+                                               : verify<F2>(proof, len, pi_from(pi), ac_from(consts), opt);
     if (!r.empty()) { set_err(err, errcap, r); return 1; }
     return 0;
   } catch (const std::exception& ex) { set_err(err, errcap, ex.what()); return 1; }
@@ -198,6 +202,7 @@ int orc_prove_air(const u64* trace, unsigned n_log2, const uint32_t desc[6], con
     for (size_t j = 0; j < air.width; j++) for (size_t i = 0; i < n; i++) { if (trace[j * n + i] >= P) { set_err(err, errcap, "non-canonical trace element"); return 1; } t[j][i] = F1(trace[j * n + i]); }
     StageTimes st; std::vector<u8> bytes;
     if (opt.ext == XFG_EXT_NONE) bytes = prove<F1>(t, air, opt, &st, keep_debug ? &g_dbg1 : nullptr);
+    else if (opt.ext == XFG_EXT_CUBIC) bytes = prove<F3>(t, air, opt, &st, keep_debug ? &g_dbg3 : nullptr);
     else bytes = prove<F2>(t, air, opt, &st, keep_debug ? &g_dbg2 : nullptr);
     if (keep_debug) g_dbg_ext = opt.ext;
     if (stage_ms) for (int i = 0; i < ST_COUNT; i++) stage_ms[i] = st.ms[i];
@@ -212,7 +217,7 @@ int orc_verify_air(const u8* proof, size_t len, const uint32_t desc[6], const u6
   try {
     ProofOptions opt = opts_from(o); std::string e = opt.validate(); if (!e.empty()) { set_err(err, errcap, e); return 1; }
     AirDef air = air_from(desc, pub, consts, code, outs, asr);
-    std::string r = (opt.ext == XFG_EXT_NONE) ? verify<F1>(proof, len, air, opt) : verify<F2>(proof, len, air, opt);
+    std::string r = (opt.ext == XFG_EXT_NONE) ? verify<F1>(proof, len, air, opt) : (opt.ext == XFG_EXT_CUBIC) ? verify<F3>(proof, len, air, opt) : verify<F2>(proof, len, air, opt);
     if (!r.empty()) { set_err(err, errcap, r); return 1; }
     return 0;
   } catch (const std::exception& ex) { set_err(err, errcap, ex.what()); return 1; }

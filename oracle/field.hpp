@@ -36,7 +36,7 @@ inline u64 finv(u64 a) { return fpow(a, P - 2); }
 // primitive 2^k-th root of unity: G^(2^(32-k))  (A.1; winter-math `get_root_of_unity`)
 inline u64 root_of_unity(unsigned k) { u64 r = XFG_TWO_ADIC_ROOT; for (unsigned i = k; i < XFG_TWO_ADICITY; i++) r = fmul(r, r); return r; }
 
-// ---- element types: F1 = base field, F2 = quadratic extension; same interface so the prover is generic ----
+// ---- element types: F1 = base field, F2 = quadratic extension, F3 = cubic extension; same interface so the prover is generic ----
 struct F1 {
   u64 v;
   static constexpr int DEG = 1;
@@ -86,6 +86,45 @@ struct F2 {  // a0 + a1*x, x^2 = x - 2
   bool is_zero() const { return a0 == 0 && a1 == 0; }
   u64 limb(int i) const { return i ? a1 : a0; }
   void set_limb(int i, u64 x) { (i ? a1 : a0) = x; }
+};
+
+struct F3 {  // a0 + a1*x + a2*x^2, x^3 = x + 1  (winter-math 0.8.4 `impl ExtensibleField<3> for f64::BaseElement`: irreducible x^3 - x - 1;
+             // pinned by the proofs the reference binary emits with FieldExtension::Cubic, tests/golden/reference_proofs_options.json)
+  u64 a[3];
+  static constexpr int DEG = 3;
+  F3() : a{0, 0, 0} {}
+  F3(u64 x0, u64 x1, u64 x2) : a{x0, x1, x2} {}
+  static F3 zero() { return F3(); }
+  static F3 one() { return F3(1, 0, 0); }
+  static F3 from_base(u64 b) { return F3(b, 0, 0); }
+  F3 operator+(F3 o) const { return F3(fadd(a[0], o.a[0]), fadd(a[1], o.a[1]), fadd(a[2], o.a[2])); }
+  F3 operator-(F3 o) const { return F3(fsub(a[0], o.a[0]), fsub(a[1], o.a[1]), fsub(a[2], o.a[2])); }
+  F3 operator-() const { return F3(fneg(a[0]), fneg(a[1]), fneg(a[2])); }
+  // schoolbook product c0..c4, then x^3 = x + 1, x^4 = x^2 + x
+  F3 operator*(F3 o) const {
+    const u64* b = o.a;
+    u64 c0 = fmul(a[0], b[0]), c1 = fadd(fmul(a[0], b[1]), fmul(a[1], b[0])), c2 = fadd(fadd(fmul(a[0], b[2]), fmul(a[1], b[1])), fmul(a[2], b[0]));
+    u64 c3 = fadd(fmul(a[1], b[2]), fmul(a[2], b[1])), c4 = fmul(a[2], b[2]);
+    return F3(fadd(c0, c3), fadd(fadd(c1, c3), c4), fadd(c2, c4));
+  }
+  F3 mul_base(u64 b) const { return F3(fmul(a[0], b), fmul(a[1], b), fmul(a[2], b)); }
+  // inverse through the matrix of "multiply by this element" in the basis 1, x, x^2 (columns e * 1, e * x, e * x^2): the first column of
+  // its inverse (Cramer's rule) holds the coefficients of e^-1.  The field is unique, so the value equals winter-math's Frobenius-based inv().
+  F3 inv() const {
+    const F3 c0 = *this, c1 = *this * F3(0, 1, 0), c2 = *this * F3(0, 0, 1);
+    // M = [c0 c1 c2] (columns); solve M b = (1, 0, 0)
+    auto det2 = [](u64 p, u64 q, u64 r, u64 s) { return fsub(fmul(p, s), fmul(q, r)); };
+    const u64 m00 = c0.a[0], m10 = c0.a[1], m20 = c0.a[2], m01 = c1.a[0], m11 = c1.a[1], m21 = c1.a[2], m02 = c2.a[0], m12 = c2.a[1], m22 = c2.a[2];
+    const u64 k0 = det2(m11, m12, m21, m22), k1 = det2(m10, m12, m20, m22), k2 = det2(m10, m11, m20, m21);
+    const u64 det = fadd(fsub(fmul(m00, k0), fmul(m01, k1)), fmul(m02, k2));
+    const u64 di = finv(det);
+    return F3(fmul(k0, di), fmul(fneg(k1), di), fmul(k2, di));
+  }
+  bool operator==(F3 o) const { return a[0] == o.a[0] && a[1] == o.a[1] && a[2] == o.a[2]; }
+  bool operator!=(F3 o) const { return !(*this == o); }
+  bool is_zero() const { return a[0] == 0 && a[1] == 0 && a[2] == 0; }
+  u64 limb(int i) const { return a[i]; }
+  void set_limb(int i, u64 x) { a[i] = x; }
 };
 
 template <class E> inline E epow(E b, u64 e) { E r = E::one(); while (e) { if (e & 1) r = r * b; b = b * b; e >>= 1; } return r; }

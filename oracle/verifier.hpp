@@ -55,7 +55,7 @@ std::string verify(const u8* proof, size_t proof_len, AirDef air, const ProofOpt
   if (!rd.ok) return "truncated proof";
   if (opt.num_queries != acceptable.num_queries || opt.blowup != acceptable.blowup || opt.grinding != acceptable.grinding ||
       opt.ext != acceptable.ext || opt.folding != acceptable.folding || opt.rem_max_deg != acceptable.rem_max_deg) return "UnacceptableProofOptions";
-  if ((int)opt.ext != (E::DEG == 1 ? XFG_EXT_NONE : XFG_EXT_QUADRATIC)) return "field extension mismatch";
+  if ((int)opt.ext != (E::DEG == 1 ? XFG_EXT_NONE : E::DEG == 2 ? XFG_EXT_QUADRATIC : XFG_EXT_CUBIC)) return "field extension mismatch";
   const size_t n = size_t(1) << lg, b = opt.blowup, N = n * b, F = opt.folding;
   const size_t num_layers = opt.num_fri_layers(N);
   if (burn_mint_pi) air = burn_mint_air(*pi, air.ac, n);      // the burn-mint assertions depend on the trace length

@@ -24,6 +24,35 @@ def case_ids():
     return [c["name"] for c in cases()]
 
 
+# proofs for `ProofOptions` other than the reference's default (blowup 2..128, folding 2/4/8/16, remainder degree 0..255, all three extensions):
+# oracle/a64emu/make_reference_option_vectors.py
+OPTIONS_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_proofs_options.json")
+
+
+def load_options():
+    return json.load(open(OPTIONS_PATH))
+
+
+def option_cases():
+    return load_options()["cases"]
+
+
+def option_case_ids():
+    return [c["name"] for c in option_cases()]
+
+
+def fri_shape_refused(n_log2, options):
+    """the rule behind the reference's own panics (fixture key "refused"): a FRI layer of fewer than two rows, or an empty remainder"""
+    _, blowup, _, _, folding, rem = options
+    lb, lf = blowup.bit_length() - 1, folding.bit_length() - 1
+    l = n_log2 + lb
+    while (1 << l) > (rem + 1) * blowup:
+        if l < lf + 1:
+            return True
+        l -= lf
+    return l < lb
+
+
 def proof_bytes(c):
     return zlib.decompress(base64.b64decode(c["proof_zlib_b64"]))
 

@@ -1,0 +1,93 @@
+"""`ProofOptions` generality pinned against the REFERENCE ITSELF (CPU tests).
+
+`XfgBurnMintProver::with_options` (src/burn_mint_prover.rs:44-49) accepts every `ProofOptions::new` value.  The reference's own Winterfell
+0.8.3 prover (executed from its shipped binary by oracle/a64emu) emitted tests/golden/reference_proofs_options.json for blowup factors
+2..128, FRI folding factors 2/4/8/16, remainder degrees 0..255 and all three field extensions.  Checked here, on any box:
+
+  1. the oracle's bytes equal the reference's on every case (this is what pins oracle/field.hpp F3, the cubic extension);
+  2. the PRODUCT's general-options pipeline - its launch sequence and per-thread kernel bodies (xfg-stark_b200/csrc/general_*.cuh), executed
+     on the host by tests/host_emul - emits the same bytes; the GPU runs the same bodies as CUDA kernels (tests/test_gpu_options.py);
+  3. option sets the reference itself refuses with a panic are refused with an error code.
+"""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+import goemul
+import orc
+import refvec
+
+
+@pytest.mark.parametrize("name", refvec.option_case_ids())
+def test_oracle_and_emulated_pipeline_equal_reference_proof(name):
+    c = next(x for x in refvec.option_cases() if x["name"] == name)
+    ref = refvec.proof_bytes(c)
+    assert hashlib.sha256(ref).hexdigest() == c["proof_sha256"] and len(ref) == c["proof_len"]
+    pi, ac, o, n = refvec.statement(c)
+    t = refvec.trace(c, pi, ac)
+    air = refvec.air_program(c, pi, ac).flatten()
+    assert orc.prove_air(air, t, o) == ref
+    assert orc.verify_air(ref, air, o) == ""
+    assert goemul.prove_air(air, t, o) == ref
+    if refvec.is_normalised(c):                                  # 64 rows: the normalised AIR (last step n - 1) IS the source's AIR
+        assert orc.prove(t, pi, ac, o) == ref
+        assert orc.verify(ref, pi, ac, o) == ""
+        assert goemul.prove_burn_mint(t, pi, ac, o) == ref       # the C++ AIR description the product uses for the burn-mint entry points
+        R = (1 << 64) % orc.P
+        mont = np.array([[(int(v) * R) % orc.P for v in row] for row in t], dtype=np.uint64)
+        assert goemul.prove_burn_mint(mont, pi, ac, o, montgomery=True) == ref
+
+
+def test_option_vectors_cover_the_option_space():
+    cs = refvec.option_cases()
+    assert {c["options"][3] for c in cs} == {1, 2, 3}
+    assert {c["options"][1] for c in cs} >= {2, 4, 8, 16, 32, 64, 128}
+    assert {c["options"][4] for c in cs} == {2, 4, 8, 16}
+    assert {c["options"][5] for c in cs} >= {0, 1, 3, 7, 15, 31, 63, 255}
+    assert {c["n_log2"] for c in cs} >= {6, 8, 9, 10, 11, 12, 13}
+
+
+def test_shapes_the_reference_refuses_are_refused():
+    ref = refvec.load_options()["refused"]
+    assert len(ref) >= 3 and all("FRI layer" in r["panic"] or "TooFewLeaves" in r["panic"] for r in ref)
+    for r in ref:
+        o = tuple(r["options"]); n = 1 << r["n_log2"]
+        assert refvec.fri_shape_refused(r["n_log2"], o)
+        t, pi, ac = orc.synthetic_case(n, 1)
+        with pytest.raises(goemul.EmulError) as e:
+            goemul.prove_burn_mint(t, pi, ac, o)
+        assert e.value.code == 2
+    for c in refvec.option_cases() + refvec.cases():             # ... and nothing the reference proves is refused
+        assert not refvec.fri_shape_refused(c["n_log2"], tuple(c["options"]))
+
+
+def test_emulated_pipeline_equals_oracle_on_a_seeded_option_sweep():
+    rng = random.Random(20261019)
+    done = 0
+    while done < 40:
+        n_log2 = rng.choice([3, 4, 5, 6, 7, 8, 9])
+        blowup = rng.choice([2, 4, 8, 16, 32, 64, 128]); folding = rng.choice([2, 4, 8, 16]); rem = rng.choice([0, 1, 3, 7, 15, 31, 63, 127, 255])
+        o = (rng.randrange(1, min(255, (blowup << n_log2) - 1) + 1), blowup, rng.randrange(0, 9), rng.choice([1, 2, 3]), folding, rem)
+        if refvec.fri_shape_refused(n_log2, o):
+            continue
+        index = rng.randrange(1 << 20)
+        t, pi, ac = orc.synthetic_case(1 << n_log2, index)
+        expect = orc.prove(t, pi, ac, o)
+        assert goemul.prove_burn_mint(t, pi, ac, o) == expect, (n_log2, o)
+        assert orc.verify(expect, pi, ac, o) == ""
+        done += 1
+
+
+def test_emulated_pipeline_detects_bad_traces():
+    t, pi, ac = orc.synthetic_case(64, 3)
+    o = (20, 4, 2, 3, 4, 3)
+    bad = t.copy(); bad[4, 17] = 2
+    with pytest.raises(goemul.EmulError) as e:
+        goemul.prove_burn_mint(bad, pi, ac, o)
+    assert e.value.code == 5
+    bad = t.copy(); bad[2, 5] = orc.P + 1
+    with pytest.raises(goemul.EmulError) as e:
+        goemul.prove_burn_mint(bad, pi, ac, o)
+    assert e.value.code == 1

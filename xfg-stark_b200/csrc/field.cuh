@@ -62,7 +62,7 @@ XFG_HD u64 gl_inv(u64 x) {
 // primitive 2^k-th root of unity = G^(2^(32-k))  (A.1)
 XFG_HD u64 gl_root_of_unity(unsigned k) { u64 r = XFG_TWO_ADIC_ROOT; for (unsigned i = k; i < XFG_TWO_ADICITY; i++) r = gl_sqr(r); return r; }
 
-// ---- extension element, generic over degree D in {1, 2}: limb l of element i lives in array l (SoA in HBM) ----
+// ---- extension element, generic over degree D in {1, 2} (and 3, below): limb l of element i lives in array l (SoA in HBM) ----
 template <int D> struct Ext;
 template <> struct Ext<1> {
   u64 a0;
@@ -105,13 +105,52 @@ XFG_HD Ext<2> ext_inv_with_norm_inv(Ext<2> a, u64 ninv) { return Ext<2>(gl_mul(g
 XFG_HD Ext<1> ext_inv_with_norm_inv(Ext<1>, u64 ninv) { return Ext<1>(ninv); }
 XFG_HD Ext<2> ext_inv(Ext<2> a) { return ext_inv_with_norm_inv(a, gl_inv(ext_norm(a))); }
 XFG_HD bool is_zero(Ext<2> a) { return (a.a0 | a.a1) == 0; }
+// ---- cubic extension F_p[x]/(x^3 - x - 1) (winter-math 0.8.4 `impl ExtensibleField<3> for f64::BaseElement`; FieldExtension::Cubic of
+// `ProofOptions`, src/burn_mint_prover.rs:44-49).  Used by the general-options pipeline (general_bodies.cuh); the tuned 8/8 kernels stay on degrees 1 and 2.
+template <> struct Ext<3> {
+  u64 a[3];
+  XFG_HD Ext() : a{0, 0, 0} {}
+  XFG_HD explicit Ext(u64 x) : a{x, 0, 0} {}
+  XFG_HD Ext(u64 x, u64 y, u64 z) : a{x, y, z} {}
+  XFG_HD static Ext from_base(u64 b) { return Ext(b); }
+  XFG_HD u64 limb(int i) const { return a[i]; }
+  XFG_HD void set_limb(int i, u64 v) { a[i] = v; }
+};
+XFG_HD Ext<3> operator+(Ext<3> a, Ext<3> b) { return Ext<3>(gl_add(a.a[0], b.a[0]), gl_add(a.a[1], b.a[1]), gl_add(a.a[2], b.a[2])); }
+XFG_HD Ext<3> operator-(Ext<3> a, Ext<3> b) { return Ext<3>(gl_sub(a.a[0], b.a[0]), gl_sub(a.a[1], b.a[1]), gl_sub(a.a[2], b.a[2])); }
+// schoolbook product c0..c4, then x^3 = x + 1 and x^4 = x^2 + x
+XFG_HD Ext<3> operator*(Ext<3> a, Ext<3> b) {
+  const u64 c0 = gl_mul(a.a[0], b.a[0]), c1 = gl_add(gl_mul(a.a[0], b.a[1]), gl_mul(a.a[1], b.a[0]));
+  const u64 c2 = gl_add(gl_add(gl_mul(a.a[0], b.a[2]), gl_mul(a.a[1], b.a[1])), gl_mul(a.a[2], b.a[0]));
+  const u64 c3 = gl_add(gl_mul(a.a[1], b.a[2]), gl_mul(a.a[2], b.a[1])), c4 = gl_mul(a.a[2], b.a[2]);
+  return Ext<3>(gl_add(c0, c3), gl_add(gl_add(c1, c3), c4), gl_add(c2, c4));
+}
+XFG_HD Ext<3> mul_base(Ext<3> a, u64 b) { return Ext<3>(gl_mul(a.a[0], b), gl_mul(a.a[1], b), gl_mul(a.a[2], b)); }
+XFG_HD Ext<3> add_base(Ext<3> a, u64 b) { return Ext<3>(gl_add(a.a[0], b), a.a[1], a.a[2]); }
+XFG_HD bool is_zero(Ext<3> a) { return (a.a[0] | a.a[1] | a.a[2]) == 0; }
+// a^-1: the columns a, a x, a x^2 are the matrix of "multiply by a" in the basis 1, x, x^2; the first column of its inverse (cofactors over the
+// determinant = the norm of a) holds the coefficients of a^-1.   a x = (a2, a0 + a2, a1),   a x^2 = (a1, a1 + a2, a0 + a2)
+XFG_HD Ext<3> ext_inv(Ext<3> e) {
+  const u64 m00 = e.a[0], m10 = e.a[1], m20 = e.a[2];
+  const u64 m01 = e.a[2], m11 = gl_add(e.a[0], e.a[2]), m21 = e.a[1];
+  const u64 m02 = e.a[1], m12 = gl_add(e.a[1], e.a[2]), m22 = m11;
+  const u64 k0 = gl_sub(gl_mul(m11, m22), gl_mul(m12, m21)), k1 = gl_sub(gl_mul(m10, m22), gl_mul(m12, m20)), k2 = gl_sub(gl_mul(m10, m21), gl_mul(m11, m20));
+  const u64 det = gl_add(gl_sub(gl_mul(m00, k0), gl_mul(m01, k1)), gl_mul(m02, k2));
+  const u64 di = gl_inv(det);
+  return Ext<3>(gl_mul(k0, di), gl_mul(gl_neg(k1), di), gl_mul(k2, di));
+}
+// the element `x` (the basis element of limb 1) times a: used to assemble H(z) from the limb polynomials of the composition column
+template <int D> XFG_HD Ext<D> ext_mul_x(Ext<D> a);
+template <> XFG_HD Ext<1> ext_mul_x<1>(Ext<1> a) { return a; }
+template <> XFG_HD Ext<2> ext_mul_x<2>(Ext<2> a) { return Ext<2>(gl_neg(gl_dbl(a.a1)), gl_add(a.a0, a.a1)); }          // x^2 = x - 2
+template <> XFG_HD Ext<3> ext_mul_x<3>(Ext<3> a) { return Ext<3>(a.a[2], gl_add(a.a[0], a.a[2]), a.a[1]); }           // x^3 = x + 1
 template <int D> XFG_HD Ext<D> ext_pow(Ext<D> b, u64 e) { Ext<D> r(1); while (e) { if (e & 1) r = r * b; b = b * b; e >>= 1; } return r; }
 
 // power of a fixed base through a two-level table: base^e = lo[e & 4095] * hi[e >> 12]
 static constexpr int POW_LO_BITS = 12;
 static constexpr u32 POW_LO = 1u << POW_LO_BITS;
 struct PowTable { const u64* lo; const u64* hi; };
-XFG_D u64 pow_lookup(const PowTable& t, u64 e) {
+XFG_HD u64 pow_lookup(const PowTable& t, u64 e) {
   u64 l = t.lo[e & (POW_LO - 1)], h = e >> POW_LO_BITS;
   return h ? gl_mul(l, t.hi[h]) : l;
 }

@@ -19,7 +19,10 @@
 #include <vector>
 #include "../../include/xfg_stark.h"
 #include "burn_mint_host.hpp"
+#include "proof_bytes.hpp"
+#include "air_compile.hpp"
 #include "generic_air.cuh"
+#include "general.cuh"
 #include "merkle.cuh"
 #include "ntt.cuh"
 #include "stark_kernels.cuh"
@@ -75,6 +78,7 @@ struct GraphKey {      // everything that is baked into the captured launch sequ
 };
 struct GraphEntry { cudaGraphExec_t exec; unsigned launches; };
 struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
+struct GoPlanHolder { GoPlan plan; std::vector<void*> allocs; };   // a general-options plan and the device tables it owns (general_api.inc)
 
 struct Slot {
   cudaStream_t st = nullptr, copy_st = nullptr, aux_st[3] = {nullptr, nullptr, nullptr};   // copy_st: column-wise trace upload overlapped with the first NTTs; aux_st: every other column group
@@ -90,6 +94,7 @@ struct Slot {
   // generic AIR front-end (xfg_prove_air): compiled program + AIR-sized state; W = trace width of the proof in flight
   GenProgram* d_prog = nullptr; GenProgram* h_prog = nullptr; GenState* d_gen = nullptr; u64 (*h_ood)[2] = nullptr;
   bool generic = false; u32 W = XFG_TRACE_WIDTH, seed_count = 8 + XFG_NUM_PUB_INPUTS;
+  GoState* d_go = nullptr; GoState* h_go = nullptr;   // state of a general-options proof (allocated on first use)
   std::map<GraphKey, GraphEntry> graphs;            // whole-proof CUDA graphs, one per (plan, extension, options, trace pointer)
   cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
   // in-flight proof (batch mode)
@@ -111,6 +116,7 @@ struct xfg_ctx {
   std::vector<Slot> slots;
   u64 *tw_fwd = nullptr, *tw_inv = nullptr;
   std::map<u64, Plan> plans;
+  std::map<std::array<u32, 4>, GoPlanHolder> go_plans;   // general-options plans (general_api.inc), keyed by (log2 n, blowup, folding, remainder degree)
   std::string last_error;
   bool profiling = false, graphs = true;
   std::vector<std::string> prof_names; std::vector<float> prof_ms; std::vector<unsigned> prof_launches;   // last profiled proof
@@ -126,11 +132,16 @@ int fail(xfg_ctx* ctx, int code, const std::string& msg) { if (ctx) ctx->last_er
 
 std::vector<u64> pow_series(u64 base, size_t count) { std::vector<u64> v(count); u64 x = 1; for (size_t i = 0; i < count; i++) { v[i] = x; x = gl_mul(x, base); } return v; }
 
-// ProofOptions::new range checks (A.2) + what this backend implements
-int check_options(xfg_ctx* ctx, const xfg_options* o, u32 n_log2) {
+// ProofOptions::new range checks (A.2).  Options outside the tuned set (blowup 8, folding 8, remainder degree >= 7, None / Quadratic) are
+// served by the general-options pipeline (general_api.inc: go_needed); `tuned_only` callers (the batch verifier) refuse them instead.
+bool go_needed(const xfg_options& o);
+int prove_general(xfg_ctx* ctx, const xfg_air_desc& air, const xfg_air_consts* bm, const u64* h_trace, const u64* const* h_cols, u32 form, const u64* d_trace, bool fill,
+                  u32 n_log2, const xfg_options& o, u8* out, size_t cap, size_t* out_len, xfg_stage_times* times);
+int prove_general_burn_mint(xfg_ctx* ctx, const xfg_air_consts& air, const u64* h_trace, const u64* const* h_cols, u32 form, const u64* d_trace, bool fill,
+                            u32 n_log2, const xfg_options& o, u8* out, size_t cap, size_t* out_len, xfg_stage_times* times);
+int check_options(xfg_ctx* ctx, const xfg_options* o, u32 n_log2, bool tuned_only = false) {
   auto pow2 = [](u32 x) { return x && !(x & (x - 1)); };
-  if (o->field_extension == XFG_EXT_CUBIC) return fail(ctx, XFG_ERR_UNSUPPORTED_EXTENSION, "UnsupportedFieldExtension: cubic");
-  if (o->field_extension != XFG_EXT_NONE && o->field_extension != XFG_EXT_QUADRATIC) return fail(ctx, XFG_ERR_BAD_OPTIONS, "invalid field extension");
+  if (o->field_extension != XFG_EXT_NONE && o->field_extension != XFG_EXT_QUADRATIC && o->field_extension != XFG_EXT_CUBIC) return fail(ctx, XFG_ERR_BAD_OPTIONS, "invalid field extension");
   if (o->num_queries < 1) return fail(ctx, XFG_ERR_BAD_OPTIONS, "number of queries must be greater than 0");
   if (o->num_queries > 255) return fail(ctx, XFG_ERR_BAD_OPTIONS, "number of queries cannot be greater than 255");
   if (!pow2(o->blowup_factor)) return fail(ctx, XFG_ERR_BAD_OPTIONS, "blowup factor must be a power of 2");
@@ -138,10 +149,9 @@ int check_options(xfg_ctx* ctx, const xfg_options* o, u32 n_log2) {
   if (o->grinding_factor > 32) return fail(ctx, XFG_ERR_BAD_OPTIONS, "grinding factor cannot be greater than 32");
   if (!pow2(o->fri_folding_factor) || o->fri_folding_factor < 2 || o->fri_folding_factor > 16) return fail(ctx, XFG_ERR_BAD_OPTIONS, "FRI folding factor must be a power of 2 in 2..16");
   if (o->fri_remainder_max_degree > 255 || !pow2(o->fri_remainder_max_degree + 1)) return fail(ctx, XFG_ERR_BAD_OPTIONS, "FRI polynomial remainder degree must be one less than a power of two");
-  if (o->blowup_factor != 8) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "this backend implements blowup factor 8 (the reference's setting)");
-  if (o->fri_folding_factor != 8) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "this backend implements FRI folding factor 8 (the reference's setting)");
-  if (o->fri_remainder_max_degree < 7) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "this backend needs fri_remainder_max_degree >= 7");
-  if (o->num_queries >= (8u << n_log2)) return fail(ctx, XFG_ERR_BAD_OPTIONS, "number of queries must be smaller than the LDE domain size");
+  if (tuned_only && o->field_extension == XFG_EXT_CUBIC) return fail(ctx, XFG_ERR_UNSUPPORTED_EXTENSION, "the cubic extension is not supported on this path");
+  if (tuned_only && go_needed(*o)) return fail(ctx, XFG_ERR_UNSUPPORTED_OPTIONS, "this path implements blowup factor 8, FRI folding factor 8 and fri_remainder_max_degree >= 7 (the reference's settings)");
+  if ((u64)o->num_queries >= ((u64)o->blowup_factor << n_log2)) return fail(ctx, XFG_ERR_BAD_OPTIONS, "number of queries must be smaller than the LDE domain size");
   return XFG_OK;
 }
 
@@ -232,17 +242,6 @@ void carve(const Slot& s, const Plan& p, int D, Carve& c, std::vector<std::pair<
   for (u32 l = 0; l < p.num_layers; l++) c.fri_tree[l] = reinterpret_cast<Digest*>(take(size_t(1) << p.layer_log[l]));   // 2 * Nl/8 digests
   c.rem_in = take((size_t)D << p.rem_log); c.rem_coef = take((size_t)D << p.rem_log);
   c.words = (size_t)(w - s.slab);
-}
-
-// coin seed elements: Context::to_elements() then the public inputs (A.4)
-void seed_elements(u32 ln, const xfg_options& o, u32 width, const u64* pub_inputs, u32 num_pub, u64* out) {
-  int k = 0;
-  out[k++] = (u64)width << 8;
-  out[k++] = XFG_P & 0xFFFFFFFFull; out[k++] = XFG_P >> 32;
-  out[k++] = (u64)o.field_extension << 16 | (u64)o.fri_folding_factor << 8 | o.fri_remainder_max_degree;
-  out[k++] = o.grinding_factor; out[k++] = o.blowup_factor; out[k++] = o.num_queries;
-  out[k++] = (u64)(u32)(size_t(1) << ln);
-  for (u32 i = 0; i < num_pub; i++) out[k++] = pub_inputs[i];
 }
 
 // layout of the material buffer for this proof; fills the gather tasks
@@ -449,53 +448,7 @@ int launch_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options&
   return launch_prepared(ctx, s, p, D, o, d_trace, timed);
 }
 
-// ---- host serialisation ----
-struct Out { std::vector<u8> b;
-  void u8_(u32 v) { b.push_back((u8)v); } void u16_(size_t v) { b.push_back((u8)v); b.push_back((u8)(v >> 8)); }
-  void u32_(size_t v) { for (int i = 0; i < 4; i++) b.push_back((u8)(v >> (8 * i))); } void u64_(u64 v) { for (int i = 0; i < 8; i++) b.push_back((u8)(v >> (8 * i))); }
-  void raw(const void* p, size_t n) { const u8* q = (const u8*)p; b.insert(b.end(), q, q + n); } };
-
-// BatchMerkleProof::serialize_nodes of MerkleTree::prove_batch(positions) (A.11), built from the per-position sibling paths:
-// path(q, lvl) = tree[((M + pos[q]) >> lvl) ^ 1].  Follows the crate's bookkeeping exactly (norm = sorted unique (index & ~1); at every level
-// `nodes[i]` is indexed by the position i in the current node list), without its BTreeMap: the ancestors (M + pos) >> lvl =
-// (M >> lvl) + (pos >> lvl) are monotone in pos, so the owner of a node is found by binary search over the positions sorted once
-// (any queried leaf below a node yields the same sibling digest).  ~10 us for 42 positions in a 2^23-leaf tree (the linear-search version: 35 us,
-// seven trees per proof).
-void batch_paths(const u32* pos, u32 cnt, const u64* paths, u32 depth, u64 M, Out& out) {
-  auto path = [&](u32 q, u32 lvl) { return reinterpret_cast<const u8*>(paths + ((size_t)q * depth + lvl) * 4); };
-  u32 ord[256]; for (u32 q = 0; q < cnt; q++) ord[q] = q;
-  std::sort(ord, ord + cnt, [&](u32 a, u32 b) { return pos[a] < pos[b]; });
-  auto owner = [&](u64 heap_index, u32 lvl) -> int {
-    const u64 key = heap_index - (M >> lvl); u32 lo = 0, hi = cnt;
-    while (lo < hi) { const u32 mid = (lo + hi) / 2; if (((u64)pos[ord[mid]] >> lvl) < key) lo = mid + 1; else hi = mid; }
-    return (lo < cnt && ((u64)pos[ord[lo]] >> lvl) == key) ? (int)ord[lo] : -1;
-  };
-  u64 cur[256], next[256]; u32 nn = 0, nnext = 0;
-  static thread_local std::vector<const u8*> flat; flat.resize((size_t)256 * (depth + 2)); u32 ncount[256];
-  const size_t stride = depth + 2;
-  u64 norm[256];
-  for (u32 i = 0; i < cnt; i++) { const u64 v = pos[ord[i]] & ~u64(1); if (!nn || norm[nn - 1] != v) norm[nn++] = v; }
-  for (u32 k = 0; k < nn; k++) {
-    const u64 index = norm[k]; ncount[k] = 0;
-    for (u64 i = index; i < index + 2; i++) if (owner(M + i, 0) < 0) flat[k * stride + ncount[k]++] = path((u32)owner(M + (i ^ 1), 0), 0);
-    next[nnext++] = (index + M) >> 1;
-  }
-  for (u32 d = 1; d < depth; d++) {
-    const u32 nc = nnext; for (u32 i = 0; i < nc; i++) cur[i] = next[i];
-    nnext = 0;
-    u32 i = 0;
-    while (i < nc) {
-      const u64 sib = cur[i] ^ 1;
-      if (i + 1 < nc && cur[i + 1] == sib) i += 1;
-      else flat[i * stride + ncount[i]++] = path((u32)owner(cur[i], d), d);
-      next[nnext++] = sib >> 1; i += 1;
-    }
-  }
-  size_t total = 1; for (u32 k = 0; k < nn; k++) total += 1 + 32 * (size_t)ncount[k];
-  const size_t base = out.b.size(); out.b.resize(base + total);
-  u8* w = out.b.data() + base; *w++ = (u8)nn;
-  for (u32 k = 0; k < nn; k++) { *w++ = (u8)ncount[k]; for (u32 j = 0; j < ncount[k]; j++) { std::memcpy(w, flat[k * stride + j], 32); w += 32; } }
-}
+// ---- host serialisation (byte writer, batch Merkle paths, seed elements: proof_bytes.hpp) ----
 // StarkProof::to_bytes (A.12)
 void assemble(const Plan& p, int D, u32 W, const u64 (*ood_frame)[2], const xfg_options& o, const ProofState& s, const u64* mat, const GatherTasks& g, std::vector<u8>& bytes) {
   Out out; out.b.reserve(size_t(1) << 18);
@@ -616,6 +569,7 @@ int prove_common(xfg_ctx* ctx, const u64* h_trace, const u64* d_trace, u32 n_log
   if (n_log2 > ctx->max_log) return fail(ctx, XFG_ERR_TOO_LARGE, "trace longer than the context was created for");
   int rc;
   if ((rc = check_options(ctx, o, n_log2)) || (rc = check_air(ctx, air))) return rc;
+  if (go_needed(*o)) return prove_general_burn_mint(ctx, *air, h_trace, h_cols, form, d_trace, fill, n_log2, *o, out, cap, out_len, times);   // options outside the tuned 8/8 set
   CU(cudaSetDevice(ctx->device));
   drain_slots(ctx);
   const Plan* p; if ((rc = get_plan(ctx, n_log2, o->fri_remainder_max_degree, &p))) return rc;
@@ -729,6 +683,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
     cudaFree(s.d_air); cudaFreeHost(s.h_air);
     cudaFree(s.d_prog); cudaFreeHost(s.h_prog); cudaFree(s.d_gen); cudaFreeHost(s.h_ood);
+    cudaFree(s.d_go); cudaFreeHost(s.h_go);
     for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
@@ -741,6 +696,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     if (s.st) cudaStreamDestroy(s.st);
   }
   for (auto& kv : ctx->plans) { cudaFree(kv.second.slab); cudaFree(kv.second.direct); }
+  for (auto& kv : ctx->go_plans) for (void* d : kv.second.allocs) cudaFree(d);
   if (ctx->vbufs.h) cudaFreeHost(ctx->vbufs.h);
   if (ctx->vbufs.d) cudaFree(ctx->vbufs.d);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv);
@@ -792,10 +748,23 @@ int xfg_prove_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint64_t* cons
   int rc; if ((rc = check_options(ctx, o, n_log2))) return rc;
   CU(cudaSetDevice(ctx->device));
   drain_slots(ctx);
+  for (uint32_t i = 0; i < count; i++) out_lens[i] = 0;   // a proof that fails (or is never started) keeps length 0
+  if (go_needed(*o)) {   // general-options pipeline: one proof after the other on slot 0
+    const auto t0 = std::chrono::steady_clock::now(); int first = XFG_OK; unsigned launches = 0;
+    for (uint32_t i = 0; i < count; i++) {
+      if ((rc = check_air(ctx, &airs[i]))) return rc;
+      if (!traces[i]) return fail(ctx, XFG_ERR_BAD_ARGS, "null trace");
+      rc = prove_general_burn_mint(ctx, airs[i], traces[i], nullptr, XFG_FORM_CANONICAL, nullptr, false, n_log2, *o, out + (size_t)i * out_stride, out_stride, &out_lens[i], nullptr);
+      if (rc) { out_lens[i] = 0; if (!first) first = rc; }
+      launches += g_xfg_launches;
+    }
+    g_xfg_launches = launches;
+    if (total_ms) *total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return first;
+  }
   const Plan* p; if ((rc = get_plan(ctx, n_log2, o->fri_remainder_max_degree, &p))) return rc;
   const int D = o->field_extension == XFG_EXT_QUADRATIC ? 2 : 1; const size_t S = ctx->slots.size();
   g_xfg_launches = 0;
-  for (uint32_t i = 0; i < count; i++) out_lens[i] = 0;   // a proof that fails (or is never started) keeps length 0
   cudaEvent_t e0 = ctx->slots[0].ev[XFG_NUM_STAGES + 2], e1 = ctx->slots[0].ev[XFG_NUM_STAGES + 1];
   if (total_ms) { CU(cudaDeviceSynchronize()); CU(cudaEventRecord(e0, ctx->slots[0].st)); }
   int first_err = XFG_OK;
@@ -842,3 +811,4 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn, uint64_t mint, 
 #include "wide.inc"
 #include "verify_api.inc"
 #include "air_api.inc"
+#include "general_api.inc"
