@@ -117,11 +117,11 @@ def test_batches_and_errors_with_other_options(ctx):
     with pytest.raises(xs.XfgError) as e:
         ctx.prove(bad, airs[1], _opts(xs, o))
     assert e.value.code == 1
-    with xs.Context(device=0, max_n_log2=8, num_slots=1) as small:    # workspaces are sized for blowup 8: 128 does not fit at the context's maximum length
-        with pytest.raises(xs.XfgError) as e:
-            small.prove(cases[0][0], airs[0], _opts(xs, (42, 128, 4, 3, 8, 31)))
-        assert e.value.code == 9
+    with xs.Context(device=0, max_n_log2=8, num_slots=1) as small:    # slot workspaces are sized for blowup 8: a blowup-128 proof at the context's maximum length gets its own
+        o128 = (42, 128, 4, 3, 8, 31)
+        assert small.prove(cases[0][0], airs[0], _opts(xs, o128)) == orc.prove(cases[0][0], cases[0][1], cases[0][2], o128)
         assert small.prove(cases[0][0], airs[0], _opts(xs, o)) == proofs[0]
+        assert small.prove(cases[0][0], airs[0]) == orc.prove(*cases[0])
     # the tuned pipeline is untouched by a general proof on the same context
     t, pi, ac = cases[2]
     assert ctx.prove(t, airs[2]) == orc.prove(t, pi, ac)

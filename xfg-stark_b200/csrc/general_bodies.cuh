@@ -18,7 +18,7 @@
 namespace xfg {
 
 static constexpr int GO_MAX_LAYERS = 32;      // folding factor 2 on a 2^27-point domain
-static constexpr int GO_OOD_CHUNKS = 256;     // partial sums per polynomial of the out-of-domain evaluation
+static constexpr int GO_OOD_CHUNKS = 2048;    // partial sums per polynomial of the out-of-domain evaluation (fewer for traces shorter than that)
 static constexpr int GO_MAX_EXT = 3;
 
 #if defined(__CUDACC__)

@@ -89,7 +89,7 @@ inline void go_carve(u64* base, const GoPlan& p, int D, u32 W, GoCarve& c) {
   c.deep = take(D * N); c.fri_evals[0] = c.deep;
   for (u32 l = 1; l <= p.num_layers; l++) c.fri_evals[l] = take((size_t)D << p.layer_log[l]);
   for (u32 l = 0; l < p.num_layers; l++) c.fri_tree[l] = reinterpret_cast<Digest*>(take((size_t)8 << (p.layer_log[l] - p.lf)));   // 2 * Nl/F digests
-  c.ood_partial = take((size_t)(W + D) * GO_OOD_CHUNKS * 2 * GO_MAX_EXT); c.ood_sums = take((size_t)(W + D) * 2 * GO_MAX_EXT);
+  c.ood_partial = take((size_t)(W + D) * std::min<size_t>(GO_OOD_CHUNKS, n) * 2 * GO_MAX_EXT); c.ood_sums = take((size_t)(W + D) * 2 * GO_MAX_EXT);
   c.words = (size_t)(w - base);
 }
 

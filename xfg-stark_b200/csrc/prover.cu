@@ -95,6 +95,7 @@ struct Slot {
   GenProgram* d_prog = nullptr; GenProgram* h_prog = nullptr; GenState* d_gen = nullptr; u64 (*h_ood)[2] = nullptr;
   bool generic = false; u32 W = XFG_TRACE_WIDTH, seed_count = 8 + XFG_NUM_PUB_INPUTS;
   GoState* d_go = nullptr; GoState* h_go = nullptr;   // state of a general-options proof (allocated on first use)
+  u64* go_slab = nullptr; size_t go_slab_words = 0;    // its workspace when the slab above is too small (blowup > 8, cubic extension at the maximum length)
   std::map<GraphKey, GraphEntry> graphs;            // whole-proof CUDA graphs, one per (plan, extension, options, trace pointer)
   cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
   // in-flight proof (batch mode)
@@ -683,7 +684,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     cudaFreeHost(s.h_state); cudaFreeHost(s.h_material); cudaFreeHost(s.h_seed); cudaFreeHost(s.h_trace);
     cudaFree(s.d_air); cudaFreeHost(s.h_air);
     cudaFree(s.d_prog); cudaFreeHost(s.h_prog); cudaFree(s.d_gen); cudaFreeHost(s.h_ood);
-    cudaFree(s.d_go); cudaFreeHost(s.h_go);
+    cudaFree(s.d_go); cudaFreeHost(s.h_go); cudaFree(s.go_slab);
     for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
