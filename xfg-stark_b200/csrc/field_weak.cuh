@@ -24,11 +24,29 @@ __device__ __forceinline__ u64 w_pack(u32 lo, u32 hi) { return ((u64)hi << 32) |
 #define XFG_WEAK_MADFIX 0
 #endif
 // r + c * EPS for c in {0, 1} (mod 2^64)
+#if XFG_WEAK_MADFIX >= 2
+// 2, 3, 4 (round 2): the multiplier 2^32 - 1 comes from __constant__ memory, so ptxas cannot expand the product into IMAD.HI + IMAD + moves (one
+// IMAD.WIDE per fix-up), and the carry is materialised on the FMA pipe (madc.lo = IMAD.X).  3: only the butterfly additions w_add_c use the product
+// form; 4: w_add_c and w_canon.  Static SASS of ntt_pass_r16<.., 10> (tools/sass_pipes.py): ALU-pipe instructions 3229 -> 3148 (3) / 3034 (4), IMAD.WIDE
+// + IMAD.HI 498 -> 578 / 692.  MEASURED SLOWER all the same (2^20 rows, quadratic; ntt.lde_trace 1.123 ms -> 1.135 (3) / 1.168 (4), whole proof 3.977 ->
+// 3.999 / 4.061): an IMAD.WIDE costs the kernel more than the two ALU-pipe instructions it replaces.
+static __constant__ u32 g_w_eps2 = 0xFFFFFFFFu;
+__device__ __forceinline__ u64 w_fix_eps(u32 c, u64 r) { u64 o; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(o) : "r"(c), "r"(g_w_eps2), "l"(r)); return o; }
+#else
 __device__ __forceinline__ u64 w_fix_eps(u32 c, u64 r) { u64 o; asm("mad.wide.u32 %0, %1, 0xffffffff, %2;" : "=l"(o) : "r"(c), "l"(r)); return o; }
+#endif
 
+// (Round 2, not kept: the fix-up as a PREDICATED mad.wide on the carry predicate with multiplicands from __constant__ / device memory.  ptxas splits
+// the mad, hoists the loop-invariant product 1 * EPS into a register pair and if-converts the guarded addition back to IADD3 + IMAD.X + 2 SEL, i.e.
+// more ALU-pipe work than the select form: 3229 -> 3932 ALU instructions in ntt_pass_r16<.., 10>; see tools/sass_pipes.py.)
 // weak -> canonical.  x >= p  <=>  x + EPS carries out of bit 64, and then x - p = x + EPS (mod 2^64)
 __device__ __forceinline__ u64 w_canon(u64 x) {
-#if XFG_WEAK_MADFIX
+#if XFG_WEAK_MADFIX == 4
+  u32 c;       // 4 = 3 + w_canon: carry of x + EPS materialised on the FMA pipe (madc.lo), then x + c * EPS as one IMAD.WIDE
+  asm("{\n\t .reg .u32 t0, t1;\n\t add.cc.u32 t0, %1, 0xffffffff;\n\t addc.cc.u32 t1, %2, 0;\n\t madc.lo.u32 %0, %3, %3, 0;\n\t}"
+      : "=r"(c) : "r"((u32)x), "r"((u32)(x >> 32)), "r"(0u));
+  return w_fix_eps(c, x);
+#elif XFG_WEAK_MADFIX == 1 || XFG_WEAK_MADFIX == 2
   u32 c;
   asm("{\n\t .reg .u32 t0, t1;\n\t add.cc.u32 t0, %1, 0xffffffff;\n\t addc.cc.u32 t1, %2, 0;\n\t addc.u32 %0, 0, 0;\n\t}"
       : "=r"(c) : "r"((u32)x), "r"((u32)(x >> 32)));
@@ -46,8 +64,8 @@ __device__ __forceinline__ u64 w_canon(u64 x) {
 __device__ __forceinline__ u64 w_add_c(u64 a, u64 b) {
 #if XFG_WEAK_MADFIX
   u32 s0, s1, c;
-  asm("{\n\t add.cc.u32 %0, %3, %5;\n\t addc.cc.u32 %1, %4, %6;\n\t addc.u32 %2, 0, 0;\n\t}"
-      : "=&r"(s0), "=&r"(s1), "=&r"(c) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  asm("{\n\t add.cc.u32 %0, %3, %5;\n\t addc.cc.u32 %1, %4, %6;\n\t madc.lo.u32 %2, %7, %7, 0;\n\t}"
+      : "=&r"(s0), "=&r"(s1), "=&r"(c) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)), "r"(0u));
   return w_fix_eps(c, w_pack(s0, s1));
 #else
   // The carry mask is built as setp/selp so that ptxas keeps it one SEL on the carry predicate (5 instructions in all).
@@ -71,7 +89,7 @@ __device__ __forceinline__ u64 w_mul_eps(u32 a) { u64 r; asm("mul.wide.u32 %0, %
 // a * EPS is at most 2^32 - 2, so bit 64 was carried out exactly when the sum's high word is below b1 (one 32-bit compare); the
 // wrapped sum is then <= 2^64 - 2^33, so + EPS cannot carry again.
 __device__ __forceinline__ u64 w_eps_madd(u32 a, u32 b0, u32 b1) {
-#if XFG_WEAK_MADFIX
+#if XFG_WEAK_MADFIX == 1 || XFG_WEAK_MADFIX == 2
   u64 r; u32 c;
   asm("{\n\t .reg .u64 b; .reg .pred p; .reg .u32 h;\n\t mov.b64 b, {%3, %4};\n\t mad.wide.u32 %0, %2, 0xffffffff, b;\n\t mov.b64 {_, h}, %0;\n\t"
       "setp.lt.u32 p, h, %4;\n\t selp.u32 %1, 1, 0, p;\n\t}"
