@@ -22,7 +22,7 @@
 /* FieldExtension discriminants (D) */
 #define XFG_EXT_NONE          1
 #define XFG_EXT_QUADRATIC     2
-#define XFG_EXT_CUBIC         3 /* not supported: XFG_ERR_UNSUPPORTED_EXTENSION */
+#define XFG_EXT_CUBIC         3 /* F_p[x]/(x^3 - x - 1); proved by the general-options pipeline */
 
 /* ---- A.2 reference ProofOptions (src/burn_mint_prover.rs:28-35; real argument meaning per (D)) ---- */
 #define XFG_DEF_NUM_QUERIES   42

@@ -23,14 +23,19 @@ extern "C" {
 
 typedef struct xfg_ctx xfg_ctx;
 
-/* replaces winter_air::ProofOptions as built at src/burn_mint_prover.rs:28-35 (argument meaning per SURVEY.md A.2) */
+/* replaces winter_air::ProofOptions as built at src/burn_mint_prover.rs:28-35 and accepted by XfgBurnMintProver::with_options
+ * (src/burn_mint_prover.rs:44-49); argument meaning and ranges per ProofOptions::new.  Every value ProofOptions::new accepts
+ * is served.  The reference's own setting (blowup 8, folding 8, remainder degree >= 7, None / Quadratic) runs on the tuned pipeline; anything
+ * else - blowup 2..128, folding 2/4/16, remainder degree 0..3, FieldExtension::Cubic - on the general-options pipeline (same bytes as
+ * Winterfell, pinned against proofs of the reference binary; a few times slower).  Shapes on which Winterfell itself panics (a FRI layer of one
+ * row, an empty remainder) return XFG_ERR_BAD_OPTIONS. */
 typedef struct xfg_options {
-  uint32_t num_queries;              /* 1..255 */
-  uint32_t blowup_factor;            /* this backend: 8 */
+  uint32_t num_queries;              /* 1..255, smaller than the LDE domain */
+  uint32_t blowup_factor;            /* power of two, 2..128 */
   uint32_t grinding_factor;          /* 0..32 */
-  uint32_t field_extension;          /* XFG_EXT_NONE = 1, XFG_EXT_QUADRATIC = 2 */
-  uint32_t fri_folding_factor;       /* this backend: 8 */
-  uint32_t fri_remainder_max_degree; /* 2^k - 1, 7..255 */
+  uint32_t field_extension;          /* XFG_EXT_NONE = 1, XFG_EXT_QUADRATIC = 2, XFG_EXT_CUBIC = 3 */
+  uint32_t fri_folding_factor;       /* 2, 4, 8 or 16 */
+  uint32_t fri_remainder_max_degree; /* 2^k - 1, 0..255 */
 } xfg_options;
 
 /* replaces BurnMintPublicInputs (src/burn_mint_air.rs:23-71) plus the constants XfgBurnMintAir derives from them and the
@@ -62,8 +67,8 @@ enum {
   XFG_OK = 0,
   XFG_ERR_BAD_ARGS = 1,            /* null pointer, size out of range, non-canonical element */
   XFG_ERR_BAD_OPTIONS = 2,         /* ProofOptions::new range checks (A.2) */
-  XFG_ERR_UNSUPPORTED_OPTIONS = 3, /* valid for Winterfell, not implemented by this backend (blowup != 8, folding != 8) */
-  XFG_ERR_UNSUPPORTED_EXTENSION = 4, /* mirrors ProverError::UnsupportedFieldExtension (cubic) */
+  XFG_ERR_UNSUPPORTED_OPTIONS = 3, /* valid for Winterfell, not implemented: AIR of transition degree > 2; batch VERIFICATION of proofs made with options outside the tuned set */
+  XFG_ERR_UNSUPPORTED_EXTENSION = 4, /* mirrors ProverError::UnsupportedFieldExtension: the batch verifier does not take cubic-extension proofs (the prover does) */
   XFG_ERR_UNSATISFIED_CONSTRAINT = 5, /* mirrors ProverError::UnsatisfiedTransitionConstraintError / MismatchedConstraintPolynomialDegree */
   XFG_ERR_BUFFER_TOO_SMALL = 6,    /* *out_len holds the required size */
   XFG_ERR_CUDA = 7,                /* CUDA runtime error; see xfg_last_error */
