@@ -139,6 +139,18 @@ XFG_HD Ext<3> ext_inv(Ext<3> e) {
   const u64 di = gl_inv(det);
   return Ext<3>(gl_mul(k0, di), gl_mul(gl_neg(k1), di), gl_mul(k2, di));
 }
+// a^-1 = adj(a) / N(a) with N(a) in the base field: lets a caller batch the base-field inversions of several extension elements
+//   degree 1: adj = 1, N = a;   degree 2: adj = (a0 + a1, -a1), N = a0^2 + a0 a1 + 2 a1^2;   degree 3: first column of the adjugate, N = det (see ext_inv)
+XFG_HD u64 ext_norm_adj(Ext<1> a, Ext<1>& adj) { adj = Ext<1>(1); return a.a0; }
+XFG_HD u64 ext_norm_adj(Ext<2> a, Ext<2>& adj) { adj = Ext<2>(gl_add(a.a0, a.a1), gl_neg(a.a1)); return ext_norm(a); }
+XFG_HD u64 ext_norm_adj(Ext<3> e, Ext<3>& adj) {
+  const u64 m00 = e.a[0], m10 = e.a[1], m20 = e.a[2];
+  const u64 m01 = e.a[2], m11 = gl_add(e.a[0], e.a[2]), m21 = e.a[1];
+  const u64 m02 = e.a[1], m12 = gl_add(e.a[1], e.a[2]), m22 = m11;
+  const u64 k0 = gl_sub(gl_mul(m11, m22), gl_mul(m12, m21)), k1 = gl_sub(gl_mul(m10, m22), gl_mul(m12, m20)), k2 = gl_sub(gl_mul(m10, m21), gl_mul(m11, m20));
+  adj = Ext<3>(k0, gl_neg(k1), k2);
+  return gl_add(gl_sub(gl_mul(m00, k0), gl_mul(m01, k1)), gl_mul(m02, k2));
+}
 // the element `x` (the basis element of limb 1) times a: used to assemble H(z) from the limb polynomials of the composition column
 template <int D> XFG_HD Ext<D> ext_mul_x(Ext<D> a);
 template <> XFG_HD Ext<1> ext_mul_x<1>(Ext<1> a) { return a; }

@@ -196,39 +196,56 @@ template <int D> struct GoStepFri {
 //   H(x) = T(x) (x - g^(n-1)) / (x^n - 1) + sum_groups B_g(x) / (x - g^step_g)
 // out: [limb][k'][m]
 // ------------------------------------------------------------------------------------------------------------------
+static constexpr int GO_PTS = 4;   // points per thread of the constraint and DEEP bodies: their base-field inversions are batched (Montgomery's trick)
+// in-place batch inversion of cnt non-zero base-field values (one gl_inv)
+XFG_HD void go_batch_inv(u64* v, int cnt) {
+  u64 pre[2 * GO_PTS]; u64 acc = 1;
+  for (int i = 0; i < cnt; i++) { pre[i] = acc; acc = gl_mul(acc, v[i]); }
+  acc = gl_inv(acc);
+  for (int i = cnt - 1; i >= 0; i--) { const u64 t = gl_mul(pre[i], acc); acc = gl_mul(acc, v[i]); v[i] = t; }
+}
+// t = k' (n / pts) + q: the thread evaluates points m = q + j n / pts, j < pts (pts = GO_PTS, or 1 for the shortest traces), of coset k'
 template <int D> struct GoConstraint {
-  const u64* lde; u32 ln, lb; const GenProgram* prog; const GoState* s; PowTable wn; u64 s_ce[2], zinv[2], g_last; u64* out;
+  const u64* lde; u32 ln, lb, pts; const GenProgram* prog; const GoState* s; PowTable wn; u64 s_ce[2], zinv[2], g_last; u64* out;
   XFG_HD void operator()(size_t t) const {
-    const size_t n = size_t(1) << ln, N = n << lb, kp = t >> ln, m = t & (n - 1), mn = (m + 1) & (n - 1);
+    const size_t n = size_t(1) << ln, N = n << lb, per = n / pts, kp = t / per, q = t % per;
     const size_t k = kp << (lb - 1);
     const u64* base = lde + k * n;
     const u32 T = prog->num_constraints, A = prog->num_assertions, G = prog->num_groups, NI = prog->num_instr;
-    u64 slot[GEN_MAX_SLOTS];
-    Ext<D> ts;
-    for (u32 i = 0; i < NI; i++) {
-      const GenInstr in = prog->code[i];
-      const u32 op = in.w0 & 15u, dst = in.w0 >> 8;
-      u64 v[2];
-      for (int q = 0; q < 2; q++) {
-        const u32 kind = (in.w0 >> (4 + 2 * q)) & 3u, idx = q ? in.w1 >> 16 : in.w1 & 0xFFFFu;
-        v[q] = kind == GK_SLOT ? slot[idx] : kind == GK_CONST ? prog->constants[idx] : base[(size_t)idx * N + (kind == GK_CUR ? m : mn)];
-        if (op == GOP_OUT) break;
+    Ext<D> u[GO_PTS], num[GO_PTS]; u64 den[GO_PTS];
+    for (u32 j = 0; j < pts; j++) {
+      const size_t m = q + j * per, mn = (m + 1) & (n - 1);
+      u64 slot[GEN_MAX_SLOTS];
+      Ext<D> ts;
+      for (u32 i = 0; i < NI; i++) {
+        const GenInstr in = prog->code[i];
+        const u32 op = in.w0 & 15u, dst = in.w0 >> 8;
+        u64 v[2];
+        for (int o = 0; o < 2; o++) {
+          const u32 kind = (in.w0 >> (4 + 2 * o)) & 3u, idx = o ? in.w1 >> 16 : in.w1 & 0xFFFFu;
+          v[o] = kind == GK_SLOT ? slot[idx] : kind == GK_CONST ? prog->constants[idx] : base[(size_t)idx * N + (kind == GK_CUR ? m : mn)];
+          if (op == GOP_OUT) break;
+        }
+        if (op == GOP_OUT) { ts = ts + mul_base(go_ld<D>(s->coef[dst]), v[0]); continue; }
+        slot[dst] = op == GOP_MUL ? gl_mul(v[0], v[1]) : op == GOP_ADD ? gl_add(v[0], v[1]) : gl_sub(v[0], v[1]);
       }
-      if (op == GOP_OUT) { ts = ts + mul_base(go_ld<D>(s->coef[dst]), v[0]); continue; }
-      slot[dst] = op == GOP_MUL ? gl_mul(v[0], v[1]) : op == GOP_ADD ? gl_add(v[0], v[1]) : gl_sub(v[0], v[1]);
+      const u64 x = gl_mul(s_ce[kp], pow_lookup(wn, m));
+      Ext<D> nm; u64 dn = 1; u32 ai = 0;
+      for (u32 g = 0; g < G; g++) {      // the boundary sum as one fraction: one inversion per point whatever the number of divisors
+        Ext<D> bs;
+        for (; ai < A && prog->asr[ai].group == g; ai++)
+          bs = bs + mul_base(go_ld<D>(s->coef[T + ai]), gl_sub(base[(size_t)prog->asr[ai].column * N + m], prog->asr[ai].value));
+        const u64 xg = gl_sub(x, prog->group_point[g]);
+        nm = mul_base(nm, xg) + mul_base(bs, dn);
+        dn = gl_mul(dn, xg);
+      }
+      u[j] = mul_base(ts, gl_mul(gl_sub(x, g_last), zinv[kp])); num[j] = nm; den[j] = dn;
     }
-    const u64 x = gl_mul(s_ce[kp], pow_lookup(wn, m));
-    Ext<D> num; u64 den = 1; u32 ai = 0;
-    for (u32 g = 0; g < G; g++) {      // the boundary sum as one fraction: one inversion per point whatever the number of divisors
-      Ext<D> bs;
-      for (; ai < A && prog->asr[ai].group == g; ai++)
-        bs = bs + mul_base(go_ld<D>(s->coef[T + ai]), gl_sub(base[(size_t)prog->asr[ai].column * N + m], prog->asr[ai].value));
-      const u64 xg = gl_sub(x, prog->group_point[g]);
-      num = mul_base(num, xg) + mul_base(bs, den);
-      den = gl_mul(den, xg);
+    go_batch_inv(den, (int)pts);
+    for (u32 j = 0; j < pts; j++) {
+      const Ext<D> h = u[j] + mul_base(num[j], den[j]);
+      for (int l = 0; l < D; l++) out[((size_t)l * 2 + kp) * n + q + j * per] = h.limb(l);
     }
-    const Ext<D> h = mul_base(ts, gl_mul(gl_sub(x, g_last), zinv[kp])) + mul_base(num, gl_inv(den));
-    for (int l = 0; l < D; l++) out[((size_t)l * 2 + kp) * n + m] = h.limb(l);
   }
 };
 // composition coefficients from the two un-scaled coset interpolants (see combine_kernel, stark_kernels.cu): h = (A0 + A1) / 2, and A0 - A1
@@ -264,12 +281,22 @@ template <int D> struct GoOodPartial {
     }
   }
 };
-// t = p * 2 + point: sums[t] = sum of the chunk partials
+// two-level sum of the chunk partials: t = (p * 2 + point) * groups + g adds chunks g, g + groups, ... into part2; then (groups = 1, chunks = the
+// first level's groups) the group sums into sums[p * 2 + point]
 template <int D> struct GoOodSum {
-  const u64* partial; u32 chunks; u64* sums;
+  const u64* partial; u32 chunks, groups; u64* sums;
   XFG_HD void operator()(size_t t) const {
-    const size_t p = t >> 1, w = t & 1; Ext<D> r;
-    for (u32 c = 0; c < chunks; c++) r = r + go_ld<D>(partial + ((p * chunks + c) * 2 + w) * GO_MAX_EXT);
+    const size_t pw = t / groups, g = t % groups, p = pw >> 1, w = pw & 1; Ext<D> r;
+    for (u32 c = (u32)g; c < chunks; c += groups) r = r + go_ld<D>(partial + ((p * chunks + c) * 2 + w) * GO_MAX_EXT);
+    go_st<D>(sums + t * GO_MAX_EXT, r);
+  }
+};
+// second level: part2 holds `groups` consecutive group sums per (polynomial, point)
+template <int D> struct GoOodSum2 {
+  const u64* part2; u32 groups; u64* sums;
+  XFG_HD void operator()(size_t t) const {
+    Ext<D> r;
+    for (u32 g = 0; g < groups; g++) r = r + go_ld<D>(part2 + (t * groups + g) * GO_MAX_EXT);
     go_st<D>(sums + t * GO_MAX_EXT, r);
   }
 };
@@ -304,17 +331,29 @@ template <int D> struct GoStepOod {
 // t = k n + m; written in natural order [limb][B m + k] = the evaluations of FRI layer 0
 // ------------------------------------------------------------------------------------------------------------------
 template <int D> struct GoDeep {
-  const u64* lde; const u64* hlde; u32 ln, lb, W; const GoState* s; PowTable wn; const u64* s_k; u64* deep;
+  const u64* lde; const u64* hlde; u32 ln, lb, W, pts; const GoState* s; PowTable wn; const u64* s_k; u64* deep;
+  // t = k (n / pts) + q: points m = q + j n / pts, j < pts; 1 / (x - w) = adj(x - w) / N(x - w) with the 2 pts norms inverted together
   XFG_HD void operator()(size_t t) const {
-    const size_t n = size_t(1) << ln, N = n << lb, k = t >> ln, m = t & (n - 1), i = (m << lb) | k;
-    const u64 x = gl_mul(s_k[k], pow_lookup(wn, m));
-    Ext<D> st;
-    for (u32 c = 0; c < W; c++) st = st + mul_base(go_ld<D>(s->dcoef[c]), lde[(size_t)c * N + t]);
-    Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + t]);
-    const Ext<D> P = st + go_ld<D>(s->dcoef[W]) * h - go_ld<D>(s->deep_c1), Q = st - go_ld<D>(s->deep_c2);
-    const Ext<D> xe(x);
-    const Ext<D> r = P * ext_inv(xe - go_ld<D>(s->z)) + Q * ext_inv(xe - go_ld<D>(s->zg));
-    for (int l = 0; l < D; l++) deep[(size_t)l * N + i] = r.limb(l);
+    const size_t n = size_t(1) << ln, N = n << lb, per = n / pts, k = t / per, q = t % per;
+    const Ext<D> z = go_ld<D>(s->z), zg = go_ld<D>(s->zg), c1 = go_ld<D>(s->deep_c1), c2 = go_ld<D>(s->deep_c2), delta = go_ld<D>(s->dcoef[W]);
+    Ext<D> pa[GO_PTS], qa[GO_PTS]; u64 nrm[2 * GO_PTS];
+    for (u32 j = 0; j < pts; j++) {
+      const size_t m = q + j * per, at = k * n + m;
+      const u64 x = gl_mul(s_k[k], pow_lookup(wn, m));
+      Ext<D> st;
+      for (u32 c = 0; c < W; c++) st = st + mul_base(go_ld<D>(s->dcoef[c]), lde[(size_t)c * N + at]);
+      Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + at]);
+      const Ext<D> xe(x);
+      Ext<D> az, azg;
+      nrm[2 * j] = ext_norm_adj(xe - z, az); nrm[2 * j + 1] = ext_norm_adj(xe - zg, azg);
+      pa[j] = (st + delta * h - c1) * az; qa[j] = (st - c2) * azg;
+    }
+    go_batch_inv(nrm, (int)(2 * pts));
+    for (u32 j = 0; j < pts; j++) {
+      const size_t m = q + j * per, i = (m << lb) | k;
+      const Ext<D> r = mul_base(pa[j], nrm[2 * j]) + mul_base(qa[j], nrm[2 * j + 1]);
+      for (int l = 0; l < D; l++) deep[(size_t)l * N + i] = r.limb(l);
+    }
   }
 };
 

@@ -74,7 +74,7 @@ template <class Up> inline void go_plan_tables(GoPlan& p, Up up) {
 
 // workspace of one proof (all offsets in u64 words from the base; every region 64-byte aligned)
 struct GoCarve {
-  u64 *trace_in, *trace_coef, *lde, *ce, *ce_tmp, *h_coef, *h_lde, *deep, *ood_partial, *ood_sums;
+  u64 *trace_in, *trace_coef, *lde, *ce, *ce_tmp, *h_coef, *h_lde, *deep, *ood_partial, *ood_part2, *ood_sums;
   Digest *trace_tree, *comp_tree;
   u64* fri_evals[GO_MAX_LAYERS + 1]; Digest* fri_tree[GO_MAX_LAYERS];
   size_t words;
@@ -89,7 +89,7 @@ inline void go_carve(u64* base, const GoPlan& p, int D, u32 W, GoCarve& c) {
   c.deep = take(D * N); c.fri_evals[0] = c.deep;
   for (u32 l = 1; l <= p.num_layers; l++) c.fri_evals[l] = take((size_t)D << p.layer_log[l]);
   for (u32 l = 0; l < p.num_layers; l++) c.fri_tree[l] = reinterpret_cast<Digest*>(take((size_t)8 << (p.layer_log[l] - p.lf)));   // 2 * Nl/F digests
-  c.ood_partial = take((size_t)(W + D) * std::min<size_t>(GO_OOD_CHUNKS, n) * 2 * GO_MAX_EXT); c.ood_sums = take((size_t)(W + D) * 2 * GO_MAX_EXT);
+  c.ood_partial = take((size_t)(W + D) * std::min<size_t>(GO_OOD_CHUNKS, n) * 2 * GO_MAX_EXT); c.ood_part2 = take((size_t)(W + D) * 2 * 32 * GO_MAX_EXT); c.ood_sums = take((size_t)(W + D) * 2 * GO_MAX_EXT);
   c.words = (size_t)(w - base);
 }
 
@@ -125,8 +125,9 @@ void go_enqueue_d(BK& bk, const GoPlan& p, const GoCarve& c, GoState* s, const G
   bk.merkle_upper(c.trace_tree, N);
   bk.run(1, GoStepTrace<D>{s, c.trace_tree, ncoef});
   // 2 ---- evaluate_constraints
-  { GoConstraint<D> k{}; k.lde = c.lde; k.ln = ln; k.lb = p.lb; k.prog = prog; k.s = s; k.wn = p.ntt.wn_fwd; k.s_ce[0] = p.s_ce[0]; k.s_ce[1] = p.s_ce[1];
-    k.zinv[0] = p.zinv[0]; k.zinv[1] = p.zinv[1]; k.g_last = p.g_last; k.out = c.ce; bk.run(2 * n, k); }
+  const u32 pts = n >= 1024 ? GO_PTS : 1;   // points per thread of the constraint / DEEP bodies (batched inversions); short traces keep one point per thread
+  { GoConstraint<D> k{}; k.lde = c.lde; k.ln = ln; k.lb = p.lb; k.pts = pts; k.prog = prog; k.s = s; k.wn = p.ntt.wn_fwd; k.s_ce[0] = p.s_ce[0]; k.s_ce[1] = p.s_ce[1];
+    k.zinv[0] = p.zinv[0]; k.zinv[1] = p.zinv[1]; k.g_last = p.g_last; k.out = c.ce; bk.run(2 * n / pts, k); }
   // 3 ---- commit_to_constraint_evaluations: coset interpolation (2 cosets of n points), composition column, LDE, commitment
   { NttJob j{}; j.src = c.ce; j.dst = c.ce_tmp; j.ln = ln; j.batch = 2 * D; j.src_tstride = n; j.dst_tstride = n; j.src_div = 1;
     j.inverse = true; j.scale = p.n_inv; j.post_lo = p.un_lo; j.post_hi = p.un_hi; j.post_hi_stride = p.un_hi_stride; j.post_div = 2; bk.ntt(j); }
@@ -139,10 +140,12 @@ void go_enqueue_d(BK& bk, const GoPlan& p, const GoCarve& c, GoState* s, const G
   // 4 ---- build_deep_composition_poly: OOD frame + DEEP coefficients
   const u32 chunks = (u32)std::min<size_t>(GO_OOD_CHUNKS, n);
   bk.run((size_t)(W + D) * chunks, GoOodPartial<D>{c.trace_coef, c.h_coef, ln, W, chunks, s, c.ood_partial});
-  bk.run((size_t)(W + D) * 2, GoOodSum<D>{c.ood_partial, chunks, c.ood_sums});
+  { const u32 groups = chunks >= 64 ? 32 : 1;      // two-level sum: 32 group sums per (polynomial, point), then their sum
+    if (groups > 1) { bk.run((size_t)(W + D) * 2 * groups, GoOodSum<D>{c.ood_partial, chunks, groups, c.ood_part2}); bk.run((size_t)(W + D) * 2, GoOodSum2<D>{c.ood_part2, groups, c.ood_sums}); }
+    else bk.run((size_t)(W + D) * 2, GoOodSum<D>{c.ood_partial, chunks, 1, c.ood_sums}); }
   bk.run(1, GoStepOod<D>{s, c.ood_sums, W});
   // 5 ---- evaluate_deep_composition_poly (pointwise)
-  bk.run(N, GoDeep<D>{c.lde, c.h_lde, ln, p.lb, W, s, p.ntt.wn_fwd, p.d_sk, c.deep});
+  bk.run(N / pts, GoDeep<D>{c.lde, c.h_lde, ln, p.lb, W, pts, s, p.ntt.wn_fwd, p.d_sk, c.deep});
   // 6 ---- compute_fri_layers
   for (u32 l = 0; l < p.num_layers; l++) {
     const u32 lNl = p.layer_log[l]; const u64 Nl = u64(1) << lNl, R = Nl >> p.lf;
