@@ -312,7 +312,8 @@ def run_air(args, rank, world, local):
                                   f"{'quadratic' if e == 2 else 'no'} extension, 42 queries, {W + 2} assertions on 3 steps", "l2": "working set >> L2 at the default size; no explicit flush"},
            "proof_bytes": len(proof), "clocks": clocks,
            "e2e": {"value": e2e_ms / (args.steps * world), "unit": "ms", "h2d_bytes_per_step": times2["h2d_bytes"], "d2h_bytes_per_step": times2["d2h_bytes"]},
-           "gpu_launches": times["kernel_launches"] * args.steps, "device_ms_per_proof": times["device_ms"],
+           "other_options": other_options,
+        "gpu_launches": times["kernel_launches"] * args.steps, "device_ms_per_proof": times["device_ms"],
            "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},
            "roofline": {"bound": "hbm", "kernel": top["name"], "achieved": top["gbps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": None,
                         "peak_source": peak_src, "launch_ms": top["ms"], "alg_bytes": top["alg_bytes"],
@@ -451,6 +452,19 @@ def main():
         raise
     except Exception as e:
         callers["error"] = repr(e)
+    # `with_options` (src/burn_mint_prover.rs:44-49) outside the reference's own setting: the general-options pipeline on the same device-resident
+    # trace (auxiliary: folding factor 4, and the cubic extension); their bytes are checked against the oracle by tests/test_gpu_options.py
+    other_options = {}
+    try:
+        for name, o in (("blowup8_folding4_quadratic", (42, 8, 4, 2, 4, 31)), ("blowup8_folding8_cubic", (42, 8, 4, 3, 8, 31))):
+            oo = xs.ProofOptions(*o)
+            oo_fn = lambda: ctx.prove_device(d_trace.data_ptr(), args.n_log2, air, oo)
+            oo_fn()
+            k_o = max(3, args.steps // 3)
+            ms_o, pr_o = timed_region(oo_fn, k_o)
+            other_options[name] = {"options": list(o), "ms_per_proof": ms_o / (k_o * world), "steps": k_o, "proof_bytes": len(pr_o)}
+    except Exception as e:
+        other_options["error"] = repr(e)
     clocks = sampler.stop()
     assert proof == proof2, "device-resident and host-buffer proofs differ"
     # sustained: >= 2.5 s of back-to-back proofs with its own clock samples (thermal / power behaviour of a long batch of large proofs)
@@ -526,6 +540,7 @@ def main():
         "e2e_callers_ms": {"pinned_contiguous_canonical": e2e_ms / (args.steps * world), "from_inputs_device_built_trace": callers.get("from_inputs"),
                            "registered_montgomery_columns": callers.get("mont_cols"), "pageable_contiguous_canonical": callers.get("pageable"), "error": callers.get("error"),
                            "note": "same proof bytes on every path (asserted); from_inputs uploads only the 1 KB init block of the proof state, the others also the 7 x n x 8 B trace"},
+        "other_options": other_options,
         "gpu_launches": times["kernel_launches"] * args.steps,
         "device_ms_per_proof": times["device_ms"],
         "stages_ms": {k: round(v, 4) for k, v in times.items() if k in xs.STAGE_NAMES},

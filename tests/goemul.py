@@ -7,12 +7,14 @@ import subprocess
 import numpy as np
 
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
-_SO = os.path.join(_DIR, "libgo_emul.so")
+_SO = os.environ.get("GO_EMUL_LIB") or os.path.join(_DIR, "libgo_emul.so")
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _lib = None
 
 
 def build():
+    if os.environ.get("GO_EMUL_LIB"):
+        return _SO
     csrc = os.path.join(_ROOT, "xfg-stark_b200", "csrc")
     srcs = [os.path.join(_DIR, "go_emul.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp"))]
     srcs += [os.path.join(_ROOT, "include", "xfg_stark.h"), os.path.join(_ROOT, "include", "xfg", "spec.h")]
@@ -21,6 +23,20 @@ def build():
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-I", cuda_inc, "-o", _SO, os.path.join(_DIR, "go_emul.cpp")])
     return _SO
+
+
+def build_asan():
+    """the same harness under AddressSanitizer, with poisoned guard zones between the workspace regions; None when g++ has no libasan"""
+    so = os.path.join(_DIR, "libgo_emul_asan.so")
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        return None, None
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    src = os.path.join(_DIR, "go_emul.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(_SO) if os.path.exists(_SO) else 0):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address", "-fno-omit-frame-pointer", "-Wno-unknown-pragmas",
+                               "-I", cuda_inc, "-o", so, src])
+    return so, asan
 
 
 def lib():

@@ -4,6 +4,10 @@
 // against the reference's own proofs on a CPU-only box, before (and independently of) the GPU parity tests.  Nothing in the product library
 // links or loads this file; the product launches the same bodies as CUDA kernels only (general.cu) and has no CPU path.
 #include <cstdio>
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -62,8 +66,21 @@ int prove(const xfg_air_desc& air, const u64* trace, u32 n_log2, const uint32_t 
   if (int rc = compile_air_impl(e, air, n_log2, *prog, steps)) { set_err(err, errcap, e); return rc; }
   for (size_t g = 0; g < steps.size(); g++) prog->group_point[g] = gl_pow(p.g_n, steps[g]);
   const u32 W = air.width;
-  GoCarve c; go_carve(nullptr, p, D, W, c);
-  std::vector<u64> slab(c.words, 0xA5A5A5A5A5A5A5A5ull); go_carve(slab.data(), p, D, W, c);
+  // under AddressSanitizer (tests/test_options_pins.py::test_emulated_pipeline_under_address_sanitizer) every region of the workspace is followed by a
+  // poisoned guard zone, so an out-of-range index in any body - the same index arithmetic the CUDA kernels run - aborts the run
+#if defined(__SANITIZE_ADDRESS__)
+  const size_t gap = 64;
+#else
+  const size_t gap = 0;
+#endif
+  std::vector<std::pair<size_t, size_t>> gaps;
+  GoCarve c; go_carve(nullptr, p, D, W, c, gap);
+  std::vector<u64> slab(c.words, 0xA5A5A5A5A5A5A5A5ull); go_carve(slab.data(), p, D, W, c, gap, &gaps);
+#if defined(__SANITIZE_ADDRESS__)
+  for (auto& g : gaps) __asan_poison_memory_region(slab.data() + g.first, g.second * 8);
+  struct Unpoison { std::vector<u64>& s; ~Unpoison() { __asan_unpoison_memory_region(s.data(), s.size() * 8); } } unpoison{slab};
+  if (getenv("GO_EMUL_POKE")) c.trace_coef[((size_t)W * p.n + 7) & ~size_t(7)] = 1;      // self-test of the checker: one word past a region must abort
+#endif
   std::memcpy(c.trace_in, trace, (size_t)W * p.n * 8);
   std::unique_ptr<GoState> st(new GoState); std::memset(st.get(), 0, sizeof(GoState));
   seed_elements(n_log2, o, W, air.pub_inputs, air.num_pub_inputs, st->seed_limbs);

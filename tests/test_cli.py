@@ -47,3 +47,18 @@ def test_generate_matches_oracle(tmp_path, ext):
     opts = (42, 8, 4, 2 if ext == "quadratic" else 1, 8, 31)
     assert proof == orc.prove(orc.build_trace(pi, ac, 64), pi, ac, opts)
     assert orc.verify(proof, pi, ac, opts) == ""
+
+
+@pytest.mark.gpu
+def test_generate_with_other_proof_options(tmp_path):
+    """`with_options` through the CLI: cubic extension, blowup 16, folding 4"""
+    from xfg_stark_b200 import cli
+    out = tmp_path / "proof.json"
+    assert cli.main(["generate", "-i", os.path.join(HERE, "golden", "data_package.json"), "-o", str(out), "--trace-log2", "7", "--extension", "cubic",
+                     "--blowup", "16", "--folding", "4", "--queries", "30", "--grinding", "6", "--remainder-degree", "15"]) == 0
+    proof = bytes(json.load(open(out))["proof_data"])
+    a = cli.prover_arguments(package())
+    pi, ac, _ = orc.pack_inputs(a["burn_amount"], a["mint_amount"], a["tx_prefix_hash"], a["recipient_address"], a["secret"], a["network_id"], a["target_chain_id"], a["commitment_version"])
+    opts = (30, 16, 6, 3, 4, 15)
+    assert proof == orc.prove(orc.build_trace(pi, ac, 128), pi, ac, opts)
+    assert orc.verify(proof, pi, ac, opts) == ""

@@ -91,3 +91,38 @@ def test_emulated_pipeline_detects_bad_traces():
     with pytest.raises(goemul.EmulError) as e:
         goemul.prove_burn_mint(bad, pi, ac, o)
     assert e.value.code == 1
+
+
+ASAN_SWEEP = r"""
+import random, sys
+sys.path.insert(0, sys.argv[1])
+import goemul, orc, refvec
+rng = random.Random(7); done = 0
+while done < 16:
+    n_log2 = rng.choice([3, 4, 5, 6, 7, 8, 10, 11])
+    blowup = rng.choice([2, 4, 8, 16, 32, 64, 128]); folding = rng.choice([2, 4, 8, 16]); rem = rng.choice([0, 1, 3, 7, 15, 31, 63, 127, 255])
+    o = (rng.randrange(1, min(255, (blowup << n_log2) - 1) + 1), blowup, rng.randrange(0, 6), rng.choice([1, 2, 3]), folding, rem)
+    if refvec.fri_shape_refused(n_log2, o):
+        continue
+    t, pi, ac = orc.synthetic_case(1 << n_log2, done)
+    assert goemul.prove_burn_mint(t, pi, ac, o) == orc.prove(t, pi, ac, o), (n_log2, o)
+    done += 1
+print("asan sweep ok")
+"""
+
+
+def test_emulated_pipeline_under_address_sanitizer():
+    """memory safety of the general-options kernel bodies: the index arithmetic the CUDA kernels run, executed under AddressSanitizer with a poisoned
+    guard zone after every workspace region (compute-sanitizer is closed on the GPU pool)"""
+    import os
+    import subprocess
+    import sys
+    so, asan = goemul.build_asan()
+    if so is None:
+        pytest.skip("g++ has no libasan here")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", GO_EMUL_LIB=so)
+    r = subprocess.run([sys.executable, "-c", ASAN_SWEEP, here], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "asan sweep ok" in r.stdout, r.stderr[-2000:]
+    r = subprocess.run([sys.executable, "-c", ASAN_SWEEP, here], env=dict(env, GO_EMUL_POKE="1"), capture_output=True, text=True, timeout=900)      # the checker itself
+    assert r.returncode != 0 and "use-after-poison" in r.stderr

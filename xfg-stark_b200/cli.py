@@ -93,7 +93,10 @@ def main(argv=None):
     sub = ap.add_subparsers(dest="cmd", required=True)
     g = sub.add_parser("generate"); g.add_argument("-i", "--input", required=True); g.add_argument("-o", "--output", required=True)
     g.add_argument("--trace-log2", type=int, default=6, help="trace length 2^k (6 = the reference's 64 rows)")
-    g.add_argument("--extension", choices=["none", "quadratic"], default="none")
+    g.add_argument("--extension", choices=["none", "quadratic", "cubic"], default="none")
+    # ProofOptions::new arguments (XfgBurnMintProver::with_options, src/burn_mint_prover.rs:44-49); defaults = the reference's (src/burn_mint_prover.rs:28-35)
+    g.add_argument("--queries", type=int, default=42); g.add_argument("--blowup", type=int, default=8); g.add_argument("--grinding", type=int, default=4)
+    g.add_argument("--folding", type=int, default=8); g.add_argument("--remainder-degree", type=int, default=31)
     v = sub.add_parser("validate"); v.add_argument("-i", "--input", required=True)
     args = ap.parse_args(argv)
     pkg = json.load(open(args.input))
@@ -108,7 +111,9 @@ def main(argv=None):
         print("Data package validated successfully")
         return 0
     from ._binding import FieldExtension, ProofOptions, XfgBurnMintProver
-    opts = ProofOptions(field_extension=FieldExtension.QUADRATIC if args.extension == "quadratic" else FieldExtension.NONE)
+    ext = {"none": FieldExtension.NONE, "quadratic": FieldExtension.QUADRATIC, "cubic": FieldExtension.CUBIC}[args.extension]
+    opts = ProofOptions(num_queries=args.queries, blowup_factor=args.blowup, grinding_factor=args.grinding, field_extension=ext,
+                        fri_folding_factor=args.folding, fri_remainder_max_degree=args.remainder_degree)
     prover = XfgBurnMintProver.with_options(128, opts, trace_log2=args.trace_log2)
     out = generate_proof(pkg, prover)
     json.dump(out, open(args.output, "w"), indent=2)

@@ -5,6 +5,7 @@
 //
 // Stage order = winter-prover 0.8.3 `Prover::prove` / `generate_proof`, as in prover.cu: enqueue_proof.
 #pragma once
+#include <utility>
 #include <vector>
 #include "general_bodies.cuh"
 #include "proof_bytes.hpp"
@@ -79,9 +80,10 @@ struct GoCarve {
   u64* fri_evals[GO_MAX_LAYERS + 1]; Digest* fri_tree[GO_MAX_LAYERS];
   size_t words;
 };
-inline void go_carve(u64* base, const GoPlan& p, int D, u32 W, GoCarve& c) {
+// gap / gaps: optional guard words after every region (the emulation harness poisons them under AddressSanitizer: tests/host_emul)
+inline void go_carve(u64* base, const GoPlan& p, int D, u32 W, GoCarve& c, size_t gap = 0, std::vector<std::pair<size_t, size_t>>* gaps = nullptr) {
   u64* w = base; const size_t n = p.n, N = p.N;
-  auto take = [&](size_t k) { u64* r = w; w += (k + 7) & ~size_t(7); return r; };
+  auto take = [&](size_t k) { u64* r = w; w += (k + 7) & ~size_t(7); if (gaps) gaps->push_back({(size_t)(w - base), gap}); w += gap; return r; };
   c.trace_in = take(W * n); c.trace_coef = take(W * n); c.lde = take(W * N);
   c.trace_tree = reinterpret_cast<Digest*>(take(8 * N));
   c.ce = take(2 * D * n); c.ce_tmp = take(2 * D * n); c.h_coef = take(D * n); c.h_lde = take(D * N);
