@@ -79,6 +79,25 @@ def test_product_never_touches_the_oracle():
     assert "oracle" not in out
 
 
+def test_product_has_no_host_execution_of_the_general_pipeline():
+    """tests/host_emul runs the general-options kernel bodies on the host for CPU-only parity tests; the product must never do that: the package
+    does not load, import or build the harness (the sources only name it in comments), the host backend (`HostBK`) exists only in the harness,
+    and the library exports no emulation entry point"""
+    pkg = os.path.join(ROOT, "xfg-stark_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".inc", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "go_emul" not in txt and "goemul" not in txt and "HostBK" not in txt, os.path.join(dp, f)
+                for line in txt.splitlines():
+                    if "host_emul" in line:
+                        assert line.lstrip().startswith(("//", "*", "#")), (f, line)      # named in comments only
+    syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(pkg, "libxfgstark.so")], capture_output=True, text=True).stdout
+    assert "emul" not in syms
+    out = subprocess.run(["ldd", os.path.join(pkg, "libxfgstark.so")], capture_output=True, text=True).stdout
+    assert "go_emul" not in out
+
+
 def test_host_mirror_matches_oracle():
     import xfg_stark_b200 as xs
     for idx in range(6):
