@@ -39,7 +39,8 @@
 #define XFG_STD_BURN          8000000ULL      /* :208 */
 #define XFG_LARGE_BURN        8000000000ULL   /* :215-216 = 8e6 * 1000 as a field element */
 #define XFG_CE_BLOWUP         2   /* A.3: max(next_pow2(deg-1), 2) for declared degree 1 */
-#define XFG_NUM_COMP_COLS     1   /* A.3 */
+#define XFG_NUM_COMP_COLS     1   /* A.3 (the burn-mint AIR: degree 2) */
+#define XFG_AIR_MAX_DEGREE    9   /* generic AIRs: highest transition-constraint degree served (ce_blowup 8, 8 composition columns) */
 #define XFG_FINAL_STATE       3   /* :393 */
 
 /* public-input slots, order of src/burn_mint_air.rs:54-71 */

@@ -125,7 +125,7 @@ inline std::vector<Assertion> get_assertions(const PublicInputs& pi, const AirCo
           {4, 0, 0}, {5, 0, c.nullifier}, {6, 0, c.commitment}, {4, n - 1, XFG_FINAL_STATE}};
 }
 
-// ---- generic degree-<=2 AIR: a straight-line program over the evaluation frame --------------------
+// ---- generic AIR (transition degrees up to 9 = up to 8 composition columns): a straight-line program over the evaluation frame --------------------
 // Value ids: [0, w) = current row, [w, 2w) = next row, [2w, 2w + C) = constants, 2w + C + i = result of instruction i.
 // This is the role of a user's `Air::evaluate_transition` body (e.g. the 4-column XfgBurnAir sketch, src/winterfell_air.rs:87-127);
 // Winterfell's own rules around it - assertion ordering (A.8), ce_blowup 2 and one composition column for degrees <= 2 (A.3) -
@@ -139,6 +139,11 @@ struct AirDef {
   std::vector<u64> pub_inputs;              // ToElements order; appended to the coin seed after Context::to_elements
   std::vector<u64> constants; std::vector<Instr> code; std::vector<u32> outputs;   // outputs[j] = value id of constraint j
   std::vector<Assertion> assertions;        // Winterfell's sorted order (stride, first_step, column) = (step, column) for single assertions
+  u32 max_degree = 2;                       // highest transition-constraint degree d (computed by validate_air); winter-air derives from it (A.3):
+  // ce_blowup = max(2, next_pow2(d - 1))   (TransitionConstraintDegree::min_blowup_factor; pinned by running the reference binary with declared degrees 3, 4, 5)
+  size_t ce_blowup() const { size_t c = 2; while (c + 1 < max_degree) c <<= 1; return c; }
+  // composition columns = max(1, d - 1)    (AirContext::num_constraint_composition_columns: ceil((d (n-1) - (n-1)) / n) for n > d)
+  size_t comp_columns() const { return max_degree > 2 ? max_degree - 1 : 1; }
 };
 inline AirDef burn_mint_air(const PublicInputs& pi, const AirConsts& c, size_t n) {
   AirDef a; a.burn_mint = true; a.ac = c; a.width = XFG_TRACE_WIDTH; a.num_transition = XFG_NUM_TRANSITION;
@@ -159,9 +164,11 @@ inline std::string validate_air(AirDef& a, size_t n) {
     const Instr& in = a.code[i]; const size_t id = 2 * w + C + i;
     if (in.a >= id || in.b >= id || in.op > OP_MUL) return "invalid instruction";
     deg[id] = in.op == OP_MUL ? deg[in.a] + deg[in.b] : std::max(deg[in.a], deg[in.b]);
-    if (deg[id] > 2) return "transition constraint degree above 2 is not supported";
+    if (deg[id] > XFG_AIR_MAX_DEGREE) return "transition constraint degree above 9 is not supported";
   }
-  for (u32 o : a.outputs) { if (o >= deg.size()) return "invalid constraint output"; if (deg[o] == 0) return "transition constraint degree must be at least one"; }
+  a.max_degree = 1;
+  for (u32 o : a.outputs) { if (o >= deg.size()) return "invalid constraint output"; if (deg[o] == 0) return "transition constraint degree must be at least one"; a.max_degree = std::max(a.max_degree, deg[o]); }
+  if (a.max_degree >= n) return "transition constraint degree must be smaller than the trace length";
   std::sort(a.assertions.begin(), a.assertions.end(), [](const Assertion& x, const Assertion& y) { return x.step != y.step ? x.step < y.step : x.column < y.column; });
   for (size_t i = 0; i < a.assertions.size(); i++) {
     const Assertion& s = a.assertions[i];

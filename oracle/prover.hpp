@@ -68,7 +68,7 @@ template <class E> struct FriLayerData { std::vector<E> evals; MerkleTree tree; 
 template <class E>
 std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const AirDef& air,
                       const ProofOptions& opt, StageTimes* times = nullptr, ProverDebug<E>* dbg = nullptr) {
-  const size_t W = air.width, NT = air.num_transition, n = trace[0].size(), b = opt.blowup, N = n * b, c = XFG_CE_BLOWUP, F = opt.folding;
+  const size_t W = air.width, NT = air.num_transition, n = trace[0].size(), b = opt.blowup, N = n * b, c = air.ce_blowup(), K = air.comp_columns(), F = opt.folding;
   if (trace.size() != W) throw std::runtime_error("trace width does not match the AIR");
   if (n < 8 || (n & (n - 1))) throw std::runtime_error("trace length must be a power of two >= 8");
   if (b < c) throw std::runtime_error("blowup factor too small");
@@ -130,12 +130,13 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const AirDef& a
 
   // 3 ----- commit_to_constraint_evaluations: composition poly, its LDE and commitment (A.9)
   interpolate_poly_with_offset(hev, offset);
-  for (size_t k = n; k < cn; k++) if (!hev[k].is_zero()) throw std::runtime_error("UnsatisfiedTransitionConstraintError");
-  std::vector<E> hpoly(hev.begin(), hev.begin() + n);   // k = 1 column of n coefficients
-  std::vector<E> hlde = evaluate_poly_with_offset(hpoly, offset, b);
+  for (size_t k = K * n; k < cn; k++) if (!hev[k].is_zero()) throw std::runtime_error("UnsatisfiedTransitionConstraintError");
+  // CompositionPoly::new: column i = coefficients [i n, (i + 1) n) of the composition polynomial (K = 1 for degrees <= 2)
+  std::vector<std::vector<E>> hcols(K), hldes(K);
+  for (size_t i = 0; i < K; i++) { hcols[i].assign(hev.begin() + i * n, hev.begin() + (i + 1) * n); hldes[i] = evaluate_poly_with_offset(hcols[i], offset, b); }
   std::vector<Digest> cleaves(N);
 #pragma omp parallel for num_threads(T) schedule(static)
-  for (size_t i = 0; i < N; i++) cleaves[i] = hash_elements(&hlde[i], 1);
+  for (size_t i = 0; i < N; i++) { std::vector<E> row(K); for (size_t j = 0; j < K; j++) row[j] = hldes[j][i]; cleaves[i] = hash_elements(row.data(), K); }
   MerkleTree ctree(std::move(cleaves));
   coin.reseed(ctree.root());
   st.ms[ST_COMMIT_CONSTRAINTS] = tm.lap();
@@ -148,10 +149,12 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const AirDef& a
   for (size_t j = 0; j < W; j++) { frame.push_back(tz[j]); frame.push_back(tzg[j]); }   // interleaved per column (D)
   std::vector<u8> ood_trace_bytes; ood_trace_bytes.push_back(2); put_elems(ood_trace_bytes, frame);
   coin.reseed(hash_elements(frame));
-  E hz = eval_poly<E, E>(hpoly, z);
-  std::vector<u8> ood_eval_bytes; put_elem(ood_eval_bytes, hz);
-  coin.reseed(hash_elements(&hz, 1));
-  std::vector<E> dcoef(W + XFG_NUM_COMP_COLS);
+  std::vector<E> hzs(K);
+  for (size_t i = 0; i < K; i++) hzs[i] = eval_poly<E, E>(hcols[i], z);
+  const E hz = hzs[0];
+  std::vector<u8> ood_eval_bytes; put_elems(ood_eval_bytes, hzs);
+  coin.reseed(hash_elements(hzs));
+  std::vector<E> dcoef(W + K);
   for (auto& x : dcoef) x = coin.draw<E>();
   std::vector<E> t1(n), t2(n);
 #pragma omp parallel for num_threads(T) schedule(static)
@@ -160,9 +163,12 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const AirDef& a
   { E s1 = E::zero(), s2 = E::zero(); for (size_t j = 0; j < W; j++) { s1 = s1 + dcoef[j] * tz[j]; s2 = s2 + dcoef[j] * tzg[j]; }
     t1[0] = t1[0] - s1; t2[0] = t2[0] - s2; }
   syn_div_in_place(t1, z); syn_div_in_place(t2, zg);
-  std::vector<E> hq(hpoly); hq[0] = hq[0] - hz; syn_div_in_place(hq, z);
   std::vector<E> deep(n);
-  for (size_t k = 0; k < n; k++) deep[k] = t1[k] + t2[k] + dcoef[W] * hq[k];
+  for (size_t k = 0; k < n; k++) deep[k] = t1[k] + t2[k];
+  for (size_t i = 0; i < K; i++) {
+    std::vector<E> hq(hcols[i]); hq[0] = hq[0] - hzs[i]; syn_div_in_place(hq, z);
+    for (size_t k = 0; k < n; k++) deep[k] = deep[k] + dcoef[W + i] * hq[k];
+  }
   st.ms[ST_BUILD_DEEP] = tm.lap();
 
   // 5 ----- evaluate_deep_composition_poly over the LDE domain
@@ -216,7 +222,7 @@ std::vector<u8> prove(const std::vector<std::vector<F1>>& trace, const AirDef& a
   { std::vector<u8> vals; for (size_t p : positions) for (size_t j = 0; j < W; j++) put_elem(vals, lde[j][p]);
     std::vector<u8> paths = trace_tree.prove_batch(positions).serialize_nodes();
     put_u32(out, vals.size()); put_bytes(out, vals); put_u32(out, paths.size()); put_bytes(out, paths); }
-  { std::vector<u8> vals; for (size_t p : positions) put_elem(vals, hlde[p]);
+  { std::vector<u8> vals; for (size_t p : positions) for (size_t i = 0; i < K; i++) put_elem(vals, hldes[i][p]);
     std::vector<u8> paths = ctree.prove_batch(positions).serialize_nodes();
     put_u32(out, vals.size()); put_bytes(out, vals); put_u32(out, paths.size()); put_bytes(out, paths); }
   put_u16(out, ood_trace_bytes.size()); put_bytes(out, ood_trace_bytes);

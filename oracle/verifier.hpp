@@ -91,7 +91,8 @@ std::string verify(const u8* proof, size_t proof_len, AirDef air, const ProofOpt
   if (ood_t.empty() || ood_t[0] != 2) return "bad OOD frame";
   std::vector<E> frame, hz;
   if (!read_elems(std::vector<u8>(ood_t.begin() + 1, ood_t.end()), 2 * W, frame)) return "bad OOD frame";
-  if (!read_elems(ood_e, XFG_NUM_COMP_COLS, hz)) return "bad OOD evaluations";
+  const size_t K = air.comp_columns();
+  if (!read_elems(ood_e, K, hz)) return "bad OOD evaluations";
   coin.reseed(hash_elements(frame));
   const u64 g_n = root_of_unity(ilog2(n)), g_last = fpow(g_n, n - 1);
   {
@@ -107,12 +108,15 @@ std::string verify(const u8* proof, size_t proof_len, AirDef air, const ProofOpt
       for (; k < asr.size() && asr[k].step == step; k++) bsum = bsum + bcoef[k] * (cur[asr[k].column] - E::from_base(asr[k].value));
       result = result + bsum * (z - E::from_base(fpow(g_n, step))).inv();
     }
-    if (result != hz[0]) return "InconsistentOodConstraintEvaluations";
+    // the composition polynomial at z from its K columns: sum_i z^(i n) H_i(z)
+    E hsum = E::zero(), zp = E::one();
+    for (size_t i = 0; i < K; i++) { hsum = hsum + hz[i] * zp; zp = zp * zn; }
+    if (result != hsum) return "InconsistentOodConstraintEvaluations";
   }
   coin.reseed(hash_elements(hz));
 
   // ---- (4) DEEP coefficients, FRI alphas ----
-  std::vector<E> dcoef(W + XFG_NUM_COMP_COLS); for (auto& x : dcoef) x = coin.draw<E>();
+  std::vector<E> dcoef(W + K); for (auto& x : dcoef) x = coin.draw<E>();
   std::vector<E> alphas;
   for (size_t l = 0; l < num_layers; l++) { coin.reseed(cmd(2 + l)); alphas.push_back(coin.draw<E>()); }
   coin.reseed(rem_commit);
@@ -127,14 +131,14 @@ std::string verify(const u8* proof, size_t proof_len, AirDef air, const ProofOpt
   // ---- (6) trace / constraint openings ----
   std::vector<F1> trows; std::vector<E> crows;
   if (!read_elems(tq_vals, positions.size() * W, trows)) return "bad trace query values";
-  if (!read_elems(cq_vals, positions.size(), crows)) return "bad constraint query values";
+  if (!read_elems(cq_vals, positions.size() * K, crows)) return "bad constraint query values";
   {
     std::vector<Digest> lv(positions.size());
     for (size_t i = 0; i < positions.size(); i++) lv[i] = hash_elements(&trows[i * W], W);
     BatchMerkleProof bp; Digest root;
     if (!BatchMerkleProof::deserialize(tq_paths.data(), tq_paths.size(), lv, ilog2(N), bp)) return "bad trace query paths";
     if (!bp.get_root(positions, root) || root != trace_root) return "TraceQueryDoesNotMatchCommitment";
-    for (size_t i = 0; i < positions.size(); i++) lv[i] = hash_elements(&crows[i], 1);
+    for (size_t i = 0; i < positions.size(); i++) lv[i] = hash_elements(&crows[i * K], K);
     BatchMerkleProof cp;
     if (!BatchMerkleProof::deserialize(cq_paths.data(), cq_paths.size(), lv, ilog2(N), cp)) return "bad constraint query paths";
     if (!cp.get_root(positions, root) || root != constraint_root) return "ConstraintQueryDoesNotMatchCommitment";
@@ -151,7 +155,7 @@ std::string verify(const u8* proof, size_t proof_len, AirDef air, const ProofOpt
       E t = E::from_base(trows[i * W + j].v);
       acc = acc + dcoef[j] * ((t - frame[2 * j]) * i1 + (t - frame[2 * j + 1]) * i2);
     }
-    acc = acc + dcoef[W] * (crows[i] - hz[0]) * i1;
+    for (size_t k = 0; k < K; k++) acc = acc + dcoef[W + k] * (crows[i * K + k] - hz[k]) * i1;
     evaluations[i] = acc;
   }
 

@@ -58,12 +58,13 @@ void set_err(char* err, size_t cap, const std::string& s) { if (err && cap) snpr
 int prove(const xfg_air_desc& air, const u64* trace, u32 n_log2, const uint32_t o6[6], u64 in_scale, u8* out, size_t cap, size_t* out_len, char* err, size_t errcap) {
   xfg_options o{}; o.num_queries = o6[0]; o.blowup_factor = o6[1]; o.grinding_factor = o6[2]; o.field_extension = o6[3]; o.fri_folding_factor = o6[4]; o.fri_remainder_max_degree = o6[5];
   const int D = (int)o.field_extension;
-  GoPlan p;
-  if (const char* why = go_plan_shape(p, n_log2, o.blowup_factor, o.fri_folding_factor, o.fri_remainder_max_degree)) { set_err(err, errcap, why); return XFG_ERR_BAD_OPTIONS; }
-  std::vector<std::unique_ptr<std::vector<u64>>> keep;
-  go_plan_tables(p, [&](const std::vector<u64>& v) { keep.emplace_back(new std::vector<u64>(v)); return (const u64*)keep.back()->data(); });
   std::unique_ptr<GenProgram> prog(new GenProgram); std::vector<u64> steps; std::string e;
   if (int rc = compile_air_impl(e, air, n_log2, *prog, steps)) { set_err(err, errcap, e); return rc; }
+  const u32 K = go_comp_columns(prog->max_degree);
+  GoPlan p;
+  if (const char* why = go_plan_shape(p, n_log2, o.blowup_factor, o.fri_folding_factor, o.fri_remainder_max_degree, prog->max_degree)) { set_err(err, errcap, why); return XFG_ERR_BAD_OPTIONS; }
+  std::vector<std::unique_ptr<std::vector<u64>>> keep;
+  go_plan_tables(p, [&](const std::vector<u64>& v) { keep.emplace_back(new std::vector<u64>(v)); return (const u64*)keep.back()->data(); });
   for (size_t g = 0; g < steps.size(); g++) prog->group_point[g] = gl_pow(p.g_n, steps[g]);
   const u32 W = air.width;
   // under AddressSanitizer (tests/test_options_pins.py::test_emulated_pipeline_under_address_sanitizer) every region of the workspace is followed by a
@@ -74,8 +75,8 @@ int prove(const xfg_air_desc& air, const u64* trace, u32 n_log2, const uint32_t 
   const size_t gap = 0;
 #endif
   std::vector<std::pair<size_t, size_t>> gaps;
-  GoCarve c; go_carve(nullptr, p, D, W, c, gap);
-  std::vector<u64> slab(c.words, 0xA5A5A5A5A5A5A5A5ull); go_carve(slab.data(), p, D, W, c, gap, &gaps);
+  GoCarve c; go_carve(nullptr, p, D, W, K, c, gap);
+  std::vector<u64> slab(c.words, 0xA5A5A5A5A5A5A5A5ull); go_carve(slab.data(), p, D, W, K, c, gap, &gaps);
 #if defined(__SANITIZE_ADDRESS__)
   for (auto& g : gaps) __asan_poison_memory_region(slab.data() + g.first, g.second * 8);
   struct Unpoison { std::vector<u64>& s; ~Unpoison() { __asan_unpoison_memory_region(s.data(), s.size() * 8); } } unpoison{slab};
@@ -85,14 +86,14 @@ int prove(const xfg_air_desc& air, const u64* trace, u32 n_log2, const uint32_t 
   std::unique_ptr<GoState> st(new GoState); std::memset(st.get(), 0, sizeof(GoState));
   seed_elements(n_log2, o, W, air.pub_inputs, air.num_pub_inputs, st->seed_limbs);
   st->seed_count = 8 + air.num_pub_inputs; st->error_flags = 0; st->nonce = ~0ull;
-  std::vector<GoGatherTask> tasks; const size_t mat_words = go_gather_tasks(p, D, W, o.num_queries, c, tasks);
+  std::vector<GoGatherTask> tasks; const size_t mat_words = go_gather_tasks(p, D, W, K, o.num_queries, c, tasks);
   std::vector<u64> material(mat_words, 0);
   HostBK bk;
-  go_enqueue(bk, D, p, c, st.get(), prog.get(), W, air.num_constraints + air.num_assertions, c.trace_in, in_scale, o.num_queries, o.grinding_factor, tasks, material.data());
+  go_enqueue(bk, D, p, c, st.get(), prog.get(), W, K, air.num_assertions, air.num_constraints + air.num_assertions, c.trace_in, in_scale, o.num_queries, o.grinding_factor, tasks, material.data());
   if (st->error_flags & ERR_FLAG_NONCANONICAL) { set_err(err, errcap, "non-canonical trace element"); return XFG_ERR_BAD_ARGS; }
   if (st->error_flags & ERR_FLAG_DEGREE) { set_err(err, errcap, "UnsatisfiedTransitionConstraintError"); return XFG_ERR_UNSATISFIED_CONSTRAINT; }
   if (st->error_flags & ERR_FLAG_COIN) { set_err(err, errcap, "FailedToDrawFieldElement"); return XFG_ERR_INTERNAL; }
-  std::vector<u8> bytes; go_assemble(p, D, W, o, *st, material.data(), tasks, bytes);
+  std::vector<u8> bytes; go_assemble(p, D, W, K, o, *st, material.data(), tasks, bytes);
   *out_len = bytes.size();
   if (bytes.size() > cap) { set_err(err, errcap, "output buffer too small"); return XFG_ERR_BUFFER_TOO_SMALL; }
   std::memcpy(out, bytes.data(), bytes.size());

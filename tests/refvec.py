@@ -41,6 +41,18 @@ def option_case_ids():
     return [c["name"] for c in option_cases()]
 
 
+# proofs of AIRs that DECLARE transition degrees above 2 (several constraint composition columns): oracle/a64emu/make_reference_degree_vectors.py
+DEGREES_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_proofs_degrees.json")
+
+
+def degree_cases():
+    return json.load(open(DEGREES_PATH))["cases"]
+
+
+def degree_case_ids():
+    return [c["name"] for c in degree_cases()]
+
+
 def fri_shape_refused(n_log2, options):
     """the rule behind the reference's own panics (fixture key "refused"): a FRI layer of fewer than two rows, or an empty remainder"""
     _, blowup, _, _, folding, rem = options
@@ -84,4 +96,4 @@ def air_program(c, pi, ac):
     if root not in sys.path:
         sys.path.insert(0, root)
     from xfg_stark_b200 import air as A
-    return A.burn_mint_air(pi, ac[0], ac[1], ac[2], ac[3], 1 << c["n_log2"], last_step=c["last_step"])
+    return A.burn_mint_air(pi, ac[0], ac[1], ac[2], ac[3], 1 << c["n_log2"], last_step=c["last_step"], pad_degree=c.get("declared_degree"))

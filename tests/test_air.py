@@ -72,9 +72,9 @@ def test_oracle_generic_rejects_bad_traces_and_airs():
     g = dict(f); g["asr"] = f["asr"].copy(); g["asr"][0, 2] = 5            # wrong assertion value: boundary quotient is not a polynomial
     with pytest.raises(RuntimeError, match="UnsatisfiedTransitionConstraintError"):
         orc.prove_air(g, trace)
-    b = A.AirBuilder(1); x = b.cur(0); b.constraint(b.nxt(0) - x * x * x); b.assert_single(0, 0, 2)
-    with pytest.raises(RuntimeError, match="degree above 2"):
-        orc.prove_air(b.flatten(), np.full((1, 8), 1, dtype=np.uint64))
+    b = A.AirBuilder(1); x = b.cur(0); y = x * x * x; b.constraint(b.nxt(0) - y * y * y * x); b.assert_single(0, 0, 1)
+    with pytest.raises(RuntimeError, match="degree above 9"):
+        orc.prove_air(b.flatten(), np.full((1, 16), 1, dtype=np.uint64))
     b = A.AirBuilder(1); b.constraint(b.nxt(0) - b.cur(0)); b.assert_single(0, 0, 2); b.assert_single(0, 0, 2)
     with pytest.raises(RuntimeError, match="duplicate assertion"):
         orc.prove_air(b.flatten(), np.full((1, 8), 2, dtype=np.uint64))
@@ -130,7 +130,11 @@ def test_compiler_validation_codes():
             xs.air_compile_check(b, n_log2)
         return e.value.code
     b = A.AirBuilder(1); x = b.cur(0); b.constraint(b.nxt(0) - x * x * x); b.assert_single(0, 0, 1)
-    assert code(b) == 3                                          # degree 3: XFG_ERR_UNSUPPORTED_OPTIONS
+    assert xs.air_compile_check(b, 3)["num_instr"] > 0           # degree 3 compiles (two composition columns, general pipeline)
+    b = A.AirBuilder(1); x = b.cur(0); y = x * x * x; b.constraint(b.nxt(0) - y * y * y * x); b.assert_single(0, 0, 1)
+    assert code(b, 4) == 3                                       # degree 10: XFG_ERR_UNSUPPORTED_OPTIONS
+    b = A.AirBuilder(1); x = b.cur(0); y = x * x * x; b.constraint(b.nxt(0) - y * y * y); b.assert_single(0, 0, 1)
+    assert code(b, 3) == 1                                       # degree 9 on an 8-row trace: the degree must be smaller than the trace length
     b = A.AirBuilder(1); b.constraint(b.nxt(0) - b.cur(0))
     assert code(b) == 1                                          # no assertion
     b = A.AirBuilder(1); b.assert_single(0, 0, 1)

@@ -129,3 +129,36 @@ def test_batches_and_errors_with_other_options(ctx):
     with pytest.raises(xs.XfgError) as e:
         ctx.verify_batch([proofs[0]], [airs[0]], _opts(xs, o))
     assert e.value.code in (3, 4)
+
+
+@pytest.mark.parametrize("name", refvec.degree_case_ids())
+def test_gpu_proof_equals_reference_proof_with_declared_degrees(ctx, name):
+    """AIRs declaring transition degrees 3 .. 9 (d - 1 composition columns): bytes of the reference binary"""
+    import xfg_stark_b200 as xs
+    c = next(x for x in refvec.degree_cases() if x["name"] == name)
+    pi, ac, o, n = refvec.statement(c)
+    assert ctx.prove_air(refvec.air_program(c, pi, ac), refvec.trace(c, pi, ac), _opts(xs, o)) == refvec.proof_bytes(c)
+
+
+def test_real_higher_degree_airs_equal_oracle(ctx):
+    """constraints of actual degree 3 .. 9: every composition column non-zero; default options route here as well (several columns)"""
+    import xfg_stark_b200 as xs
+    from xfg_stark_b200 import air as A
+    for d, o, w, n in [(3, (42, 8, 4, 2, 8, 31), 3, 256), (4, (42, 8, 4, 1, 8, 31), 2, 4096), (5, (30, 4, 2, 3, 4, 7), 3, 256), (6, (42, 8, 4, 2, 8, 31), 1, 2048),
+                       (9, (42, 16, 4, 2, 8, 31), 2, 128), (3, (20, 2, 0, 1, 2, 0), 4, 64), (7, (33, 8, 3, 3, 2, 15), 2, 512), (3, (42, 8, 4, 2, 8, 31), 5, 1 << 14)]:
+        air, t = A.power_map_air(w, n, d, seed=d)
+        orc.set_threads(orc.max_threads())
+        expect = orc.prove_air(air.flatten(), t, o)
+        orc.set_threads(1)
+        assert ctx.prove_air(air, t, _opts(xs, o)) == expect, (d, o)
+        bad = t.copy(); bad[0, n // 3] ^= 1
+        with pytest.raises(xs.XfgError) as e:
+            ctx.prove_air(air, bad, _opts(xs, o))
+        assert e.value.code == 5, (d, o)
+    air, t = A.power_map_air(2, 64, 5, seed=1)
+    with pytest.raises(xs.XfgError) as e:
+        ctx.prove_air(air, t, _opts(xs, (20, 2, 0, 1, 2, 1)))       # degree 5 needs a constraint-evaluation blowup of 4
+    assert e.value.code == 2
+    proofs, _ = ctx.prove_air_batch([A.power_map_air(2, 128, 3, seed=9)[0], A.fibonacci_air(128)[0]], [A.power_map_air(2, 128, 3, seed=9)[1], A.fibonacci_air(128)[1]])
+    assert proofs[0] == orc.prove_air(A.power_map_air(2, 128, 3, seed=9)[0].flatten(), A.power_map_air(2, 128, 3, seed=9)[1], (42, 8, 4, 1, 8, 31))
+    assert proofs[1] == orc.prove_air(A.fibonacci_air(128)[0].flatten(), A.fibonacci_air(128)[1], (42, 8, 4, 1, 8, 31))

@@ -40,6 +40,43 @@ def test_oracle_and_emulated_pipeline_equal_reference_proof(name):
         assert goemul.prove_burn_mint(mont, pi, ac, o, montgomery=True) == ref
 
 
+@pytest.mark.parametrize("name", refvec.degree_case_ids())
+def test_oracle_and_emulated_pipeline_equal_reference_proof_with_declared_degrees(name):
+    """AIRs declaring transition degrees 3 .. 9: d - 1 composition columns, constraint-evaluation blowup next_pow2(d - 1).  The program writes constraint 1
+    as an expression of that degree with the same values (c0^d - c0^d), which is what the reference computes under the declared degree."""
+    c = next(x for x in refvec.degree_cases() if x["name"] == name)
+    ref = refvec.proof_bytes(c)
+    assert hashlib.sha256(ref).hexdigest() == c["proof_sha256"]
+    pi, ac, o, n = refvec.statement(c)
+    t = refvec.trace(c, pi, ac)
+    air = refvec.air_program(c, pi, ac).flatten()
+    assert orc.prove_air(air, t, o) == ref
+    assert orc.verify_air(ref, air, o) == ""
+    assert goemul.prove_air(air, t, o) == ref
+
+
+def test_real_higher_degree_airs_emulated_pipeline_equals_oracle():
+    """constraints of ACTUAL degree 3 .. 9 (every composition column non-zero): the oracle's verifier accepts the oracle's proof (the OOD check recombines
+    the columns as sum_i z^(i n) H_i(z)), the emulated product pipeline emits the same bytes, and a violated trace is refused - also where the columns
+    leave no vanishing coefficient to check (degrees 3, 5, 9: validated on the trace itself)"""
+    from xfg_stark_b200 import air as A
+    for d, o, w, n in [(3, (42, 8, 4, 2, 8, 31), 3, 256), (4, (42, 8, 4, 1, 8, 31), 2, 1024), (5, (30, 4, 2, 3, 4, 7), 3, 256), (6, (42, 8, 4, 2, 8, 31), 1, 2048),
+                       (9, (42, 16, 4, 2, 8, 31), 2, 128), (3, (20, 2, 0, 1, 2, 0), 4, 64), (7, (33, 8, 3, 3, 2, 15), 2, 512), (8, (42, 128, 0, 1, 16, 255), 1, 64)]:
+        air, t = A.power_map_air(w, n, d, seed=d)
+        f = air.flatten()
+        expect = orc.prove_air(f, t, o)
+        assert orc.verify_air(expect, f, o) == "", (d, o)
+        assert goemul.prove_air(f, t, o) == expect, (d, o)
+        bad = t.copy(); bad[0, n // 3] ^= 1
+        with pytest.raises(goemul.EmulError) as e:
+            goemul.prove_air(f, bad, o)
+        assert e.value.code == 5, (d, o)
+    air, t = A.power_map_air(2, 64, 5, seed=1)                    # degree 5 needs a constraint-evaluation blowup of 4: refused with blowup 2
+    with pytest.raises(goemul.EmulError) as e:
+        goemul.prove_air(air.flatten(), t, (20, 2, 0, 1, 2, 1))
+    assert e.value.code == 2
+
+
 def test_option_vectors_cover_the_option_space():
     cs = refvec.option_cases()
     assert {c["options"][3] for c in cs} == {1, 2, 3}

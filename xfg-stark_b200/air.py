@@ -158,6 +158,34 @@ def gl_add_np(a, b):
     return np.where(s >= np.uint64(P), s - np.uint64(P), s)
 
 
+def power_map_air(width, n, degree, seed=1):
+    """`width` registers with x_j' = x_j^(degree-1) * x_{(j+1) mod width} + c_j: transition constraints of actual degree `degree` (3 .. 9), so the
+    composition polynomial really fills degree - 1 columns (and, from degree 4, a constraint-evaluation domain of 4 n or 8 n points).
+    Assertions: every register at step 0, register 0 at step n - 1."""
+    rng = np.random.default_rng(seed)
+    c = rng.integers(0, P, size=width, dtype=np.uint64)
+    air = AirBuilder(width)
+    for j in range(width):
+        pw = air.cur((j + 1) % width)
+        for _ in range(degree - 1):
+            pw = pw * air.cur(j)
+        air.constraint(air.nxt(j) - (pw + int(c[j])))
+    t = np.zeros((width, n), dtype=np.uint64)
+    x = rng.integers(0, P, size=width, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(n):
+            t[:, i] = x
+            y = np.roll(x, -1)
+            for _ in range(degree - 1):
+                y = gl_mul_np(y, x)
+            x = gl_add_np(y, c)
+    for j in range(width):
+        air.assert_single(j, 0, int(t[j, 0]))
+    air.assert_single(0, n - 1, int(t[0, n - 1]))
+    air.pub_inputs = [int(v) for v in t[:min(width, 8), 0]] + [int(t[0, n - 1])]
+    return air, t
+
+
 def wide_quadratic_air(width, n, seed=1, extra_steps=()):
     """The "wide synthetic AIR" of BASELINE config 5 with actual constraints: `width` registers, register j evolves as
     x_j' = x_j * x_{(j+1) mod width} + c_j (degree 2, every register reads its neighbour).  Assertions: every register at step 0,
@@ -181,14 +209,22 @@ def wide_quadratic_air(width, n, seed=1, extra_steps=()):
     return air, t
 
 
-def burn_mint_air(pub_inputs, txn, rcpt, nullifier, commitment, n, last_step=None):
+def burn_mint_air(pub_inputs, txn, rcpt, nullifier, commitment, n, last_step=None, pad_degree=None):
     """The normalised XfgBurnMintAir (src/burn_mint_air.rs:356-377 constraints, :383-394 assertions, :54-71 public inputs) written
     with the builder: the generic pipeline must emit the same proof bytes as the hand-written burn-mint kernels."""
     pi = [int(v) for v in pub_inputs]
     air = AirBuilder(7, pi)
     c = [air.cur(i) for i in range(7)]
     air.constraint((c[0] - 8_000_000) * (c[0] - 8_000_000_000))
-    air.constraint(c[1] - c[0])
+    if pad_degree is None:
+        air.constraint(c[1] - c[0])
+    else:
+        # the same values written as an expression of degree `pad_degree` (c0^d - c0^d = 0): what the reference computes when constraint 1 DECLARES that
+        # degree (TransitionConstraintDegree::new(d)) - more composition columns (d - 1) and, from d = 4, a larger constraint-evaluation domain
+        pw = c[0]
+        for _ in range(pad_degree - 1):
+            pw = pw * c[0]
+        air.constraint((c[1] - c[0]) + pw - pw)
     air.constraint(c[2] - int(txn))
     air.constraint(c[3] - int(rcpt))
     d = air.nxt(4) - c[4]

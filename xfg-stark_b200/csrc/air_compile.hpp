@@ -34,12 +34,16 @@ inline int compile_air_impl(std::string& err, const xfg_air_desc& d, u32 n_log2,
     const xfg_air_instr& in = d.code[i];
     if (in.op > XFG_OP_MUL || in.a >= first + i || in.b >= first + i) return fail(XFG_ERR_BAD_ARGS, "invalid instruction");
     deg[first + i] = in.op == XFG_OP_MUL ? deg[in.a] + deg[in.b] : std::max(deg[in.a], deg[in.b]);
-    if (deg[first + i] > 2) return fail(XFG_ERR_UNSUPPORTED_OPTIONS, "transition constraint degree above 2 is not supported");
+    if (deg[first + i] > XFG_AIR_MAX_DEGREE) return fail(XFG_ERR_UNSUPPORTED_OPTIONS, "transition constraint degree above 9 is not supported");
   }
+  u32 max_degree = 1;
   for (u32 j = 0; j < T; j++) {
     if (d.constraint_values[j] >= total) return fail(XFG_ERR_BAD_ARGS, "invalid constraint output");
     if (deg[d.constraint_values[j]] == 0) return fail(XFG_ERR_BAD_ARGS, "transition constraint degree must be at least one");
+    max_degree = std::max(max_degree, deg[d.constraint_values[j]]);
   }
+  if ((u64)max_degree >= (u64(1) << n_log2)) return fail(XFG_ERR_BAD_ARGS, "transition constraint degree must be smaller than the trace length");
+  prog.max_degree = max_degree; prog.pad_ = 0;
   // assertions in winter-air's order: (stride, first_step, column) = (step, column) for single assertions (A.8)
   std::vector<xfg_assertion> asr(d.assertions, d.assertions + A);
   std::sort(asr.begin(), asr.end(), [](const xfg_assertion& x, const xfg_assertion& y) { return x.step != y.step ? x.step < y.step : x.column < y.column; });
@@ -50,7 +54,7 @@ inline int compile_air_impl(std::string& err, const xfg_air_desc& d, u32 n_log2,
     if (asr[i].value >= XFG_P) return fail(XFG_ERR_BAD_ARGS, "non-canonical assertion value");
     if (i && asr[i - 1].step == asr[i].step && asr[i - 1].column == asr[i].column) return fail(XFG_ERR_BAD_ARGS, "duplicate assertion");
     if (group_steps.empty() || group_steps.back() != asr[i].step) group_steps.push_back(asr[i].step);
-    prog.asr[i] = GenAssertion{asr[i].column, (u32)group_steps.size() - 1, asr[i].value};
+    prog.asr[i] = GenAssertion{asr[i].column, (u32)group_steps.size() - 1, asr[i].value}; prog.asr_step[i] = asr[i].step;
   }
   if (group_steps.size() > XFG_AIR_MAX_GROUPS) return fail(XFG_ERR_UNSUPPORTED_OPTIONS, "too many distinct assertion steps for this backend");
   // liveness: instructions that (transitively) feed a constraint; last use of every instruction result
@@ -85,6 +89,24 @@ inline int compile_air_impl(std::string& err, const xfg_air_desc& d, u32 n_log2,
   prog.width = w; prog.num_constraints = T; prog.num_assertions = A; prog.num_groups = (u32)group_steps.size(); prog.num_instr = pc; prog.num_slots = num_slots;
   for (u32 i = 0; i < C; i++) prog.constants[i] = d.constants[i];
   return XFG_OK;
+}
+
+// highest transition-constraint degree of a description (0 if it is malformed - the compiler then reports why): decides the pipeline, since the tuned
+// kernels assume one composition column (degree <= 2)
+inline u32 air_max_degree(const xfg_air_desc& d) {
+  const u32 w = d.width, first = 2 * w + d.num_constants;
+  if (!d.code && d.num_instr) return 0;
+  if (!d.constraint_values || w < 1 || w > XFG_AIR_MAX_WIDTH || d.num_instr > XFG_AIR_MAX_INSTR || d.num_constants > XFG_AIR_MAX_CONSTANTS) return 0;
+  std::vector<u32> deg(first + d.num_instr, 0);
+  for (u32 i = 0; i < 2 * w; i++) deg[i] = 1;
+  for (u32 i = 0; i < d.num_instr; i++) {
+    const xfg_air_instr& in = d.code[i];
+    if (in.op > XFG_OP_MUL || in.a >= first + i || in.b >= first + i) return 0;
+    deg[first + i] = std::min<u32>(64, in.op == XFG_OP_MUL ? deg[in.a] + deg[in.b] : std::max(deg[in.a], deg[in.b]));
+  }
+  u32 m = 1;
+  for (u32 j = 0; j < d.num_constraints; j++) { if (d.constraint_values[j] >= deg.size()) return 0; m = std::max(m, deg[d.constraint_values[j]]); }
+  return m;
 }
 
 // the normalised XfgBurnMintAir (src/burn_mint_air.rs:356-377 constraints, :383-394 assertions with the last step n - 1) as an AIR

@@ -31,10 +31,10 @@ struct GpuBK {
 };
 }  // namespace
 
-void go_launch(cudaStream_t st, int D, const GoPlan& p, const GoCarve& c, GoState* s, const GenProgram* prog, u32 W, u32 ncoef, const u64* trace_src, u64 in_scale,
+void go_launch(cudaStream_t st, int D, const GoPlan& p, const GoCarve& c, GoState* s, const GenProgram* prog, u32 W, u32 K, u32 num_assertions, u32 ncoef, const u64* trace_src, u64 in_scale,
                u32 num_queries, u32 grinding, const std::vector<GoGatherTask>& tasks, u64* material) {
   GpuBK bk{st, &p};
-  go_enqueue(bk, D, p, c, s, prog, W, ncoef, trace_src, in_scale, num_queries, grinding, tasks, material);
+  go_enqueue(bk, D, p, c, s, prog, W, K, num_assertions, ncoef, trace_src, in_scale, num_queries, grinding, tasks, material);
 }
 
 }  // namespace xfg

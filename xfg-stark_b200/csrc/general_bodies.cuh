@@ -20,6 +20,7 @@ namespace xfg {
 static constexpr int GO_MAX_LAYERS = 32;      // folding factor 2 on a 2^27-point domain
 static constexpr int GO_OOD_CHUNKS = 2048;    // partial sums per polynomial of the out-of-domain evaluation (fewer for traces shorter than that)
 static constexpr int GO_MAX_EXT = 3;
+static constexpr int GO_MAX_CE = 8;           // constraint-evaluation blowup (and composition columns) for transition degrees up to XFG_AIR_MAX_DEGREE = 9
 
 #if defined(__CUDACC__)
 #define GO_NOINLINE __host__ __device__ __noinline__
@@ -35,9 +36,9 @@ struct GoState {
   Digest seed; u64 counter;
   Digest trace_root, constraint_root, fri_roots[GO_MAX_LAYERS], remainder_commitment;
   u64 coef[GEN_MAX_CONSTRAINTS + GEN_MAX_ASSERTIONS][GO_MAX_EXT];   // transition coefficients, then boundary coefficients (A.8)
-  u64 z[GO_MAX_EXT], zg[GO_MAX_EXT], hz[GO_MAX_EXT];
+  u64 z[GO_MAX_EXT], zg[GO_MAX_EXT], hz[GO_MAX_CE][GO_MAX_EXT];     // hz[i] = H_i(z), one per composition column
   u64 ood_frame[2 * GEN_MAX_WIDTH][GO_MAX_EXT];                     // T_0(z), T_0(zg), T_1(z), ... (A.9)
-  u64 dcoef[GEN_MAX_WIDTH + 1][GO_MAX_EXT];
+  u64 dcoef[GEN_MAX_WIDTH + GO_MAX_CE][GO_MAX_EXT];                 // trace columns, then composition columns
   u64 deep_c1[GO_MAX_EXT], deep_c2[GO_MAX_EXT];
   u64 alphas[GO_MAX_LAYERS][GO_MAX_EXT];
   u64 remainder[MAX_REMAINDER][GO_MAX_EXT]; u32 remainder_len;
@@ -192,9 +193,9 @@ template <int D> struct GoStepFri {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// evaluate_constraints (A.8): t = k' n + m over the constraint-evaluation domain = LDE cosets 0 and B/2
+// evaluate_constraints (A.8): over the constraint-evaluation domain = LDE cosets k' B / ce, k' < ce
 //   H(x) = T(x) (x - g^(n-1)) / (x^n - 1) + sum_groups B_g(x) / (x - g^step_g)
-// out: [limb][k'][m]
+// out: [limb][k'][m], k' < ce = the constraint-evaluation blowup (2 for degrees <= 3, 4 for 4-5, 8 for 6-9)
 // ------------------------------------------------------------------------------------------------------------------
 static constexpr int GO_PTS = 4;   // points per thread of the constraint and DEEP bodies: their base-field inversions are batched (Montgomery's trick)
 // in-place batch inversion of cnt non-zero base-field values (one gl_inv)
@@ -206,10 +207,10 @@ XFG_HD void go_batch_inv(u64* v, int cnt) {
 }
 // t = k' (n / pts) + q: the thread evaluates points m = q + j n / pts, j < pts (pts = GO_PTS, or 1 for the shortest traces), of coset k'
 template <int D> struct GoConstraint {
-  const u64* lde; u32 ln, lb, pts; const GenProgram* prog; const GoState* s; PowTable wn; u64 s_ce[2], zinv[2], g_last; u64* out;
+  const u64* lde; u32 ln, lb, lce, pts; const GenProgram* prog; const GoState* s; PowTable wn; u64 s_ce[GO_MAX_CE], zinv[GO_MAX_CE], g_last; u64* out;
   XFG_HD void operator()(size_t t) const {
     const size_t n = size_t(1) << ln, N = n << lb, per = n / pts, kp = t / per, q = t % per;
-    const size_t k = kp << (lb - 1);
+    const size_t k = kp << (lb - lce);       // constraint-evaluation coset k' = LDE coset k' B / ce
     const u64* base = lde + k * n;
     const u32 T = prog->num_constraints, A = prog->num_assertions, G = prog->num_groups, NI = prog->num_instr;
     Ext<D> u[GO_PTS], num[GO_PTS]; u64 den[GO_PTS];
@@ -244,20 +245,51 @@ template <int D> struct GoConstraint {
     go_batch_inv(den, (int)pts);
     for (u32 j = 0; j < pts; j++) {
       const Ext<D> h = u[j] + mul_base(num[j], den[j]);
-      for (int l = 0; l < D; l++) out[((size_t)l * 2 + kp) * n + q + j * per] = h.limb(l);
+      for (int l = 0; l < D; l++) out[(((size_t)l << lce) + kp) * n + q + j * per] = h.limb(l);
     }
   }
 };
-// composition coefficients from the two un-scaled coset interpolants (see combine_kernel, stark_kernels.cu): h = (A0 + A1) / 2, and A0 - A1
-// (the upper half of the 2n-point interpolant) must vanish - otherwise the trace does not satisfy the AIR
+// composition coefficients from the ce un-scaled coset interpolants A_c (c < ce): on coset c, x^n = 7^n w_ce^c, so for the composition polynomial
+// H = sum_i x^(i n) H_i (H_i of degree < n):  A_c = sum_i (7^n w_ce^c)^i H_i,  i.e.  H_i[j] = 7^(-n i) / ce * sum_c w_ce^(-c i) A_c[j]  (a size-ce inverse
+// DFT per coefficient).  Columns i < K are the composition columns (CompositionPoly::new: coefficients [i n, (i + 1) n)); the others must vanish -
+// otherwise the trace does not satisfy the AIR.  a: [limb][c][n] -> h: [column][limb][n].   ce = 2, K = 1: h = (A0 + A1) / 2 as combine_kernel.
+struct GoCombineConsts { u64 wi[GO_MAX_CE]; u64 scale[GO_MAX_CE]; };    // w_ce^-e;  7^(-n i) / ce
 struct GoCombine {
-  const u64* a; u32 ln; int D; u64 inv2; u64* h; GoState* s;
+  const u64* a; u32 ln, lce, K; int D; GoCombineConsts cc; u64* h; GoState* s;
   XFG_HD void operator()(size_t j) const {
-    const size_t n = size_t(1) << ln; bool bad = false;
+    const size_t n = size_t(1) << ln; const u32 ce = 1u << lce; bool bad = false;
     for (int l = 0; l < D; l++) {
-      const u64 a0 = a[(size_t)l * 2 * n + j], a1 = a[(size_t)l * 2 * n + n + j];
-      h[(size_t)l * n + j] = gl_mul(gl_add(a0, a1), inv2);
-      bad |= a0 != a1;
+      u64 av[GO_MAX_CE];
+      for (u32 c = 0; c < ce; c++) av[c] = a[(((size_t)l << lce) + c) * n + j];
+      for (u32 i = 0; i < ce; i++) {
+        u64 acc = 0;
+        for (u32 c = 0; c < ce; c++) acc = gl_add(acc, gl_mul(av[c], cc.wi[(c * i) & (ce - 1)]));
+        if (i < K) h[((size_t)i * D + l) * n + j] = gl_mul(acc, cc.scale[i]);
+        else bad |= acc != 0;
+      }
+    }
+    if (bad) go_flag(&s->error_flags, ERR_FLAG_DEGREE);
+  }
+};
+// where the composition columns leave no vanishing coefficient to check (K = ce: degrees 3, 5, 9), the trace is validated directly, as winter-prover
+// does in debug builds: every transition constraint on every step but the last, every assertion.  t < n - 1: step t;  t >= n - 1: assertion t - (n - 1)
+struct GoValidate {
+  const u64* trace; u32 ln; const GenProgram* prog; GoState* s;
+  XFG_HD void operator()(size_t t) const {
+    const size_t n = size_t(1) << ln;
+    if (t >= n - 1) { const GenAssertion& as = prog->asr[t - (n - 1)]; const u64 step = prog->asr_step[t - (n - 1)]; if (trace[(size_t)as.column * n + step] != as.value) go_flag(&s->error_flags, ERR_FLAG_DEGREE); return; }
+    u64 slot[GEN_MAX_SLOTS]; bool bad = false;
+    for (u32 i = 0; i < prog->num_instr; i++) {
+      const GenInstr in = prog->code[i];
+      const u32 op = in.w0 & 15u, dst = in.w0 >> 8;
+      u64 v[2];
+      for (int o = 0; o < 2; o++) {
+        const u32 kind = (in.w0 >> (4 + 2 * o)) & 3u, idx = o ? in.w1 >> 16 : in.w1 & 0xFFFFu;
+        v[o] = kind == GK_SLOT ? slot[idx] : kind == GK_CONST ? prog->constants[idx] : trace[(size_t)idx * n + (kind == GK_CUR ? t : t + 1)];
+        if (op == GOP_OUT) break;
+      }
+      if (op == GOP_OUT) { bad |= v[0] != 0; continue; }
+      slot[dst] = op == GOP_MUL ? gl_mul(v[0], v[1]) : op == GOP_ADD ? gl_add(v[0], v[1]) : gl_sub(v[0], v[1]);
     }
     if (bad) go_flag(&s->error_flags, ERR_FLAG_DEGREE);
   }
@@ -302,24 +334,26 @@ template <int D> struct GoOodSum2 {
 };
 // send_ood_trace_states / send_ood_constraint_evaluations, DEEP coefficients, and the constants of the DEEP quotients (A.9)
 template <int D> struct GoStepOod {
-  GoState* s; const u64* sums; u32 W;
+  GoState* s; const u64* sums; u32 W, K;
   XFG_HD void operator()(size_t) const {
     GoCoin c = go_coin_load(s);
     for (u32 t = 0; t < 2 * W; t++) for (int l = 0; l < GO_MAX_EXT; l++) s->ood_frame[t][l] = sums[(size_t)t * GO_MAX_EXT + l];   // sums[(2 j + w)] = T_j(z | zg): already interleaved
     const u64* fr = &s->ood_frame[0][0];
     go_reseed(c, go_hash_stream((int)(2 * W * D), [fr](int li) { return fr[(size_t)(li / D) * GO_MAX_EXT + (li % D)]; }));
-    // H(z) = sum_l x^l P_l(z): the composition column's limb polynomials have base-field coefficients
-    Ext<D> hz;
-    for (int l = D - 1; l >= 0; l--) hz = ext_mul_x<D>(hz) + go_ld<D>(sums + (size_t)(2 * (W + l)) * GO_MAX_EXT);
-    go_st<D>(s->hz, hz);
-    const u64* hp = s->hz;
-    go_reseed(c, go_hash_stream(D, [hp](int li) { return hp[li]; }));
+    // H_i(z) = sum_l x^l P_{i,l}(z): the limb polynomials of composition column i have base-field coefficients (polynomial W + i D + l)
+    for (u32 i = 0; i < K; i++) {
+      Ext<D> hz;
+      for (int l = D - 1; l >= 0; l--) hz = ext_mul_x<D>(hz) + go_ld<D>(sums + (size_t)(2 * (W + i * D + l)) * GO_MAX_EXT);
+      go_st<D>(s->hz[i], hz);
+    }
+    const u64* hp = &s->hz[0][0];
+    go_reseed(c, go_hash_stream((int)(K * D), [hp](int li) { return hp[(size_t)(li / D) * GO_MAX_EXT + (li % D)]; }));
     bool ok = true;
-    for (u32 j = 0; j <= W; j++) { u64 v[GO_MAX_EXT] = {0, 0, 0}; ok &= go_draw<D>(c, v); for (int l = 0; l < GO_MAX_EXT; l++) s->dcoef[j][l] = l < D ? v[l] : 0; }
+    for (u32 j = 0; j < W + K; j++) { u64 v[GO_MAX_EXT] = {0, 0, 0}; ok &= go_draw<D>(c, v); for (int l = 0; l < GO_MAX_EXT; l++) s->dcoef[j][l] = l < D ? v[l] : 0; }
     if (!ok) s->error_flags |= ERR_FLAG_COIN;
     Ext<D> c1, c2;
     for (u32 j = 0; j < W; j++) { const Ext<D> g = go_ld<D>(s->dcoef[j]); c1 = c1 + g * go_ld<D>(s->ood_frame[2 * j]); c2 = c2 + g * go_ld<D>(s->ood_frame[2 * j + 1]); }
-    c1 = c1 + go_ld<D>(s->dcoef[W]) * hz;
+    for (u32 i = 0; i < K; i++) c1 = c1 + go_ld<D>(s->dcoef[W + i]) * go_ld<D>(s->hz[i]);
     go_st<D>(s->deep_c1, c1); go_st<D>(s->deep_c2, c2);
     go_coin_store(s, c);
   }
@@ -327,26 +361,27 @@ template <int D> struct GoStepOod {
 
 // ------------------------------------------------------------------------------------------------------------------
 // DEEP composition, pointwise (A.9; the same field elements as the reference's coefficient-domain quotients):
-//   D(x) = (S_T(x) + delta H(x) - C1) / (x - z) + (S_T(x) - C2) / (x - z g),   S_T = sum_j gamma_j T_j(x)
+//   D(x) = (S_T(x) + sum_i delta_i H_i(x) - C1) / (x - z) + (S_T(x) - C2) / (x - z g),   S_T = sum_j gamma_j T_j(x)
 // t = k n + m; written in natural order [limb][B m + k] = the evaluations of FRI layer 0
 // ------------------------------------------------------------------------------------------------------------------
 template <int D> struct GoDeep {
-  const u64* lde; const u64* hlde; u32 ln, lb, W, pts; const GoState* s; PowTable wn; const u64* s_k; u64* deep;
+  const u64* lde; const u64* hlde; u32 ln, lb, W, K, pts; const GoState* s; PowTable wn; const u64* s_k; u64* deep;
   // t = k (n / pts) + q: points m = q + j n / pts, j < pts; 1 / (x - w) = adj(x - w) / N(x - w) with the 2 pts norms inverted together
   XFG_HD void operator()(size_t t) const {
     const size_t n = size_t(1) << ln, N = n << lb, per = n / pts, k = t / per, q = t % per;
-    const Ext<D> z = go_ld<D>(s->z), zg = go_ld<D>(s->zg), c1 = go_ld<D>(s->deep_c1), c2 = go_ld<D>(s->deep_c2), delta = go_ld<D>(s->dcoef[W]);
+    const Ext<D> z = go_ld<D>(s->z), zg = go_ld<D>(s->zg), c1 = go_ld<D>(s->deep_c1), c2 = go_ld<D>(s->deep_c2);
     Ext<D> pa[GO_PTS], qa[GO_PTS]; u64 nrm[2 * GO_PTS];
     for (u32 j = 0; j < pts; j++) {
       const size_t m = q + j * per, at = k * n + m;
       const u64 x = gl_mul(s_k[k], pow_lookup(wn, m));
       Ext<D> st;
       for (u32 c = 0; c < W; c++) st = st + mul_base(go_ld<D>(s->dcoef[c]), lde[(size_t)c * N + at]);
-      Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + at]);
+      Ext<D> sh = st;
+      for (u32 i = 0; i < K; i++) { Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[((size_t)i * D + l) * N + at]); sh = sh + go_ld<D>(s->dcoef[W + i]) * h; }
       const Ext<D> xe(x);
       Ext<D> az, azg;
       nrm[2 * j] = ext_norm_adj(xe - z, az); nrm[2 * j + 1] = ext_norm_adj(xe - zg, azg);
-      pa[j] = (st + delta * h - c1) * az; qa[j] = (st - c2) * azg;
+      pa[j] = (sh - c1) * az; qa[j] = (st - c2) * azg;
     }
     go_batch_inv(nrm, (int)(2 * pts));
     for (u32 j = 0; j < pts; j++) {

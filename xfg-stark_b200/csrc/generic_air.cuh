@@ -28,9 +28,11 @@ struct GenAssertion { u32 column, group; u64 value; };
 // the compiled AIR, one copy per proof slot in device memory (written by the host through a pinned mirror)
 struct GenProgram {
   u32 width, num_constraints, num_assertions, num_groups, num_instr, num_slots;
+  u32 max_degree, pad_;                     // highest transition-constraint degree: > 2 means several composition columns (general-options pipeline only)
   u64 group_point[GEN_MAX_GROUPS];          // g^step of each boundary-constraint group: the root of its divisor (x - g^step)
   u64 constants[GEN_MAX_CONSTS];
   GenAssertion asr[GEN_MAX_ASSERTIONS + 1]; // sorted (step, column): groups are contiguous runs
+  u32 asr_step[GEN_MAX_ASSERTIONS + 1];     // step of each assertion (trace validation of the general-options pipeline)
   GenInstr code[GEN_MAX_INSTR];
 };
 
