@@ -67,7 +67,7 @@ enum {
   XFG_OK = 0,
   XFG_ERR_BAD_ARGS = 1,            /* null pointer, size out of range, non-canonical element */
   XFG_ERR_BAD_OPTIONS = 2,         /* ProofOptions::new range checks (A.2) */
-  XFG_ERR_UNSUPPORTED_OPTIONS = 3, /* valid for Winterfell, not implemented: AIR of transition degree > 2; batch VERIFICATION of proofs made with options outside the tuned set */
+  XFG_ERR_UNSUPPORTED_OPTIONS = 3, /* valid for Winterfell, not implemented: AIR of transition degree > 9; batch VERIFICATION of proofs made with options outside the tuned set */
   XFG_ERR_UNSUPPORTED_EXTENSION = 4, /* mirrors ProverError::UnsupportedFieldExtension: the batch verifier does not take cubic-extension proofs (the prover does) */
   XFG_ERR_UNSATISFIED_CONSTRAINT = 5, /* mirrors ProverError::UnsatisfiedTransitionConstraintError / MismatchedConstraintPolynomialDegree */
   XFG_ERR_BUFFER_TOO_SMALL = 6,    /* *out_len holds the required size */
@@ -168,7 +168,8 @@ typedef struct xfg_air_desc {
 int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t max_width, xfg_ctx** out);
 /* replaces `air.prove(trace)` (winter_prover::Prover::prove) for the AIR described by `air`; trace: column-major, air->width
  * columns x 2^n_log2 rows, host memory (or device memory for the *_device variant).  Errors: XFG_ERR_BAD_ARGS for a malformed
- * description, XFG_ERR_UNSUPPORTED_OPTIONS for degree > 2 / too many groups / too many live values,
+ * description, XFG_ERR_UNSUPPORTED_OPTIONS for degree > 9 / too many groups / too many live values (degrees 3..9 = 2..8 constraint composition
+ * columns run on the general-options pipeline),
  * XFG_ERR_UNSATISFIED_CONSTRAINT when the trace violates a constraint or an assertion. */
 int xfg_prove_air(xfg_ctx* ctx, const xfg_air_desc* air, const uint64_t* trace_colmajor, uint32_t n_log2, const xfg_options* options,
                   uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
