@@ -138,8 +138,9 @@ int xfg_prove_burn_mint_from_inputs(xfg_ctx* ctx, uint64_t burn_amount, uint64_t
                                     const xfg_options* options, uint8_t* out, size_t out_cap, size_t* out_len, xfg_stage_times* times);
 
 /* ---- generic AIR front-end ----
- * The same pipeline for any main-segment-only AIR whose transition constraints have degree <= 2 (then ce_blowup = 2 and the
- * composition polynomial is one column) and whose assertions are single-point.  The AIR is a straight-line
+ * The same pipeline for any main-segment-only AIR whose transition constraints have degree <= 9 and whose assertions are single-point (degree <= 2:
+ * ce_blowup = 2 and one composition column, SURVEY.md A.3, on the tuned kernels; degree d = 3..9: d - 1 composition columns and ce_blowup =
+ * next_pow2(d - 1), on the general-options pipeline).  The AIR is a straight-line
  * program over the evaluation frame: what the body of `Air::evaluate_transition` computes (e.g. the 4-column XfgBurnAir sketch,
  * src/winterfell_air.rs:87-127, whose constraints are `current[i] - constant`), given as data instead of Rust code.
  * Value ids: [0, width) = frame.current()[i]; [width, 2*width) = frame.next()[i]; [2*width, 2*width + num_constants) =
