@@ -240,6 +240,9 @@ typedef struct xfg_verify_times {
 int xfg_verify_burn_mint_batch(xfg_ctx* ctx, uint32_t count, const uint8_t* const* proofs, const size_t* proof_lens,
                                const xfg_air_consts* air /* count entries */, const xfg_options* acceptable,
                                int32_t* results /* count entries */, xfg_verify_times* times /* optional */);
+/* the same for proofs of AIRs given as data (the verification counterpart of xfg_prove_air): any ProofOptions, transition degree <= 9; airs: count entries */
+int xfg_verify_air_batch(xfg_ctx* ctx, uint32_t count, const uint8_t* const* proofs, const size_t* proof_lens, const xfg_air_desc* airs,
+                         const xfg_options* acceptable, int32_t* results /* count entries */, xfg_verify_times* times /* optional */);
 const char* xfg_verify_strerror(int code);
 
 /* ---- stage entry points (kernel-level parity tests; host buffers in and out) ---- */

@@ -138,6 +138,8 @@ extern "C" {
                                  cur: *const u64, next: *const u64, out: *mut u64) -> c_int;
     pub fn xfg_verify_burn_mint_batch(ctx: *mut xfg_ctx, count: u32, proofs: *const *const u8, proof_lens: *const usize, air: *const xfg_air_consts,
                                       acceptable: *const xfg_options, results: *mut i32, times: *mut xfg_verify_times) -> c_int;
+    pub fn xfg_verify_air_batch(ctx: *mut xfg_ctx, count: u32, proofs: *const *const u8, proof_lens: *const usize, airs: *const xfg_air_desc,
+                                acceptable: *const xfg_options, results: *mut i32, times: *mut xfg_verify_times) -> c_int;
     pub fn xfg_verify_strerror(code: c_int) -> *const c_char;
     pub fn xfg_ntt(ctx: *mut xfg_ctx, data: *mut u64, n_log2: u32, batch: u32, inverse: c_int) -> c_int;
     pub fn xfg_lde_commit(ctx: *mut xfg_ctx, cols_colmajor: *const u64, n_log2: u32, cols: u32, lde_out: *mut u64, root_out: *mut u8) -> c_int;

@@ -47,6 +47,7 @@ def lib():
         vp, sz, u32, cp = C.c_void_p, C.c_size_t, C.c_uint32, C.c_char_p
         L.go_emul_prove_air.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, vp, vp, sz, vp, cp, sz]
         L.go_emul_prove_burn_mint.argtypes = [vp, vp, vp, u32, vp, C.c_int, vp, sz, vp, cp, sz]
+        L.go_emul_verify_air.argtypes = [vp, vp, vp, vp, vp, vp, cp, sz, vp]
         _lib = L
     return _lib
 
@@ -81,3 +82,18 @@ def prove_burn_mint(trace, pi, ac, options, montgomery=False):
     if rc:
         raise EmulError(rc, err.value.decode())
     return out.raw[:ln.value]
+
+
+VERDICTS = ["", "ProofDeserializationError", "UnacceptableProofOptions", "InconsistentOodConstraintEvaluations", "QuerySeedProofOfWorkVerificationFailed",
+            "NumberOfQueriesMismatch", "TraceQueryDoesNotMatchCommitment", "ConstraintQueryDoesNotMatchCommitment", "LayerCommitmentMismatch", "InvalidLayerFolding",
+            "RemainderCommitmentMismatch", "RemainderDegreeMismatch", "InvalidRemainderFolding", "DegreeTruncation", "FailedToDrawFieldElement"]      # XFG_VERIFY_* in order
+
+
+def verify_air(flat, proof, options):
+    """-> '' when the product's general verifier body accepts, else the name of the failing check (winterfell's VerifierError variants)"""
+    desc = np.ascontiguousarray(flat["desc"], dtype=np.uint32); pub = np.ascontiguousarray(flat["pub"], dtype=np.uint64)
+    consts = np.ascontiguousarray(flat["consts"], dtype=np.uint64); code = np.ascontiguousarray(flat["code"], dtype=np.uint32)
+    outs = np.ascontiguousarray(flat["outs"], dtype=np.uint32); asr = np.ascontiguousarray(flat["asr"], dtype=np.uint64)
+    o = np.asarray(options, dtype=np.uint32)
+    rc = lib().go_emul_verify_air(_p(desc), _p(pub), _p(consts), _p(code), _p(outs), _p(asr), bytes(proof), len(proof), _p(o))
+    return VERDICTS[rc]

@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../xfg-stark_b200/csrc/general_pipeline.cuh"
 #include "../../xfg-stark_b200/csrc/air_compile.hpp"
+#include "../../xfg-stark_b200/csrc/general_verify_host.hpp"
 
 using namespace xfg;
 
@@ -113,6 +114,25 @@ int go_emul_prove_air(const uint32_t desc[6], const u64* pub, const u64* consts,
   xfg_air_desc d{}; d.width = desc[0]; d.num_pub_inputs = desc[1]; d.num_constants = desc[2]; d.num_instr = desc[3]; d.num_constraints = desc[4]; d.num_assertions = desc[5];
   d.pub_inputs = pub; d.constants = consts; d.code = ins.data(); d.constraint_values = outs; d.assertions = as.data();
   return prove(d, trace, n_log2, o, 1, out, cap, out_len, err, errcap);
+}
+// verification of one proof by the product's general verifier body (general_verify.cuh) run on the host; returns the XFG_VERIFY_* code
+int go_emul_verify_air(const uint32_t desc[6], const u64* pub, const u64* consts, const uint32_t* code, const uint32_t* outs, const u64* asr,
+                       const u8* proof, size_t len, const uint32_t o6[6]) {
+  std::vector<xfg_air_instr> ins(desc[3]); for (uint32_t i = 0; i < desc[3]; i++) { ins[i].op = code[3 * i]; ins[i].a = code[3 * i + 1]; ins[i].b = code[3 * i + 2]; }
+  std::vector<xfg_assertion> as(desc[5]); for (uint32_t i = 0; i < desc[5]; i++) { as[i].column = (uint32_t)asr[3 * i]; as[i].step = (uint32_t)asr[3 * i + 1]; as[i].value = asr[3 * i + 2]; }
+  xfg_air_desc d{}; d.width = desc[0]; d.num_pub_inputs = desc[1]; d.num_constants = desc[2]; d.num_instr = desc[3]; d.num_constraints = desc[4]; d.num_assertions = desc[5];
+  d.pub_inputs = pub; d.constants = consts; d.code = ins.data(); d.constraint_values = outs; d.assertions = as.data();
+  xfg_options o{}; o.num_queries = o6[0]; o.blowup_factor = o6[1]; o.grinding_factor = o6[2]; o.field_extension = o6[3]; o.fri_folding_factor = o6[4]; o.fri_remainder_max_degree = o6[5];
+  std::vector<u8> bytes(((len + 7) & ~size_t(7)) + 8, 0); if (len) std::memcpy(bytes.data(), proof, len);
+  GoVerifyRec rec; std::vector<u8> progs;
+  go_verify_prepare(bytes.data(), len, d, o, 0, rec, progs);
+  if (progs.empty()) progs.resize(8);
+  std::unique_ptr<GoVerifyWork> work(new GoVerifyWork); int result = -1;
+  HostBK bk;
+  if (o.field_extension == 1) bk.run(1, GoVerify<1>{&rec, bytes.data(), progs.data(), work.get(), o, &result});
+  else if (o.field_extension == 2) bk.run(1, GoVerify<2>{&rec, bytes.data(), progs.data(), work.get(), o, &result});
+  else bk.run(1, GoVerify<3>{&rec, bytes.data(), progs.data(), work.get(), o, &result});
+  return result;
 }
 // the burn-mint statement through the C++ AIR description the product uses for it (air_compile.hpp: BurnMintAirDesc); montgomery != 0: the trace
 // is in Montgomery form (x * 2^64 mod p), undone by the interpolation's scale as in the product

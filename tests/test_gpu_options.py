@@ -21,7 +21,7 @@ def _opts(xs, o):
 @pytest.fixture(scope="module")
 def ctx():
     import xfg_stark_b200 as xs
-    with xs.Context(device=0, max_n_log2=17, num_slots=2) as c:
+    with xs.Context(device=0, max_n_log2=17, num_slots=2, max_width=16) as c:
         yield c
 
 
@@ -125,10 +125,9 @@ def test_batches_and_errors_with_other_options(ctx):
     # the tuned pipeline is untouched by a general proof on the same context
     t, pi, ac = cases[2]
     assert ctx.prove(t, airs[2]) == orc.prove(t, pi, ac)
-    # the batch verifier implements the tuned option set only
-    with pytest.raises(xs.XfgError) as e:
-        ctx.verify_batch([proofs[0]], [airs[0]], _opts(xs, o))
-    assert e.value.code in (3, 4)
+    # batch verification with these options: the general verifier (one thread per proof)
+    assert ctx.verify_batch(proofs, airs, _opts(xs, o)) == ["", "", ""]
+    assert ctx.verify_batch([proofs[0]], [airs[1]], _opts(xs, o)) != [""]
 
 
 @pytest.mark.parametrize("name", refvec.degree_case_ids())
@@ -162,3 +161,41 @@ def test_real_higher_degree_airs_equal_oracle(ctx):
     proofs, _ = ctx.prove_air_batch([A.power_map_air(2, 128, 3, seed=9)[0], A.fibonacci_air(128)[0]], [A.power_map_air(2, 128, 3, seed=9)[1], A.fibonacci_air(128)[1]])
     assert proofs[0] == orc.prove_air(A.power_map_air(2, 128, 3, seed=9)[0].flatten(), A.power_map_air(2, 128, 3, seed=9)[1], (42, 8, 4, 1, 8, 31))
     assert proofs[1] == orc.prove_air(A.fibonacci_air(128)[0].flatten(), A.fibonacci_air(128)[1], (42, 8, 4, 1, 8, 31))
+
+
+def test_general_verifier_gives_the_oracle_verdicts(ctx):
+    """xfg_verify_air_batch / xfg_verify_burn_mint_batch outside the tuned option set: every tampered proof gets the oracle verifier's verdict"""
+    import xfg_stark_b200 as xs
+    import test_options_pins as T
+    from xfg_stark_b200 import air as A
+    builders = {"burn-mint": None}
+    t, pi, ac = orc.synthetic_case(64, 1)
+    s = orc.synthetic_inputs(1)
+    bm_consts = xs.pack_inputs(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"], s["version"])
+    bm = A.burn_mint_air(pi, ac[0], ac[1], ac[2], ac[3], 64)
+    a3, t3 = A.power_map_air(2, 256, 3, seed=3); a5, t5 = A.power_map_air(2, 128, 5, seed=5); w9, tw = A.wide_quadratic_air(9, 512, seed=4)
+    cases = [("burn-mint cubic folding 4", bm, t, (30, 16, 3, 3, 4, 7)), ("burn-mint blowup 2 folding 2", bm, t, (20, 2, 0, 2, 2, 0)), ("degree 3", a3, t3, (42, 8, 4, 2, 8, 31)),
+             ("degree 5 cubic folding 16", a5, t5, (25, 4, 2, 3, 16, 7)), ("nine columns", w9, tw, (42, 8, 4, 1, 8, 31))]
+    for name, air, tr, o in cases:
+        f = air.flatten()
+        proof = ctx.prove_air(air, tr, _opts(xs, o))
+        assert proof == orc.prove_air(f, tr, o)
+        bad = T.tampered(proof, 150) + [proof]
+        ours = ctx.verify_air_batch(bad, [air] * len(bad), _opts(xs, o))
+        theirs = [orc.verify_air(b, f, o) for b in bad]
+        assert ours[-1] == "" and theirs[-1] == "", name
+        mism = [(i, a, b) for i, (a, b) in enumerate(zip(ours, theirs)) if not T.same_verdict(a, b)]
+        assert not mism, (name, mism[:5])
+        assert len({a for a, b in zip(ours, theirs) if a in T.CRYPTO and a == b}) >= 5
+        if name.startswith("burn-mint"):      # the burn-mint entry point routes here for these options
+            res = ctx.verify_batch(bad, [bm_consts] * len(bad), _opts(xs, o))
+            assert res == ours, name
+    # the reference binary's own proofs for other options and declared degrees
+    for c in refvec.option_cases()[:8] + refvec.degree_cases()[:6]:
+        rpi, rac, ro, rn = refvec.statement(c)
+        assert ctx.verify_air_batch([refvec.proof_bytes(c)], [refvec.air_program(c, rpi, rac)], _opts(xs, ro)) == [""], c["name"]
+    # a batch of 256 proofs at once (one thread each)
+    air, tr, o = bm, t, (30, 16, 3, 3, 4, 7)
+    proof = ctx.prove_air(air, tr, _opts(xs, o))
+    res, times = ctx.verify_air_batch([proof] * 256, [air] * 256, _opts(xs, o), want_times=True)
+    assert res == [""] * 256 and times["kernel_ms"] > 0

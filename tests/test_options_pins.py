@@ -77,6 +77,67 @@ def test_real_higher_degree_airs_emulated_pipeline_equals_oracle():
     assert e.value.code == 2
 
 
+CRYPTO = {"UnacceptableProofOptions", "InconsistentOodConstraintEvaluations", "QuerySeedProofOfWorkVerificationFailed", "NumberOfQueriesMismatch",
+          "TraceQueryDoesNotMatchCommitment", "ConstraintQueryDoesNotMatchCommitment", "LayerCommitmentMismatch", "InvalidLayerFolding",
+          "RemainderCommitmentMismatch", "RemainderDegreeMismatch", "InvalidRemainderFolding", "DegreeTruncation"}
+
+
+def same_verdict(ours, oracle):
+    """as tests/test_gpu_verify.py: parse-level rejections are one code on the product side"""
+    if oracle == "":
+        return ours == ""
+    if ours == "":
+        return False
+    return ours == "ProofDeserializationError" or (oracle in CRYPTO and ours == oracle)
+
+
+def verifier_cases():
+    from xfg_stark_b200 import air as A
+    t, pi, ac = orc.synthetic_case(64, 1)
+    bm = A.burn_mint_air(pi, ac[0], ac[1], ac[2], ac[3], 64).flatten()
+    a3, t3 = A.power_map_air(2, 256, 3, seed=3); a5, t5 = A.power_map_air(2, 128, 5, seed=5); w9, tw = A.wide_quadratic_air(9, 512, seed=4)
+    return [("burn-mint default", bm, t, (42, 8, 4, 1, 8, 31)), ("burn-mint cubic folding 4", bm, t, (30, 16, 3, 3, 4, 7)), ("burn-mint blowup 2 folding 2", bm, t, (20, 2, 0, 2, 2, 0)),
+            ("degree 3", a3.flatten(), t3, (42, 8, 4, 2, 8, 31)), ("degree 5 cubic folding 16", a5.flatten(), t5, (25, 4, 2, 3, 16, 7)), ("nine columns", w9.flatten(), tw, (42, 8, 4, 1, 8, 31))]
+
+
+def tampered(proof, count=120):
+    rng = np.random.default_rng(len(proof))
+    offs = sorted(set(range(0, 64)) | set(range(len(proof) - 48, len(proof))) | {int(x) for x in rng.integers(0, len(proof), size=count)})
+    bad = []
+    for off in offs:
+        b = bytearray(proof); b[off] ^= 1 << int(rng.integers(0, 8)); bad.append(bytes(b))
+    return bad + [proof[:-1], proof + b"\0", proof[:len(proof) // 2], b""]
+
+
+def test_emulated_general_verifier_gives_the_oracle_verdicts():
+    """the product's one-thread-per-proof verifier body (general_verify.cuh) run on the host: accepts what the oracle verifier accepts and names the same
+    failing check on ~240 tampered proofs per case (options incl. cubic / folding 2..16, multi-column AIRs)"""
+    for name, f, tr, o in verifier_cases():
+        proof = orc.prove_air(f, tr, o)
+        assert orc.verify_air(proof, f, o) == "" and goemul.verify_air(f, proof, o) == "", name
+        fired = set()
+        for b in tampered(proof):
+            ours, theirs = goemul.verify_air(f, b, o), orc.verify_air(b, f, o)
+            assert ours != "" and same_verdict(ours, theirs), (name, ours, theirs)
+            if ours in CRYPTO and ours == theirs:
+                fired.add(ours)
+        assert len(fired) >= 5, (name, fired)
+        other = list(o); other[0] += 1
+        assert goemul.verify_air(f, proof, tuple(other)) == "UnacceptableProofOptions" == orc.verify_air(proof, f, tuple(other))
+
+
+def test_emulated_general_verifier_accepts_the_reference_binaries_proofs():
+    for c in refvec.option_cases() + refvec.degree_cases() + refvec.cases()[:4]:
+        pi, ac, o, n = refvec.statement(c)
+        air = refvec.air_program(c, pi, ac).flatten()
+        assert goemul.verify_air(air, refvec.proof_bytes(c), o) == "", c["name"]
+    # a shape both verifiers reject although the prover serves it: the degree bound n is not divisible by the folding factor at the second layer
+    from xfg_stark_b200 import air as A
+    a5, t5 = A.power_map_air(2, 128, 5, seed=5); o = (25, 4, 2, 3, 16, 3)
+    p = orc.prove_air(a5.flatten(), t5, o)
+    assert orc.verify_air(p, a5.flatten(), o) == "DegreeTruncation" == goemul.verify_air(a5.flatten(), p, o)
+
+
 def test_option_vectors_cover_the_option_space():
     cs = refvec.option_cases()
     assert {c["options"][3] for c in cs} == {1, 2, 3}

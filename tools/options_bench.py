@@ -44,6 +44,10 @@ def main():
                 assert p2 == proof
                 ms.append(t["device_ms"]); launches = t["kernel_launches"]
             row = {"name": name, "options": list(o), "device_ms": round(statistics.median(ms), 4), "launches": launches, "proof_bytes": len(proof)}
+            # batch verification of 512 copies (tuned options: one thread block per proof, verify.cu; anything else: one thread per proof, general_verify.cuh)
+            res, vt = ctx.verify_batch([proof] * 512, [air] * 512, opts, want_times=True)
+            assert res == [""] * 512
+            row["verify_512"] = {"kernel_ms": round(vt["kernel_ms"], 3), "total_ms": round(vt["total_ms"], 3), "proofs_per_s": round(512 / (vt["total_ms"] / 1e3))}
             if args.check:
                 tr, pi, ac = orc.synthetic_case(1 << n_log2, 0)
                 orc.set_threads(orc.max_threads())

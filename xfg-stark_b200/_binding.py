@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = ["xfg_create", "xfg_destroy", "xfg_strerror", "xfg_last_error
                     "xfg_burn_mint_build_trace", "xfg_prove_burn_mint_from_inputs", "xfg_ntt", "xfg_lde_commit",
                     "xfg_merkle_root", "xfg_eval_constraints", "xfg_fri_fold_layer", "xfg_hash_rows", "xfg_set_profiling", "xfg_set_graphs", "xfg_int_pipe_peak", "xfg_get_profile", "xfg_field_selftest", "xfg_wide_create", "xfg_wide_destroy",
                     "xfg_wide_recv_ptr", "xfg_wide_ipc_handle", "xfg_wide_open_peers", "xfg_wide_set_peer_ptrs", "xfg_wide_extend",
-                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_air_compile_check", "xfg_pipe_probe",
+                    "xfg_wide_commit", "xfg_wide_read_recv", "xfg_verify_burn_mint_batch", "xfg_verify_air_batch", "xfg_verify_strerror", "xfg_create_ex", "xfg_prove_air", "xfg_prove_air_device", "xfg_prove_air_batch", "xfg_air_compile_check", "xfg_pipe_probe",
                     "xfg_prove_burn_mint_cols", "xfg_host_register", "xfg_host_unregister",
                     "xfg_debug_guard_fill", "xfg_debug_guard_check", "xfg_debug_poke_guard"]
 
@@ -139,6 +139,7 @@ def load_library():
     L.xfg_burn_mint_build_trace.argtypes = [C.POINTER(AirConsts), u32, vp]
     L.xfg_prove_burn_mint_from_inputs.argtypes = [vp] + inputs + [u32, C.POINTER(_Options)] + prove_tail
     L.xfg_verify_burn_mint_batch.argtypes = [vp, u32, vp, vp, C.POINTER(AirConsts), C.POINTER(_Options), vp, C.POINTER(VerifyTimes)]
+    L.xfg_verify_air_batch.argtypes = [vp, u32, vp, vp, vp, C.POINTER(_Options), vp, C.POINTER(VerifyTimes)]
     L.xfg_verify_strerror.argtypes = [i]; L.xfg_verify_strerror.restype = C.c_char_p
     L.xfg_ntt.argtypes = [vp, vp, u32, u32, i]
     L.xfg_lde_commit.argtypes = [vp, vp, u32, u32, vp, vp]
@@ -397,6 +398,25 @@ class Context:
         air_arr = (AirConsts * cnt)(*airs)
         res = np.zeros(cnt, dtype=np.int32); vt = VerifyTimes(); o = options._c()
         self._check(self._lib.xfg_verify_burn_mint_batch(self._h, cnt, ptrs, lens, air_arr, C.byref(o), _ptr(res), C.byref(vt)))
+        out = [self._lib.xfg_verify_strerror(int(r)).decode() for r in res]
+        return (out, vt.as_dict()) if want_times else out
+
+    def verify_air_batch(self, proofs, airs, options=ProofOptions(), want_times=False):
+        """proofs of AIRs given as data (AirBuilder, one per proof): any ProofOptions, transition degree <= 9.  -> list of rejection reasons ('' = accepted)"""
+        cnt = len(proofs)
+        if cnt == 0:
+            return ([], VerifyTimes().as_dict()) if want_times else []
+        if len(airs) != cnt:
+            raise XfgError(1, "one AIR description per proof is required")
+        descs, keep = [], []
+        for a in airs:
+            d, k, _ = self._air_desc(a); descs.append(d); keep.append(k)
+        bufs = [np.frombuffer(bytes(p), dtype=np.uint8) if len(p) else np.zeros(1, dtype=np.uint8) for p in proofs]
+        ptrs = (C.c_void_p * cnt)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_size_t * cnt)(*[len(p) for p in proofs])
+        darr = (_AirDesc * cnt)(*descs)
+        res = np.zeros(cnt, dtype=np.int32); vt = VerifyTimes(); o = options._c()
+        self._check(self._lib.xfg_verify_air_batch(self._h, cnt, ptrs, lens, darr, C.byref(o), _ptr(res), C.byref(vt)))
         out = [self._lib.xfg_verify_strerror(int(r)).decode() for r in res]
         return (out, vt.as_dict()) if want_times else out
 

@@ -37,4 +37,11 @@ void go_launch(cudaStream_t st, int D, const GoPlan& p, const GoCarve& c, GoStat
   go_enqueue(bk, D, p, c, s, prog, W, K, num_assertions, ncoef, trace_src, in_scale, num_queries, grinding, tasks, material);
 }
 
+void go_verify_launch(cudaStream_t st, int D, u32 count, const GoVerifyRec* recs, const u8* bytes, const u8* progs, GoVerifyWork* work, const xfg_options& opt, int* results) {
+  GpuBK bk{st, nullptr};
+  if (D == 1) bk.run(count, GoVerify<1>{recs, bytes, progs, work, opt, results});
+  else if (D == 2) bk.run(count, GoVerify<2>{recs, bytes, progs, work, opt, results});
+  else bk.run(count, GoVerify<3>{recs, bytes, progs, work, opt, results});
+}
+
 }  // namespace xfg

@@ -23,6 +23,7 @@
 #include "air_compile.hpp"
 #include "generic_air.cuh"
 #include "general.cuh"
+#include "general_verify_host.hpp"
 #include "merkle.cuh"
 #include "ntt.cuh"
 #include "stark_kernels.cuh"
@@ -140,6 +141,7 @@ int prove_general(xfg_ctx* ctx, const xfg_air_desc& air, const xfg_air_consts* b
                   u32 n_log2, const xfg_options& o, u8* out, size_t cap, size_t* out_len, xfg_stage_times* times);
 int prove_general_burn_mint(xfg_ctx* ctx, const xfg_air_consts& air, const u64* h_trace, const u64* const* h_cols, u32 form, const u64* d_trace, bool fill,
                             u32 n_log2, const xfg_options& o, u8* out, size_t cap, size_t* out_len, xfg_stage_times* times);
+int verify_general_burn_mint(xfg_ctx* ctx, u32 count, const u8* const* proofs, const size_t* lens, const xfg_air_consts* air, const xfg_options& o, int32_t* results, xfg_verify_times* times);
 int check_options(xfg_ctx* ctx, const xfg_options* o, u32 n_log2, bool tuned_only = false) {
   auto pow2 = [](u32 x) { return x && !(x & (x - 1)); };
   if (o->field_extension != XFG_EXT_NONE && o->field_extension != XFG_EXT_QUADRATIC && o->field_extension != XFG_EXT_CUBIC) return fail(ctx, XFG_ERR_BAD_OPTIONS, "invalid field extension");
