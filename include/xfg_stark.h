@@ -27,7 +27,7 @@ typedef struct xfg_ctx xfg_ctx;
  * (src/burn_mint_prover.rs:44-49); argument meaning and ranges per ProofOptions::new.  Every value ProofOptions::new accepts
  * is served.  The reference's own setting (blowup 8, folding 8, remainder degree >= 7, None / Quadratic) runs on the tuned pipeline; anything
  * else - blowup 2..128, folding 2/4/16, remainder degree 0..3, FieldExtension::Cubic - on the general-options pipeline (same bytes as
- * Winterfell, pinned against proofs of the reference binary; a few times slower).  Shapes on which Winterfell itself panics (a FRI layer of one
+* Winterfell, pinned against proofs of the reference binary; about 1.5x slower at equal work).  Verification covers the same option space.  Shapes on which Winterfell itself panics (a FRI layer of one
  * row, an empty remainder) return XFG_ERR_BAD_OPTIONS. */
 typedef struct xfg_options {
   uint32_t num_queries;              /* 1..255, smaller than the LDE domain */
@@ -67,8 +67,8 @@ enum {
   XFG_OK = 0,
   XFG_ERR_BAD_ARGS = 1,            /* null pointer, size out of range, non-canonical element */
   XFG_ERR_BAD_OPTIONS = 2,         /* ProofOptions::new range checks (A.2) */
-  XFG_ERR_UNSUPPORTED_OPTIONS = 3, /* valid for Winterfell, not implemented: AIR of transition degree > 9; batch VERIFICATION of proofs made with options outside the tuned set */
-  XFG_ERR_UNSUPPORTED_EXTENSION = 4, /* mirrors ProverError::UnsupportedFieldExtension: the batch verifier does not take cubic-extension proofs (the prover does) */
+  XFG_ERR_UNSUPPORTED_OPTIONS = 3, /* valid for Winterfell, not implemented: AIR of transition degree > 9, too many assertion steps / live values */
+  XFG_ERR_UNSUPPORTED_EXTENSION = 4, /* mirrors ProverError::UnsupportedFieldExtension (kept for the Rust mapping; every extension of f64 is served) */
   XFG_ERR_UNSATISFIED_CONSTRAINT = 5, /* mirrors ProverError::UnsatisfiedTransitionConstraintError / MismatchedConstraintPolynomialDegree */
   XFG_ERR_BUFFER_TOO_SMALL = 6,    /* *out_len holds the required size */
   XFG_ERR_CUDA = 7,                /* CUDA runtime error; see xfg_last_error */
