@@ -27,8 +27,8 @@ typedef struct xfg_ctx xfg_ctx;
  * (src/burn_mint_prover.rs:44-49); argument meaning and ranges per ProofOptions::new.  Every value ProofOptions::new accepts
  * is served.  The reference's own setting (blowup 8, folding 8, remainder degree >= 7, None / Quadratic) runs on the tuned pipeline; anything
  * else - blowup 2..128, folding 2/4/16, remainder degree 0..3, FieldExtension::Cubic - on the general-options pipeline (same bytes as
-* Winterfell, pinned against proofs of the reference binary; about 1.5x slower at equal work).  Verification covers the same option space.  Shapes on which Winterfell itself panics (a FRI layer of one
- * row, an empty remainder) return XFG_ERR_BAD_OPTIONS. */
+ * Winterfell, pinned against proofs of the reference binary; about 1.5x slower at equal work).  Verification covers the same option space.
+ * Shapes on which Winterfell itself panics (a FRI layer of one row, an empty remainder) return XFG_ERR_BAD_OPTIONS. */
 typedef struct xfg_options {
   uint32_t num_queries;              /* 1..255, smaller than the LDE domain */
   uint32_t blowup_factor;            /* power of two, 2..128 */
