@@ -199,3 +199,27 @@ def test_general_verifier_gives_the_oracle_verdicts(ctx):
     proof = ctx.prove_air(air, tr, _opts(xs, o))
     res, times = ctx.verify_air_batch([proof] * 256, [air] * 256, _opts(xs, o), want_times=True)
     assert res == [""] * 256 and times["kernel_ms"] > 0
+
+
+def test_full_size_round_trips_and_verifier_cross_check():
+    """BASELINE's full trace length (2^20 rows) through the general-options pipeline: prove -> verify round trips (size-independent property; the oracle
+    PROVER needs seconds per case at this size, its verifier milliseconds), and the two GPU verifiers against each other on a tuned-pipeline proof"""
+    import torch
+    import xfg_stark_b200 as xs
+    from xfg_stark_b200 import air as A
+    n_log2 = 20
+    s = orc.synthetic_inputs(3)
+    consts = xs.pack_inputs(s["burn"], s["mint"], s["tx_prefix_hash"], s["recipient"], s["secret"], s["network_id"], s["target_chain_id"], s["version"])
+    tr, pi, ac = orc.synthetic_case(1 << n_log2, 3)
+    bm = A.burn_mint_air(pi, ac[0], ac[1], ac[2], ac[3], 1 << n_log2)
+    with xs.Context(device=0, max_n_log2=n_log2, num_slots=1) as c:
+        dev = torch.from_numpy(np.ascontiguousarray(tr).view(np.int64)).cuda()
+        for o in [(42, 8, 4, 2, 4, 31), (42, 8, 4, 3, 8, 31), (42, 4, 4, 1, 16, 7)]:
+            proof = c.prove_device(dev.data_ptr(), n_log2, consts, _opts(xs, o))
+            assert orc.verify(proof, pi, ac, o) == "", o                                   # the oracle verifier accepts
+            assert c.verify_batch([proof], [consts], _opts(xs, o)) == [""], o              # ... and so does the general GPU verifier
+            bad = bytearray(proof); bad[len(bad) // 3] ^= 4
+            assert c.verify_batch([bytes(bad)], [consts], _opts(xs, o)) != [""]
+        tuned = c.prove_device(dev.data_ptr(), n_log2, consts, _opts(xs, (42, 8, 4, 2, 8, 31)))
+        assert c.verify_batch([tuned], [consts], _opts(xs, (42, 8, 4, 2, 8, 31))) == [""]  # block-per-proof verifier (verify.cu)
+        assert c.verify_air_batch([tuned], [bm], _opts(xs, (42, 8, 4, 2, 8, 31))) == [""]  # thread-per-proof verifier on the same bytes
