@@ -124,7 +124,7 @@ impl Prover for GpuBurnMintProver {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Generic AIR front-end: any main-segment AIR with transition degree <= 2 and single-point assertions,
+// Generic AIR front-end: any main-segment AIR with transition degree <= 9 and single-point assertions,
 // e.g. the 4-register `XfgBurnAir` sketch (src/winterfell_air.rs:87-127).  The AIR's `evaluate_transition` body is
 // recorded once as a straight-line program; `prove` then goes through `xfg_prove_air`.
 // ------------------------------------------------------------------------------------------------------------------

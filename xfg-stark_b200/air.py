@@ -3,7 +3,7 @@
 ``AirBuilder`` records what the body of a Winterfell ``Air::evaluate_transition`` computes (e.g. the 4-column ``XfgBurnAir``
 sketch, src/winterfell_air.rs:87-127) as a straight-line program over ``frame.current()`` / ``frame.next()``, plus the
 ``Assertion::single`` list of ``get_assertions`` (src/winterfell_air.rs:117-124) and the public-input elements.  ``flatten()``
-gives the arrays of ``xfg_air_desc`` (include/xfg_stark.h).  Constraints must have degree <= 2 (ce_blowup 2, one composition
+gives the arrays of ``xfg_air_desc`` (include/xfg_stark.h).  Constraints may have degree <= 9 (degree <= 2: ce_blowup 2, one composition
 column); the library rejects anything else.
 
 The module also holds the example AIRs used by the tests and ``bench.py --workload air``; their traces are generated on the

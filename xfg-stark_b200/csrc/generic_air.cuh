@@ -1,4 +1,4 @@
-// generic_air.cuh — device-side representation of a generic degree-<=2 AIR and the launchers of the
+// generic_air.cuh — device-side representation of a generic AIR (the kernels launched from here serve degree <= 2, general_bodies.cuh the rest) and the launchers of the
 // kernels that depend on the AIR: coefficient draws, constraint evaluation (a register-machine interpreter), the end of the
 // out-of-domain step and the DEEP composition for a run-time trace width.
 //
