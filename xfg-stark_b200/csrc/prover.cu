@@ -78,6 +78,10 @@ struct GraphKey {      // everything that is baked into the captured launch sequ
   }
 };
 struct GraphEntry { cudaGraphExec_t exec; unsigned launches; };
+struct GoGraphKey {    // what a general-options launch sequence bakes in (general_api.inc)
+  const void* plan; const void* base; const void* trace; int D; u32 W, K, num_assertions, ncoef, q, g; u64 in_scale;
+  bool operator<(const GoGraphKey& o) const { return std::tie(plan, base, trace, D, W, K, num_assertions, ncoef, q, g, in_scale) < std::tie(o.plan, o.base, o.trace, o.D, o.W, o.K, o.num_assertions, o.ncoef, o.q, o.g, o.in_scale); }
+};
 struct ProfRec { const char* name; size_t e0, e1; unsigned launches; };
 struct GoPlanHolder { GoPlan plan; std::vector<void*> allocs; };   // a general-options plan and the device tables it owns (general_api.inc)
 
@@ -96,6 +100,7 @@ struct Slot {
   GenProgram* d_prog = nullptr; GenProgram* h_prog = nullptr; GenState* d_gen = nullptr; u64 (*h_ood)[2] = nullptr;
   bool generic = false; u32 W = XFG_TRACE_WIDTH, seed_count = 8 + XFG_NUM_PUB_INPUTS;
   GoState* d_go = nullptr; GoState* h_go = nullptr;   // state of a general-options proof (allocated on first use)
+  std::map<GoGraphKey, GraphEntry> go_graphs;            // whole-proof CUDA graphs of the general-options pipeline
   u64* go_slab = nullptr; size_t go_slab_words = 0;    // its workspace when the slab above is too small (blowup > 8, cubic extension at the maximum length)
   std::map<GraphKey, GraphEntry> graphs;            // whole-proof CUDA graphs, one per (plan, extension, options, trace pointer)
   cudaEvent_t ev[XFG_NUM_STAGES + 3] = {nullptr};
@@ -688,6 +693,7 @@ void xfg_destroy(xfg_ctx* ctx) {
     cudaFree(s.d_prog); cudaFreeHost(s.h_prog); cudaFree(s.d_gen); cudaFreeHost(s.h_ood);
     cudaFree(s.d_go); cudaFreeHost(s.h_go); cudaFree(s.go_slab);
     for (auto& kv : s.graphs) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& kv : s.go_graphs) cudaGraphExecDestroy(kv.second.exec);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     for (auto& e : s.pev) if (e) cudaEventDestroy(e);
     for (auto& e : s.col_ev) if (e) cudaEventDestroy(e);
