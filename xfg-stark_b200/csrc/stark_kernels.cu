@@ -268,6 +268,15 @@ template <int D> __device__ __forceinline__ Ext<D> deep_mul_conj(const DeepPoint
 #endif
 // WC = compile-time trace width (the burn-mint AIR: 7, loops over the columns unrolled) or 0 = run-time width `width_rt` (generic
 // AIR front-end, up to XFG_AIR_MAX_WIDTH columns); dcoef = width + 1 DEEP coefficients of 2 limbs.
+// XFG_DEEP_PREFETCH (burn-mint instantiation, WC != 0): the WC + D values of point j + 1 are fetched with cp.async (global -> shared, no registers) while
+// point j is computed; the plain loop consumes its loads right after issuing them (ncu source page: 10 % of the kernel's warp samples sit on the first use
+// of a loaded value, `long_scoreboard`, with 4 warps per scheduler to hide it)
+#ifndef XFG_DEEP_PREFETCH
+#define XFG_DEEP_PREFETCH 1
+#endif
+__device__ __forceinline__ void cp_async8(u64* smem_dst, const u64* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 template <int D, int WC>
 __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
                                                              const u64* __restrict__ dcoef, u32 width_rt,
@@ -286,14 +295,32 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
   const Ext<D> delta(sc[2 * W], sc[2 * W + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]);
   const DeepPoint<D> pz{cc[4], cc[5], gl_neg(gl_dbl(cc[5])), gl_dbl(gl_sqr(cc[5]))}, pzg{cc[6], cc[7], gl_neg(gl_dbl(cc[7])), gl_dbl(gl_sqr(cc[7]))};
   u64 x = gl_mul(s_k[k], pow_lookup(wn, a)), acc = 1;      // x_j = x_0 * w_8^j  (m = a + j n/8)
+  constexpr bool PF = XFG_DEEP_PREFETCH && WC != 0;
+  __shared__ u64 pf[PF ? WC + D : 1][PF ? DEEP_THREADS : 1];      // one buffer (static shared memory is capped at 48 KB): read into registers, then refilled
+  auto fetch = [&](int j) {      // point j of this thread -> pf[.][tid]
+    const size_t idx = (size_t)k * n + a + (size_t)j * n8;
+#pragma unroll
+    for (int c = 0; c < (PF ? WC : 0); c++) cp_async8(&pf[c][tid], lde + (size_t)c * N + idx);
+#pragma unroll
+    for (int l = 0; l < (PF ? D : 0); l++) cp_async8(&pf[(PF ? WC : 0) + l][tid], hlde + (size_t)l * N + idx);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (PF) fetch(0);
 #pragma unroll DEEP_UNROLL
   for (int j = 0; j < 8; j++) {
     const size_t idx = (size_t)k * n + a + (size_t)j * n8;
+    u64 pv[PF ? WC + D : 1];
+    if (PF) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < WC + D; c++) pv[c] = pf[c][tid];
+      if (j + 1 < 8) fetch(j + 1);
+    }
     DotAcc sa[D];     // S_T = sum_c gamma_c T_c(x): un-reduced dot product, one reduction per limb
 #pragma unroll
-    for (int c = 0; c < W; c++) { const u64 tv = lde[(size_t)c * N + idx]; for (int l = 0; l < D; l++) sa[l].fma(sc[2 * c + l], tv); }
+    for (int c = 0; c < W; c++) { const u64 tv = PF ? pv[c] : lde[(size_t)c * N + idx]; for (int l = 0; l < D; l++) sa[l].fma(sc[2 * c + l], tv); }
     Ext<D> st; for (int l = 0; l < D; l++) st.set_limb(l, sa[l].result());
-    Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, hlde[(size_t)l * N + idx]);
+    Ext<D> h; for (int l = 0; l < D; l++) h.set_limb(l, PF ? pv[(PF ? WC : 0) + l] : hlde[(size_t)l * N + idx]);
     u64 uz, uzg;
     const u64 nz = deep_norm<D>(pz, x, uz), nzg = deep_norm<D>(pzg, x, uzg);
     const Ext<D> pc = deep_mul_conj<D>(pz, uz, st + delta * h - c1), qc = deep_mul_conj<D>(pzg, uzg, st - c2);
