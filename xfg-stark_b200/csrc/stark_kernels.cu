@@ -15,6 +15,10 @@ namespace xfg {
 template <int D> __device__ __forceinline__ Ext<D> ld_ext(const u64 (*p)[2], int i) { return Ext<D>(p[i][0], p[i][1]); }
 template <int D> __device__ __forceinline__ Ext<D> ld_ext1(const u64* p) { return Ext<D>(p[0], p[1]); }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): the prefetches of the constraint and DEEP kernels (no registers held while the load is in flight)
+__device__ __forceinline__ void cp_async8(u64* smem_dst, const u64* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 // in-register Montgomery batch inversion of K non-zero base-field values
 template <int K> __device__ __forceinline__ void batch_inv(u64 (&v)[K]) {
   u64 pre[K]; u64 acc = 1;
@@ -40,6 +44,9 @@ static constexpr int CE_PTS = XFG_CE_PTS, CE_THREADS = XFG_CE_THREADS;
 #ifndef XFG_CE_MINB
 #define XFG_CE_MINB 8
 #endif
+#ifndef XFG_CE_PREFETCH
+#define XFG_CE_PREFETCH 1
+#endif
 // The loops over the CE_PTS points are NOT unrolled and the per-point intermediates live in shared memory ([point][word][thread],
 // conflict-free): the fully unrolled version was 160 KB of SASS and stalled on instruction fetch (ncu: no_instruction).
 template <int D>
@@ -57,13 +64,35 @@ __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(con
   const u64 sk = kp ? s_k1 : s_k0, zinv = kp ? zinv1 : zinv0;
   const u64 large_burn = gl_mul(XFG_STD_BURN, 1000);
   u64 acc = 1;
+  // XFG_CE_PREFETCH: the 8 loads of point q + 1 run as cp.async (global -> shared) under the arithmetic of point q (ncu source page: 28 % of the plain
+  // kernel's warp samples were `long_scoreboard` on the first use of a loaded value)
+#if XFG_CE_PREFETCH
+  __shared__ u64 pf[XFG_TRACE_WIDTH + 1][CE_THREADS];
+  auto fetch = [&](int q) {
+    const size_t m = t + q * per, mn = (m + 1) & (n - 1);
+#pragma unroll
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) cp_async8(&pf[j][tid], lde + (size_t)j * N + (size_t)k * n + m);
+    cp_async8(&pf[XFG_TRACE_WIDTH][tid], lde + (size_t)4 * N + (size_t)k * n + mn);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0);
+#endif
 #pragma unroll 1
   for (int q = 0; q < CE_PTS; q++) {
     const size_t m = t + q * per, mn = (m + 1) & (n - 1);
     u64 c[XFG_TRACE_WIDTH];
+#if XFG_CE_PREFETCH
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < XFG_TRACE_WIDTH; j++) c[j] = pf[j][tid];
+    const u64 nxt4 = pf[XFG_TRACE_WIDTH][tid];
+    if (q + 1 < CE_PTS) fetch(q + 1);
+    (void)mn;
+#else
 #pragma unroll
     for (int j = 0; j < XFG_TRACE_WIDTH; j++) c[j] = lde[(size_t)j * N + (size_t)k * n + m];
     const u64 nxt4 = lde[(size_t)4 * N + (size_t)k * n + mn];
+#endif
     // src/burn_mint_air.rs:356-377
     u64 r[XFG_NUM_TRANSITION];
     r[0] = gl_mul(gl_sub(c[0], XFG_STD_BURN), gl_sub(c[0], large_burn));
@@ -274,9 +303,6 @@ template <int D> __device__ __forceinline__ Ext<D> deep_mul_conj(const DeepPoint
 #ifndef XFG_DEEP_PREFETCH
 #define XFG_DEEP_PREFETCH 1
 #endif
-__device__ __forceinline__ void cp_async8(u64* smem_dst, const u64* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 template <int D, int WC>
 __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const u64* __restrict__ lde, const u64* __restrict__ hlde, u32 ln, const ProofState* __restrict__ ps,
                                                              const u64* __restrict__ dcoef, u32 width_rt,
