@@ -137,6 +137,29 @@ __device__ __forceinline__ u64 w_inv(u64 x) {
   return w_canon(w_mul(w_sqr_n(t31, 33), t32));
 }
 
+// Block-wide batch inversion (Montgomery's trick across the CTA): thread i hands in a non-zero value (weak allowed; 1 for a thread without work) and
+// receives its inverse (weak).  Warp 0 multiplies the block's THREADS values up (lane l owns values l, l + 32, ...), runs the ONE x^(p-2) chain and
+// unwinds; the other warps wait at the barrier.  The chain is 72 dependent multiplications however many lanes run it, so one chain per block issues
+// 32 / THREADS of the warp-instructions that one chain per warp does.  buf: THREADS words of shared memory.  Every thread of the block must call it.
+template <int THREADS> __device__ __forceinline__ u64 cta_inv(u64 v, u64* buf) {
+  constexpr int G = THREADS / 32;
+  static_assert(THREADS % 32 == 0 && G >= 1, "whole warps");
+  const u32 tid = threadIdx.x;
+  buf[tid] = v;
+  __syncthreads();
+  if (tid < 32) {
+    u64 pre[G]; u64 acc = buf[tid];
+#pragma unroll
+    for (int g = 1; g < G; g++) { pre[g] = acc; acc = w_mul(acc, buf[g * 32 + tid]); }
+    acc = w_inv(acc);
+#pragma unroll
+    for (int g = G - 1; g >= 1; g--) { const u64 t = w_mul(pre[g], acc); acc = w_mul(acc, buf[g * 32 + tid]); buf[g * 32 + tid] = t; }
+    buf[tid] = acc;
+  }
+  __syncthreads();
+  return buf[tid];
+}
+
 // two-level power table lookup with a weak result (see pow_lookup in field.cuh)
 __device__ __forceinline__ u64 w_pow_lookup(const PowTable& t, u64 e) {
   const u64 l = t.lo[e & (POW_LO - 1)], h = e >> POW_LO_BITS;

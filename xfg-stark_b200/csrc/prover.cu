@@ -656,7 +656,7 @@ int xfg_create_ex(int device, uint32_t max_n_log2, uint32_t num_slots, uint32_t 
   auto bail = [&](int rc) { xfg_destroy(ctx); return rc; };
 #define CUB(call) do { if ((call) != cudaSuccess) return bail(XFG_ERR_CUDA); } while (0)
   CUB(cudaSetDevice(device));
-  ntt_init(true);
+  ntt_init(true); stark_init();
   { const u64 w = gl_root_of_unity(NTT_TW_LOG); std::vector<u64> f = pow_series(w, 1u << (NTT_TW_LOG - 1)), b = pow_series(gl_inv(w), 1u << (NTT_TW_LOG - 1));
     CUB(cudaMalloc(&ctx->tw_fwd, f.size() * 8)); CUB(cudaMalloc(&ctx->tw_inv, b.size() * 8));
     CUB(cudaMemcpy(ctx->tw_fwd, f.data(), f.size() * 8, cudaMemcpyHostToDevice)); CUB(cudaMemcpy(ctx->tw_inv, b.data(), b.size() * 8, cudaMemcpyHostToDevice));

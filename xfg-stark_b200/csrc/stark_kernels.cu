@@ -37,6 +37,17 @@ template <int K> __device__ __forceinline__ void batch_inv(u64 (&v)[K]) {
 #ifndef XFG_CE_PTS
 #define XFG_CE_PTS 8      // 8 points per thread share one inversion (30 % of the 4-point kernel was the inversion): 0.210 -> 0.188 ms at 2^20
 #endif
+// XFG_DEEP_CTA_INV / XFG_CE_CTA_INV: the one inversion per thread (72 dependent multiplications, a fifth to a third of these kernels' instructions when
+// every warp runs its own chain) becomes one inversion per BLOCK (cta_inv, field_weak.cuh).  Measured at 2^20 rows / quadratic (B200, round 2):
+//   DEEP        0.602 -> 0.561 ms (128 threads; 256 threads / 2 blocks per SM: 0.565)                                  -> kept (default 1)
+//   constraints 0.175 -> 0.182 ms (64 threads), 0.175 (128 threads), 0.176 (128 threads, 4 points per thread)          -> not kept (default 0):
+//   that kernel is bound by latency (ALU pipe 57 % busy), so the instructions saved are paid back by the two barriers
+#ifndef XFG_DEEP_CTA_INV
+#define XFG_DEEP_CTA_INV 1
+#endif
+#ifndef XFG_CE_CTA_INV
+#define XFG_CE_CTA_INV 0
+#endif
 #ifndef XFG_CE_THREADS
 #define XFG_CE_THREADS 64
 #endif
@@ -52,7 +63,8 @@ static constexpr int CE_PTS = XFG_CE_PTS, CE_THREADS = XFG_CE_THREADS;
 template <int D>
 __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(const u64* __restrict__ lde, u32 ln, const AirParams* __restrict__ airp, const ProofState* __restrict__ ps,
                                                                  PowTable wn, u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* __restrict__ out, size_t out_tstride) {
-  __shared__ u64 sh[CE_PTS][2 * D + 2][CE_THREADS];      // per point: u (D), w (D), d, prefix
+  extern __shared__ u64 ce_dsm[];
+  u64 (*sh)[2 * D + 2][CE_THREADS] = reinterpret_cast<u64 (*)[2 * D + 2][CE_THREADS]>(ce_dsm);   // [CE_PTS points][u (D), w (D), d, prefix][thread]
   __shared__ u64 sc[(XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS) * 2];
   const AirParams air = *airp;                            // AIR constants live in device memory so that the launch is CUDA-graph replayable
   const size_t n = size_t(1) << ln, N = 8 * n;
@@ -60,7 +72,8 @@ __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(con
   const size_t per = n / CE_PTS, t = (size_t)blockIdx.x * blockDim.x + tid;
   if (tid < (XFG_NUM_TRANSITION + XFG_NUM_ASSERTIONS) * 2) sc[tid] = (&ps->tcoef[0][0])[tid];   // tcoef[7][2] then bcoef[8][2], contiguous
   __syncthreads();
-  if (t >= per) return;
+  const bool active = t < per;
+  if (!XFG_CE_CTA_INV && !active) return;
   const u64 sk = kp ? s_k1 : s_k0, zinv = kp ? zinv1 : zinv0;
   const u64 large_burn = gl_mul(XFG_STD_BURN, 1000);
   u64 acc = 1;
@@ -75,10 +88,10 @@ __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(con
     cp_async8(&pf[XFG_TRACE_WIDTH][tid], lde + (size_t)4 * N + (size_t)k * n + mn);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  fetch(0);
+  if (active) fetch(0);
 #endif
 #pragma unroll 1
-  for (int q = 0; q < CE_PTS; q++) {
+  for (int q = 0; q < (active ? CE_PTS : 0); q++) {
     const size_t m = t + q * per, mn = (m + 1) & (n - 1);
     u64 c[XFG_TRACE_WIDTH];
 #if XFG_CE_PREFETCH
@@ -123,7 +136,13 @@ __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(con
     sh[q][2 * D][tid] = dd; sh[q][2 * D + 1][tid] = acc;
     acc = gl_mul(acc, dd);
   }
+#if XFG_CE_CTA_INV
+  __shared__ u64 invbuf[CE_THREADS];
+  acc = cta_inv<CE_THREADS>(acc, invbuf);      // a thread without work hands in 1
+  if (!active) return;
+#else
   acc = w_inv(acc);
+#endif
 #pragma unroll 1
   for (int q = CE_PTS - 1; q >= 0; q--) {
     const size_t m = t + q * per;
@@ -133,11 +152,12 @@ __global__ void __launch_bounds__(CE_THREADS, XFG_CE_MINB) constraint_kernel(con
   }
 }
 
+static size_t ce_smem(int D) { return (size_t)CE_PTS * (2 * D + 2) * CE_THREADS * sizeof(u64); }
 void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const AirParams* air, const ProofState* ps, PowTable wn,
                         u64 s_k0, u64 s_k1, u64 zinv0, u64 zinv1, u64* out, size_t out_tstride) {
   const size_t per = (size_t(1) << ln) / CE_PTS; dim3 grid((unsigned)((per + CE_THREADS - 1) / CE_THREADS), 2);
-  if (D == 1) constraint_kernel<1><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out, out_tstride);
-  else constraint_kernel<2><<<grid, CE_THREADS, 0, st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out, out_tstride);
+  if (D == 1) constraint_kernel<1><<<grid, CE_THREADS, ce_smem(1), st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out, out_tstride);
+  else constraint_kernel<2><<<grid, CE_THREADS, ce_smem(2), st>>>(lde, ln, air, ps, wn, s_k0, s_k1, zinv0, zinv1, out, out_tstride);
   XFG_LAUNCHED(1);
 }
 
@@ -264,7 +284,10 @@ void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef
 // Thread (k, a) computes the 8 points m = a + j*n/8 - exactly the 8 elements of row 8a + k of the first FRI layer - with one
 // batched inversion, writes them coset-major and hashes the row into the layer-0 FRI tree.
 // ------------------------------------------------------------------------------------------------------------------
-static constexpr int DEEP_THREADS = 128;
+#ifndef XFG_DEEP_THREADS
+#define XFG_DEEP_THREADS 128
+#endif
+static constexpr int DEEP_THREADS = XFG_DEEP_THREADS;
 #ifndef XFG_DEEP_UNROLL
 #define XFG_DEEP_UNROLL 1   // points of the first loop interleaved per iteration (A/B switch).  Measured at 2^20 rows / quadratic (round 2): 1 -> 0.633 ms, 2 -> 0.676, 4 -> 0.692
                             // (128 registers, no spills in all three: the larger loop body costs instruction-cache hits, as the fully unrolled kernel of round 1 did)
@@ -309,18 +332,20 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
                                                              PowTable wn, const u64* __restrict__ s_k, u64 w8, u64* __restrict__ deep, Digest* __restrict__ fri_tree0) {
   constexpr int MAXW = WC ? WC : XFG_AIR_MAX_WIDTH;
   const int W = WC ? WC : (int)width_rt;
-  __shared__ u64 sh[8][D + 2][DEEP_THREADS];          // per point: numerator -> result (D), n_z n_zg, prefix
+  extern __shared__ u64 deep_dsm[];
+  u64 (*sh)[D + 2][DEEP_THREADS] = reinterpret_cast<u64 (*)[D + 2][DEEP_THREADS]>(deep_dsm);   // [8 points][numerator -> result (D), n_z n_zg, prefix][thread]
   __shared__ u64 sc[2 * (MAXW + 1) + 8];              // dcoef[W + 1][2], then (at 2 (MAXW + 1)) c1, c2, z, zg
   const size_t n = size_t(1) << ln, N = 8 * n, n8 = n / 8;
   const u32 k = blockIdx.y, tid = threadIdx.x; const size_t a = (size_t)blockIdx.x * blockDim.x + tid;
   for (u32 i = tid; i < 2u * (W + 1); i += DEEP_THREADS) sc[i] = dcoef[i];
   if (tid < 8) { const u64* src = tid < 2 ? ps->deep_c1 : tid < 4 ? ps->deep_c2 : tid < 6 ? ps->z : ps->zg; sc[2 * (MAXW + 1) + tid] = src[tid & 1]; }
   __syncthreads();
-  if (a >= n8) return;
+  const bool active = a < n8;
+  if (!XFG_DEEP_CTA_INV && !active) return;
   const u64* cc = sc + 2 * (MAXW + 1);
   const Ext<D> delta(sc[2 * W], sc[2 * W + 1]), c1(cc[0], cc[1]), c2(cc[2], cc[3]);
   const DeepPoint<D> pz{cc[4], cc[5], gl_neg(gl_dbl(cc[5])), gl_dbl(gl_sqr(cc[5]))}, pzg{cc[6], cc[7], gl_neg(gl_dbl(cc[7])), gl_dbl(gl_sqr(cc[7]))};
-  u64 x = gl_mul(s_k[k], pow_lookup(wn, a)), acc = 1;      // x_j = x_0 * w_8^j  (m = a + j n/8)
+  u64 x = gl_mul(s_k[k], pow_lookup(wn, active ? a : 0)), acc = 1;      // x_j = x_0 * w_8^j  (m = a + j n/8)
   constexpr bool PF = XFG_DEEP_PREFETCH && WC != 0;
   __shared__ u64 pf[PF ? WC + D : 1][PF ? DEEP_THREADS : 1];      // one buffer (static shared memory is capped at 48 KB): read into registers, then refilled
   auto fetch = [&](int j) {      // point j of this thread -> pf[.][tid]
@@ -331,9 +356,9 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
     for (int l = 0; l < (PF ? D : 0); l++) cp_async8(&pf[(PF ? WC : 0) + l][tid], hlde + (size_t)l * N + idx);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (PF) fetch(0);
+  if (PF && active) fetch(0);
 #pragma unroll DEEP_UNROLL
-  for (int j = 0; j < 8; j++) {
+  for (int j = 0; j < (active ? 8 : 0); j++) {
     const size_t idx = (size_t)k * n + a + (size_t)j * n8;
     u64 pv[PF ? WC + D : 1];
     if (PF) {
@@ -356,7 +381,13 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
     sh[j][D][tid] = den; sh[j][D + 1][tid] = acc;
     acc = gl_mul(acc, den); x = gl_mul_pow2<24>(x);      // x_j = x_0 * w_8^j, w_8 = 2^24
   }
+#if XFG_DEEP_CTA_INV
+  __shared__ u64 invbuf[DEEP_THREADS];
+  acc = cta_inv<DEEP_THREADS>(acc, invbuf);      // a thread without work hands in 1
+  if (!active) return;
+#else
   acc = w_inv(acc);
+#endif
 #pragma unroll 1
   for (int j = 7; j >= 0; j--) {
     const size_t idx = (size_t)k * n + a + (size_t)j * n8;
@@ -371,16 +402,28 @@ __global__ void __launch_bounds__(DEEP_THREADS, XFG_DEEP_MINB) deep_kernel(const
     store_digest(fri_tree0 + n + 8 * a + k, b3_hash_limbs<8 * D>(row));
   }
 }
+static size_t deep_smem(int D) { return (size_t)8 * (D + 2) * DEEP_THREADS * sizeof(u64); }
 void launch_deep(cudaStream_t st, int D, const u64* lde, const u64* hlde, u32 ln, const ProofState* ps, const u64* dcoef, u32 width, PowTable wn, const u64* s_k,
                  u64* deep, Digest* fri_tree0) {
   const size_t n8 = (size_t(1) << ln) / 8; dim3 grid((unsigned)((n8 + DEEP_THREADS - 1) / DEEP_THREADS), 8);
   const u64 w8 = gl_root_of_unity(3);
+  const size_t sm = deep_smem(D);
   if (width == XFG_TRACE_WIDTH) {
-    if (D == 1) deep_kernel<1, XFG_TRACE_WIDTH><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
-    else deep_kernel<2, XFG_TRACE_WIDTH><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
-  } else if (D == 1) deep_kernel<1, 0><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
-  else deep_kernel<2, 0><<<grid, DEEP_THREADS, 0, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
+    if (D == 1) deep_kernel<1, XFG_TRACE_WIDTH><<<grid, DEEP_THREADS, sm, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
+    else deep_kernel<2, XFG_TRACE_WIDTH><<<grid, DEEP_THREADS, sm, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
+  } else if (D == 1) deep_kernel<1, 0><<<grid, DEEP_THREADS, sm, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
+  else deep_kernel<2, 0><<<grid, DEEP_THREADS, sm, st>>>(lde, hlde, ln, ps, dcoef, width, wn, s_k, w8, deep, fri_tree0);
   XFG_LAUNCHED(1);
+}
+// Opt-in dynamic shared memory sizes are per device: called by every xfg_create for its own device (needed once XFG_DEEP_THREADS / XFG_CE_THREADS
+// push the staging arrays past 48 KB; harmless below)
+void stark_init() {
+  cudaFuncSetAttribute(constraint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem(1));
+  cudaFuncSetAttribute(constraint_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem(2));
+  cudaFuncSetAttribute(deep_kernel<1, XFG_TRACE_WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deep_smem(1));
+  cudaFuncSetAttribute(deep_kernel<2, XFG_TRACE_WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deep_smem(2));
+  cudaFuncSetAttribute(deep_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deep_smem(1));
+  cudaFuncSetAttribute(deep_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)deep_smem(2));
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ void launch_constraints(cudaStream_t st, int D, const u64* lde, u32 ln, const Ai
 void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64* h, ProofState* ps);
 u32 ood_num_blocks(u32 ln);
 void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef, u32 ln, u32 width, const ProofState* ps, u64* partial);
+void stark_init();   // per-device kernel attributes (dynamic shared memory opt-in); xfg_create calls it
 void launch_deep(cudaStream_t st, int D, const u64* lde, const u64* hlde, u32 ln, const ProofState* ps, const u64* dcoef, u32 width, PowTable wn, const u64* s_k,
                  u64* deep, Digest* fri_tree0);
 void launch_fri_fold(cudaStream_t st, int D, const u64* src, size_t src_limb_stride, int src_coset, u32 lNl, u32 layer, const ProofState* ps,
