@@ -201,4 +201,13 @@ template <int S> __device__ __forceinline__ u64 w_mul_pow2(u64 x) {
   return w_sub_c(w_mul_eps(y0), w_pack(y1, y2));        // (y2:y1) < 2^63: canonical
 }
 
+// -x for a weak x -> weak:  ~x = 2^64 - 1 - x stands for EPS - 1 - x, so -x = ~x - (EPS - 1)
+__device__ __forceinline__ u64 w_neg(u64 x) { return w_sub_c(~x, GL_EPS - 1); }
+// x * 2^E for a compile-time E in [0, 192) (2 has order 192; 2^96 = -1), x weak -> weak
+template <int E> __device__ __forceinline__ u64 w_mul_pow2_any(u64 x) {
+  static_assert(E >= 0 && E < 192, "exponent out of range");
+  if (E < 96) return w_mul_pow2<(E < 96 ? E : 0)>(x);
+  return w_neg(w_mul_pow2<(E >= 96 ? E - 96 : 0)>(x));
+}
+
 }  // namespace xfg

@@ -120,17 +120,40 @@ template <int LOGR, bool INV, int STAGE> struct DftStep<LOGR, INV, STAGE, (1 << 
 };
 template <int LOGR, bool INV> struct DftStep<LOGR, INV, LOGR, 0> { static __device__ __forceinline__ void run(u64 (&)[1 << LOGR]) {} };
 
-template <int LOGR, bool INV, int EPT>
+// Inter-pass twiddles of a pass whose sub-transform length ns * R is 64: w_64 = 2^3, so the twiddle w_64^(+-k r) of input r is the
+// compile-time shift 2^(+-3 K r) once k = K is known - one IMAD.WIDE and 8 - 13 instructions instead of a full 64 x 64-bit product
+template <int K, bool INV, int R, int r = 1> struct Pow2Twiddle {
+  static __device__ __forceinline__ void run(u64 (&v)[R]) {
+    constexpr int e = (3 * K * r) % 192, E = INV ? (192 - e) % 192 : e;
+    v[r] = w_mul_pow2_any<E>(v[r]);
+    Pow2Twiddle<K, INV, R, r + 1>::run(v);
+  }
+};
+template <int K, bool INV, int R> struct Pow2Twiddle<K, INV, R, R> { static __device__ __forceinline__ void run(u64 (&)[R]) {} };
+
+// POW2 (ns = 4, R = 16, one item per thread): the items are dealt to the threads so that k = j mod 4 is the same for a whole warp
+// (bits [1:0] of the item's row swapped with the two lowest warp-uniform bits), and the warp branches once on k into the shift twiddles.
+template <int LOGR, bool INV, int EPT, bool POW2 = false>
 __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __restrict__ TW, u32 Llog, u32 Tlog, u32 TP, u32 ns_log, u32 tid, u32 nthreads) {
   constexpr int R = 1 << LOGR, ITEMS = EPT / R;
+  static_assert(!POW2 || (LOGR == 4 && ITEMS == 1), "POW2: radix 16, one item per thread");
   const u32 Tm = (1u << Tlog) - 1, stride = 1u << (Llog - LOGR), nsm = (1u << ns_log) - 1, tsh = Llog - ns_log - LOGR;
+  const u32 wl = 5 - Tlog;      // POW2: rows per warp = 2^wl (>= 4: Tlog <= 3)
+  auto row_of = [&](u32 jt) -> u32 { return POW2 ? (jt & ~(3u | (3u << wl))) | ((jt & 3u) << wl) | ((jt >> wl) & 3u) : jt; };
   u64 v[ITEMS][R];
 #pragma unroll
   for (int q = 0; q < ITEMS; q++) {
-    const u32 w = tid + q * nthreads, col = w & Tm, j = w >> Tlog, k = j & nsm;
+    const u32 w = tid + q * nthreads, col = w & Tm, j = row_of(w >> Tlog), k = j & nsm;
 #pragma unroll
     for (int r = 0; r < R; r++) v[q][r] = S[(j + r * stride) * TP + col];
-    if (ns_log) {
+    if (POW2) {
+      switch (k) {      // warp-uniform
+        case 1: Pow2Twiddle<1, INV, R>::run(v[q]); break;
+        case 2: Pow2Twiddle<2, INV, R>::run(v[q]); break;
+        case 3: Pow2Twiddle<3, INV, R>::run(v[q]); break;
+        default: break;
+      }
+    } else if (ns_log) {
 #pragma unroll
       for (int r = 1; r < R; r++) v[q][r] = w_mul(v[q][r], TW[(k * r) << tsh]);
     }
@@ -139,7 +162,7 @@ __device__ __forceinline__ void stockham_pass(u64* __restrict__ S, const u64* __
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < ITEMS; q++) {
-    const u32 w = tid + q * nthreads, col = w & Tm, j = w >> Tlog, k = j & nsm;
+    const u32 w = tid + q * nthreads, col = w & Tm, j = row_of(w >> Tlog), k = j & nsm;
     const u32 j0 = ((j >> ns_log) << (ns_log + LOGR)) | k;
 #pragma unroll
     for (int r = 0; r < R; r++) S[(j0 + ((u32)r << ns_log)) * TP + col] = v[q][brev_c(r, LOGR)];
@@ -159,6 +182,14 @@ __host__ __device__ constexpr u32 r16_radix_packed_c(u32 Llog) {
   return Llog == 8 ? 0x44u : Llog == 9 ? 0x234u : Llog == 10 ? 0x244u : Llog == 11 ? 0x344u : 0x444u;
 }
 
+// XFG_R16_POW2TW (2^10-point tiles): 0 = radix plan 16 x 16 x 4, every inter-pass twiddle from the table; 1 = 4 x 16 x 16 with shift twiddles
+// between the first two passes (Pow2Twiddle: 0.94 full multiplications per element instead of 1.69); 2 = the 4 x 16 x 16 order with table twiddles.
+// Measured at 2^20 rows / quadratic (B200, round 2; parity green with 1): trace LDE 1.124 (0) / 1.121 (1) / 1.186 ms (2), the four NTT families together
+// 1.664 / 1.668 / 1.750 ms.  The shift form takes three of a product's four IMAD.WIDE off the heavy FMA half, but costs as many ALU-pipe
+// instructions (shifts and carry fix-ups: 10 - 11 against ~10), and the ALU pipe is the one that binds: neutral, so the simpler plan stays.
+#ifndef XFG_R16_POW2TW
+#define XFG_R16_POW2TW 0
+#endif
 #ifndef XFG_R16_MINB
 #define XFG_R16_MINB 2   // 64 registers: measured best (1: 126 regs 2.26 ms, 2: 1.77 ms, 3: 1.84 ms, 4: 1.95 ms for the 2^20 trace LDE)
 #endif
@@ -224,6 +255,13 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : XFG_R16_MINB) ntt_pas
   }
   __syncthreads();
   u32 ns_log = 0;
+  if (LLOG == 10 && XFG_R16_POW2TW) {
+    // 1024 = 4 x 16 x 16: the twiddles between the first two passes are 64th roots of unity = powers of two (shifts); only the last pass
+    // multiplies by table twiddles: 0.94 full multiplications per element instead of 1.69 with the 16 x 16 x 4 plan
+    stockham_pass<2, INV, EPT>(S, TW, 10, Tlog, TP, 0, tid, nthreads);
+    stockham_pass<4, INV, EPT, XFG_R16_POW2TW == 1>(S, TW, 10, Tlog, TP, 2, tid, nthreads);
+    stockham_pass<4, INV, EPT>(S, TW, 10, Tlog, TP, 6, tid, nthreads);
+  } else
 #pragma unroll
   for (u32 ps = 0; ps < num_radix; ps++) {
     const u32 lr = (radix_logs >> (4 * ps)) & 15;
