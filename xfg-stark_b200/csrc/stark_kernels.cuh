@@ -55,7 +55,10 @@ void launch_int_peak(cudaStream_t st, const u32* in, u32* out, u32 blocks, u32 i
 void launch_pipe_probe(cudaStream_t st, int mode, const u32* in, u32* out, u32 blocks, u32 iters);
 void launch_field_selftest(cudaStream_t st, u32 op, const u64* a, const u64* b, size_t n, u64* out);
 // fri_tail.cu: the FRI layers of at most 2^FRI_TAIL_MAX_LOG evaluations, the remainder, the grinding nonce and the query positions in one launch
-static constexpr u32 FRI_TAIL_MAX_LOG = 14, FRI_TAIL_MAX_GRIND = 12, NTT_TW_LOG_TAIL = 12;
+#ifndef XFG_FRI_TAIL_MAX_LOG
+#define XFG_FRI_TAIL_MAX_LOG 14
+#endif
+static constexpr u32 FRI_TAIL_MAX_LOG = XFG_FRI_TAIL_MAX_LOG, FRI_TAIL_MAX_GRIND = 12, NTT_TW_LOG_TAIL = 12;
 struct FriTailArgs {
   u32 first_layer, num_layers, layer_log[MAX_LAYERS + 1];      // layers [first_layer, num_layers) are folded here
   u64* evals[MAX_LAYERS + 1]; u64 limb_stride[MAX_LAYERS + 1]; // evaluations of layer l: natural order [limb][i] (layer 0: coset-major DEEP evaluations)
