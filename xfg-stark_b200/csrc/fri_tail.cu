@@ -1,4 +1,4 @@
-// fri_tail.cu — the latency-bound end of the proof in ONE launch: every FRI layer with at most 2^14 evaluations (tree, commitment,
+// fri_tail.cu — the latency-bound end of the proof in ONE launch: every FRI layer with at most 2^13 evaluations (FRI_TAIL_MAX_LOG) (tree, commitment,
 // alpha, fold, rows of the next layer), the remainder (coset interpolation, commitment), the proof-of-work nonce and the query positions.
 //
 // Replaces the tail of winter-fri 0.8.3 `FriProver::build_layers` (per layer: `hash_values` -> `MerkleTree::new` -> `commit_fri_layer` ->

@@ -374,7 +374,7 @@ int enqueue_proof(xfg_ctx* ctx, Slot& s, const Plan& p, int D, const xfg_options
   { const u64* dcoef = gen ? &s.d_gen->dcoef[0][0] : reinterpret_cast<const u64*>(reinterpret_cast<const char*>(s.d_state) + offsetof(ProofState, dcoef));
     PROF("deep", launch_deep(st, D, c.lde, c.h_lde, ln, s.d_state, dcoef, W, p.ntt.wn_fwd, p.d_sk, c.deep, p.num_layers ? c.fri_tree[0] : nullptr)); }
   mark();
-  // 6 ---- compute_fri_layers: one tree / commit / fold launch set per large layer; every layer of <= 2^14 evaluations, the remainder, the
+  // 6 ---- compute_fri_layers: one tree / commit / fold launch set per large layer; every layer of <= 2^13 evaluations (FRI_TAIL_MAX_LOG), the remainder, the
   //   ---- grinding nonce and the query positions (7) run in ONE single-CTA launch (fri_tail.cu)
   u32 first_tail = p.num_layers;
   while (first_tail > 0 && p.layer_log[first_tail - 1] <= FRI_TAIL_MAX_LOG) first_tail--;

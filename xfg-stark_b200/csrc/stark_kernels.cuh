@@ -55,8 +55,11 @@ void launch_int_peak(cudaStream_t st, const u32* in, u32* out, u32 blocks, u32 i
 void launch_pipe_probe(cudaStream_t st, int mode, const u32* in, u32* out, u32 blocks, u32 iters);
 void launch_field_selftest(cudaStream_t st, u32 op, const u64* a, const u64* b, size_t n, u64* out);
 // fri_tail.cu: the FRI layers of at most 2^FRI_TAIL_MAX_LOG evaluations, the remainder, the grinding nonce and the query positions in one launch
+// Measured (B200, round 2; ms per proof at 2^20 rows / quadratic, 2^16 rows / no extension, 1024 x 2^16 proofs/s): 14 -> 3.880, 0.4855, 4699;
+// 13 -> 3.855, 0.4852, 4766; 12 -> 3.856, 0.482, 4725; 11 -> 3.854, 0.483, 4775.  At 14 the 2^14-evaluation layer of a 2^20-row proof (tree 20 us + fold
+// 28 us on ONE SM) sits in the tail; as two multi-CTA launches it costs half.  Below 13 the gain is within the noise and every layer adds two launches.
 #ifndef XFG_FRI_TAIL_MAX_LOG
-#define XFG_FRI_TAIL_MAX_LOG 14
+#define XFG_FRI_TAIL_MAX_LOG 13
 #endif
 static constexpr u32 FRI_TAIL_MAX_LOG = XFG_FRI_TAIL_MAX_LOG, FRI_TAIL_MAX_GRIND = 12, NTT_TW_LOG_TAIL = 12;
 struct FriTailArgs {
