@@ -9,7 +9,7 @@ python bench.py --workload verify > gpurun_out/${T}_verify.json 2>/dev/null
 python bench.py --workload air > gpurun_out/${T}_air.json 2>/dev/null
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-preload --headline-only > gpurun_out/${T}_plain.json 2>/dev/null || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-preload --headline-only > gpurun_out/${T}_ncu_ll.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'commit_rows_kernel|ntt_pass_r16|deep_kernel|constraint_kernel|fri_fold_kernel|ood_kernel|fri_tail_kernel|tree_' -c 24 -f -o gpurun_out/${T}_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-preload --headline-only > gpurun_out/${T}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'commit_rows_kernel|ntt_pass_r16|deep_kernel|constraint_kernel|fri_fold_kernel|ood_kernel|fri_tail_kernel|tree_' -c 26 -f -o gpurun_out/${T}_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-preload --headline-only > gpurun_out/${T}_ncu_full.log 2>&1
 ls -la gpurun_out/${T}_prof.ncu-rep
 # gpurun copies back at most 64 MiB: keep the raw metric table (CSV) and the summary, drop the report itself
 ncu -i gpurun_out/${T}_prof.ncu-rep --page raw --csv > gpurun_out/${T}_ncu_raw.csv 2>/dev/null
