@@ -192,6 +192,10 @@ void launch_combine(cudaStream_t st, const u64* a, u32 ln, int D, u64 inv2, u64*
 #ifndef XFG_OOD_SHARE
 #define XFG_OOD_SHARE 0
 #endif
+#ifndef XFG_OOD_LOCAL_POW
+#define XFG_OOD_LOCAL_POW 1
+#endif
+static constexpr u32 OOD_THREADS = 256;
 template <int D>
 __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_coef, const u64* __restrict__ h_coef, u32 ln, u32 width, u32 polys_per_block,
                                                    const ProofState* __restrict__ ps, u64* __restrict__ partial) {
@@ -202,21 +206,53 @@ __global__ void __launch_bounds__(256) ood_kernel(const u64* __restrict__ trace_
   // powers of the two evaluation points shared by the block: sq[w][b] = pt_w^(2^b), b < 32 (one lane per (w, b) chain would be
   // serial anyway: thread w squares 31 times), then every thread assembles pt^t and pt^TOT from the set bits of t / TOT
   __shared__ u64 sq[2][32][2];
+  const int nbits = (int)ln < 1 ? 1 : (int)ln;      // every exponent is < n = 2^ln
   if (tid < 2) {
     Ext<D> x = ld_ext1<D>(tid == 0 ? ps->z : ps->zg);
-    for (int b = 0; b < 32; b++) { sq[tid][b][0] = x.limb(0); sq[tid][b][1] = D == 2 ? x.limb(1) : 0; x = x * x; }
+    for (int b = 0; b < nbits; b++) { sq[tid][b][0] = x.limb(0); sq[tid][b][1] = D == 2 ? x.limb(1) : 0; x = x * x; }
   }
   __syncthreads();
-  auto pw = [&](int w, size_t e) { Ext<D> r(1); for (int b = 0; b < 32; b++) if ((e >> b) & 1) r = r * Ext<D>(sq[w][b][0], sq[w][b][1]); return r; };
+  auto pw = [&](int w, size_t e) { Ext<D> r(1); for (int b = 0; b < nbits; b++) if ((e >> b) & 1) r = r * Ext<D>(sq[w][b][0], sq[w][b][1]); return r; };
   // table of (pt^TOT)^i, i < n/TOT, so that a thread's share  sum_i c[t + i TOT] pt^(i TOT)  is a plain dot product of base-field
   // coefficients with table limbs: accumulated un-reduced (DotAcc), 4 cheap fma per coefficient instead of 2 extension Horner steps
   __shared__ u64 tab[OOD_MAX_STEPS][2][2];
   const size_t steps = n > TOT ? n / TOT : 1;
   for (size_t i = tid; i < steps; i += blockDim.x) for (int w = 0; w < 2; w++) { const Ext<D> v = pw(w, i * TOT); tab[i][w][0] = v.limb(0); tab[i][w][1] = D == 2 ? v.limb(1) : 0; }
+#if XFG_OOD_LOCAL_POW
+  __shared__ u64 lp[2][OOD_THREADS][2];      // pt_w^i, i < 256
+  __shared__ u64 bp[2][2];                   // pt_w^(first exponent of this block)
+  if (tid >= OOD_THREADS - 2) {              // the last two threads: they have no table entry to compute unless steps = 256
+    const u32 w = tid - (OOD_THREADS - 2);
+    const Ext<D> b = pw((int)w, (size_t)blockIdx.x * OOD_THREADS);
+    bp[w][0] = b.limb(0); bp[w][1] = D == 2 ? b.limb(1) : 0;
+    lp[w][0][0] = 1; lp[w][0][1] = 0;
+  }
+#endif
   __syncthreads();
   // the powers pt^t of this thread serve every polynomial of the block's group (blockIdx.y): wide traces amortise the set-up above
   Ext<D> pt[2];
+#if XFG_OOD_LOCAL_POW
+  // pt^t = pt^(block base) * pt^tid.  The 256 powers pt^tid are built by doubling - thread i multiplies ONCE, at step floor(log2 i):
+  // lp[i] = lp[i - 2^s] * pt^(2^s) - and the base by one thread per point: 2 extension multiplications per thread and point instead of one per set
+  // bit of t (a warp ran ~14 per point, a third of the kernel's instructions).  Exponents beyond n are never used (t < n is checked below).
+#pragma unroll 1
+  for (int sft = 0; (1 << sft) < OOD_THREADS; sft++) {
+    if ((tid >> sft) == 1 && sft < nbits) {
+#pragma unroll
+      for (int w = 0; w < 2; w++) {
+        const Ext<D> v = Ext<D>(lp[w][tid - (1u << sft)][0], lp[w][tid - (1u << sft)][1]) * Ext<D>(sq[w][sft][0], sq[w][sft][1]);
+        lp[w][tid][0] = v.limb(0); lp[w][tid][1] = D == 2 ? v.limb(1) : 0;
+      }
+    }
+    __syncthreads();
+  }
+  if (t < n) {
+#pragma unroll
+    for (int w = 0; w < 2; w++) pt[w] = Ext<D>(lp[w][tid][0], lp[w][tid][1]) * Ext<D>(bp[w][0], bp[w][1]);
+  }
+#else
   if (t < n) { pt[0] = pw(0, t); pt[1] = pw(1, t); }
+#endif
   __shared__ u64 red[2][8][4];
 #pragma unroll 1
   for (u32 poly = p0; poly < p1; poly++) {
@@ -272,8 +308,8 @@ void launch_ood(cudaStream_t st, int D, const u64* trace_coef, const u64* h_coef
   ppb = P;
 #endif
   dim3 grid(nb, (P + ppb - 1) / ppb);
-  if (D == 1) ood_kernel<1><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
-  else ood_kernel<2><<<grid, 256, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
+  if (D == 1) ood_kernel<1><<<grid, OOD_THREADS, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
+  else ood_kernel<2><<<grid, OOD_THREADS, 0, st>>>(trace_coef, h_coef, ln, width, ppb, ps, partial);
   XFG_LAUNCHED(1);
 }
 
